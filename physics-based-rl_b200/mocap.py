@@ -1,0 +1,267 @@
+"""DeepMimic mocap txt -> MuJoCo-layout reference trajectories (host side, setup time, float64).
+
+Mirror of the reference's converter interface (/root/reference/utils/SimpleConverter.py:15-238,
+helpers /root/reference/some_math/math_utils.py:15-65 and
+/root/reference/some_math/transformations.py:1031-1097,1174-1193), restated with plain numpy:
+pyquaternion and jax are not needed.  Same attribute names (`data`, `data_pos`, `data_vel`,
+`durations`, `total_time`, `duration_dict`) and the same quirks:
+
+  * Y-up left-handed -> Z-up right-handed:  pos (x,y,z)->(x,-z,y), quat (w,x,y,z)->(w,x,-z,y);
+  * 3-dof joints become intrinsic X-Y-Z Euler angles ('rxyz');
+  * angular "velocity" = axis*angle/dt of conj(q_cur)*q_prev (i.e. the negative of the usual
+    body-frame rate), first frame velocity 0, frame k uses the duration of frame k-1;
+  * quaternions are not normalised.
+
+`MotionTable` (bottom) is the build-defined part: the packed per-clip tables the CUDA kernels
+interpolate in mimic mode ("parity unpinned").
+"""
+from __future__ import annotations
+
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+
+from .util_data import BODY_JOINTS, BODY_JOINTS_IN_DP_ORDER, DOF_DEF
+
+MOTION_NAMES = ["walk", "punch", "kick", "jump", "backflip", "getup_facedown", "getup_faceup"]
+
+
+# ---- small quaternion helpers (w,x,y,z) ------------------------------------------------------
+def _qmul(a, b):
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return np.array([aw * bw - ax * bx - ay * by - az * bz,
+                     aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw])
+
+
+def align_position(pos):
+    """(x, y, z) -> (x, -z, y)   (math_utils.py:15-22)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    assert pos.shape[0] == 3
+    return np.array([pos[0], -pos[2], pos[1]])
+
+
+def align_rotation(rot):
+    """Similarity by Rx(+90deg): (w, x, y, z) -> (w, x, -z, y)   (math_utils.py:25-42)."""
+    c = math.sqrt(0.5)
+    left = np.array([c, c, 0.0, 0.0])
+    right = np.array([c, -c, 0.0, 0.0])
+    return _qmul(_qmul(left, np.asarray(rot, dtype=np.float64)), right)
+
+
+def calc_rot_vel(seg_0, seg_1, dura):
+    """axis*angle/dura of conj(seg_0)*seg_1 with pyquaternion's conventions (math_utils.py:46-65)."""
+    q0 = np.asarray(seg_0, dtype=np.float64)
+    q1 = np.asarray(seg_1, dtype=np.float64)
+    qd = _qmul(np.array([q0[0], -q0[1], -q0[2], -q0[3]]), q1)
+    n = np.linalg.norm(qd)
+    if abs(1.0 - n * n) >= 1e-14 and n > 0:
+        qd = qd / n
+    vn = np.linalg.norm(qd[1:])
+    axis = qd[1:] / vn if vn >= 1e-17 else np.zeros(3)
+    angle = 2.0 * math.atan2(vn, qd[0])
+    angle = ((angle + math.pi) % (2.0 * math.pi)) - math.pi
+    if angle == -math.pi:
+        angle = math.pi
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = angle / dura * axis
+    return [w[0], w[1], w[2]]
+
+
+def euler_xyz_from_quat_xyzw(q_xyzw):
+    """Intrinsic X-Y-Z Euler angles of a quaternion given as (x, y, z, w)  == the reference's
+    `euler_from_quaternion(q, axes='rxyz')` (transformations.py:1089, 1031-1086)."""
+    x, y, z, w = [float(v) for v in q_xyzw]
+    nq = x * x + y * y + z * z + w * w
+    if nq < np.finfo(float).eps * 4.0:
+        return (0.0, 0.0, 0.0)
+    s = 2.0 / nq
+    m00 = 1.0 - s * (y * y + z * z)
+    m01 = s * (x * y - z * w)
+    m02 = s * (x * z + y * w)
+    m12 = s * (y * z - x * w)
+    m22 = 1.0 - s * (x * x + y * y)
+    cy = math.sqrt(m22 * m22 + m12 * m12)
+    if cy > np.finfo(float).eps * 4.0:
+        ex = -math.atan2(m12, m22)
+        ey = math.atan2(m02, cy)
+        ez = -math.atan2(m01, m00)
+    else:  # gimbal lock: transformations.py falls back to az = 0 (pre-swap)
+        m10 = s * (x * y + z * w)
+        m11 = 1.0 - s * (x * x + z * z)
+        ex = 0.0
+        ey = math.atan2(m02, cy)
+        ez = math.atan2(m10, m11)
+    return (ex, ey, ez)
+
+
+class SimpleConverter(object):
+    """Same public surface as /root/reference/utils/SimpleConverter.py:15."""
+
+    def __init__(self, file) -> None:
+        self.pos_dim = 3
+        self.rot_dim = 4
+        self.file = file
+        self.load_data()
+
+    def load_data(self):
+        with open(self.file, "r") as fin:
+            data = json.load(fin)
+        self.loop = data.get("Loop", "none")
+        self.motions = np.array(data["Frames"], dtype=np.float64)
+        self.data = np.full(self.motions.shape, np.nan)
+        self.dt = self.motions[0][0]
+
+    def load_mocap(self):
+        self.read_raw_data()
+        self.convert_to_mujoco_data()
+        self.create_dict_duration()
+
+    def read_raw_data(self):
+        self.all_states = []
+        durations = []
+        self.total_time = 0.0
+        for frame in self.motions:
+            self.total_time += frame[0]
+            durations.append(frame[0])
+            state = {"root_pos": align_position(frame[1:4]), "root_rot": align_rotation(frame[4:8])}
+            off = 8
+            for joint in BODY_JOINTS_IN_DP_ORDER:
+                if DOF_DEF[joint] == 1:
+                    state[joint] = frame[off:off + 1].copy()
+                    off += 1
+                else:
+                    state[joint] = align_rotation(frame[off:off + 4])
+                    off += 4
+            self.all_states.append(state)
+        self.durations = np.array(durations)
+
+    def convert_to_mujoco_data(self):
+        self.data_vel, self.data_pos = [], []
+        for k, state in enumerate(self.all_states):
+            dura = self.durations[k] if k == 0 else self.durations[k - 1]
+            vel, ang = [], []
+            self.data[k, 0] = dura
+            self.data[k, 1:4] = state["root_pos"]
+            self.data[k, 4:8] = state["root_rot"]
+            if k == 0:
+                vel += [0.0] * 6
+            else:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    vel += ((self.data[k, 1:4] - self.data[k - 1, 1:4]) * 1.0 / dura).tolist()
+                vel += calc_rot_vel(self.data[k, 4:8], self.data[k - 1, 4:8], dura)
+            ang += state["root_pos"].tolist() + state["root_rot"].tolist()
+            off = 8
+            for joint in BODY_JOINTS:
+                n = 1 if DOF_DEF[joint] == 1 else 4
+                self.data[k, off:off + n] = state[joint]
+                if n == 1:
+                    if k == 0:
+                        vel += [0.0]
+                    else:
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            vel += ((self.data[k, off:off + 1] - self.data[k - 1, off:off + 1]) / dura).tolist()
+                    ang += state[joint].tolist()
+                else:
+                    if k == 0:
+                        vel += [0.0, 0.0, 0.0]
+                    else:
+                        vel += calc_rot_vel(self.data[k, off:off + 4], self.data[k - 1, off:off + 4], dura)
+                    q = state[joint]
+                    ang += list(euler_xyz_from_quat_xyzw([q[1], q[2], q[3], q[0]]))
+                off += n
+            self.data_vel.append(np.array(vel))
+            self.data_pos.append(np.array(ang))
+
+    def create_dict_duration(self):
+        # the reference accumulates with jp.cumsum, i.e. in float32 (SimpleConverter.py:226-238)
+        cum = np.cumsum(self.durations.astype(np.float32), dtype=np.float32)
+        cum = np.concatenate([np.zeros(1, dtype=np.float32), cum[:-1]])
+        self.duration_dict = {i: [float(cum[i]), float(self.durations[i])] for i in range(len(self.durations))}
+
+
+# --------------------------------------------------------------------------------------------
+# Build-defined: packed motion tables for mimic mode
+# --------------------------------------------------------------------------------------------
+FRAME_STRIDE = 80  # floats per frame in the device table (16-byte multiple for cp.async.bulk)
+# frame layout: [0:35] qpos (root pos, root quat, 28 hinge angles), [35:69] qvel (hinge rates by
+# finite differences of the Euler angles, root rates in MuJoCo convention), [69] frame start time,
+# [70] frame duration, [71:80] pad.
+
+
+def _quat_conj(q):
+    return np.array([q[0], -q[1], -q[2], -q[3]])
+
+
+class MotionTable:
+    """All clips packed into one float32 table + per-clip header, for the device."""
+
+    def __init__(self, clips):
+        """clips: list of (name, SimpleConverter-like with data_pos, durations, loop)."""
+        self.names = [c[0] for c in clips]
+        frames, hdr = [], []
+        start = 0
+        for name, conv in clips:
+            pos = np.asarray(conv.data_pos, dtype=np.float64)
+            dur = np.asarray(conv.durations, dtype=np.float64)
+            F = pos.shape[0]
+            vel = self.reference_qvel(pos, dur)
+            t0 = np.concatenate([[0.0], np.cumsum(dur)[:-1]])
+            tab = np.zeros((F, FRAME_STRIDE), dtype=np.float32)
+            tab[:, 0:35] = pos
+            tab[:, 35:69] = vel
+            tab[:, 69] = t0
+            tab[:, 70] = dur
+            frames.append(tab)
+            total = float(dur[:-1].sum())  # last frame has dt = 0 in every DeepMimic file
+            hdr.append((start, F, total, 1.0 if conv.loop == "wrap" else 0.0))
+            start += F
+        self.frames = np.concatenate(frames, axis=0)
+        self.header = np.asarray(hdr, dtype=np.float64)  # (nclip, 4): first frame, n frames, duration, wrap
+
+    @staticmethod
+    def reference_qvel(pos, dur):
+        """MuJoCo-convention qvel by forward differences (root linear: world frame; root angular:
+        body-local; hinges: Euler-angle rates).  Last frame repeats the previous velocity."""
+        F = pos.shape[0]
+        vel = np.zeros((F, 34))
+        for k in range(F - 1):
+            h = dur[k] if dur[k] > 0 else dur[max(k - 1, 0)]
+            vel[k, 0:3] = (pos[k + 1, 0:3] - pos[k, 0:3]) / h
+            q0 = pos[k, 3:7] / np.linalg.norm(pos[k, 3:7])
+            q1 = pos[k + 1, 3:7] / np.linalg.norm(pos[k + 1, 3:7])
+            dq = _qmul(_quat_conj(q0), q1)
+            if dq[0] < 0:
+                dq = -dq
+            vn = np.linalg.norm(dq[1:])
+            ang = 2.0 * math.atan2(vn, dq[0])
+            vel[k, 3:6] = (dq[1:] / vn * ang / h) if vn > 1e-12 else 0.0
+            d = pos[k + 1, 7:] - pos[k, 7:]
+            d = (d + np.pi) % (2 * np.pi) - np.pi
+            vel[k, 6:] = d / h
+        if F > 1:
+            vel[F - 1] = vel[F - 2]
+        return vel
+
+    def save(self, path):
+        np.savez_compressed(path, frames=self.frames, header=self.header, names=np.array(self.names))
+
+    @staticmethod
+    def load(path):
+        z = np.load(path, allow_pickle=False)
+        t = MotionTable.__new__(MotionTable)
+        t.frames, t.header, t.names = z["frames"], z["header"], [str(s) for s in z["names"]]
+        return t
+
+
+def load_motion_dir(motion_dir, names=MOTION_NAMES):
+    clips = []
+    for n in names:
+        c = SimpleConverter(str(Path(motion_dir) / f"humanoid3d_{n}.txt"))
+        c.load_mocap()
+        clips.append((n, c))
+    return clips
