@@ -129,3 +129,103 @@ class OracleData:
         d = OracleData(self._orc)
         d.buf[:] = self.buf
         return d
+
+
+class _EnvBuffers(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics")]
+
+
+class OracleEnv:
+    """Batched env state + reset/step/replay through the oracle's env layer (pbrl_oracle_env.c)."""
+
+    def __init__(self, orc: Oracle, N: int, nthreads: int = 0):
+        self.orc, self.N, self.nthreads = orc, N, nthreads
+        r = orc.real
+        self.qpos = np.zeros((N, orc.nq), r)
+        self.qvel = np.zeros((N, orc.nv), r)
+        self.time = np.zeros(N, r)
+        self.warm = np.zeros((N, orc.nv), r)
+        self.ctrl = np.zeros((N, orc.nu), r)
+        self.qpos_lag = np.zeros((N, orc.nq), r)
+        self.qvel_lag = np.zeros((N, orc.nv), r)
+        self.obs = np.zeros((N, orc.nq + orc.nv), r)
+        self.reward = np.zeros((N, 3), r)
+        self.done = np.zeros(N, r)
+        self.metrics = np.zeros((N, 3), r)
+
+    def _bufs(self):
+        b = _EnvBuffers()
+        for n, _ in _EnvBuffers._fields_:
+            setattr(b, n, getattr(self, n).ctypes.data)
+        return b
+
+    def _p(self, a):
+        return None if a is None else np.ascontiguousarray(a, dtype=self.orc.real).ctypes.data_as(ctypes.c_void_p)
+
+    def reset(self):
+        b = self._bufs()
+        self.orc.lib.orc_env_reset.restype = None
+        self.orc.lib.orc_env_reset(self.orc.model_ptr, ctypes.c_int(self.N), ctypes.byref(b))
+
+    def set_state(self, qpos, qvel, time=None):
+        """Reference-state initialisation: state and lag state both at (qpos, qvel)."""
+        self.qpos[:] = qpos
+        self.qvel[:] = qvel
+        self.qpos_lag[:] = qpos
+        self.qvel_lag[:] = qvel
+        self.warm[:] = 0
+        self.ctrl[:] = 0
+        self.time[:] = 0 if time is None else time
+
+    def step(self, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF):
+        r = self.orc.real
+        action = np.ascontiguousarray(action, dtype=r)
+        cols = 1 if action.ndim == 2 else action.shape[2]
+        R = ctypes.c_double if r == np.float64 else ctypes.c_float
+        b = self._bufs()
+        keep = [np.ascontiguousarray(kp, dtype=r), np.ascontiguousarray(kd, dtype=r),
+                None if pd_time is None else np.ascontiguousarray(pd_time, dtype=r)]
+        self.orc.lib.orc_env_step.restype = None
+        self.orc.lib.orc_env_step(self.orc.model_ptr, ctypes.c_int(self.N), ctypes.c_int(n_frames),
+                                  ctypes.c_int(pd_mode), ctypes.c_int(cols), action.ctypes.data_as(ctypes.c_void_p),
+                                  keep[0].ctypes.data_as(ctypes.c_void_p), keep[1].ctypes.data_as(ctypes.c_void_p),
+                                  R(pd_dt), None if keep[2] is None else keep[2].ctypes.data_as(ctypes.c_void_p),
+                                  ctypes.c_uint(ctrl_mask), ctypes.byref(b), ctypes.c_int(self.nthreads))
+
+    def replay(self, qpos, qvel, want_poses=False):
+        r = self.orc.real
+        qpos = np.ascontiguousarray(qpos, dtype=r)
+        qvel = np.ascontiguousarray(qvel, dtype=r)
+        N = qpos.shape[0]
+        obs = np.zeros((N, self.orc.nq + self.orc.nv), r)
+        reward = np.zeros((N, 3), r)
+        done = np.zeros(N, r)
+        xpos = np.zeros((N, self.orc.nbody, 3), r) if want_poses else None
+        xquat = np.zeros((N, self.orc.nbody, 4), r) if want_poses else None
+        self.orc.lib.orc_env_replay.restype = None
+        self.orc.lib.orc_env_replay(self.orc.model_ptr, ctypes.c_int(N), self._p(qpos), self._p(qvel),
+                                    obs.ctypes.data_as(ctypes.c_void_p), reward.ctypes.data_as(ctypes.c_void_p),
+                                    done.ctypes.data_as(ctypes.c_void_p),
+                                    None if xpos is None else xpos.ctypes.data_as(ctypes.c_void_p),
+                                    None if xquat is None else xquat.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_int(self.nthreads))
+        return obs, reward, done, xpos, xquat
+
+    def pd_torque(self, action, kp, kd, pd_mode, pd_dt, time=None, want_qM=False):
+        r = self.orc.real
+        action = np.ascontiguousarray(action, dtype=r)
+        cols = 1 if action.ndim == 2 else action.shape[2]
+        tau = np.zeros((self.N, self.orc.nu), r)
+        qM = np.zeros((self.N, self.orc.nv, self.orc.nv), r) if want_qM else None
+        bias = np.zeros((self.N, self.orc.nv), r) if want_qM else None
+        t = np.ascontiguousarray(self.time if time is None else time, dtype=r)
+        R = ctypes.c_double if r == np.float64 else ctypes.c_float
+        self.orc.lib.orc_env_pd_torque.restype = None
+        self.orc.lib.orc_env_pd_torque(self.orc.model_ptr, ctypes.c_int(self.N), ctypes.c_int(pd_mode),
+                                       ctypes.c_int(cols), self._p(action), self._p(self.qpos), self._p(self.qvel),
+                                       self._p(self.qpos_lag), self._p(self.qvel_lag), self._p(kp), self._p(kd),
+                                       self._p(t), R(pd_dt), tau.ctypes.data_as(ctypes.c_void_p),
+                                       None if qM is None else qM.ctypes.data_as(ctypes.c_void_p),
+                                       None if bias is None else bias.ctypes.data_as(ctypes.c_void_p))
+        return (tau, qM, bias) if want_qM else tau

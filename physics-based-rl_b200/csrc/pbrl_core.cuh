@@ -1,0 +1,1026 @@
+// One-warp-per-environment physics core for the humanoid-mimic env step (sm_100a).
+//
+// Replaces what the reference runs through brax/MJX for HumanoidTrain.step
+// (/root/reference/agents_env/agent_mimic.py:58-91 -> PipelineEnv.pipeline_step -> mjx.step) with a
+// single fused kernel body: stable-PD prologue, n_frames substeps of
+//   FK -> com/cinert/cdof -> CRB -> tree-sparse LDL -> com_vel + RNE -> actuation -> plane contacts +
+//   joint limits -> primal Newton on qacc -> implicit-damping Euler -> integration,
+// and the obs/reward epilogue.  Algorithm spec: SURVEY.md App. A (upstream MuJoCo/MJX semantics).
+//
+// Structure chosen for the GPU (differs on purpose from the dense textbook form of the oracle):
+//   * one warp owns one env; all per-env data lives in that warp's shared-memory workspace `Ws`;
+//   * every stage is a lane-parallel loop over bodies / dofs / matrix entries / contact slots followed
+//     by a warp barrier; tree recursions run level by level, leaf-to-root sums as subtree gathers;
+//   * M, M + h*D, M + KD*dt and the Newton Hessian M + J^T D J all share the branch-induced sparsity
+//     of the kinematic tree (310 non-zeros) and are factorised as L^T D L without fill-in;
+//   * contact Jacobians are never formed: J x and J^T f run through the tree (spatial velocity down,
+//     spatial force up), and J^T D J is assembled like a composite-rigid-body inertia.
+//
+// The same source compiles for the host when PBRL_HOST_EMU is defined (lane loops become sequential
+// loops).  That build exists only for tests/ (logic checks without a GPU); the product library is the
+// CUDA build and has no CPU path.
+#pragma once
+#include <math.h>
+
+#include "pbrl_model.h"
+
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+#define PB_DEV __device__ __forceinline__
+#define PB_DEVN __device__ __noinline__
+#define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
+#define WSYNC() __syncwarp()
+#else
+#define PB_DEV static inline
+#define PB_DEVN static
+#define LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
+#define WSYNC() ((void)0)
+#endif
+
+namespace pbrl {
+
+constexpr int S3 = 3, S4 = 5, S6 = 7, S9 = 9, S10 = 11, S21 = 21;  // odd strides: conflict-free lane=row access
+constexpr int NEWTON_MAXIT = 12;
+constexpr int LS_MAXIT = 24;
+
+struct Ws {
+    // state
+    float qpos[36], qvel[36], warm[36], ctrl[28], qpos_lag[36], qvel_lag[36], tau[28];
+    // kinematics
+    float xpos[NB * S3], xquat[NB * S4], xmat[NB * S9], xipos[NB * S3], xaxis[NJ * S3], com[4];
+    // spatial quantities about the centre of mass, [ang; lin]
+    float cinert[NB * S10], crb[NB * S10], cdof[NV * S6], cdof_dot[NV * S6], cvel[NB * S6], cacc[NB * S6];
+    float F[NB * S6], Fsub[NB * S6], V[NB * S6], buf6[NV * S6];
+    // joint-space inertia (tree-sparse), factor, vectors
+    float M[NM], LD[NM], Dinv[36];
+    float bias[36], fsmooth[36], asmooth[36], qacc[36], Ma[36], grad[36], p[36], Mp[36], fcon[36];
+    // constraint rows: lane l owns limit row l and contact slot l (4 pyramid rows)
+    float lim_sign[32], lim_D[32], lim_aref[32], lim_jar[32], lim_jp[32];
+    int con_on[NCP], act_bits[32];
+    float con_dist[NCP], con_p[NCP * S3], con_r[NCP * S3], con_t1[NCP * S3], con_D[NCP];
+    float con_aref[NCP * 4], con_jar[NCP * 4], con_jp[NCP * 4];
+    float K[NB * S21], Ksub[NB * S21];
+    int status, niter;
+};
+
+// ---------------------------------------------------------------------------------- warp helpers
+template <class Fn>
+PB_DEV float wsum(int lane, int n, Fn f) {
+    float s = 0.f;
+    LANE_LOOP(i, n) s += f(i);
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#endif
+    (void)lane;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------- small math
+PB_DEV void cross3(const float* a, const float* b, float* r) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+PB_DEV float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+PB_DEV float dot6(const float* a, const float* b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+PB_DEV void quat_mul(const float* a, const float* b, float* r) {
+    float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+PB_DEV void quat_normalize(float* q) {
+    float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n < 1e-30f) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+    float inv = 1.0f / n;
+    q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+PB_DEV void quat_to_mat(const float* q, float* m) {
+    float w = q[0], x = q[1], y = q[2], z = q[3];
+    m[0] = w * w + x * x - y * y - z * z; m[1] = 2.f * (x * y - w * z); m[2] = 2.f * (x * z + w * y);
+    m[3] = 2.f * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2.f * (y * z - w * x);
+    m[6] = 2.f * (x * z - w * y); m[7] = 2.f * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+PB_DEV void quat_rotate(const float* q, const float* v, float* r) {  // R(q) v
+    float m[9];
+    quat_to_mat(q, m);
+    float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+          z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+PB_DEV void mat_vec(const float* m, const float* v, float* r) {
+    float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+          z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+PB_DEV void matT_vec(const float* m, const float* v, float* r) {
+    float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+          z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+// 10-float spatial inertia about the com times a motion vector
+PB_DEV void mul_inert(const float* i, const float* v, float* r) {
+    r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+    r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+    r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+    r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+    r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+    r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+PB_DEV void cross_motion(const float* v, const float* s, float* r) {
+    float a[3], b[3], c[3];
+    cross3(v, s, a); cross3(v, s + 3, b); cross3(v + 3, s, c);
+    r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+PB_DEV void cross_force(const float* v, const float* f, float* r) {
+    float a[3], b[3], c[3];
+    cross3(v, f, a); cross3(v + 3, f + 3, b); cross3(v, f + 3, c);
+    r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+// symmetric 6x6 stored as 21 floats, row-major upper triangle
+PB_DEV int sym21(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
+
+// ---------------------------------------------------------------------------------- kinematics
+PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
+    LANE_LOOP(z, 1) {
+        w.xpos[0] = w.xpos[1] = w.xpos[2] = 0.f;
+        w.xquat[0] = 1.f; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0.f;
+        for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
+        w.xipos[0] = w.xipos[1] = w.xipos[2] = 0.f;
+    }
+    WSYNC();
+    for (int lv = 1; lv < m.nlevel; lv++) {
+        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
+        LANE_LOOP(k, n) {
+            int b = m.level_body[s + k], p = m.body_parent[b];
+            float pos[3], q[4], t[3];
+            mat_vec(w.xmat + S9 * p, m.body_pos[b], t);
+            for (int c = 0; c < 3; c++) pos[c] = w.xpos[S3 * p + c] + t[c];
+            for (int c = 0; c < 4; c++) q[c] = w.xquat[S4 * p + c];
+            for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
+                int qa = m.jnt_qposadr[j];
+                if (m.jnt_type[j] == 0) {
+                    for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
+                    for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
+                    quat_normalize(q);
+                    w.xaxis[S3 * j] = 0.f; w.xaxis[S3 * j + 1] = 0.f; w.xaxis[S3 * j + 2] = 1.f;
+                } else {
+                    float ql[4], qn[4], sn, cs;
+                    quat_rotate(q, m.jnt_axis[j], w.xaxis + S3 * j);
+                    sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
+                    ql[0] = cs; ql[1] = m.jnt_axis[j][0] * sn; ql[2] = m.jnt_axis[j][1] * sn; ql[3] = m.jnt_axis[j][2] * sn;
+                    quat_mul(q, ql, qn);
+                    for (int c = 0; c < 4; c++) q[c] = qn[c];
+                }
+            }
+            quat_normalize(q);
+            for (int c = 0; c < 3; c++) w.xpos[S3 * b + c] = pos[c];
+            for (int c = 0; c < 4; c++) w.xquat[S4 * b + c] = q[c];
+            float R[9];
+            quat_to_mat(q, R);
+            for (int c = 0; c < 9; c++) w.xmat[S9 * b + c] = R[c];
+            mat_vec(R, m.body_ipos[b], t);
+            for (int c = 0; c < 3; c++) w.xipos[S3 * b + c] = pos[c] + t[c];
+        }
+        WSYNC();
+    }
+}
+
+// com, cinert, cdof  (mjx smooth.com_pos)
+PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
+    float inv = 1.0f / m.total_mass;
+    float cx = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b]; }) * inv;
+    float cy = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 1]; }) * inv;
+    float cz = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 2]; }) * inv;
+    LANE_LOOP(z, 1) { w.com[0] = cx; w.com[1] = cy; w.com[2] = cz; }
+    LANE_LOOP(b, NB) {
+        const float* R = w.xmat + S9 * b;
+        const float* I = m.body_inertia[b];  // xx yy zz xy xz yz (body frame, about ipos)
+        float A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, RA[9], Iw[6];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) RA[3 * r + c] = R[3 * r] * A[c] + R[3 * r + 1] * A[3 + c] + R[3 * r + 2] * A[6 + c];
+        // world inertia = RA R^T, six unique entries: xx yy zz xy xz yz
+        Iw[0] = RA[0] * R[0] + RA[1] * R[1] + RA[2] * R[2];
+        Iw[1] = RA[3] * R[3] + RA[4] * R[4] + RA[5] * R[5];
+        Iw[2] = RA[6] * R[6] + RA[7] * R[7] + RA[8] * R[8];
+        Iw[3] = RA[0] * R[3] + RA[1] * R[4] + RA[2] * R[5];
+        Iw[4] = RA[0] * R[6] + RA[1] * R[7] + RA[2] * R[8];
+        Iw[5] = RA[3] * R[6] + RA[4] * R[7] + RA[5] * R[8];
+        float ms = m.body_mass[b], ox = w.xipos[S3 * b] - cx, oy = w.xipos[S3 * b + 1] - cy, oz = w.xipos[S3 * b + 2] - cz;
+        float* ci = w.cinert + S10 * b;
+        ci[0] = Iw[0] + ms * (oy * oy + oz * oz);
+        ci[1] = Iw[1] + ms * (ox * ox + oz * oz);
+        ci[2] = Iw[2] + ms * (ox * ox + oy * oy);
+        ci[3] = Iw[3] - ms * ox * oy;
+        ci[4] = Iw[4] - ms * ox * oz;
+        ci[5] = Iw[5] - ms * oy * oz;
+        ci[6] = ms * ox; ci[7] = ms * oy; ci[8] = ms * oz; ci[9] = ms;
+    }
+    LANE_LOOP(i, NV) {
+        int b = m.dof_bodyid[i], kind = m.dof_kind[i];
+        float* cd = w.cdof + S6 * i;
+        if (kind < 3) {
+            for (int c = 0; c < 6; c++) cd[c] = 0.f;
+            cd[3 + kind] = 1.f;
+        } else {
+            float ax[3], off[3];
+            if (kind < 6) {
+                for (int c = 0; c < 3; c++) ax[c] = w.xmat[S9 * b + 3 * c + (kind - 3)];
+            } else {
+                for (int c = 0; c < 3; c++) ax[c] = w.xaxis[S3 * m.dof_jntid[i] + c];
+            }
+            off[0] = cx - w.xpos[S3 * b]; off[1] = cy - w.xpos[S3 * b + 1]; off[2] = cz - w.xpos[S3 * b + 2];
+            cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+            cross3(ax, off, cd + 3);
+        }
+    }
+    WSYNC();
+}
+
+// composite inertias + sparse M  (mjx smooth.crb)
+PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
+    LANE_LOOP(it, NB * 10) {
+        int b = it / 10, k = it - 10 * b;
+        float s = 0.f;
+        for (int c = b; c < m.body_subtree_end[b]; c++) s += w.cinert[S10 * c + k];
+        w.crb[S10 * b + k] = s;
+    }
+    WSYNC();
+    LANE_LOOP(i, NV) mul_inert(w.crb + S10 * m.dof_bodyid[i], w.cdof + S6 * i, w.buf6 + S6 * i);
+    WSYNC();
+    LANE_LOOP(e, NM) {
+        int r = m.M_row[e], c = m.M_col[e];
+        float v = dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
+        if (r == c) v += m.dof_armature[r];
+        w.M[e] = v;
+    }
+    WSYNC();
+}
+
+// body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne)
+PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane) {
+    LANE_LOOP(z, 1) {
+        for (int c = 0; c < 6; c++) { w.cvel[c] = 0.f; w.cacc[c] = 0.f; }
+        w.cacc[3] = -m.gx; w.cacc[4] = -m.gy; w.cacc[5] = -m.gz;
+    }
+    WSYNC();
+    for (int lv = 1; lv < m.nlevel; lv++) {
+        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
+        LANE_LOOP(k, n) {
+            int b = m.level_body[s + k], p = m.body_parent[b];
+            float v[6], a[6], cdd[6];
+            for (int c = 0; c < 6; c++) { v[c] = w.cvel[S6 * p + c]; a[c] = w.cacc[S6 * p + c]; }
+            for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
+                int da = m.jnt_dofadr[j];
+                if (m.jnt_type[j] == 0) {
+                    for (int i = 0; i < 3; i++) {
+                        for (int c = 0; c < 6; c++) { v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i]; w.cdof_dot[S6 * (da + i) + c] = 0.f; }
+                    }
+                    for (int i = 3; i < 6; i++) {
+                        cross_motion(v, w.cdof + S6 * (da + i), cdd);
+                        for (int c = 0; c < 6; c++) { w.cdof_dot[S6 * (da + i) + c] = cdd[c]; a[c] += cdd[c] * qvel[da + i]; }
+                    }
+                    for (int i = 3; i < 6; i++)
+                        for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i];
+                } else {
+                    cross_motion(v, w.cdof + S6 * da, cdd);
+                    for (int c = 0; c < 6; c++) {
+                        w.cdof_dot[S6 * da + c] = cdd[c];
+                        a[c] += cdd[c] * qvel[da];
+                        v[c] += w.cdof[S6 * da + c] * qvel[da];
+                    }
+                }
+            }
+            for (int c = 0; c < 6; c++) { w.cvel[S6 * b + c] = v[c]; w.cacc[S6 * b + c] = a[c]; }
+        }
+        WSYNC();
+    }
+}
+
+// leaf-to-root accumulation of 6-vectors as subtree gathers
+PB_DEV void subtree_sum6(const DevModel& m, const float* src, float* dst, int lane) {
+    LANE_LOOP(it, NB * 6) {
+        int b = it / 6, k = it - 6 * b;
+        float s = 0.f;
+        for (int c = b; c < m.body_subtree_end[b]; c++) s += src[S6 * c + k];
+        dst[S6 * b + k] = s;
+    }
+    WSYNC();
+}
+
+// qfrc_bias  (second half of mjx smooth.rne)
+PB_DEVN void stage_bias(const DevModel& m, Ws& w, int lane) {
+    LANE_LOOP(b, NB) {
+        float t[6], u[6], f[6];
+        mul_inert(w.cinert + S10 * b, w.cacc + S6 * b, t);
+        mul_inert(w.cinert + S10 * b, w.cvel + S6 * b, u);
+        cross_force(w.cvel + S6 * b, u, f);
+        for (int c = 0; c < 6; c++) w.F[S6 * b + c] = (b == 0) ? 0.f : t[c] + f[c];
+    }
+    WSYNC();
+    subtree_sum6(m, w.F, w.Fsub, lane);
+    LANE_LOOP(i, NV) w.bias[i] = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]);
+    WSYNC();
+}
+
+// ---------------------------------------------------------------------------------- tree-sparse L^T D L
+// LD holds the unscaled rows: LD[adr(k)+a] = L[k, anc_a(k)] * D[k]; Dinv[k] = 1/D[k].
+PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
+    for (int k = NV - 1; k >= 0; k--) {
+        int d = m.dof_depth[k];
+        if (d > 0) {
+            int adr = m.dof_Madr[k];
+            float piv = w.LD[adr];
+            if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
+            float inv = 1.0f / piv;
+            LANE_LOOP(pi, d * (d + 1) / 2) {
+                int a = m.tri_a[pi], t = m.tri_t[pi];
+                int ia = m.M_col[adr + a];
+                w.LD[m.dof_Madr[ia] + t] -= (w.LD[adr + a] * inv) * w.LD[adr + a + t];
+            }
+            WSYNC();
+        }
+    }
+    LANE_LOOP(i, NV) w.Dinv[i] = 1.0f / w.LD[m.dof_Madr[i]];
+    WSYNC();
+}
+// x <- (L^T D L)^-1 x
+PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
+    for (int k = NV - 1; k > 0; k--) {  // x <- L^-T x : scatter to ancestors
+        int d = m.dof_depth[k], adr = m.dof_Madr[k];
+        float s = x[k] * w.Dinv[k];
+        LANE_LOOP(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
+        WSYNC();
+    }
+    LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
+    WSYNC();
+    for (int lv = 1; lv < m.ndepth; lv++) {  // x <- L^-1 x : dofs of equal depth are independent
+        int s0 = m.depth_start[lv], n = m.depth_start[lv + 1] - s0;
+        LANE_LOOP(q, n) {
+            int k = m.depth_dof[s0 + q], adr = m.dof_Madr[k];
+            float s = 0.f;
+            for (int a = 1; a <= lv; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
+            x[k] -= s * w.Dinv[k];
+        }
+        WSYNC();
+    }
+}
+
+// ---------------------------------------------------------------------------------- tree products
+// V[b] = sum over ancestor dofs of cdof_i x_i  (spatial velocity of body b for generalised velocity x)
+PB_DEVN void tree_vel(const DevModel& m, Ws& w, const float* x, int lane) {
+    LANE_LOOP(z, 1) for (int c = 0; c < 6; c++) w.V[c] = 0.f;
+    WSYNC();
+    for (int lv = 1; lv < m.nlevel; lv++) {
+        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
+        LANE_LOOP(k, n) {
+            int b = m.level_body[s + k], p = m.body_parent[b];
+            float v[6];
+            for (int c = 0; c < 6; c++) v[c] = w.V[S6 * p + c];
+            for (int i = m.body_dofadr[b]; i < m.body_dofadr[b] + m.body_dofnum[b]; i++)
+                for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * i + c] * x[i];
+            for (int c = 0; c < 6; c++) w.V[S6 * b + c] = v[c];
+        }
+        WSYNC();
+    }
+}
+// out = M x using V = tree_vel(x) already in w.V (matrix-free, includes armature)
+PB_DEVN void tree_Mx_from_V(const DevModel& m, Ws& w, const float* x, float* out, int lane) {
+    LANE_LOOP(b, NB) mul_inert(w.cinert + S10 * b, w.V + S6 * b, w.F + S6 * b);
+    WSYNC();
+    subtree_sum6(m, w.F, w.Fsub, lane);
+    LANE_LOOP(i, NV) out[i] = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]) + m.dof_armature[i] * x[i];
+    WSYNC();
+}
+
+// ---------------------------------------------------------------------------------- smooth dynamics
+PB_DEVN void smooth_position(const DevModel& m, Ws& w, const float* qpos, int lane) {
+    stage_fk(m, w, qpos, lane);
+    stage_com(m, w, lane);
+    stage_crb(m, w, lane);
+}
+PB_DEVN void smooth_velocity(const DevModel& m, Ws& w, const float* qvel, int lane) {
+    stage_comvel(m, w, qvel, lane);
+    stage_bias(m, w, lane);
+}
+
+// ---------------------------------------------------------------------------------- collision with the floor plane
+// impedance of a row at penetration `pos` (mjx constraint._kbi)
+PB_DEV float impedance(const DevModel& m, float pos) {
+    float x = fabsf(pos) / m.sol_width, y;
+    if (x < m.sol_mid) y = (1.0f / powf(m.sol_mid, m.sol_power - 1.f)) * powf(x, m.sol_power);
+    else y = 1.f - (1.0f / powf(1.f - m.sol_mid, m.sol_power - 1.f)) * powf(1.f - x, m.sol_power);
+    float imp = m.sol_dmin + y * (m.sol_dmax - m.sol_dmin);
+    imp = fminf(fmaxf(imp, m.sol_dmin), m.sol_dmax);
+    if (x > 1.f) imp = m.sol_dmax;
+    return imp;
+}
+PB_DEV int argmax_masked(const float* score, const bool* ok, int n) {  // first maximum among ok[]; 0 if none
+    int best = -1;
+    for (int i = 0; i < n; i++)
+        if (ok[i] && (best < 0 || score[i] > score[best])) best = i;
+    return best < 0 ? 0 : best;
+}
+// pyramid edge e of a contact: w = n + sg*mu*t, j6 = [r x w ; w]
+PB_DEV void contact_j6(const float* r, const float* t1, float mu, int e, float* j6) {
+    float sg = (e & 1) ? -mu : mu, wv[3];
+    if (e < 2) { wv[0] = sg * t1[0]; wv[1] = sg * t1[1]; wv[2] = 1.f + sg * t1[2]; }
+    else { wv[0] = -sg * t1[1]; wv[1] = sg * t1[0]; wv[2] = 1.f; }  // t2 = n x t1, n = +z
+    cross3(r, wv, j6);
+    j6[3] = wv[0]; j6[4] = wv[1]; j6[5] = wv[2];
+}
+
+PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
+    LANE_LOOP(c, NC) {
+        int b = m.con_body[c], kind = m.con_kind[c];
+        const float* R = w.xmat + S9 * b;
+        float gp[3], t[3], dist, p[3], t1[3] = {0.f, 1.f, 0.f};
+        mat_vec(R, m.con_gpos[c], t);
+        for (int k = 0; k < 3; k++) gp[k] = w.xpos[S3 * b + k] + t[k];
+        if (kind == CON_SPHERE) {
+            float r = m.con_size[c][0];
+            dist = gp[2] - m.plane_z - r;
+            p[0] = gp[0]; p[1] = gp[1]; p[2] = gp[2] - (r + 0.5f * dist);
+        } else if (kind == CON_CAPSULE) {
+            float zl[3] = {0.f, 0.f, 1.f}, al[3], ax[3], r = m.con_size[c][0], hl = m.con_size[c][1];
+            quat_rotate(m.con_gquat[c], zl, al);
+            mat_vec(R, al, ax);
+            float bn = sqrtf(ax[0] * ax[0] + ax[1] * ax[1]);
+            if (bn >= 0.5f) { t1[0] = ax[0] / bn; t1[1] = ax[1] / bn; t1[2] = 0.f; }
+            float sg = m.con_sub[c] == 0 ? hl : -hl, ce[3] = {gp[0] + sg * ax[0], gp[1] + sg * ax[1], gp[2] + sg * ax[2]};
+            dist = ce[2] - m.plane_z - r;
+            p[0] = ce[0]; p[1] = ce[1]; p[2] = ce[2] - (r + 0.5f * dist);
+        } else {  // box corner manifold (mjx plane_convex + _manifold_points)
+            float Rl[9], Rg[9], vert[8][3], sup[8], sc[16], pl[3], nl[3], d3[3], e3[3], ab[3], ac[3], bc[3], smax;
+            bool ok[16];
+            quat_to_mat(m.con_gquat[c], Rl);
+            for (int r = 0; r < 3; r++)
+                for (int q = 0; q < 3; q++) Rg[3 * r + q] = R[3 * r] * Rl[q] + R[3 * r + 1] * Rl[3 + q] + R[3 * r + 2] * Rl[6 + q];
+            for (int v = 0; v < 8; v++)
+                for (int k = 0; k < 3; k++) vert[v][k] = (((v >> (2 - k)) & 1) ? 1.f : -1.f) * m.con_size[c][k];
+            d3[0] = -gp[0]; d3[1] = -gp[1]; d3[2] = m.plane_z - gp[2];
+            matT_vec(Rg, d3, pl);
+            nl[0] = Rg[6]; nl[1] = Rg[7]; nl[2] = Rg[8];
+            smax = -1e30f;
+            for (int v = 0; v < 8; v++) {
+                for (int k = 0; k < 3; k++) d3[k] = pl[k] - vert[v][k];
+                sup[v] = dot3(d3, nl);
+                smax = fmaxf(smax, sup[v]);
+            }
+            float thr = fmaxf(0.f, smax - 1e-3f);
+            for (int v = 0; v < 8; v++) { ok[v] = sup[v] > thr; ok[8 + v] = ok[v]; sc[v] = 0.f; }
+            int ia = argmax_masked(sc, ok, 8);
+            for (int v = 0; v < 8; v++) {
+                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                sc[v] = dot3(d3, d3);
+            }
+            int ib = argmax_masked(sc, ok, 8);
+            for (int k = 0; k < 3; k++) e3[k] = vert[ia][k] - vert[ib][k];
+            cross3(nl, e3, ab);
+            for (int v = 0; v < 8; v++) {
+                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                sc[v] = fabsf(dot3(d3, ab));
+            }
+            int ic = argmax_masked(sc, ok, 8);
+            for (int k = 0; k < 3; k++) e3[k] = vert[ia][k] - vert[ic][k];
+            cross3(nl, e3, ac);
+            for (int k = 0; k < 3; k++) e3[k] = vert[ib][k] - vert[ic][k];
+            cross3(nl, e3, bc);
+            for (int v = 0; v < 8; v++) {
+                for (int k = 0; k < 3; k++) d3[k] = vert[ib][k] - vert[v][k];
+                sc[v] = fabsf(dot3(d3, bc));
+                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                sc[8 + v] = fabsf(dot3(d3, ac));
+            }
+            int id = argmax_masked(sc, ok, 16) % 8;
+            int idx[4] = {ia, ib, ic, id}, sub = m.con_sub[c], me = idx[sub];
+            bool uniq = true;
+            for (int q = 0; q < sub; q++) uniq = uniq && (idx[q] != me);
+            dist = uniq ? -sup[me] : 1.f;
+            mat_vec(Rg, vert[me], t);
+            p[0] = gp[0] + t[0]; p[1] = gp[1] + t[1]; p[2] = gp[2] + t[2] - 0.5f * dist;
+        }
+        w.con_dist[c] = dist;
+        for (int k = 0; k < 3; k++) { w.con_p[S3 * c + k] = p[k]; w.con_r[S3 * c + k] = p[k] - w.com[k]; w.con_t1[S3 * c + k] = t1[k]; }
+    }
+    WSYNC();
+}
+
+// constraint rows: enabled flags, D, aref  (mjx constraint.make_constraint; needs cvel of the current qvel)
+PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float* qvel, int lane) {
+    LANE_LOOP(l, 32) {
+        // joint limit row l
+        w.lim_sign[l] = 0.f;
+        if (l < NLIM) {
+            int j = m.lim_jnt[l];
+            float q = qpos[m.jnt_qposadr[j]], dlo = q - m.jnt_lo[j], dhi = m.jnt_hi[j] - q;
+            float pos = fminf(dlo, dhi) - m.jnt_margin[j];
+            if (pos < 0.f) {
+                float sg = dlo < dhi ? 1.f : -1.f, imp = impedance(m, pos);
+                float Rr = fmaxf(m.dof_invweight0[m.jnt_dofadr[j]] * (1.f - imp) / imp, 1e-15f);
+                w.lim_sign[l] = sg;
+                w.lim_D[l] = 1.0f / Rr;
+                w.lim_aref[l] = -m.sol_b * (sg * qvel[m.jnt_dofadr[j]]) - m.sol_k * imp * pos;
+            }
+        }
+        // contact slot l
+        w.con_on[l] = 0;
+        if (l < NC) {
+            float pos = w.con_dist[l] - m.con_margin[l];
+            if (pos < 0.f) {
+                float imp = impedance(m, pos), j6[6];
+                float Rr = fmaxf(m.con_invweight[l] * (1.f - imp) / imp, 1e-15f);
+                w.con_on[l] = 1;
+                w.con_D[l] = 1.0f / Rr;
+                for (int e = 0; e < 4; e++) {
+                    contact_j6(w.con_r + S3 * l, w.con_t1 + S3 * l, m.con_mu[l], e, j6);
+                    w.con_aref[4 * l + e] = -m.sol_b * dot6(j6, w.cvel + S6 * m.con_body[l]) - m.sol_k * imp * pos;
+                }
+            }
+        }
+    }
+    WSYNC();
+}
+
+// residual-like products for all rows from w.V = tree_vel(x): out = J x (limits into lim_out, contacts into con_out)
+PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, float* con_out, int lane) {
+    LANE_LOOP(l, 32) {
+        if (l < NLIM && w.lim_sign[l] != 0.f) lim_out[l] = w.lim_sign[l] * x[m.jnt_dofadr[m.lim_jnt[l]]];
+        if (l < NC && w.con_on[l]) {
+            float j6[6];
+            for (int e = 0; e < 4; e++) {
+                contact_j6(w.con_r + S3 * l, w.con_t1 + S3 * l, m.con_mu[l], e, j6);
+                con_out[4 * l + e] = dot6(j6, w.V + S6 * m.con_body[l]);
+            }
+        }
+    }
+    WSYNC();
+}
+
+// out[i] -= (J^T f)_i with f_r = -D_r jar_r on active rows (jar<0); i.e. adds the constraint gradient D*jar*J
+// mode 0: out = base - J^T f   (gradient),  mode 1: out = J^T f  (qfrc_constraint)
+PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, int mode, int lane) {
+    LANE_LOOP(b, NB) {
+        float f6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, j6[6];
+        for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
+            if (!w.con_on[c]) continue;
+            for (int e = 0; e < 4; e++) {
+                float jar = w.con_jar[4 * c + e];
+                if (jar < 0.f) {
+                    float f = -w.con_D[c] * jar;
+                    contact_j6(w.con_r + S3 * c, w.con_t1 + S3 * c, m.con_mu[c], e, j6);
+                    for (int k = 0; k < 6; k++) f6[k] += f * j6[k];
+                }
+            }
+        }
+        for (int k = 0; k < 6; k++) w.F[S6 * b + k] = f6[k];
+    }
+    WSYNC();
+    subtree_sum6(m, w.F, w.Fsub, lane);
+    LANE_LOOP(i, NV) {
+        float jtf = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]);
+        int j = m.dof_jntid[i];
+        if (m.jnt_limited[j]) {
+            int l = i - m.jnt_dofadr[m.lim_jnt[0]];  // limited hinges are contiguous dofs (checked at model creation)
+            if (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) jtf += w.lim_sign[l] * (-w.lim_D[l] * w.lim_jar[l]);
+        }
+        out[i] = mode == 0 ? base[i] - jtf : jtf;
+    }
+    WSYNC();
+}
+
+// LD <- M + J^T D_active J  (tree-sparse, assembled like a composite inertia)
+PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
+    LANE_LOOP(b, NB) {
+        float k21[21], j6[6];
+        for (int q = 0; q < 21; q++) k21[q] = 0.f;
+        for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
+            if (!w.con_on[c]) continue;
+            for (int e = 0; e < 4; e++) {
+                if (w.con_jar[4 * c + e] < 0.f) {
+                    contact_j6(w.con_r + S3 * c, w.con_t1 + S3 * c, m.con_mu[c], e, j6);
+                    float D = w.con_D[c];
+                    int q = 0;
+                    for (int r = 0; r < 6; r++)
+                        for (int s = r; s < 6; s++) k21[q++] += D * j6[r] * j6[s];
+                }
+            }
+        }
+        for (int q = 0; q < 21; q++) w.K[S21 * b + q] = k21[q];
+    }
+    WSYNC();
+    LANE_LOOP(it, NB * 21) {
+        int b = it / 21, k = it - 21 * b;
+        float s = 0.f;
+        for (int c = b; c < m.body_subtree_end[b]; c++) s += w.K[S21 * c + k];
+        w.Ksub[S21 * b + k] = s;
+    }
+    WSYNC();
+    LANE_LOOP(i, NV) {
+        const float* K = w.Ksub + S21 * m.dof_bodyid[i];
+        const float* cd = w.cdof + S6 * i;
+        for (int r = 0; r < 6; r++) {
+            float s = 0.f;
+            for (int c = 0; c < 6; c++) s += K[sym21(r, c)] * cd[c];
+            w.buf6[S6 * i + r] = s;
+        }
+    }
+    WSYNC();
+    LANE_LOOP(e, NM) {
+        int r = m.M_row[e], c = m.M_col[e];
+        float v = w.M[e] + dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
+        if (r == c && m.jnt_limited[m.dof_jntid[r]]) {
+            int l = r - m.jnt_dofadr[m.lim_jnt[0]];
+            if (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) v += w.lim_D[l];
+        }
+        w.LD[e] = v;
+    }
+    WSYNC();
+}
+
+// ---------------------------------------------------------------------------------- Newton solver on qacc
+// minimise 1/2 (a-a_s)^T M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2   
+PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
+    float nrows = wsum(lane, 32, [&](int l) { return (w.lim_sign[l] != 0.f ? 1.f : 0.f) + (w.con_on[l] ? 1.f : 0.f); });
+    w.niter = 0;
+    if (nrows == 0.f) {
+        LANE_LOOP(i, NV) { w.qacc[i] = w.asmooth[i]; w.fcon[i] = 0.f; }
+        WSYNC();
+        return;
+    }
+    // start from the warm start
+    LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
+    WSYNC();
+    tree_vel(m, w, w.qacc, lane);
+    tree_Mx_from_V(m, w, w.qacc, w.Ma, lane);
+    rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
+    LANE_LOOP(l, 32) {
+        if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
+        if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) w.con_jar[4 * l + e] -= w.con_aref[4 * l + e];
+        int bits = 0;
+        if (l < NLIM && w.lim_sign[l] != 0.f) bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
+        if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
+        w.act_bits[l] = bits;
+    }
+    WSYNC();
+    int it = 0;
+    for (; it < NEWTON_MAXIT; it++) {
+        // gradient and Hessian for the current active set
+        LANE_LOOP(i, NV) w.Mp[i] = w.Ma[i] - w.fsmooth[i];
+        WSYNC();
+        rows_JTf(m, w, w.Mp, w.grad, 0, lane);
+        assemble_hessian(m, w, lane);
+        ldl_factor(m, w, lane);
+        LANE_LOOP(i, NV) w.p[i] = -w.grad[i];
+        WSYNC();
+        ldl_solve(m, w, w.p, lane);
+        tree_vel(m, w, w.p, lane);
+        tree_Mx_from_V(m, w, w.p, w.Mp, lane);
+        rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
+        // exact line search on the piecewise-quadratic cost along p (safeguarded Newton on phi')
+        float g0 = wsum(lane, NV, [&](int i) { return (w.Ma[i] - w.fsmooth[i]) * w.p[i]; });
+        float pMp = wsum(lane, NV, [&](int i) { return w.Mp[i] * w.p[i]; });
+        float alpha = 1.f, lo = 0.f, hi = -1.f;
+        float d1_0 = 0.f;
+        for (int ls = 0; ls < LS_MAXIT; ls++) {
+            float d1 = wsum(lane, 32, [&](int l) {
+                float s = 0.f;
+                if (l < NLIM && w.lim_sign[l] != 0.f) {
+                    float x = w.lim_jar[l] + alpha * w.lim_jp[l];
+                    if (x < 0.f) s += w.lim_D[l] * x * w.lim_jp[l];
+                }
+                if (l < NC && w.con_on[l])
+                    for (int e = 0; e < 4; e++) {
+                        float x = w.con_jar[4 * l + e] + alpha * w.con_jp[4 * l + e];
+                        if (x < 0.f) s += w.con_D[l] * x * w.con_jp[4 * l + e];
+                    }
+                return s;
+            });
+            float d2 = wsum(lane, 32, [&](int l) {
+                float s = 0.f;
+                if (l < NLIM && w.lim_sign[l] != 0.f) {
+                    float x = w.lim_jar[l] + alpha * w.lim_jp[l];
+                    if (x < 0.f) s += w.lim_D[l] * w.lim_jp[l] * w.lim_jp[l];
+                }
+                if (l < NC && w.con_on[l])
+                    for (int e = 0; e < 4; e++) {
+                        float x = w.con_jar[4 * l + e] + alpha * w.con_jp[4 * l + e];
+                        if (x < 0.f) s += w.con_D[l] * w.con_jp[4 * l + e] * w.con_jp[4 * l + e];
+                    }
+                return s;
+            });
+            float dphi = g0 + alpha * pMp + d1, ddphi = pMp + d2;
+            if (ls == 0) d1_0 = fabsf(g0) + fabsf(pMp) + fabsf(d1);
+            if (fabsf(dphi) <= 1e-6f * d1_0) break;
+            if (dphi < 0.f) lo = alpha; else hi = alpha;
+            float an = alpha - dphi / ddphi;
+            if (!(an > lo) || (hi > 0.f && !(an < hi))) an = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha;
+            if (an == alpha) break;
+            alpha = an;
+        }
+        // step, refresh residuals, detect active-set change
+        LANE_LOOP(i, NV) { w.qacc[i] += alpha * w.p[i]; w.Ma[i] += alpha * w.Mp[i]; }
+        float changed = wsum(lane, 32, [&](int l) {
+            int bits = 0;
+            if (l < NLIM && w.lim_sign[l] != 0.f) {
+                w.lim_jar[l] += alpha * w.lim_jp[l];
+                bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
+            }
+            if (l < NC && w.con_on[l])
+                for (int e = 0; e < 4; e++) {
+                    w.con_jar[4 * l + e] += alpha * w.con_jp[4 * l + e];
+                    bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
+                }
+            // act_bits[l] still holds the active set this iteration's Hessian was built from
+            float ch = (bits != w.act_bits[l]) ? 1.f : 0.f;
+            w.act_bits[l] = bits;
+            return ch;
+        });
+        WSYNC();
+        // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
+        if (changed == 0.f) { it++; break; }
+    }
+    if (it >= NEWTON_MAXIT) w.status |= PBRL_STATUS_SOLVER_MAXITER;
+    w.niter = it;
+    rows_JTf(m, w, w.Mp, w.fcon, 1, lane);
+}
+
+// ---------------------------------------------------------------------------------- one mjx.forward + Euler
+// forward: everything up to qacc / qfrc_constraint at (w.qpos, w.qvel, w.ctrl, w.warm)
+PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
+    smooth_position(m, w, w.qpos, lane);
+    stage_collide(m, w, lane);
+    smooth_velocity(m, w, w.qvel, lane);
+    stage_rows(m, w, w.qpos, w.qvel, lane);
+    LANE_LOOP(i, NV) {
+        float f = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
+        int a = m.dof_act[i];
+        if (a >= 0) f += m.dof_gear[i] * fminf(fmaxf(w.ctrl[a], m.dof_ctrl_lo[i]), m.dof_ctrl_hi[i]);
+        w.fsmooth[i] = f;
+        w.asmooth[i] = f;
+    }
+    LANE_LOOP(e, NM) w.LD[e] = w.M[e];
+    WSYNC();
+    ldl_factor(m, w, lane);
+    ldl_solve(m, w, w.asmooth, lane);
+    solve_constraints(m, w, lane);
+}
+
+// mjx.step: forward, warmstart <- qacc, Euler with implicit joint damping, integrate
+PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
+    forward(m, w, lane);
+    float h = m.timestep;
+    LANE_LOOP(i, NV) { w.warm[i] = w.qacc[i]; w.p[i] = w.fsmooth[i] + w.fcon[i]; }
+    LANE_LOOP(e, NM) w.LD[e] = w.M[e] + ((m.M_row[e] == m.M_col[e]) ? h * m.dof_damping[m.M_row[e]] : 0.f);
+    WSYNC();
+    ldl_factor(m, w, lane);
+    ldl_solve(m, w, w.p, lane);
+    LANE_LOOP(i, NV) w.qvel[i] += h * w.p[i];
+    WSYNC();
+    LANE_LOOP(j, NJ) {
+        int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == 0) {
+            for (int k = 0; k < 3; k++) w.qpos[qa + k] += h * w.qvel[da + k];
+            float wx = w.qvel[da + 3], wy = w.qvel[da + 4], wz = w.qvel[da + 5];
+            float nrm = sqrtf(wx * wx + wy * wy + wz * wz), ax[3] = {1.f, 0.f, 0.f}, sn, cs, ql[4], qn[4];
+            if (nrm > 1e-30f) { ax[0] = wx / nrm; ax[1] = wy / nrm; ax[2] = wz / nrm; }
+            sincosf(0.5f * h * nrm, &sn, &cs);
+            ql[0] = cs; ql[1] = ax[0] * sn; ql[2] = ax[1] * sn; ql[3] = ax[2] * sn;
+            quat_mul(w.qpos + qa + 3, ql, qn);
+            quat_normalize(qn);
+            for (int k = 0; k < 4; k++) w.qpos[qa + 3 + k] = qn[k];
+        } else {
+            w.qpos[qa] += h * w.qvel[da];
+        }
+    }
+    WSYNC();
+    time += h;
+}
+
+// ---------------------------------------------------------------------------------- PD laws
+// /root/reference/agents_env/pds_controllers_agents.py:17-34 (standard), :42-78 (feedback), :83-172 (stable).
+// M and bias are evaluated at (qpos_lag, qvel_lag): the state of the last forward.
+PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, const float* action, const float* kp,
+                       const float* kd, float time, float pd_dt, int lane) {
+    if (pd_mode == PBRL_PD_TORQUE) {
+        LANE_LOOP(a, NU) w.tau[a] = action[a * action_cols];
+        WSYNC();
+        return;
+    }
+    // target angles -> w.grad[0..NU)
+    LANE_LOOP(a, NU) {
+        if (action_cols == 4) {
+            float t = pd_mode == PBRL_PD_STABLE ? time + pd_dt : time;
+            const float* c = action + 4 * a;
+            w.grad[a] = c[0] + c[1] * t + c[2] * (t * t) + c[3] * (t * t * t);
+        } else {
+            w.grad[a] = action[a];
+        }
+    }
+    WSYNC();
+    const int qo = NQ - NU, vo = NV - NU;
+    if (pd_mode == PBRL_PD_STANDARD) {
+        LANE_LOOP(a, NU) w.tau[a] = -kp[a] * (w.qpos[qo + a] - w.grad[a]) + (-kd[a] * w.qvel[vo + a]);
+        WSYNC();
+        return;
+    }
+    smooth_position(m, w, w.qpos_lag, lane);
+    smooth_velocity(m, w, w.qvel_lag, lane);
+    if (pd_mode == PBRL_PD_FEEDBACK) {
+        LANE_LOOP(i, NV) w.p[i] = i < vo ? 0.f : -kp[i - vo] * (w.qpos[qo + i - vo] - w.grad[i - vo]) + (-kd[i - vo] * w.qvel[i]);
+        WSYNC();
+        tree_vel(m, w, w.p, lane);
+        tree_Mx_from_V(m, w, w.p, w.Mp, lane);
+        LANE_LOOP(a, NU) w.tau[a] = w.Mp[vo + a] + w.bias[vo + a];
+        WSYNC();
+        return;
+    }
+    // stable PD: qdd = (M + KD dt)^-1 (-C - KP e - KD qd);  tau = -kp e - kd (qd + qdd dt)
+    LANE_LOOP(i, NV) {
+        float e = 0.f, kpi = 0.f, kdi = 0.f;
+        if (i >= vo) { e = (w.qpos[qo + i - vo] + w.qvel[i] * pd_dt) - w.grad[i - vo]; kpi = kp[i - vo]; kdi = kd[i - vo]; }
+        w.Mp[i] = e;
+        w.p[i] = -w.bias[i] - kpi * e - kdi * w.qvel[i];
+    }
+    LANE_LOOP(e, NM) {
+        int r = m.M_row[e];
+        w.LD[e] = w.M[e] + ((r == m.M_col[e] && r >= vo) ? kd[r - vo] * pd_dt : 0.f);
+    }
+    WSYNC();
+    ldl_factor(m, w, lane);
+    ldl_solve(m, w, w.p, lane);
+    LANE_LOOP(a, NU) w.tau[a] = -kp[a] * w.Mp[vo + a] - kd[a] * (w.qvel[vo + a] + w.p[vo + a] * pd_dt);
+    WSYNC();
+}
+
+}  // namespace pbrl
+
+// =====================================================================================================
+// Env-level bodies: one call = one env handled by one warp.  Global-memory rows are read and written
+// with lane-strided (coalesced) accesses; everything in between stays in the warp's workspace.
+// =====================================================================================================
+namespace pbrl {
+
+struct StepArgs {
+    int N, n_frames, pd_mode, action_cols, reward_mode;
+    const float *action, *kp, *kd, *pd_time;
+    float pd_dt;
+    unsigned ctrl_mask;
+    PbrlBuffers buf;
+};
+
+PB_DEV void load_row(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = src[i]; }
+PB_DEV void store_row(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = src[i]; }
+
+PB_DEV void write_obs_reference(const StepArgs& a, Ws& w, int env, float done_value, int lane) {
+    const PbrlBuffers& B = a.buf;
+    if (B.obs) { store_row(B.obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(B.obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
+    LANE_LOOP(k, 3) if (B.reward) B.reward[(size_t)env * 3 + k] = 0.f;      // agent_mimic.py:84
+    LANE_LOOP(z, 1) if (B.done) B.done[env] = done_value;                  // agent_mimic.py:72
+}
+
+// HumanoidTrain.step (agent_mimic.py:58-91): PD law once, n_frames substeps with the torque held
+PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, int lane) {
+    const PbrlBuffers& B = a.buf;
+    load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
+    load_row(w.warm, B.warm + (size_t)env * NV, NV, lane);
+    load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
+    load_row(w.qpos_lag, B.qpos_lag + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel_lag, B.qvel_lag + (size_t)env * NV, NV, lane);
+    LANE_LOOP(z, 1) w.status = 0;
+    WSYNC();
+    float time = B.time[env];
+    pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
+              a.pd_time ? a.pd_time[env] : time, a.pd_dt, lane);
+    LANE_LOOP(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
+    WSYNC();
+    for (int f = 0; f < a.n_frames; f++) {
+        if (f == a.n_frames - 1) {
+            LANE_LOOP(i, NQ) w.qpos_lag[i] = w.qpos[i];
+            LANE_LOOP(i, NV) w.qvel_lag[i] = w.qvel[i];
+            WSYNC();
+        }
+        substep(m, w, time, lane);
+    }
+    float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
+    store_row(B.qpos + (size_t)env * NQ, w.qpos, NQ, lane);
+    store_row(B.qvel + (size_t)env * NV, w.qvel, NV, lane);
+    store_row(B.warm + (size_t)env * NV, w.warm, NV, lane);
+    store_row(B.ctrl + (size_t)env * NU, w.ctrl, NU, lane);
+    store_row(B.qpos_lag + (size_t)env * NQ, w.qpos_lag, NQ, lane);
+    store_row(B.qvel_lag + (size_t)env * NV, w.qvel_lag, NV, lane);
+    LANE_LOOP(z, 1) {
+        B.time[env] = time;
+        if (B.status) B.status[env] = w.status | (bad > 0.f ? PBRL_STATUS_NAN : 0);
+    }
+    write_obs_reference(a, w, env, 1.0f, lane);
+    WSYNC();
+}
+
+// HumanoidDiff.reset (agent_env_template.py:88-112): qpos0, zero velocity
+PB_DEVN void env_reset(const DevModel& m, Ws& w, const StepArgs& a, int env, int lane) {
+    const PbrlBuffers& B = a.buf;
+    LANE_LOOP(i, NQ) w.qpos[i] = m.qpos0[i];
+    LANE_LOOP(i, NV) w.qvel[i] = 0.f;
+    WSYNC();
+    store_row(B.qpos + (size_t)env * NQ, w.qpos, NQ, lane);
+    store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
+    store_row(B.qvel + (size_t)env * NV, w.qvel, NV, lane);
+    store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
+    store_row(B.warm + (size_t)env * NV, w.qvel, NV, lane);
+    store_row(B.ctrl + (size_t)env * NU, w.qvel, NU, lane);
+    LANE_LOOP(z, 1) { B.time[env] = 0.f; if (B.status) B.status[env] = 0; }
+    LANE_LOOP(k, 3) if (B.metrics) B.metrics[(size_t)env * 3 + k] = 0.f;
+    write_obs_reference(a, w, env, 0.0f, lane);
+    WSYNC();
+}
+
+// HumanoidReplay.step (agent_replay_motion.py:51-83): kinematics at the given pose, obs = [qpos, qvel]
+PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float* qvel, float* obs, float* reward,
+                        float* done, float* xpos, float* xquat, int env, int lane) {
+    load_row(w.qpos, qpos + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
+    WSYNC();
+    if (xpos || xquat) stage_fk(m, w, w.qpos, lane);
+    if (obs) { store_row(obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
+    LANE_LOOP(k, 3) if (reward) reward[(size_t)env * 3 + k] = 0.f;
+    LANE_LOOP(z, 1) if (done) done[env] = 1.0f;
+    if (xpos) LANE_LOOP(i, NB * 3) xpos[(size_t)env * NB * 3 + i] = w.xpos[i];
+    if (xquat) LANE_LOOP(i, NB * 4) xquat[(size_t)env * NB * 4 + i] = w.xquat[S4 * (i / 4) + (i & 3)];
+    WSYNC();
+}
+
+// separate-controller path (testing_pds_env3.ipynb cell 21): tau, and optionally dense qM / qfrc_bias
+PB_DEVN void env_pd(const DevModel& m, Ws& w, int pd_mode, int action_cols, const float* action, const float* qpos,
+                    const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
+                    const float* time, float pd_dt, float* tau, float* qM, float* bias, int env, int lane) {
+    load_row(w.qpos, qpos + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
+    load_row(w.qpos_lag, qpos_lag + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel_lag, qvel_lag + (size_t)env * NV, NV, lane);
+    LANE_LOOP(z, 1) w.status = 0;
+    WSYNC();
+    if (qM || bias) {
+        smooth_position(m, w, w.qpos_lag, lane);
+        smooth_velocity(m, w, w.qvel_lag, lane);
+        if (qM) {
+            LANE_LOOP(i, NV * NV) qM[(size_t)env * NV * NV + i] = 0.f;
+            WSYNC();
+            LANE_LOOP(e, NM) {
+                int r = m.M_row[e], c = m.M_col[e];
+                qM[(size_t)env * NV * NV + r * NV + c] = w.M[e];
+                qM[(size_t)env * NV * NV + c * NV + r] = w.M[e];
+            }
+        }
+        if (bias) store_row(bias + (size_t)env * NV, w.bias, NV, lane);
+        WSYNC();
+    }
+    pd_torque(m, w, pd_mode, action_cols, action + (size_t)env * NU * action_cols, kp, kd, time[env], pd_dt, lane);
+    store_row(tau + (size_t)env * NU, w.tau, NU, lane);
+    WSYNC();
+}
+
+// one mjx.forward with every stage dumped (layout: PBRL_DBG_* in pbrl.h)
+PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, const float* qvel, const float* ctrl,
+                               const float* warm, float* out, int env, int lane) {
+    load_row(w.qpos, qpos + (size_t)env * NQ, NQ, lane);
+    load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
+    load_row(w.ctrl, ctrl + (size_t)env * NU, NU, lane);
+    load_row(w.warm, warm + (size_t)env * NV, NV, lane);
+    LANE_LOOP(z, 1) w.status = 0;
+    WSYNC();
+    forward(m, w, lane);
+    float* o = out + (size_t)env * PBRL_DBG_SIZE;
+    LANE_LOOP(i, PBRL_DBG_SIZE) o[i] = 0.f;
+    WSYNC();
+    LANE_LOOP(i, NB * 3) o[PBRL_DBG_XPOS + i] = w.xpos[i];
+    LANE_LOOP(i, NB * 4) o[PBRL_DBG_XQUAT + i] = w.xquat[S4 * (i / 4) + (i & 3)];
+    LANE_LOOP(i, 3) o[PBRL_DBG_COM + i] = w.com[i];
+    LANE_LOOP(e, NM) {
+        int r = m.M_row[e], c = m.M_col[e];
+        o[PBRL_DBG_QM + r * NV + c] = w.M[e];
+        o[PBRL_DBG_QM + c * NV + r] = w.M[e];
+    }
+    LANE_LOOP(i, NV) {
+        o[PBRL_DBG_BIAS + i] = w.bias[i];
+        o[PBRL_DBG_QFRC_SMOOTH + i] = w.fsmooth[i];
+        o[PBRL_DBG_QACC_SMOOTH + i] = w.asmooth[i];
+        o[PBRL_DBG_QACC + i] = w.qacc[i];
+        o[PBRL_DBG_QFRC_CONSTRAINT + i] = w.fcon[i];
+    }
+    float nact = wsum(lane, NC, [&](int c) { return w.con_on[c] ? 1.f : 0.f; });
+    LANE_LOOP(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }
+    LANE_LOOP(c, NC) {
+        o[PBRL_DBG_CON_DIST + c] = w.con_dist[c];
+        for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_p[S3 * c + k];
+        for (int e = 0; e < 4; e++)
+            o[PBRL_DBG_CON_FORCE + 4 * c + e] = (w.con_on[c] && w.con_jar[4 * c + e] < 0.f) ? -w.con_D[c] * w.con_jar[4 * c + e] : 0.f;
+    }
+    LANE_LOOP(l, NLIM) o[PBRL_DBG_LIM_FORCE + l] = (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) ? -w.lim_D[l] * w.lim_jar[l] : 0.f;
+    WSYNC();
+}
+
+}  // namespace pbrl

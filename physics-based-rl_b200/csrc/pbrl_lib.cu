@@ -1,0 +1,325 @@
+// libpbrl.so: CUDA kernels (sm_100a) + the C ABI declared in include/pbrl.h.
+//
+// One warp per environment; WARPS_PER_CTA warps per CTA, each with its own shared-memory workspace
+// (pbrl_core.cuh: Ws).  Grids are sized to the resident capacity of the device (SM count x CTAs/SM) and
+// every warp walks a grid-stride loop over environments, so any N runs with full SMs and no tail CTA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pbrl_core.cuh"
+#include "pbrl_desc_reflect.h"
+
+using namespace pbrl;
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
+
+thread_local std::string g_error;
+int fail(const std::string& msg) { g_error = msg; return -1; }
+#define CUDA_OK(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+__device__ __forceinline__ Ws& my_ws() {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return *reinterpret_cast<Ws*>(smem_raw + (size_t)(threadIdx.x >> 5) * sizeof(Ws));
+}
+__device__ __forceinline__ int first_env() { return blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5); }
+__device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; }
+
+__global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    for (int env = first_env(); env < a.N; env += env_stride()) env_step(*gm, w, a, env, lane);
+}
+__global__ void __launch_bounds__(CTA_THREADS) k_reset(const DevModel* __restrict__ gm, StepArgs a) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    for (int env = first_env(); env < a.N; env += env_stride()) env_reset(*gm, w, a, env, lane);
+}
+__global__ void __launch_bounds__(CTA_THREADS)
+k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float* qvel, float* obs, float* reward,
+         float* done, float* xpos, float* xquat) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    for (int env = first_env(); env < N; env += env_stride())
+        env_replay(*gm, w, qpos, qvel, obs, reward, done, xpos, xquat, env, lane);
+}
+__global__ void __launch_bounds__(CTA_THREADS)
+k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
+     const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
+     const float* time, float pd_dt, float* tau, float* qM, float* bias) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    for (int env = first_env(); env < N; env += env_stride())
+        env_pd(*gm, w, pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, env, lane);
+}
+__global__ void __launch_bounds__(CTA_THREADS)
+k_debug_forward(const DevModel* __restrict__ gm, int N, const float* qpos, const float* qvel, const float* ctrl,
+                const float* warm, float* out) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    for (int env = first_env(); env < N; env += env_stride()) env_debug_forward(*gm, w, qpos, qvel, ctrl, warm, out, env, lane);
+}
+
+}  // namespace
+
+struct PbrlModel {
+    int device = 0;
+    int sm_count = 0;
+    int ctas_per_sm = 1;
+    DevModel host{};
+    DevModel* dev = nullptr;
+    DevMimic mimic{};
+    bool has_mimic = false;
+    float* frames = nullptr;
+};
+
+namespace {
+constexpr size_t SMEM_BYTES = sizeof(Ws) * WARPS_PER_CTA;
+
+template <class K>
+int prepare_kernel(K kernel, PbrlModel* m) {
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int nb = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, CTA_THREADS, SMEM_BYTES));
+    if (nb < 1) return fail("kernel does not fit on an SM");
+    if (m->ctas_per_sm == 0 || nb < m->ctas_per_sm) m->ctas_per_sm = nb;
+    return 0;
+}
+int grid_for(const PbrlModel* m, int N) {
+    int need = (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA, cap = m->sm_count * m->ctas_per_sm;
+    return need < cap ? (need > 0 ? need : 1) : cap;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char* pbrl_last_error(void) { return g_error.c_str(); }
+int pbrl_model_desc_size(void) { return (int)sizeof(PbrlModelDesc); }
+int pbrl_model_desc_field(const char* name, int* offset, int* count, int* is_int) { return model_desc_field(name, offset, count, is_int); }
+int pbrl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int device, PbrlModel** out) {
+    if (!desc || !out) return fail("null argument");
+    int ndev = pbrl_device_count();
+    if (ndev <= 0) return fail("no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail("bad device index");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("libpbrl is built for sm_100a (B200) only");
+    PbrlModel* m = new PbrlModel();
+    m->device = device;
+    m->sm_count = prop.multiProcessorCount;
+    m->ctas_per_sm = 0;
+    std::string err = build_dev_model(*desc, m->host);
+    if (!err.empty()) { delete m; return fail(err); }
+    if (prepare_kernel(k_step, m) || prepare_kernel(k_reset, m) || prepare_kernel(k_replay, m) || prepare_kernel(k_pd, m) ||
+        prepare_kernel(k_debug_forward, m)) { delete m; return -1; }
+    CUDA_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
+    CUDA_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
+    if (mimic) {
+        if (mimic->nclip < 1 || mimic->nclip > PBRL_MAXCLIP || !mimic->frames) { pbrl_model_destroy(m); return fail("bad mimic description"); }
+        DevMimic& mm = m->mimic;
+        mm.nclip = mimic->nclip; mm.nframes_total = mimic->nframes_total;
+        for (int c = 0; c < mimic->nclip; c++) {
+            mm.clip_first[c] = mimic->clip_first[c]; mm.clip_nframes[c] = mimic->clip_nframes[c];
+            mm.clip_wrap[c] = mimic->clip_wrap[c]; mm.clip_fall[c] = mimic->clip_fall_enabled[c];
+            mm.clip_duration[c] = mimic->clip_duration[c]; mm.clip_dt[c] = mimic->clip_dt[c];
+        }
+        mm.w_pose = mimic->w_pose; mm.w_vel = mimic->w_vel; mm.w_ee = mimic->w_ee; mm.w_com = mimic->w_com;
+        mm.k_pose = mimic->k_pose; mm.k_vel = mimic->k_vel; mm.k_ee = mimic->k_ee; mm.k_com = mimic->k_com;
+        mm.n_ee = mimic->n_ee;
+        for (int e = 0; e < 4; e++) { mm.ee_body[e] = mimic->ee_body[e]; for (int k = 0; k < 3; k++) mm.ee_offset[e][k] = mimic->ee_offset[3 * e + k]; }
+        mm.fall_geom_mask = mimic->fall_geom_mask;
+        size_t bytes = (size_t)mimic->nframes_total * PBRL_FRAME_STRIDE * sizeof(float);
+        CUDA_OK(cudaMalloc(&m->frames, bytes));
+        CUDA_OK(cudaMemcpy(m->frames, mimic->frames, bytes, cudaMemcpyHostToDevice));
+        m->has_mimic = true;
+    }
+    *out = m;
+    return 0;
+}
+
+void pbrl_model_destroy(PbrlModel* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->dev) cudaFree(m->dev);
+    if (m->frames) cudaFree(m->frames);
+    delete m;
+}
+
+static int check_buffers(const PbrlBuffers* b) {
+    if (!b || !b->qpos || !b->qvel || !b->time || !b->warm || !b->ctrl || !b->qpos_lag || !b->qvel_lag)
+        return fail("PbrlBuffers: state pointers must not be null");
+    return 0;
+}
+
+int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* buf, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (check_buffers(buf)) return -1;
+    if (reward_mode != PBRL_REWARD_REFERENCE) return fail("mimic reward mode is not built yet");
+    StepArgs a{};
+    a.N = N; a.reward_mode = reward_mode; a.buf = *buf;
+    k_reset<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
+    return check_launch("pbrl_reset");
+}
+
+int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp,
+              const float* kd, float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf,
+              void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (check_buffers(buf)) return -1;
+    if (!action) return fail("null action");
+    if (pd_mode < 0 || pd_mode > 3) return fail("pd_mode must be 0..3");
+    if (action_cols != 1 && action_cols != 4) return fail("action_cols must be 1 (targets/torques) or 4 (cubic coefficients)");
+    if (pd_mode != PBRL_PD_TORQUE && (!kp || !kd)) return fail("kp/kd required for the PD modes");
+    if (n_frames < 1) return fail("n_frames must be >= 1");
+    if (reward_mode != PBRL_REWARD_REFERENCE) return fail("mimic reward mode is not built yet");
+    StepArgs a{};
+    a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
+    a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
+    k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
+    return check_launch("pbrl_step");
+}
+
+int pbrl_replay(const PbrlModel* m, int N, const float* qpos, const float* qvel, float* obs, float* reward, float* done,
+                float* xpos, float* xquat, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (!qpos || !qvel) return fail("null qpos/qvel");
+    k_replay<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, obs, reward, done, xpos, xquat);
+    return check_launch("pbrl_replay");
+}
+
+int pbrl_pd_torque(const PbrlModel* m, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
+                   const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
+                   const float* time, float pd_dt, float* tau, float* qM, float* bias, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (!action || !qpos || !qvel || !qpos_lag || !qvel_lag || !kp || !kd || !time || !tau) return fail("null argument");
+    if (pd_mode < 0 || pd_mode > 3) return fail("pd_mode must be 0..3");
+    if (action_cols != 1 && action_cols != 4) return fail("action_cols must be 1 or 4");
+    k_pd<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, pd_mode, action_cols, action, qpos, qvel, qpos_lag,
+                                                                          qvel_lag, kp, kd, time, pd_dt, tau, qM, bias);
+    return check_launch("pbrl_pd_torque");
+}
+
+int pbrl_debug_forward(const PbrlModel* m, int N, const float* qpos, const float* qvel, const float* ctrl, const float* warm,
+                       float* out, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (!qpos || !qvel || !ctrl || !warm || !out) return fail("null argument");
+    k_debug_forward<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, warm, out);
+    return check_launch("pbrl_debug_forward");
+}
+
+// ------------------------------------------------------------------------------------------ host-buffer layer
+struct PbrlBatch {
+    const PbrlModel* model;
+    int N;
+    cudaStream_t stream;
+    PbrlBuffers buf;   // device
+    float* action;     // device, [N][28][4]
+    float* gains;      // device, kp[28] kd[28]
+    int* motion_id;
+    float* ref_t0;
+    std::vector<void*> allocs;
+};
+
+int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
+    if (!m || !out || N <= 0) return fail("bad argument");
+    CUDA_OK(cudaSetDevice(m->device));
+    PbrlBatch* b = new PbrlBatch();
+    b->model = m; b->N = N;
+    CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    auto alloc = [&](size_t n) -> float* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) return nullptr;
+        cudaMemsetAsync(p, 0, n * sizeof(float), b->stream);
+        b->allocs.push_back(p);
+        return (float*)p;
+    };
+    PbrlBuffers& B = b->buf;
+    B.qpos = alloc((size_t)N * NQ); B.qvel = alloc((size_t)N * NV); B.time = alloc(N); B.warm = alloc((size_t)N * NV);
+    B.ctrl = alloc((size_t)N * NU); B.qpos_lag = alloc((size_t)N * NQ); B.qvel_lag = alloc((size_t)N * NV);
+    B.obs = alloc((size_t)N * PBRL_OBS); B.reward = alloc((size_t)N * 3); B.done = alloc(N); B.metrics = alloc((size_t)N * 3);
+    B.status = (int*)alloc(N); B.stats = alloc(8);
+    b->motion_id = (int*)alloc(N); b->ref_t0 = alloc(N);
+    B.motion_id = nullptr; B.ref_t0 = nullptr;
+    b->action = alloc((size_t)N * NU * 4); b->gains = alloc(2 * NU);
+    for (void* p : b->allocs) if (!p) { pbrl_batch_destroy(b); return fail("cudaMalloc failed"); }
+    *out = b;
+    return 0;
+}
+void pbrl_batch_destroy(PbrlBatch* b) {
+    if (!b) return;
+    cudaSetDevice(b->model->device);
+    cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocs) if (p) cudaFree(p);
+    cudaStreamDestroy(b->stream);
+    delete b;
+}
+int pbrl_batch_reset_host(PbrlBatch* b, int reward_mode, const int* motion_id, const float* ref_t0, float* obs_out) {
+    if (!b) return fail("null batch");
+    CUDA_OK(cudaSetDevice(b->model->device));
+    if (motion_id) { CUDA_OK(cudaMemcpyAsync(b->motion_id, motion_id, b->N * sizeof(int), cudaMemcpyHostToDevice, b->stream)); b->buf.motion_id = b->motion_id; }
+    if (ref_t0) { CUDA_OK(cudaMemcpyAsync(b->ref_t0, ref_t0, b->N * sizeof(float), cudaMemcpyHostToDevice, b->stream)); b->buf.ref_t0 = b->ref_t0; }
+    if (pbrl_reset(b->model, b->N, reward_mode, &b->buf, b->stream)) return -1;
+    if (obs_out) CUDA_OK(cudaMemcpyAsync(obs_out, b->buf.obs, (size_t)b->N * PBRL_OBS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp,
+                         const float* kd, float pd_dt, int reward_mode, float* obs_out, float* reward_out, float* done_out,
+                         float* stats_out) {
+    if (!b || !action) return fail("null argument");
+    if (action_cols != 1 && action_cols != 4) return fail("action_cols must be 1 or 4");
+    CUDA_OK(cudaSetDevice(b->model->device));
+    const int N = b->N;
+    CUDA_OK(cudaMemcpyAsync(b->action, action, (size_t)N * NU * action_cols * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    if (kp && kd) {
+        CUDA_OK(cudaMemcpyAsync(b->gains, kp, NU * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+        CUDA_OK(cudaMemcpyAsync(b->gains + NU, kd, NU * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    }
+    if (stats_out) CUDA_OK(cudaMemsetAsync(b->buf.stats, 0, 8 * sizeof(float), b->stream));
+    if (pbrl_step(b->model, N, n_frames, pd_mode, action_cols, b->action, b->gains, b->gains + NU, pd_dt, nullptr, 0x0FFFFFFFu,
+                  reward_mode, &b->buf, b->stream)) return -1;
+    if (obs_out) CUDA_OK(cudaMemcpyAsync(obs_out, b->buf.obs, (size_t)N * PBRL_OBS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (reward_out) CUDA_OK(cudaMemcpyAsync(reward_out, b->buf.reward, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (done_out) CUDA_OK(cudaMemcpyAsync(done_out, b->buf.done, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, b->buf.stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+int pbrl_batch_get_state_host(PbrlBatch* b, float* qpos, float* qvel, float* time) {
+    if (!b) return fail("null batch");
+    CUDA_OK(cudaSetDevice(b->model->device));
+    if (qpos) CUDA_OK(cudaMemcpyAsync(qpos, b->buf.qpos, (size_t)b->N * NQ * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (qvel) CUDA_OK(cudaMemcpyAsync(qvel, b->buf.qvel, (size_t)b->N * NV * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (time) CUDA_OK(cudaMemcpyAsync(time, b->buf.time, (size_t)b->N * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+}  // extern "C"

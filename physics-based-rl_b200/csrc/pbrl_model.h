@@ -1,0 +1,224 @@
+// Device-side model constants (fp32) and their construction from the C-ABI PbrlModelDesc.
+//
+// The kernels are specialised to the dimensions of the reference's humanoid
+// (/root/reference/models/final_humanoid.xml: 14 bodies, nq 35, nv 34, nu 28, 16 geoms; SURVEY.md
+// App. B) but read the topology (parents, levels, ancestor lists, contact slots) as data.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "../../include/pbrl.h"
+
+namespace pbrl {
+
+constexpr int NB = PBRL_NBODY;
+constexpr int NQ = PBRL_NQ;
+constexpr int NV = PBRL_NV;
+constexpr int NU = PBRL_NU;
+constexpr int NJ = PBRL_NJNT;
+constexpr int NG = PBRL_NGEOM;
+constexpr int NM = 310;   // non-zeros of the tree-sparse joint-space inertia (row i: i and its ancestors)
+constexpr int NLIM = 28;  // limited hinges
+constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
+constexpr int NCP = 32;   // padded
+constexpr int NTRI = 78;  // 12*13/2 pairs of the deepest ancestor chain
+constexpr int MAXLEVEL = 8;
+constexpr int MAXDEPTH = 16;
+
+enum { DOF_FREE_T0 = 0, DOF_FREE_R0 = 3, DOF_HINGE = 6 };
+enum { CON_SPHERE = 0, CON_CAPSULE = 1, CON_BOX = 3 };
+
+struct DevModel {
+    float timestep, gx, gy, gz;
+    float sol_k, sol_b, sol_dmin, sol_dmax, sol_width, sol_mid, sol_power, meaninertia;
+    float total_mass, plane_z;
+    int nlevel;
+    int ndepth;
+    int level_start[MAXLEVEL + 1];
+    int level_body[NB];
+    int depth_start[MAXDEPTH + 1];
+    int depth_dof[NV];
+    int body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
+    int body_conadr[NB], body_connum[NB];
+    float body_pos[NB][3], body_mass[NB], body_ipos[NB][3], body_inertia[NB][6];
+    int jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ];
+    float jnt_axis[NJ][3], jnt_lo[NJ], jnt_hi[NJ], jnt_margin[NJ];
+    int dof_bodyid[NV], dof_jntid[NV], dof_parentid[NV], dof_depth[NV], dof_Madr[NV], dof_kind[NV];
+    float dof_armature[NV], dof_damping[NV], dof_invweight0[NV], dof_gear[NV], dof_ctrl_lo[NV], dof_ctrl_hi[NV];
+    int dof_act[NV];
+    int lim_jnt[NLIM];
+    int M_row[NM], M_col[NM];
+    int tri_a[NTRI], tri_t[NTRI];
+    // contact slots, sorted by body
+    int con_body[NCP], con_kind[NCP], con_sub[NCP], con_geom[NCP];
+    float con_gpos[NCP][3], con_gquat[NCP][4], con_size[NCP][3], con_margin[NCP], con_mu[NCP], con_invweight[NCP];
+    float qpos0[NQ + 1];
+};
+
+// ---- mimic configuration on the device --------------------------------------------------------
+struct DevMimic {
+    int nclip, nframes_total;
+    int clip_first[PBRL_MAXCLIP], clip_nframes[PBRL_MAXCLIP], clip_wrap[PBRL_MAXCLIP], clip_fall[PBRL_MAXCLIP];
+    float clip_duration[PBRL_MAXCLIP], clip_dt[PBRL_MAXCLIP];
+    float w_pose, w_vel, w_ee, w_com, k_pose, k_vel, k_ee, k_com;
+    int n_ee, ee_body[4];
+    float ee_offset[4][3];
+    unsigned fall_geom_mask;
+};
+
+inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
+    std::memset(&m, 0, sizeof(m));
+    if (d.nbody[0] != NB || d.nq[0] != NQ || d.nv[0] != NV || d.nu[0] != NU || d.njnt[0] != NJ || d.ngeom[0] != NG)
+        return "model dimensions differ from the humanoid the kernels are specialised to (14 bodies, nq 35, nv 34, nu 28, 29 joints, 16 geoms)";
+    m.timestep = (float)d.timestep[0];
+    m.gx = (float)d.gravity[0]; m.gy = (float)d.gravity[1]; m.gz = (float)d.gravity[2];
+    {   // mjx constraint._kbi constants
+        double timeconst = std::fmax(d.solref[0], 2.0 * d.timestep[0]), dampratio = d.solref[1];
+        double dmin = std::fmin(std::fmax(d.solimp[0], 1e-4), 0.9999), dmax = std::fmin(std::fmax(d.solimp[1], 1e-4), 0.9999);
+        double k = 1.0 / (dmax * dmax * timeconst * timeconst * dampratio * dampratio), b = 2.0 / (dmax * timeconst);
+        if (d.solref[0] <= 0) k = -d.solref[0] / (dmax * dmax);
+        if (d.solref[1] <= 0) b = -d.solref[1] / dmax;
+        m.sol_k = (float)k; m.sol_b = (float)b; m.sol_dmin = (float)dmin; m.sol_dmax = (float)dmax;
+        m.sol_width = (float)std::fmax(1e-15, d.solimp[2]);
+        m.sol_mid = (float)std::fmin(std::fmax(d.solimp[3], 1e-4), 0.9999);
+        m.sol_power = (float)std::fmax(1.0, d.solimp[4]);
+    }
+    m.meaninertia = (float)d.meaninertia[0];
+    int level[NB] = {0};
+    for (int b = 0; b < NB; b++) {
+        m.body_parent[b] = d.body_parent[b];
+        if (b > 0) {
+            if (d.body_parent[b] >= b) return "bodies must be ordered parents-first";
+            level[b] = level[d.body_parent[b]] + 1;
+        }
+        m.body_jntadr[b] = d.body_jntadr[b]; m.body_jntnum[b] = d.body_jntnum[b];
+        m.body_dofadr[b] = d.body_dofadr[b]; m.body_dofnum[b] = d.body_dofnum[b];
+        if (b > 0 && d.body_dofnum[b] == 0) return "every moving body needs at least one dof";
+        m.body_mass[b] = (float)d.body_mass[b];
+        m.total_mass += (float)d.body_mass[b];
+        for (int k = 0; k < 3; k++) { m.body_pos[b][k] = (float)d.body_pos[3 * b + k]; m.body_ipos[b][k] = (float)d.body_ipos[3 * b + k]; }
+        const double* I = d.body_inertia + 9 * b;
+        m.body_inertia[b][0] = (float)I[0]; m.body_inertia[b][1] = (float)I[4]; m.body_inertia[b][2] = (float)I[8];
+        m.body_inertia[b][3] = (float)I[1]; m.body_inertia[b][4] = (float)I[2]; m.body_inertia[b][5] = (float)I[5];
+    }
+    // depth-first order check + subtree ends
+    for (int b = 0; b < NB; b++) {
+        int e = b + 1;
+        while (e < NB) {
+            int a = e;
+            while (a > b) a = d.body_parent[a];
+            if (a != b) break;
+            e++;
+        }
+        m.body_subtree_end[b] = e;
+        for (int c = e; c < NB; c++) {  // no later body may descend from b
+            int a = c;
+            while (a > b) a = d.body_parent[a];
+            if (a == b && b != 0) return "bodies must be in depth-first order";
+        }
+    }
+    int nl = 0;
+    for (int b = 0; b < NB; b++) nl = level[b] + 1 > nl ? level[b] + 1 : nl;
+    if (nl > MAXLEVEL) return "tree too deep";
+    m.nlevel = nl;
+    int pos = 0;
+    for (int l = 0; l < nl; l++) {
+        m.level_start[l] = pos;
+        for (int b = 0; b < NB; b++) if (level[b] == l) m.level_body[pos++] = b;
+    }
+    m.level_start[nl] = pos;
+    int nlim = 0;
+    for (int j = 0; j < NJ; j++) {
+        m.jnt_type[j] = d.jnt_type[j]; m.jnt_qposadr[j] = d.jnt_qposadr[j]; m.jnt_dofadr[j] = d.jnt_dofadr[j];
+        m.jnt_limited[j] = d.jnt_limited[j];
+        for (int k = 0; k < 3; k++) {
+            m.jnt_axis[j][k] = (float)d.jnt_axis[3 * j + k];
+            if (d.jnt_pos[3 * j + k] != 0.0) return "joint anchors must sit at the body origin (jnt_pos = 0)";
+        }
+        m.jnt_lo[j] = (float)d.jnt_range[2 * j]; m.jnt_hi[j] = (float)d.jnt_range[2 * j + 1];
+        m.jnt_margin[j] = (float)d.jnt_margin[j];
+        if (d.jnt_type[j] == 0 && j != 0) return "only the first joint may be free";
+        if (d.jnt_type[j] != 0 && d.jnt_type[j] != 3) return "only free and hinge joints";
+        if (d.jnt_limited[j]) { if (nlim >= NLIM) return "too many limited joints"; m.lim_jnt[nlim++] = j; }
+    }
+    if (nlim != NLIM) return "expected 28 limited hinges";
+    for (int l = 0; l < NLIM; l++)  // the kernels map dof -> limit row by offset
+        if (d.jnt_dofadr[m.lim_jnt[l]] != d.jnt_dofadr[m.lim_jnt[0]] + l || d.jnt_type[m.lim_jnt[l]] != 3)
+            return "limited hinges must own contiguous dofs";
+    if (d.jnt_type[0] != 0) return "joint 0 must be the free root joint";
+    int madr = 0, maxdepth = 0;
+    for (int i = 0; i < NV; i++) {
+        m.dof_bodyid[i] = d.dof_bodyid[i]; m.dof_parentid[i] = d.dof_parentid[i];
+        m.dof_armature[i] = (float)d.dof_armature[i]; m.dof_damping[i] = (float)d.dof_damping[i];
+        m.dof_invweight0[i] = (float)d.dof_invweight0[i];
+        m.dof_depth[i] = d.dof_parentid[i] < 0 ? 0 : m.dof_depth[d.dof_parentid[i]] + 1;
+        if (d.dof_parentid[i] >= i) return "dof parents must precede";
+        maxdepth = m.dof_depth[i] > maxdepth ? m.dof_depth[i] : maxdepth;
+        m.dof_Madr[i] = madr;
+        for (int j = i; j >= 0; j = d.dof_parentid[j]) {
+            if (madr >= NM) return "sparse inertia layout overflow";
+            m.M_row[madr] = i; m.M_col[madr] = j; madr++;
+        }
+        m.dof_act[i] = -1; m.dof_gear[i] = 0; m.dof_ctrl_lo[i] = -1e30f; m.dof_ctrl_hi[i] = 1e30f;
+    }
+    if (madr != NM) return "sparse inertia layout size differs from 310";
+    if (maxdepth + 1 > MAXDEPTH || maxdepth * (maxdepth + 1) / 2 > NTRI) return "dof chains too deep";
+    m.ndepth = maxdepth + 1;
+    pos = 0;
+    for (int l = 0; l <= maxdepth; l++) {
+        m.depth_start[l] = pos;
+        for (int i = 0; i < NV; i++) if (m.dof_depth[i] == l) m.depth_dof[pos++] = i;
+    }
+    m.depth_start[maxdepth + 1] = pos;
+    for (int j = 0; j < NJ; j++) {
+        int n = d.jnt_type[j] == 0 ? 6 : 1;
+        for (int k = 0; k < n; k++) {
+            m.dof_jntid[d.jnt_dofadr[j] + k] = j;
+            m.dof_kind[d.jnt_dofadr[j] + k] = d.jnt_type[j] == 0 ? k : DOF_HINGE;
+        }
+    }
+    {   // pairs (a,t), a>=1, a+t<=depth, ordered by a+t so that a prefix serves every depth
+        int n = 0;
+        for (int s = 1; s <= 12; s++) for (int a = 1; a <= s; a++) { m.tri_a[n] = a; m.tri_t[n] = s - a; n++; }
+    }
+    for (int a = 0; a < NU; a++) {
+        int i = d.act_dofadr[a];
+        if (m.dof_act[i] >= 0) return "one actuator per dof";
+        m.dof_act[i] = a; m.dof_gear[i] = (float)d.act_gear[a];
+        if (d.act_ctrllimited[a]) { m.dof_ctrl_lo[i] = (float)d.act_ctrlrange[2 * a]; m.dof_ctrl_hi[i] = (float)d.act_ctrlrange[2 * a + 1]; }
+    }
+    // contact slots: every non-plane geom against the floor plane (self-collisions: SURVEY.md section 8f N2, not built)
+    int plane = -1;
+    for (int g = 0; g < NG; g++) if (d.geom_type[g] == 0) { if (plane >= 0) return "one plane only"; plane = g; }
+    if (plane < 0 || d.geom_bodyid[plane] != 0) return "the floor plane must belong to the world body";
+    if (d.geom_quat[4 * plane] != 1.0 || d.geom_pos[3 * plane] != 0 || d.geom_pos[3 * plane + 1] != 0) return "floor must be z-up at the origin";
+    m.plane_z = (float)d.geom_pos[3 * plane + 2];
+    int nc = 0;
+    for (int b = 0; b < NB; b++) {
+        m.body_conadr[b] = nc;
+        for (int g = 0; g < NG; g++) {
+            if (g == plane || d.geom_bodyid[g] != b) continue;
+            int t = d.geom_type[g], kind, n;
+            if (t == 2) { kind = CON_SPHERE; n = 1; } else if (t == 3) { kind = CON_CAPSULE; n = 2; } else if (t == 6) { kind = CON_BOX; n = 4; } else return "geom type";
+            double mu = std::fmax(d.geom_friction[3 * plane], d.geom_friction[3 * g]);
+            double margin = std::fmax(d.geom_margin[plane], d.geom_margin[g]) - std::fmax(d.geom_gap[plane], d.geom_gap[g]);
+            double tw = d.body_invweight0[2 * 0] + d.body_invweight0[2 * b];
+            double invw = (tw + mu * mu * tw) * 2.0 * mu * mu / d.impratio[0];
+            for (int s = 0; s < n; s++) {
+                if (nc >= NC) return "too many contact slots";
+                m.con_body[nc] = b; m.con_kind[nc] = kind; m.con_sub[nc] = s; m.con_geom[nc] = g;
+                for (int k = 0; k < 3; k++) { m.con_gpos[nc][k] = (float)d.geom_pos[3 * g + k]; m.con_size[nc][k] = (float)d.geom_size[3 * g + k]; }
+                for (int k = 0; k < 4; k++) m.con_gquat[nc][k] = (float)d.geom_quat[4 * g + k];
+                m.con_margin[nc] = (float)margin; m.con_mu[nc] = (float)mu; m.con_invweight[nc] = (float)invw;
+                nc++;
+            }
+        }
+        m.body_connum[b] = nc - m.body_conadr[b];
+    }
+    if (nc != NC) return "expected 29 plane contact slots";
+    for (int i = 0; i < NQ; i++) m.qpos0[i] = (float)d.qpos0[i];
+    return "";
+}
+
+}  // namespace pbrl

@@ -1,0 +1,269 @@
+"""Batched env classes with the reference's interface, running on libpbrl (CUDA, sm_100a).
+
+Mirrors, for N environments at once:
+  HumanoidDiff    /root/reference/agents_env/agent_env_template.py:33-155
+  HumanoidTrain   /root/reference/agents_env/agent_mimic.py:34-271
+  HumanoidReplay  /root/reference/agents_env/agent_replay_motion.py:34-83
+and brax's `State(pipeline_state, obs, reward, done, metrics, info)` container.  Same method names,
+argument meaning and return layout; arrays are torch CUDA tensors with a leading batch dimension
+(the reference never batches; `jax.vmap` of its step is what this replaces).
+
+Differences that are deliberate and documented:
+  * `step` updates the state buffers in place (the State passed in is donated); use `State.clone()`
+    to keep a copy.
+  * `pipeline_state.qM` / `.qfrc_bias` are evaluated on demand from the lagged state (they are the
+    fields of the last `mjx.forward`) instead of being stored per env.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import pds_controllers
+from .mjcf import ModelConst, load_model
+
+PD_TORQUE, PD_STANDARD, PD_FEEDBACK, PD_STABLE = 0, 1, 2, 3
+
+
+class PipelineState:
+    """The subset of brax.mjx `State` the reference reads."""
+
+    def __init__(self, env, qpos, qvel, time, warm, ctrl, qpos_lag, qvel_lag):
+        self._env = env
+        self.qpos, self.qvel, self.time, self.qacc_warmstart, self.ctrl = qpos, qvel, time, warm, ctrl
+        self.qpos_lag, self.qvel_lag = qpos_lag, qvel_lag
+
+    q = property(lambda self: self.qpos)
+    qd = property(lambda self: self.qvel)
+
+    @property
+    def qfrc_applied(self):
+        return torch.zeros_like(self.qvel)
+
+    def _lag_dynamics(self):
+        N = self.qpos.shape[0]
+        env = self._env
+        tau = torch.empty((N, 28), device=self.qpos.device)
+        qM = torch.empty((N, 34, 34), device=self.qpos.device)
+        bias = torch.empty((N, 34), device=self.qpos.device)
+        zeros = torch.zeros((N, 28), device=self.qpos.device)
+        _lib.check(_lib.lib().pbrl_pd_torque(
+            env.model.handle, ctypes.c_int(N), ctypes.c_int(PD_TORQUE), ctypes.c_int(1), _lib._ptr(zeros),
+            _lib._ptr(self.qpos), _lib._ptr(self.qvel), _lib._ptr(self.qpos_lag), _lib._ptr(self.qvel_lag),
+            _lib._ptr(env._kp0), _lib._ptr(env._kp0), _lib._ptr(self.time), ctypes.c_float(0.0), _lib._ptr(tau),
+            _lib._ptr(qM), _lib._ptr(bias), _lib.current_stream_ptr(self.qpos.device)))
+        return qM, bias
+
+    @property
+    def qM(self):
+        return self._lag_dynamics()[0]
+
+    @property
+    def qfrc_bias(self):
+        return self._lag_dynamics()[1]
+
+    def clone(self):
+        c = lambda t: t.clone()
+        return PipelineState(self._env, c(self.qpos), c(self.qvel), c(self.time), c(self.qacc_warmstart), c(self.ctrl),
+                             c(self.qpos_lag), c(self.qvel_lag))
+
+
+@dataclass
+class State:
+    pipeline_state: PipelineState
+    obs: torch.Tensor
+    reward: torch.Tensor
+    done: torch.Tensor
+    metrics: Dict[str, torch.Tensor] = field(default_factory=dict)
+    info: Dict[str, Any] = field(default_factory=dict)
+
+    def replace(self, **kw):
+        d = dict(pipeline_state=self.pipeline_state, obs=self.obs, reward=self.reward, done=self.done,
+                 metrics=self.metrics, info=self.info)
+        d.update(kw)
+        return State(**d)
+
+    def clone(self):
+        return State(self.pipeline_state.clone(), self.obs.clone(), self.reward.clone(), self.done.clone(),
+                     {k: v.clone() for k, v in self.metrics.items()}, dict(self.info))
+
+
+class HumanoidDiff:
+    """agent_env_template.py:33 -- loads the model, fixes timestep 0.002 and n_frames = int((1/60)/0.002) = 8."""
+
+    def __init__(self, reference_trajectory_qpos, reference_trajectory_qvel, duration_trajectory, dict_duration,
+                 model_path, **kwargs):
+        self.num_envs = int(kwargs.pop("num_envs", 1))
+        dev = kwargs.pop("device", 0)
+        self.device = torch.device("cuda", dev if isinstance(dev, int) else torch.device(dev).index or 0)
+        const = model_path if isinstance(model_path, ModelConst) else load_model(model_path)
+        self._dt = 1 / 60
+        const.timestep = float(kwargs.pop("timestep", 0.002))          # agent_env_template.py:65
+        self.n_frames = int(kwargs.pop("n_frames", int(self._dt / 0.002)))  # agent_env_template.py:68
+        self.sys = const
+        self.sys.dt = const.timestep
+        self.model = _lib.Model(const, device=self.device.index)
+        self.reference_trajectory_qpos = reference_trajectory_qpos
+        self.reference_trajectory_qvel = reference_trajectory_qvel
+        self.duration_trajectory = duration_trajectory
+        self.dict_duration = dict_duration
+        self._kp0 = torch.zeros(28, device=self.device)
+
+    dt = property(lambda self: self.sys.timestep * self.n_frames)
+    action_size = property(lambda self: self.sys.nu)
+    observation_size = property(lambda self: self.sys.nq + self.sys.nv)
+
+    def set_new_trajectory(self, trajectory):
+        self.reference_trajectory_qpos = np.asarray(trajectory.data_pos)
+        self.reference_trajectory_qvel = np.asarray(trajectory.data_vel)
+        self.duration_trajectory = trajectory.total_time
+        self.dict_duration = trajectory.duration_dict
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def _alloc_state(self):
+        N, d = self.num_envs, self.device
+        z = lambda *s: torch.zeros(s, device=d, dtype=torch.float32)
+        ps = PipelineState(self, z(N, 35), z(N, 34), z(N), z(N, 34), z(N, 28), z(N, 35), z(N, 34))
+        metrics = z(N, 3)
+        st = State(ps, z(N, 69), z(N, 3), z(N), {}, {})
+        st.info["_metrics"] = metrics
+        st.info["status"] = torch.zeros(N, device=d, dtype=torch.int32)
+        self._bind_metrics(st)
+        return st
+
+    @staticmethod
+    def _bind_metrics(st):
+        m = st.info["_metrics"]
+        st.metrics = {"step_index": m[:, 0], "pose_error": m[:, 1], "fall": m[:, 2]}
+
+    def _buffers(self, st: State):
+        ps = st.pipeline_state
+        return _lib.make_buffers(qpos=ps.qpos, qvel=ps.qvel, time=ps.time, warm=ps.qacc_warmstart, ctrl=ps.ctrl,
+                                 qpos_lag=ps.qpos_lag, qvel_lag=ps.qvel_lag, obs=st.obs, reward=st.reward, done=st.done,
+                                 metrics=st.info["_metrics"], status=st.info["status"])
+
+    def _stream(self):
+        return _lib.current_stream_ptr(self.device)
+
+    # ---- API --------------------------------------------------------------------------------------
+    def reset(self, rng=None) -> State:
+        """agent_env_template.py:88-112: qpos0, zero velocity, pipeline_init; `rng` is unused there too."""
+        st = self._alloc_state()
+        b = self._buffers(st)
+        _lib.check(_lib.lib().pbrl_reset(self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(0),
+                                         ctypes.byref(b), self._stream()))
+        return st
+
+    def pipeline_init(self, qpos, qvel) -> PipelineState:
+        c = lambda t: torch.as_tensor(t, dtype=torch.float32, device=self.device).contiguous().clone()
+        qpos, qvel = c(qpos), c(qvel)
+        N = qpos.shape[0]
+        z = lambda *s: torch.zeros(s, device=self.device)
+        return PipelineState(self, qpos, qvel, z(N), z(N, 34), z(N, 28), qpos.clone(), qvel.clone())
+
+    def _get_obs(self, data: PipelineState, action=None):
+        return torch.cat([data.qpos, data.qvel], dim=-1)  # agent_env_template.py:151-155
+
+    def _launch_step(self, st: State, action, pd_mode, pd_dt, pd_time=None, ctrl_mask=0x0FFFFFFF, kp=None, kd=None):
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
+        if action.dim() == 1 or (action.dim() == 2 and action.shape == (28, 4)):
+            action = action.expand(self.num_envs, *action.shape).contiguous()
+        cols = 1 if action.dim() == 2 else int(action.shape[2])
+        if pd_time is not None:
+            pd_time = torch.as_tensor(pd_time, dtype=torch.float32, device=self.device).expand(self.num_envs).contiguous()
+        b = self._buffers(st)
+        _lib.check(_lib.lib().pbrl_step(
+            self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(self.n_frames), ctypes.c_int(pd_mode),
+            ctypes.c_int(cols), _lib._ptr(action), _lib._ptr(kp), _lib._ptr(kd), ctypes.c_float(pd_dt),
+            _lib._ptr(pd_time), ctypes.c_uint(ctrl_mask), ctypes.c_int(0), ctypes.byref(b), self._stream()))
+        return st
+
+
+class HumanoidTrain(HumanoidDiff):
+    """agent_mimic.py:34 -- PD-driven env."""
+
+    def __init__(self, reference_trajectory_qpos, reference_trajectory_qvel, duration_trajectory, dict_duration,
+                 model_path, kp_gains, kd_gains, **kwargs):
+        super().__init__(reference_trajectory_qpos, reference_trajectory_qvel, duration_trajectory, dict_duration,
+                         model_path, **kwargs)
+        self.kp__gains = torch.as_tensor(np.asarray(kp_gains), dtype=torch.float32, device=self.device).contiguous()
+        self.kd__gains = torch.as_tensor(np.asarray(kd_gains), dtype=torch.float32, device=self.device).contiguous()
+        self.pd_function = pds_controllers.stable_pd_controller_custom_trajectory
+
+    def set_pd_callback(self, pd_control):
+        self.pd_function = pd_control
+
+    def _pd_step(self, st, target, time, ctrl_mask=0x0FFFFFFF):
+        mode = getattr(self.pd_function, "pd_mode", None)
+        if mode is not None:  # one of the built-in laws: fused into the step kernel
+            return self._launch_step(st, target, mode, self.sys.dt, pd_time=time, ctrl_mask=ctrl_mask,
+                                     kp=self.kp__gains, kd=self.kd__gains)
+        ps = st.pipeline_state  # arbitrary callable: evaluate it, then run the torque-driven step
+        torque = self.pd_function(target, self.sys, st, ps.q, ps.qd, self.kp__gains, self.kd__gains,
+                                  ps.time if time is None else time, self.sys.dt)
+        return self._launch_step(st, torque, PD_TORQUE, self.sys.dt, ctrl_mask=ctrl_mask)
+
+    def step(self, state: State, action) -> State:
+        """agent_mimic.py:58-91"""
+        return self._pd_step(state, action, None)
+
+    def step_custom_target(self, state: State, action, custom_target, time) -> State:
+        """agent_mimic.py:200-236"""
+        return self._pd_step(state, custom_target, time)
+
+    def step_custom_target_and_outside(self, state: State, action) -> State:
+        """agent_mimic.py:239-271: the torque was computed outside."""
+        return self._launch_step(state, action, PD_TORQUE, self.sys.dt)
+
+    @staticmethod
+    def _mask(*joints):
+        m = 0
+        for j in joints:
+            m |= 1 << int(j)
+        return m
+
+    def step_selected_joints_custom_target_and_joints(self, state, action, custom_target, joints1, joints2, joints3,
+                                                      joints4, joints5, joints6, time) -> State:
+        """agent_mimic.py:94-139: only joints1..4 take the new torque, the rest keep the previous ctrl."""
+        return self._pd_step(state, custom_target, time, self._mask(joints1, joints2, joints3, joints4))
+
+    def step_selected_joints_custom_target_and_joints6(self, state, action, custom_target, joints1, joints2, joints3,
+                                                       joints4, joints5, joints6, time) -> State:
+        """agent_mimic.py:145-190"""
+        return self._pd_step(state, custom_target, time, self._mask(joints1, joints2, joints3, joints4, joints5, joints6))
+
+
+class HumanoidReplay(HumanoidDiff):
+    """agent_replay_motion.py:34 -- kinematic replay: `pipeline_init` at the state's qpos/qvel."""
+
+    def step(self, state: State, action=None, want_poses=False) -> State:
+        ps = state.pipeline_state
+        N = ps.qpos.shape[0]
+        xpos = torch.empty((N, 14, 3), device=self.device) if want_poses else None
+        xquat = torch.empty((N, 14, 4), device=self.device) if want_poses else None
+        _lib.check(_lib.lib().pbrl_replay(self.model.handle, ctypes.c_int(N), _lib._ptr(ps.qpos), _lib._ptr(ps.qvel),
+                                          _lib._ptr(state.obs), _lib._ptr(state.reward), _lib._ptr(state.done),
+                                          _lib._ptr(xpos), _lib._ptr(xquat), self._stream()))
+        ps.time.zero_()  # pipeline_init builds fresh data: time = 0
+        ps.qpos_lag.copy_(ps.qpos)
+        ps.qvel_lag.copy_(ps.qvel)
+        if want_poses:
+            state.info["xpos"], state.info["xquat"] = xpos, xquat
+        return state
+
+
+_REGISTRY = {}
+
+
+def register_environment(name, cls):
+    """brax.envs.register_environment, as the notebooks use it (testing_pds_env.ipynb cell 2)."""
+    _REGISTRY[name] = cls
+
+
+def get_environment(env_name, **kwargs):
+    return _REGISTRY[env_name](**kwargs)

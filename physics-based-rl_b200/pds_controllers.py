@@ -1,0 +1,59 @@
+"""PD controllers with the reference's signatures, evaluated by the CUDA library.
+
+  *_mjx variants  /root/reference/agents_env/pds_controllers_mjx.py:17-32, 40-80, 156-191
+                  fn(target, mj_model, mj_data, mjx_data, q, qdot, kp_array, kd_array, time, dt) -> tau[N,28]
+  brax variants   /root/reference/agents_env/pds_controllers_agents.py:17-34, 42-78, 137-172
+                  fn(target, sys, state, q, qdot, kp_array, kd_array, time, dt) -> tau[N,28]
+
+Semantics follow pds_controllers_agents.py (live M / bias of the last forward); the *_mjx twins keep
+their signature but not the stale-host-M quirk.  Each function carries a
+`pd_mode` attribute so that HumanoidTrain can fuse the law into the step kernel.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _evaluate(mode, target, env_model, pipeline_state, q, qdot, kp, kd, time, dt):
+    dev = q.device
+    N = q.shape[0]
+    target = torch.as_tensor(target, dtype=torch.float32, device=dev)
+    if target.dim() == 1 or (target.dim() == 2 and tuple(target.shape) == (28, 4)):
+        target = target.expand(N, *target.shape)
+    target = target.contiguous()
+    cols = 1 if target.dim() == 2 else int(target.shape[2])
+    kp = torch.as_tensor(kp, dtype=torch.float32, device=dev).contiguous()
+    kd = torch.as_tensor(kd, dtype=torch.float32, device=dev).contiguous()
+    time = torch.as_tensor(time, dtype=torch.float32, device=dev).expand(N).contiguous()
+    tau = torch.empty((N, 28), device=dev)
+    _lib.check(_lib.lib().pbrl_pd_torque(
+        env_model.handle, ctypes.c_int(N), ctypes.c_int(mode), ctypes.c_int(cols), _lib._ptr(target),
+        _lib._ptr(q.contiguous()), _lib._ptr(qdot.contiguous()), _lib._ptr(pipeline_state.qpos_lag),
+        _lib._ptr(pipeline_state.qvel_lag), _lib._ptr(kp), _lib._ptr(kd), _lib._ptr(time), ctypes.c_float(dt),
+        _lib._ptr(tau), None, None, _lib.current_stream_ptr(dev)))
+    return tau
+
+
+def _brax(mode):
+    def fn(target, sys, state, q, qdot, kp_array, kd_array, time, dt):
+        ps = state.pipeline_state
+        return _evaluate(mode, target, ps._env.model, ps, q, qdot, kp_array, kd_array, time, dt)
+    fn.pd_mode = mode
+    return fn
+
+
+def _mjx(mode):
+    def fn(target, mj_model, mj_data, mjx_data, q, qdot, kp_array, kd_array, time, dt):
+        return _evaluate(mode, target, mjx_data._env.model, mjx_data, q, qdot, kp_array, kd_array, time, dt)
+    fn.pd_mode = mode
+    return fn
+
+
+standard_pd_controller = _brax(1)
+feedback_pd_controller = _brax(2)
+stable_pd_controller_custom_trajectory = _brax(3)
+standard_pd_controller_mjx = _mjx(1)
+feedback_pd_controller_mjx = _mjx(2)
+stable_pd_controller_custom_trajectory_mjx = _mjx(3)

@@ -1,0 +1,63 @@
+// Host emulation of the CUDA kernel bodies -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles physics-based-rl_b200/csrc/pbrl_core.cuh with PBRL_HOST_EMU (lane loops run sequentially)
+// so that the kernel LOGIC can be checked against the oracle on a machine without a GPU
+// (`pytest -m "not gpu"`).  It cannot see races or shuffle bugs; those are covered by the `-m gpu`
+// parity tests and compute-sanitizer.  Nothing in the product loads this library.
+#define PBRL_HOST_EMU 1
+#include "../../physics-based-rl_b200/csrc/pbrl_core.cuh"
+#include "../../physics-based-rl_b200/csrc/pbrl_desc_reflect.h"
+
+#include <cstdio>
+#include <vector>
+
+using namespace pbrl;
+
+static DevModel g_model;
+static std::string g_err;
+
+extern "C" {
+const char* emu_last_error() { return g_err.c_str(); }
+int emu_model_desc_size() { return (int)sizeof(PbrlModelDesc); }
+int emu_model_desc_field(const char* n, int* o, int* c, int* i) { return model_desc_field(n, o, c, i); }
+int emu_ws_bytes() { return (int)sizeof(Ws); }
+int emu_model_bytes() { return (int)sizeof(DevModel); }
+int emu_set_model(const PbrlModelDesc* d) {
+    g_err = build_dev_model(*d, g_model);
+    return g_err.empty() ? 0 : -1;
+}
+int emu_reset(int N, const PbrlBuffers* buf) {
+    std::vector<Ws> ws(1);
+    StepArgs a{};
+    a.N = N; a.buf = *buf;
+    for (int e = 0; e < N; e++) env_reset(g_model, ws[0], a, e, 0);
+    return 0;
+}
+int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp, const float* kd,
+             float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf) {
+    std::vector<Ws> ws(1);
+    StepArgs a{};
+    a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
+    a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
+    for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, 0);
+    return 0;
+}
+int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* reward, float* done, float* xpos, float* xquat) {
+    std::vector<Ws> ws(1);
+    for (int e = 0; e < N; e++) env_replay(g_model, ws[0], qpos, qvel, obs, reward, done, xpos, xquat, e, 0);
+    return 0;
+}
+int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, const float* qpos, const float* qvel,
+                  const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd, const float* time,
+                  float pd_dt, float* tau, float* qM, float* bias) {
+    std::vector<Ws> ws(1);
+    for (int e = 0; e < N; e++)
+        env_pd(g_model, ws[0], pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, e, 0);
+    return 0;
+}
+int emu_debug_forward(int N, const float* qpos, const float* qvel, const float* ctrl, const float* warm, float* out) {
+    std::vector<Ws> ws(1);
+    for (int e = 0; e < N; e++) env_debug_forward(g_model, ws[0], qpos, qvel, ctrl, warm, out, e, 0);
+    return 0;
+}
+}

@@ -1,0 +1,220 @@
+"""Parity cases shared by the host-emulation tests (no GPU) and the `-m gpu` tests (libpbrl on a B200).
+
+Each case drives a back end (helpers.EmuBackend / helpers.GpuBackend) and the oracle on identical seeded
+inputs and compares at the tolerances BASELINE.json's north_star states:
+  fp32 relative error <= 1e-5 on qpos/qvel after one substep, <= 1e-3 after 32 contact-free substeps;
+  contact-rich rollouts: matching termination / contact statistics.
+The oracle runs in float64 with a tight solver tolerance; the back end computes in fp32.
+"""
+import numpy as np
+
+from helpers import DBG, GOLDEN, Oracle, OracleEnv, random_states, relerr, row_relerr, start_trajectory, util_data
+
+TOL_1 = 1e-5    # after one substep (north_star)
+TOL_32 = 1e-3   # after 32 contact-free substeps (north_star)
+
+
+def _oracle(model):
+    return Oracle(model, "f64", tolerance=1e-14)
+
+
+def check_forward_stages(backend, model, gravity, N=24, seed=3):
+    """Every stage of one mjx.forward against the oracle's intermediates."""
+    orc = _oracle(model)
+    rng = np.random.default_rng(seed)
+    qpos, qvel = random_states(model, N, seed, gravity_heights=gravity, vel_scale=1.0, joint_frac=0.6)
+    if not gravity:  # drive a few joints past their limits so that limit rows are active
+        qpos[:, 7 + 9] = rng.uniform(-0.3, 0.0, N)   # right elbow below its lower limit 0
+        qpos[:, 7 + 17] = rng.uniform(0.0, 0.3, N)   # right knee above its upper limit 0
+    ctrl = rng.uniform(-1, 1, (N, 28))
+    warm = rng.normal(size=(N, 34))
+    out = backend.debug_forward(qpos, qvel, ctrl, warm)
+    q32, v32, c32, w32 = [np.asarray(x, np.float32) for x in (qpos, qvel, ctrl, warm)]
+    worst = {}
+    active_total = 0
+    for e in range(N):
+        d = orc.new_data()
+        d.qpos[:35], d.qvel[:34], d.ctrl[:28], d.qacc_warmstart[:34] = q32[e], v32[e], c32[e], w32[e]
+        orc.forward(d)
+        get = lambda k: out[e, DBG[k][0]:DBG[k][0] + DBG[k][1]]
+        ref = dict(xpos=d.xpos[:42], xquat=d.xquat[:56], com=d.com[:3], qM=d.qM_dense().ravel(), bias=d.qfrc_bias[:34],
+                   qfrc_smooth=d.qfrc_smooth[:34], qacc_smooth=d.qacc_smooth[:34], qacc=d.qacc[:34],
+                   qfrc_constraint=d.qfrc_constraint[:34])
+        for k, r in ref.items():
+            worst[k] = max(worst.get(k, 0.0), relerr(get(k), r))
+        nc = int(d.ncon[0])
+        n_act = int((d.con_dist[:nc] - d.con_includemargin[:nc] < 0).sum())
+        assert int(get("ncon_active")[0]) == n_act, (e, get("ncon_active"), n_act)
+        active_total += n_act + int((d.efc_force[:28] > 0).sum())
+    tol = dict(xpos=2e-6, xquat=2e-6, com=2e-6, qM=2e-6, bias=2e-5, qfrc_smooth=2e-5, qacc_smooth=2e-5, qacc=5e-5,
+               qfrc_constraint=1e-4)
+    for k, v in worst.items():
+        assert v <= tol[k], (k, v, worst)
+    assert active_total > 0, "the case must exercise active constraint rows"
+    return worst
+
+
+def _paired_envs(backend, model, N, seed, gravity):
+    orc = _oracle(model)
+    env = OracleEnv(orc, N)
+    qpos, qvel = random_states(model, N, seed, gravity_heights=gravity)
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    env.set_state(q32, v32)
+    s = backend.new_state(N)
+    s.set_state(q32, v32)
+    return env, s
+
+
+def check_one_substep(backend, model, gravity, N=32, seed=5):
+    """fp32 relative error <= 1e-5 on qpos/qvel after ONE substep (torque-driven, random ctrl)."""
+    env, s = _paired_envs(backend, model, N, seed, gravity)
+    rng = np.random.default_rng(seed)
+    tau = rng.uniform(-0.6, 0.6, (N, 28)).astype(np.float32)
+    kp, kd = util_data.generate_kp_kd_gains()
+    env.step(tau, kp, kd, pd_mode=0, n_frames=1)
+    backend.step(s, tau, kp, kd, pd_mode=0, n_frames=1)
+    eq, ev = row_relerr(s.qpos, env.qpos), row_relerr(s.qvel, env.qvel)
+    assert eq.max() <= TOL_1 and ev.max() <= TOL_1, (eq.max(), ev.max())
+    assert np.allclose(s.time, env.time, atol=1e-7)
+    assert relerr(s.qpos_lag, env.qpos_lag) <= 1e-6 and relerr(s.warm, env.warm) <= 1e-4
+    assert (s.status == 0).all()
+    return float(eq.max()), float(ev.max())
+
+
+def check_32_substeps(backend, model, pd_mode=3, N=32, seed=7):
+    """<= 1e-3 after 32 contact-free substeps (4 env steps x 8), PD targets inside the joint ranges."""
+    env, s = _paired_envs(backend, model, N, seed, gravity=False)
+    rng = np.random.default_rng(seed)
+    kp, kd = util_data.generate_kp_kd_gains()
+    lo, hi = model.jnt_range[1:, 0], model.jnt_range[1:, 1]
+    for k in range(4):
+        action = (rng.uniform(-0.6, 0.6, (N, 28)) if pd_mode == 0 else rng.uniform(lo, hi, (N, 28))).astype(np.float32)
+        env.step(action, kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=8)
+        backend.step(s, action, kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=8)
+    eq, ev = row_relerr(s.qpos, env.qpos), row_relerr(s.qvel, env.qvel)
+    assert eq.max() <= TOL_32 and ev.max() <= TOL_32, (eq.max(), ev.max())
+    assert relerr(s.obs, np.concatenate([env.qpos, env.qvel], 1)) <= TOL_32
+    assert (s.reward == 0).all() and (s.done == 1).all()  # agent_mimic.py:72,84
+    return float(eq.max()), float(ev.max())
+
+
+def check_pd_torque(backend, model, N=16, seed=11):
+    """The three PD laws + dense qM / qfrc_bias against the oracle (pds_controllers_agents.py)."""
+    env, s = _paired_envs(backend, model, N, seed, gravity=False)
+    rng = np.random.default_rng(seed)
+    kp, kd = util_data.generate_kp_kd_gains()
+    lo, hi = model.jnt_range[1:, 0], model.jnt_range[1:, 1]
+    tgt = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
+    env.step(tgt, kp, kd, pd_mode=1, n_frames=3)          # make the lag state differ from the state
+    backend.step(s, tgt, kp, kd, pd_mode=1, n_frames=3)
+    s.qpos[:], s.qvel[:], s.qpos_lag[:], s.qvel_lag[:] = env.qpos, env.qvel, env.qpos_lag, env.qvel_lag
+    out = {}
+    for mode, dt in ((1, 0.002), (2, 0.016), (3, 0.016), (3, 0.002)):
+        t_ref, qM_ref, b_ref = env.pd_torque(tgt, kp, kd, mode, dt, want_qM=True)
+        t, qM, b = backend.pd_torque(s, tgt, kp, kd, mode, dt, want_qM=True)
+        out[(mode, dt)] = relerr(t, t_ref)
+        assert relerr(t, t_ref) <= 2e-5, (mode, dt, relerr(t, t_ref))
+        assert relerr(qM, qM_ref) <= 2e-6 and relerr(b, b_ref) <= 2e-5
+    coef = np.tile(start_trajectory(), (N, 1, 1)).astype(np.float32)
+    tt = np.full(N, 1.7, np.float32)
+    t_ref = env.pd_torque(coef, kp, kd, 3, 0.016, time=tt)
+    t = backend.pd_torque(s, coef, kp, kd, 3, 0.016, time=tt)
+    assert relerr(t, t_ref) <= 2e-5
+    return out
+
+
+def check_golden_T1(backend, model_nograv, nprint=11):
+    """The reference's own known answers through the back end: testing_pds_env3.ipynb cell 21
+    (eager stable-PD with dt = env.dt = 0.016, then step_custom_target_and_outside)."""
+    g = np.load(GOLDEN / "mass_traces.npz")["T1"]
+    kp, kd = util_data.generate_kp_kd_gains()
+    coef = start_trajectory()[None].astype(np.float32)
+    s = backend.new_state(1)
+    backend.reset(s)
+    idx = [0, 1, 2, 31, 32, 33]
+    errs = []
+    for k in range(nprint):
+        t = np.clip(s.time, 1, 3).astype(np.float32)
+        tau, qM, _ = backend.pd_torque(s, coef, kp, kd, 3, 0.016, time=t, want_qM=True)
+        errs.append(float(np.abs(qM[0][np.ix_(idx, idx)] - g[k]).max()))
+        backend.step(s, tau, kp, kd, pd_mode=0, n_frames=8)
+    assert max(errs[:4]) <= 5e-7, errs       # T0 and the first prints: print precision of fp32
+    assert max(errs) <= 2e-5, errs           # prints 4..10 (tight window)
+    return errs
+
+
+def check_golden_T2_T4(backend, model_nograv, nprint=6):
+    """Jitted stable-PD inside the step (pd_dt = sys.dt) and the selected-joint variants
+    (testing_pds_env.ipynb cells 24/30/33; agent_mimic.py:94-190,200-236)."""
+    g = np.load(GOLDEN / "mass_traces.npz")
+    kp, kd = util_data.generate_kp_kd_gains()
+    coef = start_trajectory()[None].astype(np.float32)
+    idx = [0, 1, 2, 31, 32, 33]
+    out = {}
+    for name, joints in (("T2", None), ("T3", [7, 10, 13, 9]), ("T4", [7, 10, 13, 9, 17, 24])):
+        mask = 0x0FFFFFFF if joints is None else sum(1 << j for j in joints)
+        s = backend.new_state(1)
+        backend.reset(s)
+        errs = []
+        for k in range(nprint):
+            t = np.clip(s.time, 1, 3).astype(np.float32)
+            _, qM, _ = backend.pd_torque(s, coef, kp, kd, 3, 0.002, time=t, want_qM=True)
+            errs.append(float(np.abs(qM[0][np.ix_(idx, idx)] - g[name][k]).max()))
+            backend.step(s, coef, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=t, ctrl_mask=mask)
+        assert max(errs[:3]) <= 1e-6 and max(errs) <= 5e-5, (name, errs)
+        out[name] = errs
+    return out
+
+
+def check_replay(backend, model, N=64, seed=13):
+    """HumanoidReplay.step: obs = [qpos, qvel], reward zeros(3), done 1; body poses vs the oracle FK."""
+    orc = _oracle(model)
+    env = OracleEnv(orc, N)
+    qpos, qvel = random_states(model, N, seed, vel_scale=1.0, joint_frac=0.9)
+    qpos[0, 3:7] *= 0.995  # un-normalised root quaternion: FK normalises, obs echoes
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    obs_r, rew_r, done_r, xpos_r, xquat_r = env.replay(q32, v32, want_poses=True)
+    obs, rew, done, xpos, xquat = backend.replay(q32, v32, want_poses=True)
+    assert np.array_equal(obs, np.concatenate([q32, v32], 1))  # bit-exact echo
+    assert (rew == 0).all() and (done == 1).all()
+    assert relerr(xpos, xpos_r) <= 2e-6 and relerr(xquat, xquat_r) <= 2e-6
+    return relerr(xpos, xpos_r)
+
+
+def check_reset(backend, model):
+    s = backend.new_state(5)
+    s.qpos[:] = 7.0
+    s.warm[:] = 3.0
+    backend.reset(s)
+    assert np.array_equal(s.qpos, np.tile(model.qpos0.astype(np.float32), (5, 1)))
+    assert np.array_equal(s.qpos_lag, s.qpos) and (s.qvel == 0).all() and (s.qvel_lag == 0).all()
+    assert (s.warm == 0).all() and (s.ctrl == 0).all() and (s.time == 0).all()
+    assert np.array_equal(s.obs, np.concatenate([s.qpos, s.qvel], 1))
+    assert (s.reward == 0).all() and (s.done == 0).all()
+
+
+def check_contact_rollout(backend, model_grav, N=32, steps=40, seed=17):
+    """Contact-rich drop test: bodies fall from reset-like poses onto the floor.  Trajectories are compared
+    statistically (the contact problem amplifies fp32 noise): touchdown step, final root height, and the
+    early (pre-chaos) window at the 32-substep tolerance."""
+    env, s = _paired_envs(backend, model_grav, N, seed, gravity=True)
+    kp, kd = util_data.generate_kp_kd_gains()
+    tau = np.zeros((N, 28), np.float32)
+    first_ref, first = np.full(N, -1), np.full(N, -1)
+    early = None
+    for k in range(steps):
+        env.step(tau, kp, kd, pd_mode=0, n_frames=8)
+        backend.step(s, tau, kp, kd, pd_mode=0, n_frames=8)
+        if k == 3:
+            early = max(row_relerr(s.qpos, env.qpos).max(), row_relerr(s.qvel, env.qvel).max())
+        # touchdown detector: vertical root velocity stops decreasing (impact)
+        for arr, fst in ((env.qvel, first_ref), (s.qvel, first)):
+            hit = (fst < 0) & (arr[:, 2] > -9.81 * 0.016 * (k + 1) * 0.5)
+            fst[hit] = k
+    assert early <= TOL_32 * 5, early
+    assert (np.abs(first - first_ref) <= 1).mean() >= 0.9, (first, first_ref)
+    zr, z = env.qpos[:, 2], s.qpos[:, 2]
+    assert np.isfinite(s.qpos).all() and (s.status & 3 == 0).all()
+    assert abs(np.median(z) - np.median(zr)) < 0.02 and np.abs(z - zr).mean() < 0.05, (np.median(z), np.median(zr))
+    assert z.min() > 0.02  # nothing fell through the floor
+    return float(early), float(np.abs(z - zr).mean())

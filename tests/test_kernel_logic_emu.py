@@ -1,0 +1,58 @@
+"""Kernel LOGIC vs the oracle without a GPU: the kernel bodies of pbrl_core.cuh compiled for the host
+(tests/emu/emu.cpp).  The same cases run on the real CUDA path in test_gpu_parity.py."""
+import pytest
+
+import parity_cases as pc
+from helpers import EmuBackend
+
+
+@pytest.fixture(scope="module")
+def emu_nograv(model_nograv):
+    return EmuBackend(model_nograv)
+
+
+@pytest.fixture(scope="module")
+def emu_grav(model_grav):
+    return EmuBackend(model_grav)
+
+
+def test_forward_stages_limits(emu_nograv, model_nograv):
+    pc.check_forward_stages(emu_nograv, model_nograv, gravity=False)
+
+
+def test_forward_stages_contacts(emu_grav, model_grav):
+    pc.check_forward_stages(emu_grav, model_grav, gravity=True)
+
+
+def test_one_substep(emu_nograv, model_nograv, emu_grav, model_grav):
+    pc.check_one_substep(emu_nograv, model_nograv, gravity=False)
+    pc.check_one_substep(emu_grav, model_grav, gravity=True)
+
+
+@pytest.mark.parametrize("pd_mode", [0, 1, 2, 3])
+def test_32_contact_free_substeps(emu_nograv, model_nograv, pd_mode):
+    pc.check_32_substeps(emu_nograv, model_nograv, pd_mode=pd_mode, N=8)
+
+
+def test_pd_laws(emu_nograv, model_nograv):
+    pc.check_pd_torque(emu_nograv, model_nograv)
+
+
+def test_golden_T1(emu_nograv, model_nograv):
+    pc.check_golden_T1(emu_nograv, model_nograv)
+
+
+def test_golden_T2_T4(emu_nograv, model_nograv):
+    pc.check_golden_T2_T4(emu_nograv, model_nograv)
+
+
+def test_replay(emu_nograv, model_nograv):
+    pc.check_replay(emu_nograv, model_nograv)
+
+
+def test_reset(emu_nograv, model_nograv):
+    pc.check_reset(emu_nograv, model_nograv)
+
+
+def test_contact_rollout(emu_grav, model_grav):
+    pc.check_contact_rollout(emu_grav, model_grav, N=8, steps=30)

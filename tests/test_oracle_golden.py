@@ -1,0 +1,124 @@
+"""Pin the oracle: the reference's own known answers (notebook stdout) and analytic invariants."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, Oracle, OracleEnv, start_trajectory, util_data
+
+IDX = [0, 1, 2, 31, 32, 33]
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN / "mass_traces.npz")
+
+
+def _trace(orc, pd_dt, golden, nprint, selected=None, inside=False):
+    kp, kd = util_data.generate_kp_kd_gains()
+    coef = start_trajectory()[None]
+    env = OracleEnv(orc, 1)
+    env.reset()
+    mask = 0x0FFFFFFF if selected is None else sum(1 << j for j in selected)
+    errs = []
+    for k in range(nprint):
+        t = np.clip(env.time.astype(np.float32), 1, 3)
+        tau, qM, _ = env.pd_torque(coef, kp, kd, 3, pd_dt, time=t, want_qM=True)
+        errs.append(float(np.abs(qM[0][np.ix_(IDX, IDX)] - golden[k]).max()))
+        if inside:
+            env.step(coef, kp, kd, pd_mode=3, pd_dt=pd_dt, n_frames=8, pd_time=t, ctrl_mask=mask)
+        else:
+            env.step(tau, kp, kd, pd_mode=0, n_frames=8)
+    return errs
+
+
+def test_T0_mass_matrix_at_qpos0(model_nograv, golden):
+    orc = Oracle(model_nograv, "f64")
+    d = orc.new_data()
+    orc.forward(d)
+    M = d.qM_dense()
+    assert np.abs(M[np.ix_(IDX, IDX)] - golden["T1"][0]).max() <= 1.5e-7   # fp32 print precision
+    assert np.allclose(M, M.T, atol=1e-12)
+    assert np.allclose(np.diag(M)[:3], 45.0, atol=1e-9)                       # total mass
+    assert abs(M[33, 33] - 1.00531075) < 1e-8 and abs(M[32, 32] - 1.00539408) < 1e-8 and abs(M[31, 31] - 1.00143333) < 1e-8
+    assert abs(M[31, 33] - 1.0125e-3) < 1e-9
+    assert np.linalg.eigvalsh(M).min() > 0
+
+
+def test_T1_eager_stable_pd(model_nograv, golden):
+    """testing_pds_env3.ipynb cell 21: eager stable PD (dt = env.dt = 0.016) + 8-substep torque step."""
+    errs = _trace(Oracle(model_nograv, "f64", tolerance=1e-14), 0.016, golden["T1"], 11)
+    assert max(errs[:4]) <= 5e-7, errs      # SURVEY.md App. C recommended gates
+    assert max(errs[4:]) <= 1e-5, errs
+
+
+def test_T1_f32_oracle(model_nograv, golden):
+    errs = _trace(Oracle(model_nograv, "f32"), 0.016, golden["T1"], 11)
+    assert max(errs) <= 1e-5, errs
+
+
+@pytest.mark.parametrize("name,selected", [("T2", None), ("T3", [7, 10, 13, 9]), ("T4", [7, 10, 13, 9, 17, 24])])
+def test_T2_T4_jitted_stable_pd(model_nograv, golden, name, selected):
+    """testing_pds_env.ipynb cells 24/30/33: stable PD inside the step with dt = sys.dt = 0.002."""
+    errs = _trace(Oracle(model_nograv, "f64", tolerance=1e-14), 0.002, golden[name], 6, selected, inside=True)
+    assert max(errs[:3]) <= 1e-6 and max(errs) <= 3e-5, errs
+
+
+def test_ablation_limits_matter(model_nograv, golden):
+    """Dropping the joint-limit rows must break the trace: the goldens pin them."""
+    orc = Oracle(model_nograv, "f64", tolerance=1e-14)
+    orc.set_model_field("jnt_limited", np.zeros(29, np.int32))
+    errs = _trace(orc, 0.016, golden["T1"], 5)
+    assert max(errs[3:]) > 2e-5, errs
+
+
+def test_T1_statistics_long_run(model_nograv, golden):
+    """Beyond ~20 env steps the closed loop is chaotic; only statistics are comparable."""
+    kp, kd = util_data.generate_kp_kd_gains()
+    coef = start_trajectory()[None]
+    env = OracleEnv(Oracle(model_nograv, "f32"), 1)
+    env.reset()
+    vals = []
+    for k in range(200):
+        t = np.clip(env.time.astype(np.float32), 1, 3)
+        tau, qM, _ = env.pd_torque(coef, kp, kd, 3, 0.016, time=t, want_qM=True)
+        vals.append(qM[0][0, 32])
+        env.step(tau, kp, kd, pd_mode=0, n_frames=8)
+    g = golden["T1_m0_32"][:200]
+    vals = np.array(vals)
+    assert np.isfinite(vals).all()
+    assert abs(vals.min() - g.min()) < 0.02 and abs(vals.max() - g.max()) < 0.02
+    assert np.allclose(qM[0][0, 0], 45.0, atol=1e-4)
+
+
+def test_momentum_conserved_without_gravity(model_nograv):
+    """No gravity, zero ctrl, no contact: linear momentum M[0:3,:] qvel is conserved by the step."""
+    orc = Oracle(model_nograv, "f64", tolerance=1e-14)
+    rng = np.random.default_rng(0)
+    d = orc.new_data()
+    d.qpos[7:35] = rng.uniform(-0.2, 0.2, 28) * np.sign(model_nograv.jnt_range[1:, 1] + model_nograv.jnt_range[1:, 0] + 1e-9)
+    d.qpos[7 + 9] = 0.5; d.qpos[7 + 13] = 0.5; d.qpos[7 + 17] = -0.5; d.qpos[7 + 24] = -0.5   # elbows/knees inside their ranges
+    d.qvel[:34] = 0.3 * rng.normal(size=34)
+    d.qpos[2] = 2.0                                  # well above the floor: no contact
+    orc.forward(d)
+    p0 = d.qM_dense()[:3] @ d.qvel[:34]
+    for _ in range(50):
+        orc.step(d)
+    orc.forward(d)
+    p1 = d.qM_dense()[:3] @ d.qvel[:34]
+    # semi-implicit Euler conserves momentum to O(h) per unit time: 0.1 s of tumbling drifts by ~5e-5 relative
+    assert np.abs(p1 - p0).max() < 2e-4 * np.abs(p0).max()
+
+
+def test_static_stance_supports_weight(model_grav):
+    """Contact self-consistency (no reference golden exists for contacts): after touchdown the summed normal
+    force is about the body weight and penetration stays sub-millimetre (SURVEY.md App. A preamble)."""
+    orc = Oracle(model_grav, "f64", tolerance=1e-12)
+    d = orc.new_data()
+    ratios = []
+    for s in range(300):
+        orc.step(d)
+        if 120 <= s < 300:
+            nef = int(d.nefc[0])
+            ratios.append(d.efc_force[28:nef].sum() / (45 * 9.81))
+    assert 0.85 < np.mean(ratios) < 1.2, np.mean(ratios)
+    nc = int(d.ncon[0])
+    assert d.con_dist[:nc].min() > -1e-3
