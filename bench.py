@@ -42,29 +42,29 @@ WORKLOADS = {
 
 def load_assets(workload):
     mjcf = importlib.import_module(PKG + ".mjcf")
+    mocap = importlib.import_module(PKG + ".mocap")
+    mimic = importlib.import_module(PKG + ".mimic")
     asset, clips, n_env, pd_mode, descr = WORKLOADS[workload]
     model = mjcf.load_model(ROOT / PKG / "assets" / f"{asset}.model.json")
-    mocap = {c: np.load(ROOT / PKG / "assets" / f"mocap_{c}.npz") for c in clips}
-    return model, clips, mocap, n_env, pd_mode, descr
+    table = mocap.MotionTable.load(ROOT / PKG / "assets" / "motions.npz")
+    mdesc, keep = mimic.make_mimic_desc(model, table, clips)
+    return model, clips, (table, mdesc, keep), n_env, pd_mode, descr
 
 
-def synth_inputs(model, clips, mocap, n_env, rank, steps, seed=0):
-    """Seeded, shard-independent synthetic inputs keyed by the GLOBAL env id."""
+def synth_inputs(model, clips, mim, n_env, rank, steps, seed=0):
+    """Seeded, shard-independent synthetic inputs keyed by the GLOBAL env id: clip = id mod nclip, reference-state
+    init at a uniform phase of the clip, random target-angle actions inside the joint ranges."""
+    table, mdesc, _ = mim
     gid = np.arange(rank * n_env, (rank + 1) * n_env)
-    qpos = np.zeros((n_env, 35), np.float32)
-    qvel = np.zeros((n_env, 34), np.float32)
-    for k, c in enumerate(clips):
-        sel = np.where(gid % len(clips) == k)[0]
-        F = mocap[c]["data_pos"].shape[0]
-        rs = np.random.default_rng([seed, k, rank])
-        fr = rs.integers(0, F - 1, sel.size)
-        qpos[sel] = mocap[c]["data_pos"][fr]
-    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    motion_id = (gid % len(clips)).astype(np.int32)
+    dur = np.array([mdesc.clip_duration[c] for c in range(len(clips))], np.float64)
+    phase = np.array([np.random.default_rng([seed, int(g)]).random() for g in gid])
+    ref_t0 = (phase * dur[motion_id]).astype(np.float32)
     lo, hi = model.jnt_range[1:, 0].astype(np.float32), model.jnt_range[1:, 1].astype(np.float32)
     rs = np.random.default_rng([seed, 1000, rank])
     n_act = min(steps, 16)  # a ring of action batches, reused
     actions = rs.uniform(lo, hi, (n_act, n_env, 28)).astype(np.float32)
-    return qpos, qvel, actions
+    return motion_id, ref_t0, actions
 
 
 def measured_peak():
@@ -110,19 +110,19 @@ def cpu_reference_run(workload, steps, warmup, sample_envs=None, threads=None):
     (oracle/, fp32, OpenMP over envs) on a bounded sample of the same synthetic inputs."""
     from oracle.oracle import Oracle, OracleEnv
     util_data = importlib.import_module(PKG + ".util_data")
-    model, clips, mocap, n_env, pd_mode, descr = load_assets(workload)
+    model, clips, mim, n_env, pd_mode, descr = load_assets(workload)
     cores = threads or os.cpu_count() or 1
     n = sample_envs or min(n_env, 64 * cores)
-    qpos, qvel, actions = synth_inputs(model, clips, mocap, n_env, 0, steps)
+    motion_id, ref_t0, actions = synth_inputs(model, clips, mim, n_env, 0, steps)
     orc = Oracle(model, "f32")
     env = OracleEnv(orc, n, nthreads=cores)
-    env.set_state(qpos[:n], qvel[:n])
+    env.reset_mimic(mim[1], motion_id[:n], ref_t0[:n])
     kp, kd = util_data.generate_kp_kd_gains()
     for k in range(warmup):
-        env.step(actions[k % len(actions)][:n], kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=N_FRAMES)
+        env.step_mimic(actions[k % len(actions)][:n], kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=N_FRAMES)
     t0 = time.perf_counter()
     for k in range(steps):
-        env.step(actions[k % len(actions)][:n], kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=N_FRAMES)
+        env.step_mimic(actions[k % len(actions)][:n], kp, kd, pd_mode=pd_mode, pd_dt=0.002, n_frames=N_FRAMES)
     dt = time.perf_counter() - t0
     return {"value": n * N_FRAMES * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} envs x {steps} env steps x {N_FRAMES} substeps of workload '{workload}' "
@@ -170,18 +170,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model, clips, mocap, n_env, pd_mode, descr = load_assets(args.workload)
+    model, clips, mim, n_env, pd_mode, descr = load_assets(args.workload)
     if args.envs:
         n_env = args.envs
-    qpos, qvel, actions = synth_inputs(model, clips, mocap, n_env, rank, steps)
-    M = L.Model(model, device=local_rank)
+    motion_id, ref_t0, actions = synth_inputs(model, clips, mim, n_env, rank, steps)
+    M = L.Model(model, device=local_rank, mimic=mim[1])
     z = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)
-    st = dict(qpos=torch.from_numpy(qpos).to(dev), qvel=torch.from_numpy(qvel).to(dev), time=z(n_env), warm=z(n_env, 34),
-              ctrl=z(n_env, 28), obs=z(n_env, 69), reward=z(n_env, 3), done=z(n_env), metrics=z(n_env, 3),
-              status=torch.zeros(n_env, device=dev, dtype=torch.int32), stats=z(8))
-    st["qpos_lag"], st["qvel_lag"] = st["qpos"].clone(), st["qvel"].clone()
-    init = {k: v.clone() for k, v in st.items()}
+    st = dict(qpos=z(n_env, 35), qvel=z(n_env, 34), qpos_lag=z(n_env, 35), qvel_lag=z(n_env, 34), time=z(n_env),
+              warm=z(n_env, 34), ctrl=z(n_env, 28), obs=z(n_env, 69), reward=z(n_env, 3), done=z(n_env), metrics=z(n_env, 3),
+              status=torch.zeros(n_env, device=dev, dtype=torch.int32), stats=z(8),
+              motion_id=torch.from_numpy(motion_id).to(dev), ref_t0=torch.from_numpy(ref_t0).to(dev))
     bufs = L.make_buffers(**st)
+    L.check(L.lib().pbrl_reset(M.handle, n_env, 1, ctypes.byref(bufs), L.current_stream_ptr(dev)))  # reference-state init
+    torch.cuda.synchronize()
+    init = {k: v.clone() for k, v in st.items()}
     act_dev = torch.from_numpy(actions).to(dev)
     kp, kd = [torch.from_numpy(x).to(dev) for x in util_data.generate_kp_kd_gains()]
     lib = L.lib()
@@ -190,9 +192,10 @@ def main():
 
     def one_step(k):
         a = act_dev[k % act_dev.shape[0]]
+        st["stats"].zero_()
         L.check(lib.pbrl_step(M.handle, n_env, N_FRAMES, pd_mode, 1, L._ptr(a), L._ptr(kp), L._ptr(kd), ctypes.c_float(0.002),
-                              None, ctypes.c_uint(0x0FFFFFFF), 0, ctypes.byref(bufs), stream))
-        if world > 1:  # per-step reward/termination statistics all-reduce (64 B, NCCL over NVLink)
+                              None, ctypes.c_uint(0x0FFFFFFF), 1, ctypes.byref(bufs), stream))
+        if world > 1:  # per-step reward/termination statistics all-reduce (32 B, NCCL over NVLink)
             dist.all_reduce(st["stats"])
 
     def sync_all():
@@ -223,6 +226,7 @@ def main():
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t_ms = float(t_all.item())
     bad = int((st["status"] & 1).sum().item())
+    stats_last = st["stats"].cpu().numpy().tolist()
 
     # end to end through the host-buffer C-ABI layer: pinned host actions in, obs/reward/done out, every step
     batch = ctypes.c_void_p()
@@ -230,16 +234,16 @@ def main():
     h_act = torch.from_numpy(actions[: min(4, len(actions))].copy()).pin_memory()
     h_obs, h_rew, h_done = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((n_env, 69), (n_env, 3), (n_env,))]
     h_kp, h_kd = [torch.from_numpy(x.copy()) for x in util_data.generate_kp_kd_gains()]
-    # seed the batch with the same initial states (device-to-device into the batch-owned buffers is not part of
-    # the ABI; the reset path + a few steps is the public way, so e2e runs from reset states)
-    L.check(lib.pbrl_batch_reset_host(batch, 0, None, None, ctypes.c_void_p(h_obs.data_ptr())))
+    h_mid, h_t0, h_stats = torch.from_numpy(motion_id.copy()), torch.from_numpy(ref_t0.copy()), torch.zeros(8).pin_memory()
+    L.check(lib.pbrl_batch_reset_host(batch, 1, ctypes.c_void_p(h_mid.data_ptr()), ctypes.c_void_p(h_t0.data_ptr()),
+                                      ctypes.c_void_p(h_obs.data_ptr())))
     e2e_steps = max(4, steps // 4)
 
     def e2e_step(k):
         L.check(lib.pbrl_batch_step_host(batch, N_FRAMES, pd_mode, 1, ctypes.c_void_p(h_act[k % h_act.shape[0]].data_ptr()),
                                          ctypes.c_void_p(h_kp.data_ptr()), ctypes.c_void_p(h_kd.data_ptr()), ctypes.c_float(0.002),
-                                         0, ctypes.c_void_p(h_obs.data_ptr()), ctypes.c_void_p(h_rew.data_ptr()),
-                                         ctypes.c_void_p(h_done.data_ptr()), None))
+                                         1, ctypes.c_void_p(h_obs.data_ptr()), ctypes.c_void_p(h_rew.data_ptr()),
+                                         ctypes.c_void_p(h_done.data_ptr()), ctypes.c_void_p(h_stats.data_ptr())))
     for k in range(3):
         e2e_step(k)
     sync_all()
@@ -264,17 +268,19 @@ def main():
                 "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "description": descr, "envs_per_gpu": n_env, "envs_total": total_envs,
-                           "n_frames": N_FRAMES, "pd_mode": "stable", "l2_flush_between_steps": True,
+                           "n_frames": N_FRAMES, "pd_mode": "stable", "reward_mode": "mimic", "l2_flush_between_steps": True,
                            "parallelism": f"env-sharded x{world}, stats all-reduce per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,
-                        "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4,
+                        "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,
                         "steps": e2e_steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)"},
                 "gpu_launches": steps + e2e_steps + 3 + warmup,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "k_step",
                              "algorithmic_bytes_per_env_launch": BYTES_PER_ENV_LAUNCH,
                              "note": "the dynamics step is fp32-issue/latency bound (50-300 flop/B); HBM fraction is reported per the tier rule"},
-                "clocks": clocks, "nan_envs": bad}
+                "clocks": clocks, "nan_envs": bad,
+                "reward_stats_last_step": {"mean_reward": stats_last[0] / max(stats_last[5], 1), "done_frac": stats_last[2] / max(stats_last[5], 1),
+                                           "fall_frac": stats_last[3] / max(stats_last[5], 1), "n": stats_last[5]}}
         if not args.no_cpu_baseline:
             r = cpu_reference_run(args.workload, 4, 1)
             line["cpu_baseline"] = {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}

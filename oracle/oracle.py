@@ -229,3 +229,31 @@ class OracleEnv:
                                        None if qM is None else qM.ctypes.data_as(ctypes.c_void_p),
                                        None if bias is None else bias.ctypes.data_as(ctypes.c_void_p))
         return (tau, qM, bias) if want_qM else tau
+
+
+    # ---- mimic mode (build-defined; pbrl_oracle_env.c) -------------------------------------------------------
+    def reset_mimic(self, mimic_desc, motion_id, ref_t0):
+        self.motion_id = np.ascontiguousarray(motion_id, np.int32)
+        self.ref_t0 = np.ascontiguousarray(ref_t0, self.orc.real)
+        self.mimic_desc = mimic_desc
+        b = self._bufs()
+        self.orc.lib.orc_env_reset_mimic.restype = None
+        self.orc.lib.orc_env_reset_mimic(self.orc.model_ptr, ctypes.byref(mimic_desc), ctypes.c_int(self.N),
+                                         self.motion_id.ctypes.data_as(ctypes.c_void_p), self._p(self.ref_t0), ctypes.byref(b))
+
+    def step_mimic(self, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8):
+        r = self.orc.real
+        action = np.ascontiguousarray(action, dtype=r)
+        cols = 1 if action.ndim == 2 else action.shape[2]
+        R = ctypes.c_double if r == np.float64 else ctypes.c_float
+        b = self._bufs()
+        stats = np.zeros(8, np.float64)
+        kp_, kd_ = np.ascontiguousarray(kp, dtype=r), np.ascontiguousarray(kd, dtype=r)
+        self.orc.lib.orc_env_step_mimic.restype = None
+        self.orc.lib.orc_env_step_mimic(self.orc.model_ptr, ctypes.byref(self.mimic_desc), ctypes.c_int(self.N),
+                                        ctypes.c_int(n_frames), ctypes.c_int(pd_mode), ctypes.c_int(cols),
+                                        action.ctypes.data_as(ctypes.c_void_p), kp_.ctypes.data_as(ctypes.c_void_p),
+                                        kd_.ctypes.data_as(ctypes.c_void_p), R(pd_dt),
+                                        self.motion_id.ctypes.data_as(ctypes.c_void_p), self._p(self.ref_t0), ctypes.byref(b),
+                                        stats.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(self.nthreads))
+        return stats

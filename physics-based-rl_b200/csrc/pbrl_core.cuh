@@ -28,12 +28,16 @@
 #define PB_DEV __device__ __forceinline__
 #define PB_DEVN __device__ __noinline__
 #define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
+#define LANE_IF(i, n) for (int i = lane, once_ = 1; once_ && i < (n); once_ = 0)  /* n <= 32: at most one pass */
 #define WSYNC() __syncwarp()
+#define CTA_SYNC() __syncthreads()
 #else
 #define PB_DEV static inline
 #define PB_DEVN static
 #define LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
+#define LANE_IF(i, n) for (int i = 0; i < (n); i++)
 #define WSYNC() ((void)0)
+#define CTA_SYNC() ((void)0)
 #endif
 
 namespace pbrl {
@@ -58,9 +62,31 @@ struct Ws {
     int con_on[NCP], act_bits[32];
     float con_dist[NCP], con_p[NCP * S3], con_r[NCP * S3], con_t1[NCP * S3], con_D[NCP];
     float con_aref[NCP * 4], con_jar[NCP * 4], con_jp[NCP * 4];
-    float K[NB * S21], Ksub[NB * S21];
+    union {
+        struct { float K[NB * S21], Ksub[NB * S21]; };                     // Newton Hessian assembly
+        struct {                                                          // mimic epilogue (after the last substep)
+            float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * S4], rcom[4], ree[12], rerr[8];
+        };
+    };
+    alignas(16) float fr[2 * PBRL_FRAME_STRIDE];  // the two reference frames of this env step (cp.async.bulk target)
+    alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
+    float fr_u, fr_cyc;
+    int fr_phase, fr_pad;
+    // warp-uniform loop tables copied from the model once per kernel (read with a uniform index in the hot loops)
+    int kinfo[NV * 4];  // per dof k: first factor op, op count, address of row k in M/LD, depth
+    int lvl_start[MAXLEVEL + 1], dep_start[MAXDEPTH + 1];
     int status, niter;
 };
+
+PB_DEV float fast_rcp(float x) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.RCP, 1 ulp
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 
 // ---------------------------------------------------------------------------------- warp helpers
 template <class Fn>
@@ -144,7 +170,7 @@ PB_DEV int sym21(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - 
 
 // ---------------------------------------------------------------------------------- kinematics
 PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
-    LANE_LOOP(z, 1) {
+    LANE_IF(z, 1) {
         w.xpos[0] = w.xpos[1] = w.xpos[2] = 0.f;
         w.xquat[0] = 1.f; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0.f;
         for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
@@ -152,8 +178,8 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
     }
     WSYNC();
     for (int lv = 1; lv < m.nlevel; lv++) {
-        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
-        LANE_LOOP(k, n) {
+        int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
+        LANE_IF(k, n) {
             int b = m.level_body[s + k], p = m.body_parent[b];
             float pos[3], q[4], t[3];
             mat_vec(w.xmat + S9 * p, m.body_pos[b], t);
@@ -194,8 +220,8 @@ PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
     float cx = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b]; }) * inv;
     float cy = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 1]; }) * inv;
     float cz = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 2]; }) * inv;
-    LANE_LOOP(z, 1) { w.com[0] = cx; w.com[1] = cy; w.com[2] = cz; }
-    LANE_LOOP(b, NB) {
+    LANE_IF(z, 1) { w.com[0] = cx; w.com[1] = cy; w.com[2] = cz; }
+    LANE_IF(b, NB) {
         const float* R = w.xmat + S9 * b;
         const float* I = m.body_inertia[b];  // xx yy zz xy xz yz (body frame, about ipos)
         float A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, RA[9], Iw[6];
@@ -261,14 +287,14 @@ PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
 
 // body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne)
 PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane) {
-    LANE_LOOP(z, 1) {
+    LANE_IF(z, 1) {
         for (int c = 0; c < 6; c++) { w.cvel[c] = 0.f; w.cacc[c] = 0.f; }
         w.cacc[3] = -m.gx; w.cacc[4] = -m.gy; w.cacc[5] = -m.gz;
     }
     WSYNC();
     for (int lv = 1; lv < m.nlevel; lv++) {
-        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
-        LANE_LOOP(k, n) {
+        int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
+        LANE_IF(k, n) {
             int b = m.level_body[s + k], p = m.body_parent[b];
             float v[6], a[6], cdd[6];
             for (int c = 0; c < 6; c++) { v[c] = w.cvel[S6 * p + c]; a[c] = w.cacc[S6 * p + c]; }
@@ -312,7 +338,7 @@ PB_DEV void subtree_sum6(const DevModel& m, const float* src, float* dst, int la
 
 // qfrc_bias  (second half of mjx smooth.rne)
 PB_DEVN void stage_bias(const DevModel& m, Ws& w, int lane) {
-    LANE_LOOP(b, NB) {
+    LANE_IF(b, NB) {
         float t[6], u[6], f[6];
         mul_inert(w.cinert + S10 * b, w.cacc + S6 * b, t);
         mul_inert(w.cinert + S10 * b, w.cvel + S6 * b, u);
@@ -327,39 +353,51 @@ PB_DEVN void stage_bias(const DevModel& m, Ws& w, int lane) {
 
 // ---------------------------------------------------------------------------------- tree-sparse L^T D L
 // LD holds the unscaled rows: LD[adr(k)+a] = L[k, anc_a(k)] * D[k]; Dinv[k] = 1/D[k].
-PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
-    for (int k = NV - 1; k >= 0; k--) {
-        int d = m.dof_depth[k];
-        if (d > 0) {
-            int adr = m.dof_Madr[k];
-            float piv = w.LD[adr];
-            if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
-            float inv = 1.0f / piv;
-            LANE_LOOP(pi, d * (d + 1) / 2) {
-                int a = m.tri_a[pi], t = m.tri_t[pi];
-                int ia = m.M_col[adr + a];
-                w.LD[m.dof_Madr[ia] + t] -= (w.LD[adr + a] * inv) * w.LD[adr + a + t];
-            }
-            WSYNC();
-        }
+PB_DEV void init_ws_tables(const DevModel& m, Ws& w, int lane) {
+    LANE_LOOP(k, NV) {
+        w.kinfo[4 * k] = m.fac_start[k]; w.kinfo[4 * k + 1] = m.fac_cnt[k];
+        w.kinfo[4 * k + 2] = m.dof_Madr[k]; w.kinfo[4 * k + 3] = m.dof_depth[k];
     }
-    LANE_LOOP(i, NV) w.Dinv[i] = 1.0f / w.LD[m.dof_Madr[i]];
+    LANE_LOOP(l, MAXLEVEL + 1) w.lvl_start[l] = m.level_start[l];
+    LANE_LOOP(l, MAXDEPTH + 1) w.dep_start[l] = m.depth_start[l];
+    WSYNC();
+}
+
+PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
+    char* LDb = reinterpret_cast<char*>(w.LD);
+    for (int k = NV - 1; k > 0; k--) {
+        const int n = w.kinfo[4 * k + 1];
+        if (n == 0) continue;
+        const float inv = fast_rcp(w.LD[w.kinfo[4 * k + 2]]);
+        const unsigned(*ops)[2] = m.fac_op + w.kinfo[4 * k];
+        LANE_LOOP(pi, n) {
+            const unsigned ux = ops[pi][0], uy = ops[pi][1];
+            float* tgt = reinterpret_cast<float*>(LDb + (ux & 0xffffu));
+            *tgt -= (*reinterpret_cast<const float*>(LDb + (ux >> 16)) * inv) * *reinterpret_cast<const float*>(LDb + uy);
+        }
+        WSYNC();
+    }
+    LANE_LOOP(i, NV) {
+        const float piv = w.LD[m.dof_Madr[i]];
+        if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
+        w.Dinv[i] = 1.0f / piv;
+    }
     WSYNC();
 }
 // x <- (L^T D L)^-1 x
 PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
     for (int k = NV - 1; k > 0; k--) {  // x <- L^-T x : scatter to ancestors
-        int d = m.dof_depth[k], adr = m.dof_Madr[k];
-        float s = x[k] * w.Dinv[k];
-        LANE_LOOP(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
+        const int adr = w.kinfo[4 * k + 2], d = w.kinfo[4 * k + 3];
+        const float s = x[k] * w.Dinv[k];
+        LANE_IF(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
         WSYNC();
     }
     LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
     WSYNC();
     for (int lv = 1; lv < m.ndepth; lv++) {  // x <- L^-1 x : dofs of equal depth are independent
-        int s0 = m.depth_start[lv], n = m.depth_start[lv + 1] - s0;
-        LANE_LOOP(q, n) {
-            int k = m.depth_dof[s0 + q], adr = m.dof_Madr[k];
+        const int s0 = w.dep_start[lv], n = w.dep_start[lv + 1] - s0;
+        LANE_IF(q, n) {
+            const int k = m.depth_dof[s0 + q], adr = m.dof_Madr[k];
             float s = 0.f;
             for (int a = 1; a <= lv; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
             x[k] -= s * w.Dinv[k];
@@ -371,11 +409,11 @@ PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
 // ---------------------------------------------------------------------------------- tree products
 // V[b] = sum over ancestor dofs of cdof_i x_i  (spatial velocity of body b for generalised velocity x)
 PB_DEVN void tree_vel(const DevModel& m, Ws& w, const float* x, int lane) {
-    LANE_LOOP(z, 1) for (int c = 0; c < 6; c++) w.V[c] = 0.f;
+    LANE_IF(z, 1) for (int c = 0; c < 6; c++) w.V[c] = 0.f;
     WSYNC();
     for (int lv = 1; lv < m.nlevel; lv++) {
-        int s = m.level_start[lv], n = m.level_start[lv + 1] - s;
-        LANE_LOOP(k, n) {
+        int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
+        LANE_IF(k, n) {
             int b = m.level_body[s + k], p = m.body_parent[b];
             float v[6];
             for (int c = 0; c < 6; c++) v[c] = w.V[S6 * p + c];
@@ -388,7 +426,7 @@ PB_DEVN void tree_vel(const DevModel& m, Ws& w, const float* x, int lane) {
 }
 // out = M x using V = tree_vel(x) already in w.V (matrix-free, includes armature)
 PB_DEVN void tree_Mx_from_V(const DevModel& m, Ws& w, const float* x, float* out, int lane) {
-    LANE_LOOP(b, NB) mul_inert(w.cinert + S10 * b, w.V + S6 * b, w.F + S6 * b);
+    LANE_IF(b, NB) mul_inert(w.cinert + S10 * b, w.V + S6 * b, w.F + S6 * b);
     WSYNC();
     subtree_sum6(m, w.F, w.Fsub, lane);
     LANE_LOOP(i, NV) out[i] = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]) + m.dof_armature[i] * x[i];
@@ -433,7 +471,7 @@ PB_DEV void contact_j6(const float* r, const float* t1, float mu, int e, float* 
 }
 
 PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
-    LANE_LOOP(c, NC) {
+    LANE_IF(c, NC) {
         int b = m.con_body[c], kind = m.con_kind[c];
         const float* R = w.xmat + S9 * b;
         float gp[3], t[3], dist, p[3], t1[3] = {0.f, 1.f, 0.f};
@@ -510,7 +548,7 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
 
 // constraint rows: enabled flags, D, aref  (mjx constraint.make_constraint; needs cvel of the current qvel)
 PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float* qvel, int lane) {
-    LANE_LOOP(l, 32) {
+    LANE_IF(l, 32) {
         // joint limit row l
         w.lim_sign[l] = 0.f;
         if (l < NLIM) {
@@ -546,7 +584,7 @@ PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float
 
 // residual-like products for all rows from w.V = tree_vel(x): out = J x (limits into lim_out, contacts into con_out)
 PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, float* con_out, int lane) {
-    LANE_LOOP(l, 32) {
+    LANE_IF(l, 32) {
         if (l < NLIM && w.lim_sign[l] != 0.f) lim_out[l] = w.lim_sign[l] * x[m.jnt_dofadr[m.lim_jnt[l]]];
         if (l < NC && w.con_on[l]) {
             float j6[6];
@@ -562,7 +600,7 @@ PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, fl
 // out[i] -= (J^T f)_i with f_r = -D_r jar_r on active rows (jar<0); i.e. adds the constraint gradient D*jar*J
 // mode 0: out = base - J^T f   (gradient),  mode 1: out = J^T f  (qfrc_constraint)
 PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, int mode, int lane) {
-    LANE_LOOP(b, NB) {
+    LANE_IF(b, NB) {
         float f6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, j6[6];
         for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
             if (!w.con_on[c]) continue;
@@ -593,7 +631,7 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
 
 // LD <- M + J^T D_active J  (tree-sparse, assembled like a composite inertia)
 PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
-    LANE_LOOP(b, NB) {
+    LANE_IF(b, NB) {
         float k21[21], j6[6];
         for (int q = 0; q < 21; q++) k21[q] = 0.f;
         for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
@@ -645,18 +683,23 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     float nrows = wsum(lane, 32, [&](int l) { return (w.lim_sign[l] != 0.f ? 1.f : 0.f) + (w.con_on[l] ? 1.f : 0.f); });
     w.niter = 0;
-    if (nrows == 0.f) {
+    if (nrows == 0.f) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
+        LANE_LOOP(e, NM) w.LD[e] = w.M[e];
+        WSYNC();
+        ldl_factor(m, w, lane);
+        ldl_solve(m, w, w.asmooth, lane);
         LANE_LOOP(i, NV) { w.qacc[i] = w.asmooth[i]; w.fcon[i] = 0.f; }
         WSYNC();
         return;
     }
+    // with active rows the optimum does not need qacc_smooth: the cost is written with qfrc_smooth
     // start from the warm start
     LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
     WSYNC();
     tree_vel(m, w, w.qacc, lane);
     tree_Mx_from_V(m, w, w.qacc, w.Ma, lane);
     rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
-    LANE_LOOP(l, 32) {
+    LANE_IF(l, 32) {
         if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
         if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) w.con_jar[4 * l + e] -= w.con_aref[4 * l + e];
         int bits = 0;
@@ -761,10 +804,6 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
         w.fsmooth[i] = f;
         w.asmooth[i] = f;
     }
-    LANE_LOOP(e, NM) w.LD[e] = w.M[e];
-    WSYNC();
-    ldl_factor(m, w, lane);
-    ldl_solve(m, w, w.asmooth, lane);
     solve_constraints(m, w, lane);
 }
 
@@ -779,7 +818,7 @@ PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     ldl_solve(m, w, w.p, lane);
     LANE_LOOP(i, NV) w.qvel[i] += h * w.p[i];
     WSYNC();
-    LANE_LOOP(j, NJ) {
+    LANE_IF(j, NJ) {
         int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
         if (m.jnt_type[j] == 0) {
             for (int k = 0; k < 3; k++) w.qpos[qa + k] += h * w.qvel[da + k];
@@ -805,12 +844,12 @@ PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
 PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, const float* action, const float* kp,
                        const float* kd, float time, float pd_dt, int lane) {
     if (pd_mode == PBRL_PD_TORQUE) {
-        LANE_LOOP(a, NU) w.tau[a] = action[a * action_cols];
+        LANE_IF(a, NU) w.tau[a] = action[a * action_cols];
         WSYNC();
         return;
     }
     // target angles -> w.grad[0..NU)
-    LANE_LOOP(a, NU) {
+    LANE_IF(a, NU) {
         if (action_cols == 4) {
             float t = pd_mode == PBRL_PD_STABLE ? time + pd_dt : time;
             const float* c = action + 4 * a;
@@ -822,7 +861,7 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
     WSYNC();
     const int qo = NQ - NU, vo = NV - NU;
     if (pd_mode == PBRL_PD_STANDARD) {
-        LANE_LOOP(a, NU) w.tau[a] = -kp[a] * (w.qpos[qo + a] - w.grad[a]) + (-kd[a] * w.qvel[vo + a]);
+        LANE_IF(a, NU) w.tau[a] = -kp[a] * (w.qpos[qo + a] - w.grad[a]) + (-kd[a] * w.qvel[vo + a]);
         WSYNC();
         return;
     }
@@ -833,7 +872,7 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
         WSYNC();
         tree_vel(m, w, w.p, lane);
         tree_Mx_from_V(m, w, w.p, w.Mp, lane);
-        LANE_LOOP(a, NU) w.tau[a] = w.Mp[vo + a] + w.bias[vo + a];
+        LANE_IF(a, NU) w.tau[a] = w.Mp[vo + a] + w.bias[vo + a];
         WSYNC();
         return;
     }
@@ -851,7 +890,7 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
     WSYNC();
     ldl_factor(m, w, lane);
     ldl_solve(m, w, w.p, lane);
-    LANE_LOOP(a, NU) w.tau[a] = -kp[a] * w.Mp[vo + a] - kd[a] * (w.qvel[vo + a] + w.p[vo + a] * pd_dt);
+    LANE_IF(a, NU) w.tau[a] = -kp[a] * w.Mp[vo + a] - kd[a] * (w.qvel[vo + a] + w.p[vo + a] * pd_dt);
     WSYNC();
 }
 
@@ -865,10 +904,13 @@ namespace pbrl {
 
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
+    int phase_lock;  // all warps of a CTA run the same number of envs: align them at substep boundaries (I-cache sharing)
     const float *action, *kp, *kd, *pd_time;
     float pd_dt;
     unsigned ctrl_mask;
     PbrlBuffers buf;
+    const float* frames;  // device motion table (mimic mode)
+    DevMimic mm;
 };
 
 PB_DEV void load_row(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = src[i]; }
@@ -877,27 +919,36 @@ PB_DEV void store_row(float* dst, const float* src, int n, int lane) { LANE_LOOP
 PB_DEV void write_obs_reference(const StepArgs& a, Ws& w, int env, float done_value, int lane) {
     const PbrlBuffers& B = a.buf;
     if (B.obs) { store_row(B.obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(B.obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
-    LANE_LOOP(k, 3) if (B.reward) B.reward[(size_t)env * 3 + k] = 0.f;      // agent_mimic.py:84
-    LANE_LOOP(z, 1) if (B.done) B.done[env] = done_value;                  // agent_mimic.py:72
+    LANE_IF(k, 3) if (B.reward) B.reward[(size_t)env * 3 + k] = 0.f;      // agent_mimic.py:84
+    LANE_IF(z, 1) if (B.done) B.done[env] = done_value;                  // agent_mimic.py:72
 }
 
+PB_DEV void frames_prefetch(const float* frames, const DevMimic& mm, Ws& w, int clip, float t, int lane);
+PB_DEVN void mimic_epilogue(const DevModel& m, const DevMimic& mm, const float* frames, Ws& w, const PbrlBuffers& B,
+                            int env, int clip, float t, float* acc, int lane);
+
 // HumanoidTrain.step (agent_mimic.py:58-91): PD law once, n_frames substeps with the torque held
-PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, int lane) {
+PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, float* acc, int lane) {
     const PbrlBuffers& B = a.buf;
+    const bool mimic = a.reward_mode == PBRL_REWARD_MIMIC;
+    const int clip = mimic ? B.motion_id[env] : 0;
+    const float t_end = mimic ? B.ref_t0[env] + B.time[env] + (float)a.n_frames * m.timestep : 0.f;
+    if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // lands while the substeps run
     load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
     load_row(w.warm, B.warm + (size_t)env * NV, NV, lane);
     load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
     load_row(w.qpos_lag, B.qpos_lag + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel_lag, B.qvel_lag + (size_t)env * NV, NV, lane);
-    LANE_LOOP(z, 1) w.status = 0;
+    LANE_IF(z, 1) w.status = 0;
     WSYNC();
     float time = B.time[env];
     pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
               a.pd_time ? a.pd_time[env] : time, a.pd_dt, lane);
-    LANE_LOOP(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
+    LANE_IF(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
     WSYNC();
     for (int f = 0; f < a.n_frames; f++) {
+        if (a.phase_lock) CTA_SYNC();
         if (f == a.n_frames - 1) {
             LANE_LOOP(i, NQ) w.qpos_lag[i] = w.qpos[i];
             LANE_LOOP(i, NV) w.qvel_lag[i] = w.qvel[i];
@@ -912,11 +963,16 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, int 
     store_row(B.ctrl + (size_t)env * NU, w.ctrl, NU, lane);
     store_row(B.qpos_lag + (size_t)env * NQ, w.qpos_lag, NQ, lane);
     store_row(B.qvel_lag + (size_t)env * NV, w.qvel_lag, NV, lane);
-    LANE_LOOP(z, 1) {
+    LANE_IF(z, 1) {
         B.time[env] = time;
         if (B.status) B.status[env] = w.status | (bad > 0.f ? PBRL_STATUS_NAN : 0);
     }
-    write_obs_reference(a, w, env, 1.0f, lane);
+    if (mimic) {
+        if (B.obs) { store_row(B.obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(B.obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
+        mimic_epilogue(m, a.mm, a.frames, w, B, env, clip, B.ref_t0[env] + time, acc, lane);
+    } else {
+        write_obs_reference(a, w, env, 1.0f, lane);
+    }
     WSYNC();
 }
 
@@ -932,8 +988,8 @@ PB_DEVN void env_reset(const DevModel& m, Ws& w, const StepArgs& a, int env, int
     store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
     store_row(B.warm + (size_t)env * NV, w.qvel, NV, lane);
     store_row(B.ctrl + (size_t)env * NU, w.qvel, NU, lane);
-    LANE_LOOP(z, 1) { B.time[env] = 0.f; if (B.status) B.status[env] = 0; }
-    LANE_LOOP(k, 3) if (B.metrics) B.metrics[(size_t)env * 3 + k] = 0.f;
+    LANE_IF(z, 1) { B.time[env] = 0.f; if (B.status) B.status[env] = 0; }
+    LANE_IF(k, 3) if (B.metrics) B.metrics[(size_t)env * 3 + k] = 0.f;
     write_obs_reference(a, w, env, 0.0f, lane);
     WSYNC();
 }
@@ -946,8 +1002,8 @@ PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float
     WSYNC();
     if (xpos || xquat) stage_fk(m, w, w.qpos, lane);
     if (obs) { store_row(obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
-    LANE_LOOP(k, 3) if (reward) reward[(size_t)env * 3 + k] = 0.f;
-    LANE_LOOP(z, 1) if (done) done[env] = 1.0f;
+    LANE_IF(k, 3) if (reward) reward[(size_t)env * 3 + k] = 0.f;
+    LANE_IF(z, 1) if (done) done[env] = 1.0f;
     if (xpos) LANE_LOOP(i, NB * 3) xpos[(size_t)env * NB * 3 + i] = w.xpos[i];
     if (xquat) LANE_LOOP(i, NB * 4) xquat[(size_t)env * NB * 4 + i] = w.xquat[S4 * (i / 4) + (i & 3)];
     WSYNC();
@@ -961,7 +1017,7 @@ PB_DEVN void env_pd(const DevModel& m, Ws& w, int pd_mode, int action_cols, cons
     load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
     load_row(w.qpos_lag, qpos_lag + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel_lag, qvel_lag + (size_t)env * NV, NV, lane);
-    LANE_LOOP(z, 1) w.status = 0;
+    LANE_IF(z, 1) w.status = 0;
     WSYNC();
     if (qM || bias) {
         smooth_position(m, w, w.qpos_lag, lane);
@@ -990,15 +1046,21 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
     load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
     load_row(w.ctrl, ctrl + (size_t)env * NU, NU, lane);
     load_row(w.warm, warm + (size_t)env * NV, NV, lane);
-    LANE_LOOP(z, 1) w.status = 0;
+    LANE_IF(z, 1) w.status = 0;
     WSYNC();
     forward(m, w, lane);
+    // qacc_smooth is only formed by the step when no row is active; the dump always shows it
+    LANE_LOOP(i, NV) w.asmooth[i] = w.fsmooth[i];
+    LANE_LOOP(e, NM) w.LD[e] = w.M[e];
+    WSYNC();
+    ldl_factor(m, w, lane);
+    ldl_solve(m, w, w.asmooth, lane);
     float* o = out + (size_t)env * PBRL_DBG_SIZE;
     LANE_LOOP(i, PBRL_DBG_SIZE) o[i] = 0.f;
     WSYNC();
     LANE_LOOP(i, NB * 3) o[PBRL_DBG_XPOS + i] = w.xpos[i];
     LANE_LOOP(i, NB * 4) o[PBRL_DBG_XQUAT + i] = w.xquat[S4 * (i / 4) + (i & 3)];
-    LANE_LOOP(i, 3) o[PBRL_DBG_COM + i] = w.com[i];
+    LANE_IF(i, 3) o[PBRL_DBG_COM + i] = w.com[i];
     LANE_LOOP(e, NM) {
         int r = m.M_row[e], c = m.M_col[e];
         o[PBRL_DBG_QM + r * NV + c] = w.M[e];
@@ -1012,14 +1074,14 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
         o[PBRL_DBG_QFRC_CONSTRAINT + i] = w.fcon[i];
     }
     float nact = wsum(lane, NC, [&](int c) { return w.con_on[c] ? 1.f : 0.f; });
-    LANE_LOOP(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }
-    LANE_LOOP(c, NC) {
+    LANE_IF(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }
+    LANE_IF(c, NC) {
         o[PBRL_DBG_CON_DIST + c] = w.con_dist[c];
         for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_p[S3 * c + k];
         for (int e = 0; e < 4; e++)
             o[PBRL_DBG_CON_FORCE + 4 * c + e] = (w.con_on[c] && w.con_jar[4 * c + e] < 0.f) ? -w.con_D[c] * w.con_jar[4 * c + e] : 0.f;
     }
-    LANE_LOOP(l, NLIM) o[PBRL_DBG_LIM_FORCE + l] = (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) ? -w.lim_D[l] * w.lim_jar[l] : 0.f;
+    LANE_IF(l, NLIM) o[PBRL_DBG_LIM_FORCE + l] = (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) ? -w.lim_D[l] * w.lim_jar[l] : 0.f;
     WSYNC();
 }
 

@@ -6,18 +6,23 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "pbrl_core.cuh"
+#include "pbrl_mimic.cuh"
 #include "pbrl_desc_reflect.h"
 
 using namespace pbrl;
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef PBRL_WARPS_PER_CTA
+#define PBRL_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 
 thread_local std::string g_error;
@@ -38,11 +43,26 @@ __device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; 
 __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
-    for (int env = first_env(); env < a.N; env += env_stride()) env_step(*gm, w, a, env, lane);
+    init_ws_tables(*gm, w, lane);
+    frames_init(w, lane);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int env = first_env(); env < a.N; env += env_stride()) env_step(*gm, w, a, env, acc, lane);
+    if (a.buf.stats && a.reward_mode == PBRL_REWARD_MIMIC && lane < 6 && acc[5] > 0.f) {
+        float v = acc[0];  // one atomic per (warp, statistic): lane k publishes statistic k
+#pragma unroll
+        for (int k = 1; k < 6; k++) v = lane == k ? acc[k] : v;
+        atomicAdd(a.buf.stats + lane, v);
+    }
 }
 __global__ void __launch_bounds__(CTA_THREADS) k_reset(const DevModel* __restrict__ gm, StepArgs a) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
+    if (a.reward_mode == PBRL_REWARD_MIMIC && a.buf.motion_id) {
+        init_ws_tables(*gm, w, lane);
+        frames_init(w, lane);
+        for (int env = first_env(); env < a.N; env += env_stride()) env_reset_mimic(*gm, a.mm, a.frames, w, a.buf, env, lane);
+        return;
+    }
     for (int env = first_env(); env < a.N; env += env_stride()) env_reset(*gm, w, a, env, lane);
 }
 __global__ void __launch_bounds__(CTA_THREADS)
@@ -50,6 +70,7 @@ k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float*
          float* done, float* xpos, float* xquat) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
+    init_ws_tables(*gm, w, lane);
     for (int env = first_env(); env < N; env += env_stride())
         env_replay(*gm, w, qpos, qvel, obs, reward, done, xpos, xquat, env, lane);
 }
@@ -59,6 +80,7 @@ k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const
      const float* time, float pd_dt, float* tau, float* qM, float* bias) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
+    init_ws_tables(*gm, w, lane);
     for (int env = first_env(); env < N; env += env_stride())
         env_pd(*gm, w, pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, env, lane);
 }
@@ -67,6 +89,7 @@ k_debug_forward(const DevModel* __restrict__ gm, int N, const float* qpos, const
                 const float* warm, float* out) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
+    init_ws_tables(*gm, w, lane);
     for (int env = first_env(); env < N; env += env_stride()) env_debug_forward(*gm, w, qpos, qvel, ctrl, warm, out, env, lane);
 }
 
@@ -137,19 +160,8 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     CUDA_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
     CUDA_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
     if (mimic) {
-        if (mimic->nclip < 1 || mimic->nclip > PBRL_MAXCLIP || !mimic->frames) { pbrl_model_destroy(m); return fail("bad mimic description"); }
-        DevMimic& mm = m->mimic;
-        mm.nclip = mimic->nclip; mm.nframes_total = mimic->nframes_total;
-        for (int c = 0; c < mimic->nclip; c++) {
-            mm.clip_first[c] = mimic->clip_first[c]; mm.clip_nframes[c] = mimic->clip_nframes[c];
-            mm.clip_wrap[c] = mimic->clip_wrap[c]; mm.clip_fall[c] = mimic->clip_fall_enabled[c];
-            mm.clip_duration[c] = mimic->clip_duration[c]; mm.clip_dt[c] = mimic->clip_dt[c];
-        }
-        mm.w_pose = mimic->w_pose; mm.w_vel = mimic->w_vel; mm.w_ee = mimic->w_ee; mm.w_com = mimic->w_com;
-        mm.k_pose = mimic->k_pose; mm.k_vel = mimic->k_vel; mm.k_ee = mimic->k_ee; mm.k_com = mimic->k_com;
-        mm.n_ee = mimic->n_ee;
-        for (int e = 0; e < 4; e++) { mm.ee_body[e] = mimic->ee_body[e]; for (int k = 0; k < 3; k++) mm.ee_offset[e][k] = mimic->ee_offset[3 * e + k]; }
-        mm.fall_geom_mask = mimic->fall_geom_mask;
+        std::string merr = build_dev_mimic(*mimic, m->host, m->mimic);
+        if (!merr.empty()) { pbrl_model_destroy(m); return fail(merr); }
         size_t bytes = (size_t)mimic->nframes_total * PBRL_FRAME_STRIDE * sizeof(float);
         CUDA_OK(cudaMalloc(&m->frames, bytes));
         CUDA_OK(cudaMemcpy(m->frames, mimic->frames, bytes, cudaMemcpyHostToDevice));
@@ -177,9 +189,13 @@ int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* bu
     if (!m) return fail("null model");
     if (N <= 0) return 0;
     if (check_buffers(buf)) return -1;
-    if (reward_mode != PBRL_REWARD_REFERENCE) return fail("mimic reward mode is not built yet");
     StepArgs a{};
     a.N = N; a.reward_mode = reward_mode; a.buf = *buf;
+    if (reward_mode == PBRL_REWARD_MIMIC) {
+        if (!m->has_mimic) return fail("the model was created without a mimic description");
+        if (!buf->motion_id || !buf->ref_t0) return fail("mimic mode needs motion_id and ref_t0");
+        a.frames = m->frames; a.mm = m->mimic;
+    } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     k_reset<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_reset");
 }
@@ -195,10 +211,15 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     if (action_cols != 1 && action_cols != 4) return fail("action_cols must be 1 (targets/torques) or 4 (cubic coefficients)");
     if (pd_mode != PBRL_PD_TORQUE && (!kp || !kd)) return fail("kp/kd required for the PD modes");
     if (n_frames < 1) return fail("n_frames must be >= 1");
-    if (reward_mode != PBRL_REWARD_REFERENCE) return fail("mimic reward mode is not built yet");
     StepArgs a{};
+    if (reward_mode == PBRL_REWARD_MIMIC) {
+        if (!m->has_mimic) return fail("the model was created without a mimic description");
+        if (!buf->motion_id || !buf->ref_t0) return fail("mimic mode needs motion_id and ref_t0");
+        a.frames = m->frames; a.mm = m->mimic;
+    } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
+    a.phase_lock = (N % WARPS_PER_CTA == 0) && getenv("PBRL_NO_PHASE_LOCK") == nullptr;
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }

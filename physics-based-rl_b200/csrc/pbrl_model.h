@@ -22,7 +22,7 @@ constexpr int NM = 310;   // non-zeros of the tree-sparse joint-space inertia (r
 constexpr int NLIM = 28;  // limited hinges
 constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
 constexpr int NCP = 32;   // padded
-constexpr int NTRI = 78;  // 12*13/2 pairs of the deepest ancestor chain
+constexpr int NFAC = 1432;  // rank-1 update operations of one tree-sparse L^T D L factorisation
 constexpr int MAXLEVEL = 8;
 constexpr int MAXDEPTH = 16;
 
@@ -49,7 +49,10 @@ struct DevModel {
     int dof_act[NV];
     int lim_jnt[NLIM];
     int M_row[NM], M_col[NM];
-    int tri_a[NTRI], tri_t[NTRI];
+    // factorisation schedule: step k (dof k, leaf to root) owns fac_op[fac_start[k] .. +fac_cnt[k]);
+    // an op holds BYTE offsets into LD: x = target | srcA << 16, y = srcB:  LD[target] -= LD[srcA] / LD[adr(k)] * LD[srcB]
+    int fac_start[NV], fac_cnt[NV];
+    unsigned fac_op[NFAC][2];
     // contact slots, sorted by body
     int con_body[NCP], con_kind[NCP], con_sub[NCP], con_geom[NCP];
     float con_gpos[NCP][3], con_gquat[NCP][4], con_size[NCP][3], con_margin[NCP], con_mu[NCP], con_invweight[NCP];
@@ -65,7 +68,39 @@ struct DevMimic {
     int n_ee, ee_body[4];
     float ee_offset[4][3];
     unsigned fall_geom_mask;
+    int body_slot[NB];  // index of the body's 3-dof joint quaternion in a table frame, -1 for 1-dof / root / world
 };
+
+inline std::string build_dev_mimic(const PbrlMimicDesc& d, const DevModel& m, DevMimic& mm) {
+    std::memset(&mm, 0, sizeof(mm));
+    if (d.nclip < 1 || d.nclip > PBRL_MAXCLIP || !d.frames || d.nframes_total < 2) return "bad mimic description";
+    mm.nclip = d.nclip; mm.nframes_total = d.nframes_total;
+    for (int c = 0; c < d.nclip; c++) {
+        if (d.clip_nframes[c] < 2 || d.clip_first[c] < 0 || d.clip_first[c] + d.clip_nframes[c] > d.nframes_total) return "clip range outside the table";
+        if (!(d.clip_dt[c] > 0.f) || !(d.clip_duration[c] > 0.f)) return "clip duration / dt must be positive";
+        mm.clip_first[c] = d.clip_first[c]; mm.clip_nframes[c] = d.clip_nframes[c];
+        mm.clip_wrap[c] = d.clip_wrap[c]; mm.clip_fall[c] = d.clip_fall_enabled[c];
+        mm.clip_duration[c] = d.clip_duration[c]; mm.clip_dt[c] = d.clip_dt[c];
+    }
+    mm.w_pose = d.w_pose; mm.w_vel = d.w_vel; mm.w_ee = d.w_ee; mm.w_com = d.w_com;
+    mm.k_pose = d.k_pose; mm.k_vel = d.k_vel; mm.k_ee = d.k_ee; mm.k_com = d.k_com;
+    if (d.n_ee < 0 || d.n_ee > 4) return "n_ee must be 0..4";
+    mm.n_ee = d.n_ee;
+    for (int e = 0; e < d.n_ee; e++) {
+        if (d.ee_body[e] < 1 || d.ee_body[e] >= NB) return "bad end-effector body";
+        mm.ee_body[e] = d.ee_body[e];
+        for (int k = 0; k < 3; k++) mm.ee_offset[e][k] = d.ee_offset[3 * e + k];
+    }
+    mm.fall_geom_mask = d.fall_geom_mask;
+    int slot = 0;
+    for (int b = 0; b < NB; b++) {
+        mm.body_slot[b] = -1;
+        if (b > 1 && m.body_jntnum[b] == 3) mm.body_slot[b] = slot++;
+        else if (b > 1 && m.body_jntnum[b] != 1) return "mimic mode needs 1- or 3-hinge bodies";
+    }
+    if (slot != 8) return "mimic mode expects eight 3-dof joints";
+    return "";
+}
 
 inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
     std::memset(&m, 0, sizeof(m));
@@ -163,7 +198,7 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
         m.dof_act[i] = -1; m.dof_gear[i] = 0; m.dof_ctrl_lo[i] = -1e30f; m.dof_ctrl_hi[i] = 1e30f;
     }
     if (madr != NM) return "sparse inertia layout size differs from 310";
-    if (maxdepth + 1 > MAXDEPTH || maxdepth * (maxdepth + 1) / 2 > NTRI) return "dof chains too deep";
+    if (maxdepth + 1 > MAXDEPTH) return "dof chains too deep";
     m.ndepth = maxdepth + 1;
     pos = 0;
     for (int l = 0; l <= maxdepth; l++) {
@@ -178,9 +213,24 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             m.dof_kind[d.jnt_dofadr[j] + k] = d.jnt_type[j] == 0 ? k : DOF_HINGE;
         }
     }
-    {   // pairs (a,t), a>=1, a+t<=depth, ordered by a+t so that a prefix serves every depth
+    {   // elimination schedule (MuJoCo mj_factorI order): for dof k and its a-th ancestor i, row i loses
+        // (L[k,i] / D[k]) * row k from column i on
         int n = 0;
-        for (int s = 1; s <= 12; s++) for (int a = 1; a <= s; a++) { m.tri_a[n] = a; m.tri_t[n] = s - a; n++; }
+        for (int k = 0; k < NV; k++) {
+            int dk = m.dof_depth[k], adr = m.dof_Madr[k];
+            m.fac_start[k] = n;
+            for (int a = 1; a <= dk; a++) {
+                int ia = m.M_col[adr + a];
+                for (int t = 0; t + a <= dk; t++) {
+                    if (n >= NFAC) return "factorisation schedule overflow";
+                    m.fac_op[n][0] = (unsigned)(4 * (m.dof_Madr[ia] + t)) | ((unsigned)(4 * (adr + a)) << 16);
+                    m.fac_op[n][1] = (unsigned)(4 * (adr + a + t));
+                    n++;
+                }
+            }
+            m.fac_cnt[k] = n - m.fac_start[k];
+        }
+        if (n != NFAC) return "factorisation schedule size differs from 1432";
     }
     for (int a = 0; a < NU; a++) {
         int i = d.act_dofadr[a];

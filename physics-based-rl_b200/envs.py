@@ -107,7 +107,19 @@ class HumanoidDiff:
         self.n_frames = int(kwargs.pop("n_frames", int(self._dt / 0.002)))  # agent_env_template.py:68
         self.sys = const
         self.sys.dt = const.timestep
-        self.model = _lib.Model(const, device=self.device.index)
+        # mimic mode (build-defined): reward_mode="mimic" + a MotionTable
+        self.reward_mode = {"reference": 0, "mimic": 1}[kwargs.pop("reward_mode", "reference")]
+        self.motion_table = kwargs.pop("motion_table", None)
+        self._mimic_keep = None
+        mdesc = None
+        if self.reward_mode == 1:
+            from .mimic import make_mimic_desc
+            if self.motion_table is None:
+                raise ValueError("reward_mode='mimic' needs motion_table=MotionTable")
+            mdesc, frames = make_mimic_desc(const, self.motion_table, kwargs.pop("clips", None))
+            self._mimic_keep = (mdesc, frames)
+            self.clip_durations = [float(mdesc.clip_duration[c]) for c in range(mdesc.nclip)]
+        self.model = _lib.Model(const, device=self.device.index, mimic=mdesc)
         self.reference_trajectory_qpos = reference_trajectory_qpos
         self.reference_trajectory_qvel = reference_trajectory_qvel
         self.duration_trajectory = duration_trajectory
@@ -133,6 +145,10 @@ class HumanoidDiff:
         st = State(ps, z(N, 69), z(N, 3), z(N), {}, {})
         st.info["_metrics"] = metrics
         st.info["status"] = torch.zeros(N, device=d, dtype=torch.int32)
+        if self.reward_mode == 1:
+            st.info["motion_id"] = torch.zeros(N, device=d, dtype=torch.int32)
+            st.info["ref_t0"] = z(N)
+            st.info["stats"] = z(8)
         self._bind_metrics(st)
         return st
 
@@ -145,7 +161,8 @@ class HumanoidDiff:
         ps = st.pipeline_state
         return _lib.make_buffers(qpos=ps.qpos, qvel=ps.qvel, time=ps.time, warm=ps.qacc_warmstart, ctrl=ps.ctrl,
                                  qpos_lag=ps.qpos_lag, qvel_lag=ps.qvel_lag, obs=st.obs, reward=st.reward, done=st.done,
-                                 metrics=st.info["_metrics"], status=st.info["status"])
+                                 metrics=st.info["_metrics"], status=st.info["status"], motion_id=st.info.get("motion_id"),
+                                 ref_t0=st.info.get("ref_t0"), stats=st.info.get("stats"))
 
     def _stream(self):
         return _lib.current_stream_ptr(self.device)
@@ -154,8 +171,16 @@ class HumanoidDiff:
     def reset(self, rng=None) -> State:
         """agent_env_template.py:88-112: qpos0, zero velocity, pipeline_init; `rng` is unused there too."""
         st = self._alloc_state()
+        if self.reward_mode == 1:  # reference-state initialisation: clip = env id mod nclip, phase ~ U[0,1)
+            g = torch.Generator(device="cpu")
+            g.manual_seed(int(rng) if isinstance(rng, (int, np.integer)) else 0)
+            nclip = len(self.clip_durations)
+            mid = torch.arange(self.num_envs, dtype=torch.int32) % nclip
+            t0 = torch.rand(self.num_envs, generator=g) * torch.tensor(self.clip_durations)[mid.long()]
+            st.info["motion_id"].copy_(mid)
+            st.info["ref_t0"].copy_(t0)
         b = self._buffers(st)
-        _lib.check(_lib.lib().pbrl_reset(self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(0),
+        _lib.check(_lib.lib().pbrl_reset(self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(self.reward_mode),
                                          ctypes.byref(b), self._stream()))
         return st
 
@@ -180,7 +205,7 @@ class HumanoidDiff:
         _lib.check(_lib.lib().pbrl_step(
             self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(self.n_frames), ctypes.c_int(pd_mode),
             ctypes.c_int(cols), _lib._ptr(action), _lib._ptr(kp), _lib._ptr(kd), ctypes.c_float(pd_dt),
-            _lib._ptr(pd_time), ctypes.c_uint(ctrl_mask), ctypes.c_int(0), ctypes.byref(b), self._stream()))
+            _lib._ptr(pd_time), ctypes.c_uint(ctrl_mask), ctypes.c_int(self.reward_mode), ctypes.byref(b), self._stream()))
         return st
 
 

@@ -187,10 +187,16 @@ class SimpleConverter(object):
 # --------------------------------------------------------------------------------------------
 # Build-defined: packed motion tables for mimic mode
 # --------------------------------------------------------------------------------------------
-FRAME_STRIDE = 80  # floats per frame in the device table (16-byte multiple for cp.async.bulk)
-# frame layout: [0:35] qpos (root pos, root quat, 28 hinge angles), [35:69] qvel (hinge rates by
-# finite differences of the Euler angles, root rates in MuJoCo convention), [69] frame start time,
-# [70] frame duration, [71:80] pad.
+FRAME_STRIDE = 104  # floats per frame in the device table (416 B, a 16-byte multiple for cp.async.bulk)
+# frame layout (include/pbrl.h PBRL_FRAME_STRIDE):
+#   [0:35]    qpos: root pos, root quat (normalised), 28 hinge angles (intrinsic XYZ Euler per 3-dof joint)
+#   [35:69]   qvel in MuJoCo convention by forward differences (root linear: world, root angular: body-local,
+#             hinges: Euler-angle rates)
+#   [69:101]  unit quaternions (w,x,y,z) of the eight 3-dof joints in qpos order
+#             (chest, neck, right_shoulder, left_shoulder, right_hip, right_ankle, left_hip, left_ankle)
+#   [101]     frame start time   [102] frame duration   [103] pad
+SPHERICAL_JOINTS = [j for j in BODY_JOINTS if DOF_DEF[j] == 3]
+FALL_ENABLED = {"walk": 1, "punch": 1, "kick": 1, "jump": 1, "backflip": 1, "getup_facedown": 0, "getup_faceup": 0}
 
 
 def _quat_conj(q):
@@ -198,15 +204,16 @@ def _quat_conj(q):
 
 
 class MotionTable:
-    """All clips packed into one float32 table + per-clip header, for the device."""
+    """All clips packed into one float32 table + per-clip header, for the device (mimic mode; build-defined)."""
 
     def __init__(self, clips):
-        """clips: list of (name, SimpleConverter-like with data_pos, durations, loop)."""
+        """clips: list of (name, SimpleConverter with all_states / data_pos / durations / loop)."""
         self.names = [c[0] for c in clips]
         frames, hdr = [], []
         start = 0
         for name, conv in clips:
-            pos = np.asarray(conv.data_pos, dtype=np.float64)
+            pos = np.asarray(conv.data_pos, dtype=np.float64).copy()
+            pos[:, 3:7] /= np.linalg.norm(pos[:, 3:7], axis=1, keepdims=True)
             dur = np.asarray(conv.durations, dtype=np.float64)
             F = pos.shape[0]
             vel = self.reference_qvel(pos, dur)
@@ -214,27 +221,29 @@ class MotionTable:
             tab = np.zeros((F, FRAME_STRIDE), dtype=np.float32)
             tab[:, 0:35] = pos
             tab[:, 35:69] = vel
-            tab[:, 69] = t0
-            tab[:, 70] = dur
+            for k, st in enumerate(conv.all_states):
+                for j, jn in enumerate(SPHERICAL_JOINTS):
+                    q = np.asarray(st[jn], dtype=np.float64)
+                    tab[k, 69 + 4 * j:73 + 4 * j] = q / np.linalg.norm(q)
+            tab[:, 101] = t0
+            tab[:, 102] = dur
             frames.append(tab)
-            total = float(dur[:-1].sum())  # last frame has dt = 0 in every DeepMimic file
-            hdr.append((start, F, total, 1.0 if conv.loop == "wrap" else 0.0))
+            total = float(dur[:-1].sum())  # the last frame has dt = 0 in every DeepMimic file
+            hdr.append((start, F, total, 1.0 if conv.loop == "wrap" else 0.0, float(dur[0]), float(FALL_ENABLED.get(name, 1))))
             start += F
         self.frames = np.concatenate(frames, axis=0)
-        self.header = np.asarray(hdr, dtype=np.float64)  # (nclip, 4): first frame, n frames, duration, wrap
+        # (nclip, 6): first frame, n frames, duration, wrap, frame dt, fall termination enabled
+        self.header = np.asarray(hdr, dtype=np.float64)
 
     @staticmethod
     def reference_qvel(pos, dur):
-        """MuJoCo-convention qvel by forward differences (root linear: world frame; root angular:
-        body-local; hinges: Euler-angle rates).  Last frame repeats the previous velocity."""
+        """MuJoCo-convention qvel by forward differences; the last frame repeats the previous velocity."""
         F = pos.shape[0]
         vel = np.zeros((F, 34))
         for k in range(F - 1):
             h = dur[k] if dur[k] > 0 else dur[max(k - 1, 0)]
             vel[k, 0:3] = (pos[k + 1, 0:3] - pos[k, 0:3]) / h
-            q0 = pos[k, 3:7] / np.linalg.norm(pos[k, 3:7])
-            q1 = pos[k + 1, 3:7] / np.linalg.norm(pos[k + 1, 3:7])
-            dq = _qmul(_quat_conj(q0), q1)
+            dq = _qmul(_quat_conj(pos[k, 3:7]), pos[k + 1, 3:7])
             if dq[0] < 0:
                 dq = -dq
             vn = np.linalg.norm(dq[1:])
@@ -256,6 +265,9 @@ class MotionTable:
         t = MotionTable.__new__(MotionTable)
         t.frames, t.header, t.names = z["frames"], z["header"], [str(s) for s in z["names"]]
         return t
+
+    def clip_index(self, name):
+        return self.names.index(name)
 
 
 def load_motion_dir(motion_dir, names=MOTION_NAMES):

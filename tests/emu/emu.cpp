@@ -6,6 +6,7 @@
 // parity tests and compute-sanitizer.  Nothing in the product loads this library.
 #define PBRL_HOST_EMU 1
 #include "../../physics-based-rl_b200/csrc/pbrl_core.cuh"
+#include "../../physics-based-rl_b200/csrc/pbrl_mimic.cuh"
 #include "../../physics-based-rl_b200/csrc/pbrl_desc_reflect.h"
 
 #include <cstdio>
@@ -14,6 +15,9 @@
 using namespace pbrl;
 
 static DevModel g_model;
+static DevMimic g_mimic;
+static std::vector<float> g_frames;
+static bool g_has_mimic = false;
 static std::string g_err;
 
 extern "C" {
@@ -26,24 +30,42 @@ int emu_set_model(const PbrlModelDesc* d) {
     g_err = build_dev_model(*d, g_model);
     return g_err.empty() ? 0 : -1;
 }
-int emu_reset(int N, const PbrlBuffers* buf) {
+int emu_set_mimic(const PbrlMimicDesc* d) {
+    g_err = build_dev_mimic(*d, g_model, g_mimic);
+    if (!g_err.empty()) return -1;
+    g_frames.assign(d->frames, d->frames + (size_t)d->nframes_total * PBRL_FRAME_STRIDE);
+    g_has_mimic = true;
+    return 0;
+}
+int emu_reset(int N, int reward_mode, const PbrlBuffers* buf) {
     std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
+    frames_init(ws[0], 0);
     StepArgs a{};
-    a.N = N; a.buf = *buf;
-    for (int e = 0; e < N; e++) env_reset(g_model, ws[0], a, e, 0);
+    a.N = N; a.buf = *buf; a.reward_mode = reward_mode;
+    for (int e = 0; e < N; e++) {
+        if (reward_mode == PBRL_REWARD_MIMIC) env_reset_mimic(g_model, g_mimic, g_frames.data(), ws[0], a.buf, e, 0);
+        else env_reset(g_model, ws[0], a, e, 0);
+    }
     return 0;
 }
 int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp, const float* kd,
              float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf) {
     std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
     StepArgs a{};
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
-    for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, 0);
+    if (reward_mode == PBRL_REWARD_MIMIC) { a.frames = g_frames.data(); a.mm = g_mimic; }
+    frames_init(ws[0], 0);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+    if (buf->stats && reward_mode == PBRL_REWARD_MIMIC) for (int k = 0; k < 6; k++) buf->stats[k] += acc[k];
     return 0;
 }
 int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* reward, float* done, float* xpos, float* xquat) {
     std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
     for (int e = 0; e < N; e++) env_replay(g_model, ws[0], qpos, qvel, obs, reward, done, xpos, xquat, e, 0);
     return 0;
 }
@@ -51,12 +73,14 @@ int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, cons
                   const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd, const float* time,
                   float pd_dt, float* tau, float* qM, float* bias) {
     std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
     for (int e = 0; e < N; e++)
         env_pd(g_model, ws[0], pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, e, 0);
     return 0;
 }
 int emu_debug_forward(int N, const float* qpos, const float* qvel, const float* ctrl, const float* warm, float* out) {
     std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
     for (int e = 0; e < N; e++) env_debug_forward(g_model, ws[0], qpos, qvel, ctrl, warm, out, e, 0);
     return 0;
 }

@@ -17,6 +17,7 @@ desc = importlib.import_module(PKG + "._desc")
 util_data = importlib.import_module(PKG + ".util_data")
 math_utils = importlib.import_module(PKG + ".math_utils")
 mocap = importlib.import_module(PKG + ".mocap")
+mimic = importlib.import_module(PKG + ".mimic")
 ASSETS = ROOT / PKG / "assets"
 GOLDEN = ROOT / "tests" / "golden"
 
@@ -72,6 +73,9 @@ class _HostState:
         for n, w in STATE_SHAPES:
             setattr(self, n, np.zeros((N, w) if w else (N,), np.float32))
         self.status = np.zeros(N, np.int32)
+        self.motion_id = np.zeros(N, np.int32)
+        self.ref_t0 = np.zeros(N, np.float32)
+        self.stats = np.zeros(8, np.float32)
 
     def set_state(self, qpos, qvel):
         self.qpos[:] = qpos
@@ -106,6 +110,8 @@ class EmuBackend:
         """The emulation library holds one model at a time: (re)select ours before every call."""
         if self.lib.emu_set_model(self._desc.ctypes.data_as(ctypes.c_void_p)):
             raise RuntimeError(self.lib.emu_last_error().decode())
+        if getattr(self, "_mimic", None) is not None and self.lib.emu_set_mimic(ctypes.byref(self._mimic)):
+            raise RuntimeError(self.lib.emu_last_error().decode())
 
     def new_state(self, N):
         return _HostState(N)
@@ -122,12 +128,16 @@ class EmuBackend:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
-    def reset(self, s):
+    def set_mimic(self, mdesc):
+        self._mimic = mdesc
+        self._select()
+
+    def reset(self, s, reward_mode=0):
         self._select()
         b = self._bufs(s)
-        self.lib.emu_reset(s.N, ctypes.byref(b))
+        self.lib.emu_reset(s.N, reward_mode, ctypes.byref(b))
 
-    def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF):
+    def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF, reward_mode=0):
         self._select()
         a = np.ascontiguousarray(action, np.float32)
         cols = 1 if a.ndim == 2 else a.shape[2]
@@ -135,7 +145,7 @@ class EmuBackend:
         t = None if pd_time is None else np.ascontiguousarray(pd_time, np.float32)
         b = self._bufs(s)
         self.lib.emu_step(s.N, n_frames, pd_mode, cols, self._p(a), self._p(kp), self._p(kd), ctypes.c_float(pd_dt), self._p(t),
-                          ctypes.c_uint(ctrl_mask), 0, ctypes.byref(b))
+                          ctypes.c_uint(ctrl_mask), reward_mode, ctypes.byref(b))
 
     def debug_forward(self, qpos, qvel, ctrl, warm):
         self._select()
@@ -173,11 +183,11 @@ class GpuBackend:
     """libpbrl.so through the C ABI, device buffers held as torch tensors."""
     name = "gpu"
 
-    def __init__(self, model, device=0):
+    def __init__(self, model, device=0, mimic_desc=None):
         import torch
         self.torch = torch
         self.L = importlib.import_module(PKG + "._lib")
-        self.model = self.L.Model(model, device=device)
+        self.model = self.L.Model(model, device=device, mimic=mimic_desc)
         self.dev = torch.device("cuda", device)
 
     class _DevState:
@@ -190,7 +200,8 @@ class GpuBackend:
     def _up(self, s):
         t = self.torch
         d = {n: t.from_numpy(getattr(s, n)).to(self.dev) for n, _ in STATE_SHAPES}
-        d["status"] = t.from_numpy(s.status).to(self.dev)
+        for n in ("status", "motion_id", "ref_t0", "stats"):
+            d[n] = t.from_numpy(getattr(s, n)).to(self.dev)
         return d
 
     def _down(self, s, d):
@@ -203,14 +214,14 @@ class GpuBackend:
     def _stream(self):
         return self.L.current_stream_ptr(self.dev)
 
-    def reset(self, s):
+    def reset(self, s, reward_mode=0):
         d = self._up(s)
         b = self.L.make_buffers(**d)
-        self.L.check(self.L.lib().pbrl_reset(self.model.handle, s.N, 0, ctypes.byref(b), self._stream()))
+        self.L.check(self.L.lib().pbrl_reset(self.model.handle, s.N, reward_mode, ctypes.byref(b), self._stream()))
         self.torch.cuda.synchronize()
         self._down(s, d)
 
-    def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF):
+    def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF, reward_mode=0):
         a = np.ascontiguousarray(action, np.float32)
         cols = 1 if a.ndim == 2 else a.shape[2]
         d = self._up(s)
@@ -218,7 +229,7 @@ class GpuBackend:
         ad, kpd, kdd, td = self._dp(a), self._dp(kp), self._dp(kd), self._dp(pd_time)
         P = self.L._ptr
         self.L.check(self.L.lib().pbrl_step(self.model.handle, s.N, n_frames, pd_mode, cols, P(ad), P(kpd), P(kdd),
-                                            ctypes.c_float(pd_dt), P(td), ctypes.c_uint(ctrl_mask), 0, ctypes.byref(b),
+                                            ctypes.c_float(pd_dt), P(td), ctypes.c_uint(ctrl_mask), reward_mode, ctypes.byref(b),
                                             self._stream()))
         self.torch.cuda.synchronize()
         self._down(s, d)

@@ -8,7 +8,7 @@ The oracle runs in float64 with a tight solver tolerance; the back end computes 
 """
 import numpy as np
 
-from helpers import DBG, GOLDEN, Oracle, OracleEnv, random_states, relerr, row_relerr, start_trajectory, util_data
+from helpers import ASSETS, DBG, GOLDEN, Oracle, OracleEnv, mimic, mocap, random_states, relerr, row_relerr, start_trajectory, util_data
 
 TOL_1 = 1e-5    # after one substep (north_star)
 TOL_32 = 1e-3   # after 32 contact-free substeps (north_star)
@@ -218,3 +218,44 @@ def check_contact_rollout(backend, model_grav, N=32, steps=40, seed=17):
     assert abs(np.median(z) - np.median(zr)) < 0.02 and np.abs(z - zr).mean() < 0.05, (np.median(z), np.median(zr))
     assert z.min() > 0.02  # nothing fell through the floor
     return float(early), float(np.abs(z - zr).mean())
+
+
+def mimic_setup(model):
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    mdesc, keep = mimic.make_mimic_desc(model, table)
+    return table, mdesc, keep
+
+
+def check_mimic(backend, model_grav, table, mdesc, N=28, steps=3, seed=23):
+    """Mimic mode (build-defined, parity unpinned): reference-state initialisation, DeepMimic reward, termination,
+    metrics and the block-reduced statistics against the oracle's restatement of the same spec."""
+    orc = _oracle(model_grav)
+    env = OracleEnv(orc, N)
+    rng = np.random.default_rng(seed)
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    t0[:7] = 0.0                                        # exactly on the first frame
+    t0[7:14] = table.header[mid[7:14], 2] * 0.999       # just before the end (wrap / clamp handling)
+    env.reset_mimic(mdesc, mid, t0)
+    s = backend.new_state(N)
+    s.motion_id[:], s.ref_t0[:] = mid, t0
+    backend.reset(s, reward_mode=1)
+    # fp32 blend factor (t/dt - frame) and near-gimbal Euler angles cost a few 1e-6 relative
+    assert relerr(s.qpos, env.qpos) <= 2e-5 and relerr(s.qvel, env.qvel) <= 5e-5
+    assert np.array_equal(s.qpos, s.qpos_lag) and (s.time == 0).all() and (s.metrics == 0).all()
+    # the first-frame envs start exactly on the table's qpos (root pos, unit root quat, Euler angles)
+    fr = table.frames[table.header[mid[:7], 0].astype(int)]
+    assert np.abs(s.qpos[:7, :7] - fr[:, :7]).max() <= 2e-6 and np.abs(s.qpos[:7, 7:] - fr[:, 7:35]).max() <= 2e-5
+    kp, kd = util_data.generate_kp_kd_gains()
+    for k in range(steps):
+        tgt = env.qpos[:, 7:].astype(np.float32)
+        st_ref = env.step_mimic(tgt, kp, kd)
+        s.stats[:] = 0
+        backend.step(s, tgt, kp, kd, reward_mode=1)
+        assert row_relerr(s.qpos, env.qpos).max() <= 1e-3
+        assert np.abs(s.reward - env.reward).max() <= 2e-3 and (s.done == env.done).all()
+        assert np.abs(s.metrics - env.metrics).max() <= 5e-3
+        assert np.abs(s.stats[:6] - st_ref[:6]).max() <= 2e-2 and s.stats[5] == N
+        assert (s.reward[:, 0] > 0).all() and (s.reward[:, 0] <= 1.0 + 1e-6).all()
+    # a pose held exactly on the reference with zero velocity error right after reset scores close to the maximum
+    return float(env.reward[:, 0].mean())

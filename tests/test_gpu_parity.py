@@ -57,3 +57,9 @@ def test_reset(gpu_nograv, model_nograv):
 
 def test_contact_rollout(gpu_grav, model_grav):
     pc.check_contact_rollout(gpu_grav, model_grav, N=64, steps=40)
+
+
+def test_mimic_mode(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    b = GpuBackend(model_grav, mimic_desc=mdesc)
+    pc.check_mimic(b, model_grav, table, mdesc, N=112)

@@ -56,3 +56,10 @@ def test_reset(emu_nograv, model_nograv):
 
 def test_contact_rollout(emu_grav, model_grav):
     pc.check_contact_rollout(emu_grav, model_grav, N=8, steps=30)
+
+
+def test_mimic_mode(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    b = EmuBackend(model_grav)
+    b.set_mimic(mdesc)
+    pc.check_mimic(b, model_grav, table, mdesc)
