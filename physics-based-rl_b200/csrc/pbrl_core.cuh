@@ -48,22 +48,33 @@ constexpr int LS_MAXIT = 24;
 
 struct Ws {
     // state
-    float qpos[36], qvel[36], warm[36], ctrl[28], qpos_lag[36], qvel_lag[36], tau[28];
-    // kinematics
-    float xpos[NB * S3], xquat[NB * S4], xmat[NB * S9], xipos[NB * S3], xaxis[NJ * S3], com[4];
+    float qpos[36], qvel[36], warm[36], ctrl[28], qpos_lag[36], qvel_lag[36];
+    // kinematics.  xquat/xmat are dead once the contacts are found; the spatial-force scratch F/Fsub reuses them
+    float xpos[NB * S3], com[4];
+    union {
+        struct { float xquat[NB * S4], xmat[NB * S9]; };
+        struct { float F[NB * S6], Fsub[NB * S6]; };
+    };
     // spatial quantities about the centre of mass, [ang; lin]
-    float cinert[NB * S10], crb[NB * S10], cdof[NV * S6], cdof_dot[NV * S6], cvel[NB * S6], cacc[NB * S6];
-    float F[NB * S6], Fsub[NB * S6], V[NB * S6], buf6[NV * S6];
+    float cinert[NB * S10], cdof[NV * S6], cvel[NB * S6], buf6[NV * S6];
+    union {
+        float cacc[NB * S6];  // bias accelerations (com_vel -> rne)
+        float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
+    };
     // joint-space inertia (tree-sparse), factor, vectors
     float M[NM], LD[NM], Dinv[36];
-    float bias[36], fsmooth[36], asmooth[36], qacc[36], Ma[36], grad[36], p[36], Mp[36], fcon[36];
+    float fsmooth[36], qacc[36], grad[36], p[36];
+    union { float Ma[36]; float tau[28]; };      // tau: PD law output, consumed before the solver runs
+    union { float Mp[36]; float asmooth[36]; };  // asmooth: only formed when no row is active
+    union { float fcon[36]; float bias[36]; };   // bias is folded into fsmooth before the solver writes fcon
     // constraint rows: lane l owns limit row l and contact slot l (4 pyramid rows)
     float lim_sign[32], lim_D[32], lim_aref[32], lim_jar[32], lim_jp[32];
     int con_on[NCP], act_bits[32];
-    float con_dist[NCP], con_p[NCP * S3], con_r[NCP * S3], con_t1[NCP * S3], con_D[NCP];
+    float con_dist[NCP], con_r[NCP * S3], con_t1[NCP * 2], con_D[NCP];
     float con_aref[NCP * 4], con_jar[NCP * 4], con_jp[NCP * 4];
     union {
         struct { float K[NB * S21], Ksub[NB * S21]; };                     // Newton Hessian assembly
+        struct { float crb[NB * S10]; };                                   // composite inertias (only inside stage_crb)
         struct {                                                          // mimic epilogue (after the last substep)
             float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * S4], rcom[4], ree[12], rerr[8];
         };
@@ -76,6 +87,7 @@ struct Ws {
     int kinfo[NV * 4];  // per dof k: first factor op, op count, address of row k in M/LD, depth
     int lvl_start[MAXLEVEL + 1], dep_start[MAXDEPTH + 1];
     int status, niter;
+    int phase_lock, pad_;  // CTA barriers at stage-group boundaries keep the CTA's warps inside one I-cache window
 };
 
 PB_DEV float fast_rcp(float x) {
@@ -174,7 +186,6 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
         w.xpos[0] = w.xpos[1] = w.xpos[2] = 0.f;
         w.xquat[0] = 1.f; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0.f;
         for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
-        w.xipos[0] = w.xipos[1] = w.xipos[2] = 0.f;
     }
     WSYNC();
     for (int lv = 1; lv < m.nlevel; lv++) {
@@ -191,10 +202,10 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
                     for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
                     for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
                     quat_normalize(q);
-                    w.xaxis[S3 * j] = 0.f; w.xaxis[S3 * j + 1] = 0.f; w.xaxis[S3 * j + 2] = 1.f;
+                    w.buf6[S3 * j] = 0.f; w.buf6[S3 * j + 1] = 0.f; w.buf6[S3 * j + 2] = 1.f;
                 } else {
                     float ql[4], qn[4], sn, cs;
-                    quat_rotate(q, m.jnt_axis[j], w.xaxis + S3 * j);
+                    quat_rotate(q, m.jnt_axis[j], w.buf6 + S3 * j);  // world joint axis, parked in buf6 until stage_com
                     sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
                     ql[0] = cs; ql[1] = m.jnt_axis[j][0] * sn; ql[2] = m.jnt_axis[j][1] * sn; ql[3] = m.jnt_axis[j][2] * sn;
                     quat_mul(q, ql, qn);
@@ -207,8 +218,6 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
             float R[9];
             quat_to_mat(q, R);
             for (int c = 0; c < 9; c++) w.xmat[S9 * b + c] = R[c];
-            mat_vec(R, m.body_ipos[b], t);
-            for (int c = 0; c < 3; c++) w.xipos[S3 * b + c] = pos[c] + t[c];
         }
         WSYNC();
     }
@@ -217,9 +226,9 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
 // com, cinert, cdof  (mjx smooth.com_pos)
 PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
     float inv = 1.0f / m.total_mass;
-    float cx = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b]; }) * inv;
-    float cy = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 1]; }) * inv;
-    float cz = wsum(lane, NB, [&](int b) { return m.body_mass[b] * w.xipos[S3 * b + 2]; }) * inv;
+    const float cx = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b] + t[0]); }) * inv;
+    const float cy = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b + 1] + t[1]); }) * inv;
+    const float cz = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b + 2] + t[2]); }) * inv;
     LANE_IF(z, 1) { w.com[0] = cx; w.com[1] = cy; w.com[2] = cz; }
     LANE_IF(b, NB) {
         const float* R = w.xmat + S9 * b;
@@ -234,7 +243,9 @@ PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
         Iw[3] = RA[0] * R[3] + RA[1] * R[4] + RA[2] * R[5];
         Iw[4] = RA[0] * R[6] + RA[1] * R[7] + RA[2] * R[8];
         Iw[5] = RA[3] * R[6] + RA[4] * R[7] + RA[5] * R[8];
-        float ms = m.body_mass[b], ox = w.xipos[S3 * b] - cx, oy = w.xipos[S3 * b + 1] - cy, oz = w.xipos[S3 * b + 2] - cz;
+        float ip[3];
+        mat_vec(R, m.body_ipos[b], ip);
+        float ms = m.body_mass[b], ox = w.xpos[S3 * b] + ip[0] - cx, oy = w.xpos[S3 * b + 1] + ip[1] - cy, oz = w.xpos[S3 * b + 2] + ip[2] - cz;
         float* ci = w.cinert + S10 * b;
         ci[0] = Iw[0] + ms * (oy * oy + oz * oz);
         ci[1] = Iw[1] + ms * (ox * ox + oz * oz);
@@ -255,7 +266,7 @@ PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
             if (kind < 6) {
                 for (int c = 0; c < 3; c++) ax[c] = w.xmat[S9 * b + 3 * c + (kind - 3)];
             } else {
-                for (int c = 0; c < 3; c++) ax[c] = w.xaxis[S3 * m.dof_jntid[i] + c];
+                for (int c = 0; c < 3; c++) ax[c] = w.buf6[S3 * m.dof_jntid[i] + c];
             }
             off[0] = cx - w.xpos[S3 * b]; off[1] = cy - w.xpos[S3 * b + 1]; off[2] = cz - w.xpos[S3 * b + 2];
             cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
@@ -302,18 +313,17 @@ PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane)
                 int da = m.jnt_dofadr[j];
                 if (m.jnt_type[j] == 0) {
                     for (int i = 0; i < 3; i++) {
-                        for (int c = 0; c < 6; c++) { v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i]; w.cdof_dot[S6 * (da + i) + c] = 0.f; }
+                        for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i];
                     }
                     for (int i = 3; i < 6; i++) {
                         cross_motion(v, w.cdof + S6 * (da + i), cdd);
-                        for (int c = 0; c < 6; c++) { w.cdof_dot[S6 * (da + i) + c] = cdd[c]; a[c] += cdd[c] * qvel[da + i]; }
+                        for (int c = 0; c < 6; c++) a[c] += cdd[c] * qvel[da + i];
                     }
                     for (int i = 3; i < 6; i++)
                         for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i];
                 } else {
                     cross_motion(v, w.cdof + S6 * da, cdd);
                     for (int c = 0; c < 6; c++) {
-                        w.cdof_dot[S6 * da + c] = cdd[c];
                         a[c] += cdd[c] * qvel[da];
                         v[c] += w.cdof[S6 * da + c] * qvel[da];
                     }
@@ -464,7 +474,7 @@ PB_DEV int argmax_masked(const float* score, const bool* ok, int n) {  // first 
 // pyramid edge e of a contact: w = n + sg*mu*t, j6 = [r x w ; w]
 PB_DEV void contact_j6(const float* r, const float* t1, float mu, int e, float* j6) {
     float sg = (e & 1) ? -mu : mu, wv[3];
-    if (e < 2) { wv[0] = sg * t1[0]; wv[1] = sg * t1[1]; wv[2] = 1.f + sg * t1[2]; }
+    if (e < 2) { wv[0] = sg * t1[0]; wv[1] = sg * t1[1]; wv[2] = 1.f; }
     else { wv[0] = -sg * t1[1]; wv[1] = sg * t1[0]; wv[2] = 1.f; }  // t2 = n x t1, n = +z
     cross3(r, wv, j6);
     j6[3] = wv[0]; j6[4] = wv[1]; j6[5] = wv[2];
@@ -541,7 +551,8 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
             p[0] = gp[0] + t[0]; p[1] = gp[1] + t[1]; p[2] = gp[2] + t[2] - 0.5f * dist;
         }
         w.con_dist[c] = dist;
-        for (int k = 0; k < 3; k++) { w.con_p[S3 * c + k] = p[k]; w.con_r[S3 * c + k] = p[k] - w.com[k]; w.con_t1[S3 * c + k] = t1[k]; }
+        for (int k = 0; k < 3; k++) w.con_r[S3 * c + k] = p[k] - w.com[k];
+        w.con_t1[2 * c] = t1[0]; w.con_t1[2 * c + 1] = t1[1];  // tangent 1 lies in the floor plane
     }
     WSYNC();
 }
@@ -573,7 +584,7 @@ PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float
                 w.con_on[l] = 1;
                 w.con_D[l] = 1.0f / Rr;
                 for (int e = 0; e < 4; e++) {
-                    contact_j6(w.con_r + S3 * l, w.con_t1 + S3 * l, m.con_mu[l], e, j6);
+                    contact_j6(w.con_r + S3 * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
                     w.con_aref[4 * l + e] = -m.sol_b * dot6(j6, w.cvel + S6 * m.con_body[l]) - m.sol_k * imp * pos;
                 }
             }
@@ -589,7 +600,7 @@ PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, fl
         if (l < NC && w.con_on[l]) {
             float j6[6];
             for (int e = 0; e < 4; e++) {
-                contact_j6(w.con_r + S3 * l, w.con_t1 + S3 * l, m.con_mu[l], e, j6);
+                contact_j6(w.con_r + S3 * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
                 con_out[4 * l + e] = dot6(j6, w.V + S6 * m.con_body[l]);
             }
         }
@@ -608,7 +619,7 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
                 float jar = w.con_jar[4 * c + e];
                 if (jar < 0.f) {
                     float f = -w.con_D[c] * jar;
-                    contact_j6(w.con_r + S3 * c, w.con_t1 + S3 * c, m.con_mu[c], e, j6);
+                    contact_j6(w.con_r + S3 * c, w.con_t1 + 2 * c, m.con_mu[c], e, j6);
                     for (int k = 0; k < 6; k++) f6[k] += f * j6[k];
                 }
             }
@@ -638,7 +649,7 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
             if (!w.con_on[c]) continue;
             for (int e = 0; e < 4; e++) {
                 if (w.con_jar[4 * c + e] < 0.f) {
-                    contact_j6(w.con_r + S3 * c, w.con_t1 + S3 * c, m.con_mu[c], e, j6);
+                    contact_j6(w.con_r + S3 * c, w.con_t1 + 2 * c, m.con_mu[c], e, j6);
                     float D = w.con_D[c];
                     int q = 0;
                     for (int r = 0; r < 6; r++)
@@ -792,11 +803,16 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
 
 // ---------------------------------------------------------------------------------- one mjx.forward + Euler
 // forward: everything up to qacc / qfrc_constraint at (w.qpos, w.qvel, w.ctrl, w.warm)
+constexpr int LOCKS_PER_SUBSTEP = 4;  // CTA barriers per substep when the phase lock is on (see forward/substep)
 PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
+    const bool lock = w.phase_lock != 0;
+    if (lock) CTA_SYNC();
     smooth_position(m, w, w.qpos, lane);
+    if (lock) CTA_SYNC();
     stage_collide(m, w, lane);
     smooth_velocity(m, w, w.qvel, lane);
     stage_rows(m, w, w.qpos, w.qvel, lane);
+    if (lock) CTA_SYNC();
     LANE_LOOP(i, NV) {
         float f = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
         int a = m.dof_act[i];
@@ -810,6 +826,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
 // mjx.step: forward, warmstart <- qacc, Euler with implicit joint damping, integrate
 PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     forward(m, w, lane);
+    if (w.phase_lock) CTA_SYNC();
     float h = m.timestep;
     LANE_LOOP(i, NV) { w.warm[i] = w.qacc[i]; w.p[i] = w.fsmooth[i] + w.fcon[i]; }
     LANE_LOOP(e, NM) w.LD[e] = w.M[e] + ((m.M_row[e] == m.M_col[e]) ? h * m.dof_damping[m.M_row[e]] : 0.f);
@@ -947,8 +964,9 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
               a.pd_time ? a.pd_time[env] : time, a.pd_dt, lane);
     LANE_IF(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
     WSYNC();
+    LANE_IF(z, 1) w.phase_lock = a.phase_lock;
+    WSYNC();
     for (int f = 0; f < a.n_frames; f++) {
-        if (a.phase_lock) CTA_SYNC();
         if (f == a.n_frames - 1) {
             LANE_LOOP(i, NQ) w.qpos_lag[i] = w.qpos[i];
             LANE_LOOP(i, NV) w.qvel_lag[i] = w.qvel[i];
@@ -1046,20 +1064,16 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
     load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
     load_row(w.ctrl, ctrl + (size_t)env * NU, NU, lane);
     load_row(w.warm, warm + (size_t)env * NV, NV, lane);
-    LANE_IF(z, 1) w.status = 0;
+    LANE_IF(z, 1) { w.status = 0; w.phase_lock = 0; }
     WSYNC();
-    forward(m, w, lane);
-    // qacc_smooth is only formed by the step when no row is active; the dump always shows it
-    LANE_LOOP(i, NV) w.asmooth[i] = w.fsmooth[i];
-    LANE_LOOP(e, NM) w.LD[e] = w.M[e];
-    WSYNC();
-    ldl_factor(m, w, lane);
-    ldl_solve(m, w, w.asmooth, lane);
     float* o = out + (size_t)env * PBRL_DBG_SIZE;
     LANE_LOOP(i, PBRL_DBG_SIZE) o[i] = 0.f;
     WSYNC();
+    stage_fk(m, w, w.qpos, lane);  // body poses are dumped first: the workspace reuses xquat/xmat after the contact stage
     LANE_LOOP(i, NB * 3) o[PBRL_DBG_XPOS + i] = w.xpos[i];
     LANE_LOOP(i, NB * 4) o[PBRL_DBG_XQUAT + i] = w.xquat[S4 * (i / 4) + (i & 3)];
+    WSYNC();
+    forward(m, w, lane);
     LANE_IF(i, 3) o[PBRL_DBG_COM + i] = w.com[i];
     LANE_LOOP(e, NM) {
         int r = m.M_row[e], c = m.M_col[e];
@@ -1067,17 +1081,27 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
         o[PBRL_DBG_QM + c * NV + r] = w.M[e];
     }
     LANE_LOOP(i, NV) {
-        o[PBRL_DBG_BIAS + i] = w.bias[i];
+        float act = 0.f;
+        const int a = m.dof_act[i];
+        if (a >= 0) act = m.dof_gear[i] * fminf(fmaxf(w.ctrl[a], m.dof_ctrl_lo[i]), m.dof_ctrl_hi[i]);
+        o[PBRL_DBG_BIAS + i] = -m.dof_damping[i] * w.qvel[i] + act - w.fsmooth[i];  // qfrc_bias recovered from qfrc_smooth
         o[PBRL_DBG_QFRC_SMOOTH + i] = w.fsmooth[i];
-        o[PBRL_DBG_QACC_SMOOTH + i] = w.asmooth[i];
         o[PBRL_DBG_QACC + i] = w.qacc[i];
         o[PBRL_DBG_QFRC_CONSTRAINT + i] = w.fcon[i];
     }
+    WSYNC();
+    // qacc_smooth is only formed by the step when no row is active; the dump always shows it
+    LANE_LOOP(i, NV) w.asmooth[i] = w.fsmooth[i];
+    LANE_LOOP(e, NM) w.LD[e] = w.M[e];
+    WSYNC();
+    ldl_factor(m, w, lane);
+    ldl_solve(m, w, w.asmooth, lane);
+    LANE_LOOP(i, NV) o[PBRL_DBG_QACC_SMOOTH + i] = w.asmooth[i];
     float nact = wsum(lane, NC, [&](int c) { return w.con_on[c] ? 1.f : 0.f; });
     LANE_IF(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }
     LANE_IF(c, NC) {
         o[PBRL_DBG_CON_DIST + c] = w.con_dist[c];
-        for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_p[S3 * c + k];
+        for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_r[S3 * c + k] + w.com[k];
         for (int e = 0; e < 4; e++)
             o[PBRL_DBG_CON_FORCE + 4 * c + e] = (w.con_on[c] && w.con_jar[4 * c + e] < 0.f) ? -w.con_D[c] * w.con_jar[4 * c + e] : 0.f;
     }

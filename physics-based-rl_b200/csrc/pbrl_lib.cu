@@ -20,7 +20,7 @@ using namespace pbrl;
 namespace {
 
 #ifndef PBRL_WARPS_PER_CTA
-#define PBRL_WARPS_PER_CTA 4
+#define PBRL_WARPS_PER_CTA 7
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -46,7 +46,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
     init_ws_tables(*gm, w, lane);
     frames_init(w, lane);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int env = first_env(); env < a.N; env += env_stride()) env_step(*gm, w, a, env, acc, lane);
+    // every warp of the CTA makes the same number of passes so that the per-substep CTA barrier (phase lock) is legal
+    for (int base = blockIdx.x * WARPS_PER_CTA; base < a.N; base += env_stride()) {
+        const int env = base + (threadIdx.x >> 5);
+        if (env < a.N) env_step(*gm, w, a, env, acc, lane);
+        else if (a.phase_lock) for (int f = 0; f < a.n_frames * LOCKS_PER_SUBSTEP; f++) __syncthreads();
+    }
     if (a.buf.stats && a.reward_mode == PBRL_REWARD_MIMIC && lane < 6 && acc[5] > 0.f) {
         float v = acc[0];  // one atomic per (warp, statistic): lane k publishes statistic k
 #pragma unroll
@@ -219,7 +224,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
-    a.phase_lock = (N % WARPS_PER_CTA == 0) && getenv("PBRL_NO_PHASE_LOCK") == nullptr;
+    a.phase_lock = getenv("PBRL_NO_PHASE_LOCK") == nullptr;
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }
