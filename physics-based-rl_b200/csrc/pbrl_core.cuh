@@ -23,21 +23,28 @@
 #include <math.h>
 
 #include "pbrl_model.h"
+#include "pbrl_topo_gen.h"
 
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
 #define PB_DEV __device__ __forceinline__
 #define PB_DEVN __device__ __noinline__
+#define PB_MEMBER static __device__ __forceinline__
+#define PB_CX __host__ __device__ constexpr
 #define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
 #define LANE_IF(i, n) for (int i = lane, once_ = 1; once_ && i < (n); once_ = 0)  /* n <= 32: at most one pass */
 #define WSYNC() __syncwarp()
 #define CTA_SYNC() __syncthreads()
+#define CTA_OR(p) __syncthreads_or(p)
 #else
 #define PB_DEV static inline
 #define PB_DEVN static
+#define PB_MEMBER static inline
+#define PB_CX constexpr
 #define LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
 #define LANE_IF(i, n) for (int i = 0; i < (n); i++)
 #define WSYNC() ((void)0)
 #define CTA_SYNC() ((void)0)
+#define CTA_OR(p) (p)
 #endif
 
 namespace pbrl {
@@ -83,9 +90,8 @@ struct Ws {
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
     float fr_u, fr_cyc;
     int fr_phase, fr_pad;
-    // warp-uniform loop tables copied from the model once per kernel (read with a uniform index in the hot loops)
-    int kinfo[NV * 4];  // per dof k: first factor op, op count, address of row k in M/LD, depth
-    int lvl_start[MAXLEVEL + 1], dep_start[MAXDEPTH + 1];
+    // warp-uniform loop table copied from the model once per kernel
+    int lvl_start[MAXLEVEL + 1];
     int status, niter;
     int phase_lock, pad_;  // CTA barriers at stage-group boundaries keep the CTA's warps inside one I-cache window
 };
@@ -364,29 +370,42 @@ PB_DEVN void stage_bias(const DevModel& m, Ws& w, int lane) {
 // ---------------------------------------------------------------------------------- tree-sparse L^T D L
 // LD holds the unscaled rows: LD[adr(k)+a] = L[k, anc_a(k)] * D[k]; Dinv[k] = 1/D[k].
 PB_DEV void init_ws_tables(const DevModel& m, Ws& w, int lane) {
-    LANE_LOOP(k, NV) {
-        w.kinfo[4 * k] = m.fac_start[k]; w.kinfo[4 * k + 1] = m.fac_cnt[k];
-        w.kinfo[4 * k + 2] = m.dof_Madr[k]; w.kinfo[4 * k + 3] = m.dof_depth[k];
-    }
     LANE_LOOP(l, MAXLEVEL + 1) w.lvl_start[l] = m.level_start[l];
-    LANE_LOOP(l, MAXDEPTH + 1) w.dep_start[l] = m.depth_start[l];
     WSYNC();
 }
 
-PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
-    char* LDb = reinterpret_cast<char*>(w.LD);
-    for (int k = NV - 1; k > 0; k--) {
-        const int n = w.kinfo[4 * k + 1];
-        if (n == 0) continue;
-        const float inv = fast_rcp(w.LD[w.kinfo[4 * k + 2]]);
-        const unsigned(*ops)[2] = m.fac_op + w.kinfo[4 * k];
-        LANE_LOOP(pi, n) {
-            const unsigned ux = ops[pi][0], uy = ops[pi][1];
-            float* tgt = reinterpret_cast<float*>(LDb + (ux & 0xffffu));
-            *tgt -= (*reinterpret_cast<const float*>(LDb + (ux >> 16)) * inv) * *reinterpret_cast<const float*>(LDb + uy);
+// The dof tree is a compile-time constant (pbrl_topo_gen.h): both routines are unrolled over the dofs so that row
+// addresses, depths and op counts are immediates; only the per-lane op / column tables are read from the model.
+namespace topo {
+PB_CX int depth(int k) { int d = 0; while (PARENT[k] >= 0) { k = PARENT[k]; d++; } return d; }
+PB_CX int madr(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) + 1; return a; }
+PB_CX int fac_start(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) * (depth(i) + 1) / 2; return a; }
+PB_CX int max_depth() { int d = 0; for (int k = 0; k < NDOF; k++) d = depth(k) > d ? depth(k) : d; return d; }
+PB_CX int depth_count(int lv) { int n = 0; for (int k = 0; k < NDOF; k++) n += depth(k) == lv; return n; }
+PB_CX int depth_first(int lv) { int n = 0; for (int l = 0; l < lv; l++) n += depth_count(l); return n; }
+static_assert(NDOF == NV && madr(NDOF - 1) + depth(NDOF - 1) + 1 == NM && fac_start(NDOF - 1) + depth(NDOF - 1) * (depth(NDOF - 1) + 1) / 2 == NFAC,
+              "pbrl_topo_gen.h does not match the kernel dimensions");
+}  // namespace topo
+
+template <int K>
+struct FactorStep {  // eliminate dof K: rank-1 update of its ancestors' rows (MuJoCo mj_factorI order, leaf to root)
+    PB_MEMBER void run(const DevModel& m, Ws& w, char* LDb, int lane) {
+        constexpr int d = topo::depth(K), n = d * (d + 1) / 2;
+        if constexpr (n > 0) {
+            const float inv = fast_rcp(w.LD[topo::madr(K)]);
+            const unsigned(*ops)[2] = m.fac_op + topo::fac_start(K);
+            LANE_LOOP(pi, n) {
+                const unsigned ux = ops[pi][0], uy = ops[pi][1];
+                float* tgt = reinterpret_cast<float*>(LDb + (ux & 0xffffu));
+                *tgt -= (*reinterpret_cast<const float*>(LDb + (ux >> 16)) * inv) * *reinterpret_cast<const float*>(LDb + uy);
+            }
+            WSYNC();
         }
-        WSYNC();
+        if constexpr (K > 1) FactorStep<K - 1>::run(m, w, LDb, lane);
     }
+};
+PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
+    FactorStep<NV - 1>::run(m, w, reinterpret_cast<char*>(w.LD), lane);
     LANE_LOOP(i, NV) {
         const float piv = w.LD[m.dof_Madr[i]];
         if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
@@ -394,26 +413,39 @@ PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
     }
     WSYNC();
 }
-// x <- (L^T D L)^-1 x
-PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
-    for (int k = NV - 1; k > 0; k--) {  // x <- L^-T x : scatter to ancestors
-        const int adr = w.kinfo[4 * k + 2], d = w.kinfo[4 * k + 3];
-        const float s = x[k] * w.Dinv[k];
-        LANE_IF(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
-        WSYNC();
+
+template <int K>
+struct ForwardStep {  // x <- L^-T x : dof K scatters to its ancestors
+    PB_MEMBER void run(const DevModel& m, Ws& w, float* x, int lane) {
+        constexpr int d = topo::depth(K), adr = topo::madr(K);
+        if constexpr (d > 0) {
+            const float s = x[K] * w.Dinv[K];
+            LANE_IF(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
+            WSYNC();
+        }
+        if constexpr (K > 1) ForwardStep<K - 1>::run(m, w, x, lane);
     }
-    LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
-    WSYNC();
-    for (int lv = 1; lv < m.ndepth; lv++) {  // x <- L^-1 x : dofs of equal depth are independent
-        const int s0 = w.dep_start[lv], n = w.dep_start[lv + 1] - s0;
+};
+template <int LV>
+struct BackwardLevel {  // x <- L^-1 x : dofs of equal depth are independent
+    PB_MEMBER void run(const DevModel& m, Ws& w, float* x, int lane) {
+        constexpr int n = topo::depth_count(LV), s0 = topo::depth_first(LV);
         LANE_IF(q, n) {
             const int k = m.depth_dof[s0 + q], adr = m.dof_Madr[k];
             float s = 0.f;
-            for (int a = 1; a <= lv; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
+            for (int a = 1; a <= LV; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
             x[k] -= s * w.Dinv[k];
         }
         WSYNC();
+        if constexpr (LV < topo::max_depth()) BackwardLevel<LV + 1>::run(m, w, x, lane);
     }
+};
+// x <- (L^T D L)^-1 x
+PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
+    ForwardStep<NV - 1>::run(m, w, x, lane);
+    LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
+    WSYNC();
+    BackwardLevel<1>::run(m, w, x, lane);
 }
 
 // ---------------------------------------------------------------------------------- tree products
@@ -694,33 +726,41 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     float nrows = wsum(lane, 32, [&](int l) { return (w.lim_sign[l] != 0.f ? 1.f : 0.f) + (w.con_on[l] ? 1.f : 0.f); });
     w.niter = 0;
-    if (nrows == 0.f) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
+    const bool constrained = nrows > 0.f;
+    const bool coop = (w.phase_lock & 16) != 0;  // iterate in step with the other warps of the CTA (shared I-cache window)
+    if (!constrained) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
         LANE_LOOP(e, NM) w.LD[e] = w.M[e];
         WSYNC();
         ldl_factor(m, w, lane);
         ldl_solve(m, w, w.asmooth, lane);
         LANE_LOOP(i, NV) { w.qacc[i] = w.asmooth[i]; w.fcon[i] = 0.f; }
         WSYNC();
-        return;
+        if (!coop) return;
+    } else {
+        // with active rows the optimum does not need qacc_smooth: the cost is written with qfrc_smooth
+        // start from the warm start
+        LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
+        WSYNC();
+        tree_vel(m, w, w.qacc, lane);
+        tree_Mx_from_V(m, w, w.qacc, w.Ma, lane);
+        rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
+        LANE_IF(l, 32) {
+            if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
+            if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) w.con_jar[4 * l + e] -= w.con_aref[4 * l + e];
+            int bits = 0;
+            if (l < NLIM && w.lim_sign[l] != 0.f) bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
+            if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
+            w.act_bits[l] = bits;
+        }
+        WSYNC();
     }
-    // with active rows the optimum does not need qacc_smooth: the cost is written with qfrc_smooth
-    // start from the warm start
-    LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
-    WSYNC();
-    tree_vel(m, w, w.qacc, lane);
-    tree_Mx_from_V(m, w, w.qacc, w.Ma, lane);
-    rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
-    LANE_IF(l, 32) {
-        if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
-        if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) w.con_jar[4 * l + e] -= w.con_aref[4 * l + e];
-        int bits = 0;
-        if (l < NLIM && w.lim_sign[l] != 0.f) bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
-        if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
-        w.act_bits[l] = bits;
-    }
-    WSYNC();
     int it = 0;
-    for (; it < NEWTON_MAXIT; it++) {
+    bool running = constrained;
+    for (;;) {
+        const bool go = running && it < NEWTON_MAXIT;
+        if (coop) { if (!CTA_OR(go ? 1 : 0)) break; }
+        else if (!go) break;
+        if (!go) continue;
         // gradient and Hessian for the current active set
         LANE_LOOP(i, NV) w.Mp[i] = w.Ma[i] - w.fsmooth[i];
         WSYNC();
@@ -794,8 +834,10 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         });
         WSYNC();
         // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
-        if (changed == 0.f) { it++; break; }
+        it++;
+        if (changed == 0.f) running = false;
     }
+    if (!constrained) return;
     if (it >= NEWTON_MAXIT) w.status |= PBRL_STATUS_SOLVER_MAXITER;
     w.niter = it;
     rows_JTf(m, w, w.Mp, w.fcon, 1, lane);
@@ -803,16 +845,18 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
 
 // ---------------------------------------------------------------------------------- one mjx.forward + Euler
 // forward: everything up to qacc / qfrc_constraint at (w.qpos, w.qvel, w.ctrl, w.warm)
-constexpr int LOCKS_PER_SUBSTEP = 4;  // CTA barriers per substep when the phase lock is on (see forward/substep)
+// Phase lock: bit k of w.phase_lock places a CTA barrier at stage-group boundary k of every substep
+// (0 substep start, 1 after the position stage, 2 after the constraint rows, 3 after the solver).  The barriers keep
+// the CTA's warps inside one instruction-cache window; every warp of a CTA executes the same number of them.
 PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
-    const bool lock = w.phase_lock != 0;
-    if (lock) CTA_SYNC();
+    const int lock = w.phase_lock;
+    if (lock & 1) CTA_SYNC();
     smooth_position(m, w, w.qpos, lane);
-    if (lock) CTA_SYNC();
+    if (lock & 2) CTA_SYNC();
     stage_collide(m, w, lane);
     smooth_velocity(m, w, w.qvel, lane);
     stage_rows(m, w, w.qpos, w.qvel, lane);
-    if (lock) CTA_SYNC();
+    if (lock & 4) CTA_SYNC();
     LANE_LOOP(i, NV) {
         float f = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
         int a = m.dof_act[i];
@@ -826,7 +870,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
 // mjx.step: forward, warmstart <- qacc, Euler with implicit joint damping, integrate
 PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     forward(m, w, lane);
-    if (w.phase_lock) CTA_SYNC();
+    if (w.phase_lock & 8) CTA_SYNC();
     float h = m.timestep;
     LANE_LOOP(i, NV) { w.warm[i] = w.qacc[i]; w.p[i] = w.fsmooth[i] + w.fcon[i]; }
     LANE_LOOP(e, NM) w.LD[e] = w.M[e] + ((m.M_row[e] == m.M_col[e]) ? h * m.dof_damping[m.M_row[e]] : 0.f);
@@ -921,7 +965,7 @@ namespace pbrl {
 
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
-    int phase_lock;  // all warps of a CTA run the same number of envs: align them at substep boundaries (I-cache sharing)
+    int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
     const float *action, *kp, *kd, *pd_time;
     float pd_dt;
     unsigned ctrl_mask;

@@ -50,7 +50,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
     for (int base = blockIdx.x * WARPS_PER_CTA; base < a.N; base += env_stride()) {
         const int env = base + (threadIdx.x >> 5);
         if (env < a.N) env_step(*gm, w, a, env, acc, lane);
-        else if (a.phase_lock) for (int f = 0; f < a.n_frames * LOCKS_PER_SUBSTEP; f++) __syncthreads();
+        else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
+            for (int f = 0; f < a.n_frames; f++) {
+                for (int k = 0; k < __popc(a.phase_lock & 7); k++) __syncthreads();
+                if (a.phase_lock & 16) while (__syncthreads_or(0)) {}
+                if (a.phase_lock & 8) __syncthreads();
+            }
+        }
     }
     if (a.buf.stats && a.reward_mode == PBRL_REWARD_MIMIC && lane < 6 && acc[5] > 0.f) {
         float v = acc[0];  // one atomic per (warp, statistic): lane k publishes statistic k
@@ -224,7 +230,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
-    a.phase_lock = getenv("PBRL_NO_PHASE_LOCK") == nullptr;
+    { const char* e = getenv("PBRL_PHASE_LOCK"); a.phase_lock = (e ? atoi(e) : 9) & 31; }
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/pbrl.h"
+#include "pbrl_topo_gen.h"
 
 namespace pbrl {
 
@@ -198,6 +199,8 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
         m.dof_act[i] = -1; m.dof_gear[i] = 0; m.dof_ctrl_lo[i] = -1e30f; m.dof_ctrl_hi[i] = 1e30f;
     }
     if (madr != NM) return "sparse inertia layout size differs from 310";
+    for (int i = 0; i < NV; i++)
+        if (d.dof_parentid[i] != topo::PARENT[i]) return "the dof tree differs from the one the kernels were compiled for (csrc/pbrl_topo_gen.h)";
     if (maxdepth + 1 > MAXDEPTH) return "dof chains too deep";
     m.ndepth = maxdepth + 1;
     pos = 0;
