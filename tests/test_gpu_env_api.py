@@ -1,0 +1,113 @@
+"""The reference-facing Python facade (envs.py / pds_controllers.py) on the GPU: same flows as the reference's notebooks."""
+import importlib
+
+import numpy as np
+import pytest
+
+from helpers import ASSETS, GOLDEN, PKG, Oracle, OracleEnv, mocap, relerr, start_trajectory, util_data
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    return torch, importlib.import_module(PKG + ".envs"), importlib.import_module(PKG + ".pds_controllers")
+
+
+def test_eager_pd_then_step_outside_reproduces_golden_T1(mods, model_nograv):
+    """testing_pds_env3.ipynb cell 21 through the facade: eager stable-PD (dt = env.dt), step_custom_target_and_outside."""
+    torch, envs, pdc = mods
+    kp, kd = util_data.generate_kp_kd_gains()
+    envs.register_environment("humanoidMimic", envs.HumanoidTrain)
+    env = envs.get_environment("humanoidMimic", reference_trajectory_qpos=None, reference_trajectory_qvel=None,
+                               duration_trajectory=0.0, dict_duration={}, model_path=model_nograv, kp_gains=kp, kd_gains=kd,
+                               num_envs=2)
+    assert abs(env.dt - 0.016) < 1e-12 and env.sys.dt == 0.002 and env.n_frames == 8   # testing_pds_env3.ipynb cells 23-24
+    assert env.action_size == 28 and env.observation_size == 69
+    g = np.load(GOLDEN / "mass_traces.npz")["T1"]
+    coef = torch.from_numpy(start_trajectory()).cuda()
+    state = env.reset(0)
+    idx = [0, 1, 2, 31, 32, 33]
+    for k in range(8):
+        ps = state.pipeline_state
+        M = ps.qM[0].cpu().numpy()
+        assert np.abs(M[np.ix_(idx, idx)] - g[k]).max() <= 2e-5, k
+        t = torch.clamp(ps.time, 1, 3)
+        tau = pdc.stable_pd_controller_custom_trajectory(coef, env.sys, state, ps.q, ps.qd, kp, kd, t, env.dt)
+        state = env.step_custom_target_and_outside(state, tau)
+    assert state.obs.shape == (2, 69) and torch.equal(state.obs[:, :35], state.pipeline_state.qpos)
+    assert (state.reward == 0).all() and (state.done == 1).all()
+    assert set(state.metrics) == {"step_index", "pose_error", "fall"}
+
+
+def test_step_variants_and_callbacks(mods, model_nograv):
+    torch, envs, pdc = mods
+    kp, kd = util_data.generate_kp_kd_gains()
+    N = 32
+    mk = lambda: envs.HumanoidTrain(None, None, 0.0, {}, model_nograv, kp, kd, num_envs=N)
+    rng = np.random.default_rng(0)
+    lo, hi = model_nograv.jnt_range[1:, 0], model_nograv.jnt_range[1:, 1]
+    tgt = torch.from_numpy(rng.uniform(lo, hi, (N, 28)).astype(np.float32)).cuda()
+    ref = OracleEnv(Oracle(model_nograv, "f64", tolerance=1e-14), N)
+    # (1) fused built-in law == same law evaluated outside + torque step == oracle
+    for fn, mode in ((pdc.standard_pd_controller, 1), (pdc.feedback_pd_controller, 2), (pdc.stable_pd_controller_custom_trajectory, 3)):
+        a, b = mk(), mk()
+        a.set_pd_callback(fn)
+        sa, sb = a.reset(0), b.reset(0)
+        sa = a.step(sa, tgt)
+        ps = sb.pipeline_state
+        tau = fn(tgt, b.sys, sb, ps.q, ps.qd, kp, kd, ps.time, b.sys.dt)
+        sb = b.step_custom_target_and_outside(sb, tau)
+        assert torch.allclose(sa.obs, sb.obs, rtol=0, atol=1e-6)
+        ref.reset()
+        ref.step(tgt.cpu().numpy(), kp, kd, pd_mode=mode, pd_dt=0.002)
+        assert relerr(sa.obs.cpu().numpy(), np.concatenate([ref.qpos, ref.qvel], 1)) <= 1e-5
+    # (2) an arbitrary Python callable as the PD law (the reference passes plain functions)
+    c = mk()
+    c.set_pd_callback(lambda target, sys, state, q, qd, kp_, kd_, time, dt: -kp_ * (q[:, 7:] - target) - kd_ * qd[:, 6:])
+    sc = c.step(c.reset(0), tgt)
+    d = mk()
+    d.set_pd_callback(pdc.standard_pd_controller)
+    sd = d.step(d.reset(0), tgt)
+    assert torch.allclose(sc.obs, sd.obs, rtol=0, atol=1e-5)
+    # (3) selected joints: the others keep the previous ctrl (agent_mimic.py:122-125)
+    e = mk()
+    se = e.reset(0)
+    coef = torch.from_numpy(start_trajectory()).cuda()
+    se = e.step_selected_joints_custom_target_and_joints(se, None, coef, 7, 10, 13, 9, 17, 24, torch.full((N,), 2.0).cuda())
+    ctrl = se.pipeline_state.ctrl.cpu().numpy()
+    others = [i for i in range(28) if i not in (7, 10, 13, 9)]
+    assert (ctrl[:, others] == 0).all() and (np.abs(ctrl[:, [7, 10, 13, 9]]) > 0).all()
+
+
+def test_replay_env(mods, model_grav):
+    torch, envs, _ = mods
+    z = np.load(ASSETS / "mocap_punch.npz")
+    F = z["data_pos"].shape[0]
+    env = envs.HumanoidReplay(z["data_pos"], z["data_vel"], float(z["total_time"]), {}, model_grav, num_envs=F)
+    state = env.reset(0)
+    state.pipeline_state.qpos.copy_(torch.from_numpy(z["data_pos"].astype(np.float32)))   # testing_forward_env.ipynb cell 10
+    state.pipeline_state.qvel.copy_(torch.from_numpy(z["data_vel"].astype(np.float32)))
+    state = env.step(state, None, want_poses=True)
+    assert torch.equal(state.obs[:, :35], state.pipeline_state.qpos) and (state.done == 1).all() and (state.pipeline_state.time == 0).all()
+    ref = OracleEnv(Oracle(model_grav, "f64"), F)
+    _, _, _, xpos, xquat = ref.replay(z["data_pos"].astype(np.float32), z["data_vel"].astype(np.float32), want_poses=True)
+    assert relerr(state.info["xpos"].cpu().numpy(), xpos) <= 2e-6
+
+
+def test_mimic_env_rollout(mods, model_grav):
+    torch, envs, _ = mods
+    kp, kd = util_data.generate_kp_kd_gains()
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    env = envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=256, reward_mode="mimic", motion_table=table)
+    state = env.reset(3)
+    assert (state.pipeline_state.qpos[:, 2] > 0.05).all()
+    for k in range(4):
+        state.info["stats"].zero_()
+        state = env.step(state, state.pipeline_state.qpos[:, 7:].clone())
+    torch.cuda.synchronize()
+    r = state.reward[:, 0]
+    assert (r > 0).all() and (r <= 1.0 + 1e-6).all() and torch.isfinite(state.obs).all()
+    assert state.info["stats"][5].item() == 256 and (state.metrics["step_index"] == 4).all()
+    assert abs(state.info["stats"][0].item() - r.sum().item()) < 1e-2
