@@ -130,13 +130,71 @@ def cpu_reference_run(workload, steps, warmup, sample_envs=None, threads=None):
             "seconds": dt, "ms_per_step": 1e3 * dt / steps}
 
 
+def replay_bench(args, rank, local_rank, world):
+    """BASELINE configs[1]: agent_replay_motion kinematic replay of humanoid3d_walk.txt, 4096 envs, FK + obs/reward."""
+    import torch
+    L = importlib.import_module(PKG + "._lib")
+    mjcf = importlib.import_module(PKG + ".mjcf")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = mjcf.load_model(ROOT / PKG / "assets" / "final_humanoid.model.json")
+    z = np.load(ROOT / PKG / "assets" / "mocap_walk.npz")
+    n_env = args.envs or 4096
+    F = z["data_pos"].shape[0]
+    fr = (np.arange(n_env) + rank * n_env) % F
+    qpos = torch.from_numpy(z["data_pos"][fr].astype(np.float32)).to(dev)
+    qvel = torch.from_numpy(z["data_vel"][fr].astype(np.float32)).to(dev)
+    M = L.Model(model, device=local_rank)
+    obs, rew, done = torch.empty(n_env, 69, device=dev), torch.empty(n_env, 3, device=dev), torch.empty(n_env, device=dev)
+    xpos, xquat = torch.empty(n_env, 14, 3, device=dev), torch.empty(n_env, 14, 4, device=dev)
+    lib, stream = L.lib(), L.current_stream_ptr(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    def one():
+        L.check(lib.pbrl_replay(M.handle, n_env, L._ptr(qpos), L._ptr(qvel), L._ptr(obs), L._ptr(rew), L._ptr(done), L._ptr(xpos),
+                                L._ptr(xquat), stream))
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record(); one(); ev[k][1].record()
+    torch.cuda.synchronize()
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    peak, src = measured_peak()
+    bytes_env = 580 + 364
+    ach = n_env * bytes_env / (t_ms * 1e-3 / steps) / 1e9
+    print(json.dumps({"metric": "humanoid replay env-steps/sec", "value": n_env * steps / (t_ms * 1e-3), "unit": "env-steps/s",
+                      "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": t_ms / steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "replay", "description": "BASELINE configs[1]: kinematic replay of walk, FK + obs/reward + body poses",
+                                 "envs_per_gpu": n_env, "l2_flush_between_steps": True},
+                      "gpu_launches": steps + warmup,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                   "peak_source": src, "kernel": "k_replay", "algorithmic_bytes_per_env_launch": bytes_env}}))
+    return 0
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mimic_mixed", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="mimic_mixed", choices=sorted(WORKLOADS) + ["replay"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -145,6 +203,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = args.steps, max(args.warmup, 3)
 
+    if args.workload == "replay":
+        return replay_bench(args, rank, local_rank, world) if rank == 0 else 0
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -179,7 +239,9 @@ def main():
     st = dict(qpos=z(n_env, 35), qvel=z(n_env, 34), qpos_lag=z(n_env, 35), qvel_lag=z(n_env, 34), time=z(n_env),
               warm=z(n_env, 34), ctrl=z(n_env, 28), obs=z(n_env, 69), reward=z(n_env, 3), done=z(n_env), metrics=z(n_env, 3),
               status=torch.zeros(n_env, device=dev, dtype=torch.int32), stats=z(8),
-              motion_id=torch.from_numpy(motion_id).to(dev), ref_t0=torch.from_numpy(ref_t0).to(dev))
+              motion_id=torch.from_numpy(motion_id).to(dev), ref_t0=torch.from_numpy(ref_t0).to(dev),
+              # processing order: envs of the same clip share a CTA (similar contact work -> balanced phase barriers)
+              env_order=torch.from_numpy(np.argsort(motion_id, kind="stable").astype(np.int32)).to(dev))
     bufs = L.make_buffers(**st)
     L.check(L.lib().pbrl_reset(M.handle, n_env, 1, ctypes.byref(bufs), L.current_stream_ptr(dev)))  # reference-state init
     torch.cuda.synchronize()
@@ -264,6 +326,8 @@ def main():
         value = total_envs * N_FRAMES * steps / (t_ms * 1e-3)
         launch_s = t_ms * 1e-3 / steps
         achieved = n_env * BYTES_PER_ENV_LAUNCH / launch_s / 1e9
+        tr = measured_traffic()
+        traffic = tr["dram_bytes_per_launch"] if tr and tr.get("workload") == args.workload and tr.get("envs_per_gpu") == n_env else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -275,7 +339,7 @@ def main():
                         "steps": e2e_steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)"},
                 "gpu_launches": steps + e2e_steps + 3 + warmup,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "k_step",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "k_step",
                              "algorithmic_bytes_per_env_launch": BYTES_PER_ENV_LAUNCH,
                              "note": "the dynamics step is fp32-issue/latency bound (50-300 flop/B); HBM fraction is reported per the tier rule"},
                 "clocks": clocks, "nan_envs": bad,

@@ -128,6 +128,9 @@ typedef struct PbrlBuffers {
     const int* motion_id; /* [N] mimic mode, may be NULL */
     const float* ref_t0;  /* [N] clip time at reset, mimic mode, may be NULL */
     float* stats;    /* [8] accumulated with atomics: sum r, sum r^2, sum done, sum fall, sum pose_err, n, 0, 0; may be NULL */
+    const int* env_order; /* [N] optional processing order (a permutation of 0..N-1), may be NULL.  Envs that are
+                             neighbours in this order share a CTA; grouping envs of similar cost (e.g. by clip)
+                             balances the CTA-wide phase barriers of pbrl_step.  Results do not depend on it. */
 } PbrlBuffers;
 
 int pbrl_model_desc_size(void);

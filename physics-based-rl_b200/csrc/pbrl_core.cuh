@@ -80,7 +80,7 @@ struct Ws {
     float con_dist[NCP], con_r[NCP * S3], con_t1[NCP * 2], con_D[NCP];
     float con_aref[NCP * 4], con_jar[NCP * 4], con_jp[NCP * 4];
     union {
-        struct { float K[NB * S21], Ksub[NB * S21]; };                     // Newton Hessian assembly
+        struct { float K[NB * S21]; };                                     // Newton Hessian assembly (accumulated in place)
         struct { float crb[NB * S10]; };                                   // composite inertias (only inside stage_crb)
         struct {                                                          // mimic epilogue (after the last substep)
             float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * S4], rcom[4], ree[12], rerr[8];
@@ -692,15 +692,19 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
         for (int q = 0; q < 21; q++) w.K[S21 * b + q] = k21[q];
     }
     WSYNC();
-    LANE_LOOP(it, NB * 21) {
-        int b = it / 21, k = it - 21 * b;
-        float s = 0.f;
-        for (int c = b; c < m.body_subtree_end[b]; c++) s += w.K[S21 * c + k];
-        w.Ksub[S21 * b + k] = s;
+    // leaf-to-root accumulation in place: parents of each level gather their (already complete) children
+    for (int lv = m.nlevel - 2; lv >= 1; lv--) {
+        const int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
+        LANE_LOOP(it, n * 21) {
+            const int b = m.level_body[s + it / 21], k = it % 21;
+            float acc = w.K[S21 * b + k];
+            for (int c = 0; c < m.body_nchild[b]; c++) acc += w.K[S21 * m.body_child[b][c] + k];
+            w.K[S21 * b + k] = acc;
+        }
+        WSYNC();
     }
-    WSYNC();
     LANE_LOOP(i, NV) {
-        const float* K = w.Ksub + S21 * m.dof_bodyid[i];
+        const float* K = w.K + S21 * m.dof_bodyid[i];
         const float* cd = w.cdof + S6 * i;
         for (int r = 0; r < 6; r++) {
             float s = 0.f;

@@ -20,7 +20,7 @@ using namespace pbrl;
 namespace {
 
 #ifndef PBRL_WARPS_PER_CTA
-#define PBRL_WARPS_PER_CTA 7
+#define PBRL_WARPS_PER_CTA 8
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     // every warp of the CTA makes the same number of passes so that the per-substep CTA barrier (phase lock) is legal
     for (int base = blockIdx.x * WARPS_PER_CTA; base < a.N; base += env_stride()) {
-        const int env = base + (threadIdx.x >> 5);
-        if (env < a.N) env_step(*gm, w, a, env, acc, lane);
+        const int slot = base + (threadIdx.x >> 5);
+        if (slot < a.N) env_step(*gm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
         else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 7); k++) __syncthreads();

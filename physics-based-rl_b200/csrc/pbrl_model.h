@@ -42,6 +42,7 @@ struct DevModel {
     int depth_dof[NV];
     int body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
     int body_conadr[NB], body_connum[NB];
+    int body_nchild[NB], body_child[NB][4];
     float body_pos[NB][3], body_mass[NB], body_ipos[NB][3], body_inertia[NB][6];
     int jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ];
     float jnt_axis[NJ][3], jnt_lo[NJ], jnt_hi[NJ], jnt_margin[NJ];
@@ -153,6 +154,11 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             while (a > b) a = d.body_parent[a];
             if (a == b && b != 0) return "bodies must be in depth-first order";
         }
+    }
+    for (int b = 1; b < NB; b++) {
+        int p = d.body_parent[b];
+        if (m.body_nchild[p] >= 4) return "at most 4 children per body";
+        m.body_child[p][m.body_nchild[p]++] = b;
     }
     int nl = 0;
     for (int b = 0; b < NB; b++) nl = level[b] + 1 > nl ? level[b] + 1 : nl;
