@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--workload", default="mimic_mixed", choices=sorted(WORKLOADS) + ["replay"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-profile", action="store_true", help="dev: print the per-stage cycle table (needs a -DPBRL_STAGE_PROF library, PBRL_LIB=...)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,6 +276,8 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sync_all()
+    if args.stage_profile:
+        L.check(lib.pbrl_debug_stage_profile(None, None, 1))
     for k in range(steps):
         flush.zero_()  # evict the 126 MB L2 between timed iterations (outside the timed events)
         ev[k][0].record()
@@ -282,6 +285,19 @@ def main():
         ev[k][1].record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    if args.stage_profile and rank == 0:
+        cyc, hit = (ctypes.c_ulonglong * 64)(), (ctypes.c_ulonglong * 64)()
+        L.check(lib.pbrl_debug_stage_profile(cyc, hit, 0))
+        names = {0: "load", 1: "pd_torque", 2: "fk", 3: "com", 4: "crb", 5: "collide", 6: "comvel", 7: "bias", 8: "rows",
+                 9: "fsmooth", 10: "free:factor", 11: "free:solve", 12: "newton:init", 13: "newton:grad(JTf)", 14: "newton:hessian",
+                 15: "newton:factor", 16: "newton:solve", 17: "newton:Mp,Jp", 18: "newton:linesearch", 19: "newton:update",
+                 20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 26: "cta barrier wait"}
+        tot = sum(cyc)
+        print(f"stage profile: {tot / (n_env * steps * N_FRAMES):.0f} cycles per env-substep (per warp, incl. stalls)", file=sys.stderr)
+        for i in range(64):
+            if hit[i]:
+                print(f"  {i:2d} {names.get(i, '?'):22s} {100.0 * cyc[i] / tot:6.2f}%  hits/substep {hit[i] / (n_env * steps * N_FRAMES):7.3f}  "
+                      f"cycles/hit {cyc[i] / hit[i]:9.0f}", file=sys.stderr)
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t_all = torch.tensor([t_ms], device=dev)
     if world > 1:

@@ -180,6 +180,10 @@ int pbrl_pd_torque(const PbrlModel* model, int N, int pd_mode, int action_cols, 
 int pbrl_debug_forward(const PbrlModel* model, int N, const float* qpos, const float* qvel, const float* ctrl,
                        const float* warm, float* out, void* stream);
 
+/* Dev builds only (-DPBRL_STAGE_PROF): cumulative cycles / hit counts per kernel stage, 64 slots each.  The product
+ * build returns -1 ("not a profiling build"). */
+int pbrl_debug_stage_profile(unsigned long long* cycles, unsigned long long* hits, int reset);
+
 /* ---- host-buffer convenience layer: what a Python/JAX host that keeps its data on the CPU calls.
  * Owns device state for N envs and pinned staging; every call copies host->device, launches, copies
  * device->host on the handle's stream and returns after the results are in the host buffers. */

@@ -3,6 +3,7 @@ or no B200 is visible, every call raises."""
 from __future__ import annotations
 
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -11,7 +12,7 @@ import numpy as np
 from ._desc import PbrlBuffers, build_model_desc
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libpbrl.so"
+LIB_PATH = Path(os.environ["PBRL_LIB"]) if os.environ.get("PBRL_LIB") else PKG / "libpbrl.so"  # PBRL_LIB: dev builds
 CSRC = PKG / "csrc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
@@ -21,8 +22,14 @@ class PbrlError(RuntimeError):
     pass
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile csrc/pbrl_lib.cu for sm_100a into physics-based-rl_b200/libpbrl.so (in-tree)."""
+    if out is not None:
+        cmd = ["nvcc", *NVCC_FLAGS, *extra_flags, "-o", str(out), str(CSRC / "pbrl_lib.cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise PbrlError("nvcc failed:\n" + r.stderr)
+        return Path(out)
     srcs = [CSRC / "pbrl_lib.cu", CSRC / "pbrl_core.cuh", CSRC / "pbrl_model.h", CSRC / "pbrl_desc_reflect.h",
             CSRC / "pbrl_mimic.cuh", PKG.parent / "include" / "pbrl.h"]
     srcs = [s for s in srcs if s.exists()]
@@ -58,7 +65,7 @@ def check(rc):
 
 EXPORTS = ["pbrl_model_desc_size", "pbrl_model_desc_field", "pbrl_last_error", "pbrl_device_count",
            "pbrl_model_create", "pbrl_model_destroy", "pbrl_reset", "pbrl_step", "pbrl_replay", "pbrl_pd_torque",
-           "pbrl_debug_forward", "pbrl_batch_create", "pbrl_batch_destroy", "pbrl_batch_reset_host",
+           "pbrl_debug_forward", "pbrl_debug_stage_profile", "pbrl_batch_create", "pbrl_batch_destroy", "pbrl_batch_reset_host",
            "pbrl_batch_step_host", "pbrl_batch_get_state_host"]
 
 

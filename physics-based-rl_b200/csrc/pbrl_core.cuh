@@ -47,6 +47,26 @@
 #define CTA_OR(p) (p)
 #endif
 
+// Stage profiler (dev builds only, -DPBRL_STAGE_PROF): lane 0 of every warp adds the cycles since its previous mark
+// to a global per-stage counter.  Read back through pbrl_debug_stage_profile().
+#if defined(PBRL_STAGE_PROF) && defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+__device__ unsigned long long g_stage_cycles[64];
+__device__ unsigned long long g_stage_hits[64];
+#define PROF(id)                                                                      \
+    do {                                                                              \
+        if (lane == 0) {                                                              \
+            const long long t_ = clock64();                                           \
+            atomicAdd(&g_stage_cycles[id], (unsigned long long)(t_ - w.prof_t));      \
+            atomicAdd(&g_stage_hits[id], 1ull);                                       \
+            w.prof_t = t_;                                                            \
+        }                                                                             \
+    } while (0)
+#define PROF_START() do { if (lane == 0) w.prof_t = clock64(); } while (0)
+#else
+#define PROF(id) ((void)0)
+#define PROF_START() ((void)0)
+#endif
+
 namespace pbrl {
 
 constexpr int S3 = 3, S4 = 5, S6 = 7, S9 = 9, S10 = 11, S21 = 21;  // odd strides: conflict-free lane=row access
@@ -55,7 +75,7 @@ constexpr int LS_MAXIT = 24;
 
 struct Ws {
     // state
-    float qpos[36], qvel[36], warm[36], ctrl[28], qpos_lag[36], qvel_lag[36];
+    float qpos[36], qvel[36], warm[36], ctrl[28];
     // kinematics.  xquat/xmat are dead once the contacts are found; the spatial-force scratch F/Fsub reuses them
     float xpos[NB * S3], com[4];
     union {
@@ -69,11 +89,16 @@ struct Ws {
         float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
     };
     // joint-space inertia (tree-sparse), factor, vectors
-    float M[NM], LD[NM], Dinv[36];
+    float M[NM], Dinv[36];
+    union {
+        float LD[NM];                                 // factor workspace
+        alignas(16) float fr[2 * PBRL_FRAME_STRIDE];  // mimic: the two reference frames of this env step (cp.async.bulk
+    };                                                // target; issued after the last factorisation of the step)
     float fsmooth[36], qacc[36], grad[36], p[36];
     union { float Ma[36]; float tau[28]; };      // tau: PD law output, consumed before the solver runs
     union { float Mp[36]; float asmooth[36]; };  // asmooth: only formed when no row is active
     union { float fcon[36]; float bias[36]; };   // bias is folded into fsmooth before the solver writes fcon
+    // PD prologue only: the state of the last forward (qpos_lag / qvel_lag rows) is staged in fsmooth / qacc
     // constraint rows: lane l owns limit row l and contact slot l (4 pyramid rows)
     float lim_sign[32], lim_D[32], lim_aref[32], lim_jar[32], lim_jp[32];
     int con_on[NCP], act_bits[32];
@@ -86,7 +111,6 @@ struct Ws {
             float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * S4], rcom[4], ree[12], rerr[8];
         };
     };
-    alignas(16) float fr[2 * PBRL_FRAME_STRIDE];  // the two reference frames of this env step (cp.async.bulk target)
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
     float fr_u, fr_cyc;
     int fr_phase, fr_pad;
@@ -94,6 +118,9 @@ struct Ws {
     int lvl_start[MAXLEVEL + 1];
     int status, niter;
     int phase_lock, pad_;  // CTA barriers at stage-group boundaries keep the CTA's warps inside one I-cache window
+#if defined(PBRL_STAGE_PROF)
+    long long prof_t;
+#endif
 };
 
 PB_DEV float fast_rcp(float x) {
@@ -232,26 +259,40 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
 // com, cinert, cdof  (mjx smooth.com_pos)
 PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
     float inv = 1.0f / m.total_mass;
-    const float cx = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b] + t[0]); }) * inv;
-    const float cy = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b + 1] + t[1]); }) * inv;
-    const float cz = wsum(lane, NB, [&](int b) { float t[3]; mat_vec(w.xmat + S9 * b, m.body_ipos[b], t); return m.body_mass[b] * (w.xpos[S3 * b + 2] + t[2]); }) * inv;
+    float* xip = w.cvel;  // scratch: world position of each body's inertial frame (cvel is not live yet)
+    LANE_IF(b, NB) {
+        float t[3];
+        mat_vec(w.xmat + S9 * b, m.body_ipos[b], t);
+        for (int c = 0; c < 3; c++) xip[S6 * b + c] = w.xpos[S3 * b + c] + t[c];
+    }
+    WSYNC();
+    const float cx = wsum(lane, NB, [&](int b) { return m.body_mass[b] * xip[S6 * b]; }) * inv;
+    const float cy = wsum(lane, NB, [&](int b) { return m.body_mass[b] * xip[S6 * b + 1]; }) * inv;
+    const float cz = wsum(lane, NB, [&](int b) { return m.body_mass[b] * xip[S6 * b + 2]; }) * inv;
     LANE_IF(z, 1) { w.com[0] = cx; w.com[1] = cy; w.com[2] = cz; }
     LANE_IF(b, NB) {
         const float* R = w.xmat + S9 * b;
         const float* I = m.body_inertia[b];  // xx yy zz xy xz yz (body frame, about ipos)
-        float A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, RA[9], Iw[6];
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) RA[3 * r + c] = R[3 * r] * A[c] + R[3 * r + 1] * A[3 + c] + R[3 * r + 2] * A[6 + c];
-        // world inertia = RA R^T, six unique entries: xx yy zz xy xz yz
-        Iw[0] = RA[0] * R[0] + RA[1] * R[1] + RA[2] * R[2];
-        Iw[1] = RA[3] * R[3] + RA[4] * R[4] + RA[5] * R[5];
-        Iw[2] = RA[6] * R[6] + RA[7] * R[7] + RA[8] * R[8];
-        Iw[3] = RA[0] * R[3] + RA[1] * R[4] + RA[2] * R[5];
-        Iw[4] = RA[0] * R[6] + RA[1] * R[7] + RA[2] * R[8];
-        Iw[5] = RA[3] * R[6] + RA[4] * R[7] + RA[5] * R[8];
-        float ip[3];
-        mat_vec(R, m.body_ipos[b], ip);
-        float ms = m.body_mass[b], ox = w.xpos[S3 * b] + ip[0] - cx, oy = w.xpos[S3 * b + 1] + ip[1] - cy, oz = w.xpos[S3 * b + 2] + ip[2] - cz;
+        float Iw[6];
+        if (I[3] == 0.f && I[4] == 0.f && I[5] == 0.f) {  // principal axes = body axes: Iw = sum_k I_k r_k r_k^T
+            Iw[0] = I[0] * R[0] * R[0] + I[1] * R[1] * R[1] + I[2] * R[2] * R[2];
+            Iw[1] = I[0] * R[3] * R[3] + I[1] * R[4] * R[4] + I[2] * R[5] * R[5];
+            Iw[2] = I[0] * R[6] * R[6] + I[1] * R[7] * R[7] + I[2] * R[8] * R[8];
+            Iw[3] = I[0] * R[0] * R[3] + I[1] * R[1] * R[4] + I[2] * R[2] * R[5];
+            Iw[4] = I[0] * R[0] * R[6] + I[1] * R[1] * R[7] + I[2] * R[2] * R[8];
+            Iw[5] = I[0] * R[3] * R[6] + I[1] * R[4] * R[7] + I[2] * R[5] * R[8];
+        } else {
+            float A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, RA[9];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) RA[3 * r + c] = R[3 * r] * A[c] + R[3 * r + 1] * A[3 + c] + R[3 * r + 2] * A[6 + c];
+            Iw[0] = RA[0] * R[0] + RA[1] * R[1] + RA[2] * R[2];
+            Iw[1] = RA[3] * R[3] + RA[4] * R[4] + RA[5] * R[5];
+            Iw[2] = RA[6] * R[6] + RA[7] * R[7] + RA[8] * R[8];
+            Iw[3] = RA[0] * R[3] + RA[1] * R[4] + RA[2] * R[5];
+            Iw[4] = RA[0] * R[6] + RA[1] * R[7] + RA[2] * R[8];
+            Iw[5] = RA[3] * R[6] + RA[4] * R[7] + RA[5] * R[8];
+        }
+        float ms = m.body_mass[b], ox = xip[S6 * b] - cx, oy = xip[S6 * b + 1] - cy, oz = xip[S6 * b + 2] - cz;
         float* ci = w.cinert + S10 * b;
         ci[0] = Iw[0] + ms * (oy * oy + oz * oz);
         ci[1] = Iw[1] + ms * (ox * ox + oz * oz);
@@ -379,33 +420,31 @@ PB_DEV void init_ws_tables(const DevModel& m, Ws& w, int lane) {
 namespace topo {
 PB_CX int depth(int k) { int d = 0; while (PARENT[k] >= 0) { k = PARENT[k]; d++; } return d; }
 PB_CX int madr(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) + 1; return a; }
-PB_CX int fac_start(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) * (depth(i) + 1) / 2; return a; }
+PB_CX int fac_total() { int a = 0; for (int i = 0; i < NDOF; i++) a += depth(i) * (depth(i) + 1) / 2; return a; }
 PB_CX int max_depth() { int d = 0; for (int k = 0; k < NDOF; k++) d = depth(k) > d ? depth(k) : d; return d; }
 PB_CX int depth_count(int lv) { int n = 0; for (int k = 0; k < NDOF; k++) n += depth(k) == lv; return n; }
 PB_CX int depth_first(int lv) { int n = 0; for (int l = 0; l < lv; l++) n += depth_count(l); return n; }
-static_assert(NDOF == NV && madr(NDOF - 1) + depth(NDOF - 1) + 1 == NM && fac_start(NDOF - 1) + depth(NDOF - 1) * (depth(NDOF - 1) + 1) / 2 == NFAC,
+static_assert(NDOF == NV && madr(NDOF - 1) + depth(NDOF - 1) + 1 == NM && fac_total() == NFAC && max_depth() * (max_depth() + 1) / 2 <= NFACOP,
               "pbrl_topo_gen.h does not match the kernel dimensions");
 }  // namespace topo
 
 template <int K>
 struct FactorStep {  // eliminate dof K: rank-1 update of its ancestors' rows (MuJoCo mj_factorI order, leaf to root)
-    PB_MEMBER void run(const DevModel& m, Ws& w, char* LDb, int lane) {
-        constexpr int d = topo::depth(K), n = d * (d + 1) / 2;
+    PB_MEMBER void run(const DevModel& m, Ws& w, int lane) {
+        constexpr int d = topo::depth(K), n = d * (d + 1) / 2, adr = topo::madr(K);
         if constexpr (n > 0) {
-            const float inv = fast_rcp(w.LD[topo::madr(K)]);
-            const unsigned(*ops)[2] = m.fac_op + topo::fac_start(K);
+            const float inv = fast_rcp(w.LD[adr]);
             LANE_LOOP(pi, n) {
-                const unsigned ux = ops[pi][0], uy = ops[pi][1];
-                float* tgt = reinterpret_cast<float*>(LDb + (ux & 0xffffu));
-                *tgt -= (*reinterpret_cast<const float*>(LDb + (ux >> 16)) * inv) * *reinterpret_cast<const float*>(LDb + uy);
+                const int a = m.fac_a[pi], c = m.fac_c[pi];
+                w.LD[m.anc_adr[adr + a] + (c - a)] -= (w.LD[adr + a] * inv) * w.LD[adr + c];
             }
             WSYNC();
         }
-        if constexpr (K > 1) FactorStep<K - 1>::run(m, w, LDb, lane);
+        if constexpr (K > 1) FactorStep<K - 1>::run(m, w, lane);
     }
 };
 PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
-    FactorStep<NV - 1>::run(m, w, reinterpret_cast<char*>(w.LD), lane);
+    FactorStep<NV - 1>::run(m, w, lane);
     LANE_LOOP(i, NV) {
         const float piv = w.LD[m.dof_Madr[i]];
         if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
@@ -703,8 +742,10 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
         }
         WSYNC();
     }
+    // K[b][20] (lin-z, lin-z) sums D over the active rows of the subtree: zero <=> nothing to add for that body's dofs
     LANE_LOOP(i, NV) {
         const float* K = w.K + S21 * m.dof_bodyid[i];
+        if (K[20] == 0.f) continue;
         const float* cd = w.cdof + S6 * i;
         for (int r = 0; r < 6; r++) {
             float s = 0.f;
@@ -715,7 +756,8 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
     WSYNC();
     LANE_LOOP(e, NM) {
         int r = m.M_row[e], c = m.M_col[e];
-        float v = w.M[e] + dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
+        float v = w.M[e];
+        if (w.K[S21 * m.dof_bodyid[r] + 20] != 0.f) v += dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
         if (r == c && m.jnt_limited[m.dof_jntid[r]]) {
             int l = r - m.jnt_dofadr[m.lim_jnt[0]];
             if (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) v += w.lim_D[l];
@@ -736,9 +778,11 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         LANE_LOOP(e, NM) w.LD[e] = w.M[e];
         WSYNC();
         ldl_factor(m, w, lane);
+        PROF(10);
         ldl_solve(m, w, w.asmooth, lane);
         LANE_LOOP(i, NV) { w.qacc[i] = w.asmooth[i]; w.fcon[i] = 0.f; }
         WSYNC();
+        PROF(11);
         if (!coop) return;
     } else {
         // with active rows the optimum does not need qacc_smooth: the cost is written with qfrc_smooth
@@ -757,6 +801,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
             w.act_bits[l] = bits;
         }
         WSYNC();
+        PROF(12);
     }
     int it = 0;
     bool running = constrained;
@@ -769,14 +814,19 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         LANE_LOOP(i, NV) w.Mp[i] = w.Ma[i] - w.fsmooth[i];
         WSYNC();
         rows_JTf(m, w, w.Mp, w.grad, 0, lane);
+        PROF(13);
         assemble_hessian(m, w, lane);
+        PROF(14);
         ldl_factor(m, w, lane);
+        PROF(15);
         LANE_LOOP(i, NV) w.p[i] = -w.grad[i];
         WSYNC();
         ldl_solve(m, w, w.p, lane);
+        PROF(16);
         tree_vel(m, w, w.p, lane);
         tree_Mx_from_V(m, w, w.p, w.Mp, lane);
         rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
+        PROF(17);
         // exact line search on the piecewise-quadratic cost along p (safeguarded Newton on phi')
         float g0 = wsum(lane, NV, [&](int i) { return (w.Ma[i] - w.fsmooth[i]) * w.p[i]; });
         float pMp = wsum(lane, NV, [&](int i) { return w.Mp[i] * w.p[i]; });
@@ -818,6 +868,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
             if (an == alpha) break;
             alpha = an;
         }
+        PROF(18);
         // step, refresh residuals, detect active-set change
         LANE_LOOP(i, NV) { w.qacc[i] += alpha * w.p[i]; w.Ma[i] += alpha * w.Mp[i]; }
         float changed = wsum(lane, 32, [&](int l) {
@@ -840,11 +891,13 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
         it++;
         if (changed == 0.f) running = false;
+        PROF(19);
     }
     if (!constrained) return;
     if (it >= NEWTON_MAXIT) w.status |= PBRL_STATUS_SOLVER_MAXITER;
     w.niter = it;
     rows_JTf(m, w, w.Mp, w.fcon, 1, lane);
+    PROF(20);
 }
 
 // ---------------------------------------------------------------------------------- one mjx.forward + Euler
@@ -855,12 +908,25 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     const int lock = w.phase_lock;
     if (lock & 1) CTA_SYNC();
-    smooth_position(m, w, w.qpos, lane);
+    PROF(26);
+    stage_fk(m, w, w.qpos, lane);
+    PROF(2);
+    stage_com(m, w, lane);
+    PROF(3);
+    stage_crb(m, w, lane);
+    PROF(4);
     if (lock & 2) CTA_SYNC();
+    PROF(26);
     stage_collide(m, w, lane);
-    smooth_velocity(m, w, w.qvel, lane);
+    PROF(5);
+    stage_comvel(m, w, w.qvel, lane);
+    PROF(6);
+    stage_bias(m, w, lane);
+    PROF(7);
     stage_rows(m, w, w.qpos, w.qvel, lane);
+    PROF(8);
     if (lock & 4) CTA_SYNC();
+    PROF(26);
     LANE_LOOP(i, NV) {
         float f = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
         int a = m.dof_act[i];
@@ -868,6 +934,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
         w.fsmooth[i] = f;
         w.asmooth[i] = f;
     }
+    PROF(9);
     solve_constraints(m, w, lane);
 }
 
@@ -875,12 +942,15 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     forward(m, w, lane);
     if (w.phase_lock & 8) CTA_SYNC();
+    PROF(26);
     float h = m.timestep;
     LANE_LOOP(i, NV) { w.warm[i] = w.qacc[i]; w.p[i] = w.fsmooth[i] + w.fcon[i]; }
     LANE_LOOP(e, NM) w.LD[e] = w.M[e] + ((m.M_row[e] == m.M_col[e]) ? h * m.dof_damping[m.M_row[e]] : 0.f);
     WSYNC();
     ldl_factor(m, w, lane);
+    PROF(21);
     ldl_solve(m, w, w.p, lane);
+    PROF(22);
     LANE_LOOP(i, NV) w.qvel[i] += h * w.p[i];
     WSYNC();
     LANE_IF(j, NJ) {
@@ -901,13 +971,15 @@ PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     }
     WSYNC();
     time += h;
+    PROF(23);
 }
 
 // ---------------------------------------------------------------------------------- PD laws
 // /root/reference/agents_env/pds_controllers_agents.py:17-34 (standard), :42-78 (feedback), :83-172 (stable).
 // M and bias are evaluated at (qpos_lag, qvel_lag): the state of the last forward.
+// lag_q / lag_v: the state of the last forward, staged in the workspace by the caller.
 PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, const float* action, const float* kp,
-                       const float* kd, float time, float pd_dt, int lane) {
+                       const float* kd, float time, float pd_dt, const float* lag_q, const float* lag_v, int lane) {
     if (pd_mode == PBRL_PD_TORQUE) {
         LANE_IF(a, NU) w.tau[a] = action[a * action_cols];
         WSYNC();
@@ -930,8 +1002,8 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
         WSYNC();
         return;
     }
-    smooth_position(m, w, w.qpos_lag, lane);
-    smooth_velocity(m, w, w.qvel_lag, lane);
+    smooth_position(m, w, lag_q, lane);
+    smooth_velocity(m, w, lag_v, lane);
     if (pd_mode == PBRL_PD_FEEDBACK) {
         LANE_LOOP(i, NV) w.p[i] = i < vo ? 0.f : -kp[i - vo] * (w.qpos[qo + i - vo] - w.grad[i - vo]) + (-kd[i - vo] * w.qvel[i]);
         WSYNC();
@@ -998,41 +1070,46 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     const bool mimic = a.reward_mode == PBRL_REWARD_MIMIC;
     const int clip = mimic ? B.motion_id[env] : 0;
     const float t_end = mimic ? B.ref_t0[env] + B.time[env] + (float)a.n_frames * m.timestep : 0.f;
-    if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // lands while the substeps run
+    PROF_START();
     load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
     load_row(w.warm, B.warm + (size_t)env * NV, NV, lane);
     load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
-    load_row(w.qpos_lag, B.qpos_lag + (size_t)env * NQ, NQ, lane);
-    load_row(w.qvel_lag, B.qvel_lag + (size_t)env * NV, NV, lane);
+    float* lag_q = w.fsmooth;  // dead until the first substep
+    float* lag_v = w.qacc;
+    if (a.pd_mode >= PBRL_PD_FEEDBACK) {
+        load_row(lag_q, B.qpos_lag + (size_t)env * NQ, NQ, lane);
+        load_row(lag_v, B.qvel_lag + (size_t)env * NV, NV, lane);
+    }
     LANE_IF(z, 1) w.status = 0;
     WSYNC();
     float time = B.time[env];
+    PROF(0);
     pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
-              a.pd_time ? a.pd_time[env] : time, a.pd_dt, lane);
+              a.pd_time ? a.pd_time[env] : time, a.pd_dt, lag_q, lag_v, lane);
     LANE_IF(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
     WSYNC();
     LANE_IF(z, 1) w.phase_lock = a.phase_lock;
     WSYNC();
+    PROF(1);
     for (int f = 0; f < a.n_frames; f++) {
-        if (f == a.n_frames - 1) {
-            LANE_LOOP(i, NQ) w.qpos_lag[i] = w.qpos[i];
-            LANE_LOOP(i, NV) w.qvel_lag[i] = w.qvel[i];
-            WSYNC();
+        if (f == a.n_frames - 1) {  // the state entering the last forward is what the next PD law evaluates M / bias at
+            store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
+            store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
         }
         substep(m, w, time, lane);
     }
+    if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
     store_row(B.qpos + (size_t)env * NQ, w.qpos, NQ, lane);
     store_row(B.qvel + (size_t)env * NV, w.qvel, NV, lane);
     store_row(B.warm + (size_t)env * NV, w.warm, NV, lane);
     store_row(B.ctrl + (size_t)env * NU, w.ctrl, NU, lane);
-    store_row(B.qpos_lag + (size_t)env * NQ, w.qpos_lag, NQ, lane);
-    store_row(B.qvel_lag + (size_t)env * NV, w.qvel_lag, NV, lane);
     LANE_IF(z, 1) {
         B.time[env] = time;
         if (B.status) B.status[env] = w.status | (bad > 0.f ? PBRL_STATUS_NAN : 0);
     }
+    PROF(24);
     if (mimic) {
         if (B.obs) { store_row(B.obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(B.obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
         mimic_epilogue(m, a.mm, a.frames, w, B, env, clip, B.ref_t0[env] + time, acc, lane);
@@ -1040,6 +1117,7 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
         write_obs_reference(a, w, env, 1.0f, lane);
     }
     WSYNC();
+    PROF(25);
 }
 
 // HumanoidDiff.reset (agent_env_template.py:88-112): qpos0, zero velocity
@@ -1081,13 +1159,15 @@ PB_DEVN void env_pd(const DevModel& m, Ws& w, int pd_mode, int action_cols, cons
                     const float* time, float pd_dt, float* tau, float* qM, float* bias, int env, int lane) {
     load_row(w.qpos, qpos + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel, qvel + (size_t)env * NV, NV, lane);
-    load_row(w.qpos_lag, qpos_lag + (size_t)env * NQ, NQ, lane);
-    load_row(w.qvel_lag, qvel_lag + (size_t)env * NV, NV, lane);
+    float* lag_q = w.fsmooth;
+    float* lag_v = w.qacc;
+    load_row(lag_q, qpos_lag + (size_t)env * NQ, NQ, lane);
+    load_row(lag_v, qvel_lag + (size_t)env * NV, NV, lane);
     LANE_IF(z, 1) w.status = 0;
     WSYNC();
     if (qM || bias) {
-        smooth_position(m, w, w.qpos_lag, lane);
-        smooth_velocity(m, w, w.qvel_lag, lane);
+        smooth_position(m, w, lag_q, lane);
+        smooth_velocity(m, w, lag_v, lane);
         if (qM) {
             LANE_LOOP(i, NV * NV) qM[(size_t)env * NV * NV + i] = 0.f;
             WSYNC();
@@ -1100,7 +1180,7 @@ PB_DEVN void env_pd(const DevModel& m, Ws& w, int pd_mode, int action_cols, cons
         if (bias) store_row(bias + (size_t)env * NV, w.bias, NV, lane);
         WSYNC();
     }
-    pd_torque(m, w, pd_mode, action_cols, action + (size_t)env * NU * action_cols, kp, kd, time[env], pd_dt, lane);
+    pd_torque(m, w, pd_mode, action_cols, action + (size_t)env * NU * action_cols, kp, kd, time[env], pd_dt, lag_q, lag_v, lane);
     store_row(tau + (size_t)env * NU, w.tau, NU, lane);
     WSYNC();
 }

@@ -33,9 +33,20 @@ int fail(const std::string& msg) { g_error = msg; return -1; }
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
 
+// dynamic shared memory of a CTA: [DevModel copy][Ws x WARPS_PER_CTA]
+constexpr size_t MODEL_SMEM = (sizeof(DevModel) + 15) / 16 * 16;
 __device__ __forceinline__ Ws& my_ws() {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    return *reinterpret_cast<Ws*>(smem_raw + (size_t)(threadIdx.x >> 5) * sizeof(Ws));
+    return *reinterpret_cast<Ws*>(smem_raw + MODEL_SMEM + (size_t)(threadIdx.x >> 5) * sizeof(Ws));
+}
+// every CTA works from its own shared-memory copy of the model tables
+__device__ __forceinline__ const DevModel& stage_model(const DevModel* __restrict__ gm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned* src = reinterpret_cast<const unsigned*>(gm);
+    unsigned* dst = reinterpret_cast<unsigned*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return *reinterpret_cast<const DevModel*>(smem_raw);
 }
 __device__ __forceinline__ int first_env() { return blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5); }
 __device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; }
@@ -43,13 +54,14 @@ __device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; 
 __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
-    init_ws_tables(*gm, w, lane);
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
     frames_init(w, lane);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     // every warp of the CTA makes the same number of passes so that the per-substep CTA barrier (phase lock) is legal
     for (int base = blockIdx.x * WARPS_PER_CTA; base < a.N; base += env_stride()) {
         const int slot = base + (threadIdx.x >> 5);
-        if (slot < a.N) env_step(*gm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
+        if (slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
         else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 7); k++) __syncthreads();
@@ -68,22 +80,24 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
 __global__ void __launch_bounds__(CTA_THREADS) k_reset(const DevModel* __restrict__ gm, StepArgs a) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
+    const DevModel& sm = stage_model(gm);
     if (a.reward_mode == PBRL_REWARD_MIMIC && a.buf.motion_id) {
-        init_ws_tables(*gm, w, lane);
+        init_ws_tables(sm, w, lane);
         frames_init(w, lane);
-        for (int env = first_env(); env < a.N; env += env_stride()) env_reset_mimic(*gm, a.mm, a.frames, w, a.buf, env, lane);
+        for (int env = first_env(); env < a.N; env += env_stride()) env_reset_mimic(sm, a.mm, a.frames, w, a.buf, env, lane);
         return;
     }
-    for (int env = first_env(); env < a.N; env += env_stride()) env_reset(*gm, w, a, env, lane);
+    for (int env = first_env(); env < a.N; env += env_stride()) env_reset(sm, w, a, env, lane);
 }
 __global__ void __launch_bounds__(CTA_THREADS)
 k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float* qvel, float* obs, float* reward,
          float* done, float* xpos, float* xquat) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
-    init_ws_tables(*gm, w, lane);
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
     for (int env = first_env(); env < N; env += env_stride())
-        env_replay(*gm, w, qpos, qvel, obs, reward, done, xpos, xquat, env, lane);
+        env_replay(sm, w, qpos, qvel, obs, reward, done, xpos, xquat, env, lane);
 }
 __global__ void __launch_bounds__(CTA_THREADS)
 k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
@@ -91,17 +105,19 @@ k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const
      const float* time, float pd_dt, float* tau, float* qM, float* bias) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
-    init_ws_tables(*gm, w, lane);
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
     for (int env = first_env(); env < N; env += env_stride())
-        env_pd(*gm, w, pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, env, lane);
+        env_pd(sm, w, pd_mode, action_cols, action, qpos, qvel, qpos_lag, qvel_lag, kp, kd, time, pd_dt, tau, qM, bias, env, lane);
 }
 __global__ void __launch_bounds__(CTA_THREADS)
 k_debug_forward(const DevModel* __restrict__ gm, int N, const float* qpos, const float* qvel, const float* ctrl,
                 const float* warm, float* out) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
-    init_ws_tables(*gm, w, lane);
-    for (int env = first_env(); env < N; env += env_stride()) env_debug_forward(*gm, w, qpos, qvel, ctrl, warm, out, env, lane);
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
+    for (int env = first_env(); env < N; env += env_stride()) env_debug_forward(sm, w, qpos, qvel, ctrl, warm, out, env, lane);
 }
 
 }  // namespace
@@ -118,7 +134,7 @@ struct PbrlModel {
 };
 
 namespace {
-constexpr size_t SMEM_BYTES = sizeof(Ws) * WARPS_PER_CTA;
+constexpr size_t SMEM_BYTES = MODEL_SMEM + sizeof(Ws) * WARPS_PER_CTA;
 
 template <class K>
 int prepare_kernel(K kernel, PbrlModel* m) {
@@ -264,6 +280,24 @@ int pbrl_debug_forward(const PbrlModel* m, int N, const float* qpos, const float
     if (!qpos || !qvel || !ctrl || !warm || !out) return fail("null argument");
     k_debug_forward<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, warm, out);
     return check_launch("pbrl_debug_forward");
+}
+
+// dev builds (-DPBRL_STAGE_PROF) accumulate per-stage cycle counters; the product build reports "not a profiling build"
+int pbrl_debug_stage_profile(unsigned long long* cycles, unsigned long long* hits, int reset) {
+#if defined(PBRL_STAGE_PROF)
+    CUDA_OK(cudaDeviceSynchronize());
+    if (cycles) CUDA_OK(cudaMemcpyFromSymbol(cycles, g_stage_cycles, sizeof(unsigned long long) * 64));
+    if (hits) CUDA_OK(cudaMemcpyFromSymbol(hits, g_stage_hits, sizeof(unsigned long long) * 64));
+    if (reset) {
+        unsigned long long z[64] = {0};
+        CUDA_OK(cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)));
+        CUDA_OK(cudaMemcpyToSymbol(g_stage_hits, z, sizeof(z)));
+    }
+    return 0;
+#else
+    (void)cycles; (void)hits; (void)reset;
+    return fail("not a profiling build (compile with -DPBRL_STAGE_PROF)");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ host-buffer layer

@@ -24,42 +24,46 @@ constexpr int NLIM = 28;  // limited hinges
 constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
 constexpr int NCP = 32;   // padded
 constexpr int NFAC = 1432;  // rank-1 update operations of one tree-sparse L^T D L factorisation
+constexpr int NFACOP = 96;  // ops of the deepest dof (depth 13: 91), padded to a lane multiple
 constexpr int MAXLEVEL = 8;
 constexpr int MAXDEPTH = 16;
 
 enum { DOF_FREE_T0 = 0, DOF_FREE_R0 = 3, DOF_HINGE = 6 };
 enum { CON_SPHERE = 0, CON_CAPSULE = 1, CON_BOX = 3 };
 
+typedef unsigned char u8;
+typedef signed char i8;
+typedef unsigned short u16;
+
+// Compact (~6.5 KB): every CTA keeps a copy in shared memory, so the lane-indexed table lookups of the stages cost a
+// shared-memory access instead of an L1-miss / L2 round trip (the L1 is only ~28 KB next to 227 KB of workspaces).
 struct DevModel {
     float timestep, gx, gy, gz;
     float sol_k, sol_b, sol_dmin, sol_dmax, sol_width, sol_mid, sol_power, meaninertia;
     float total_mass, plane_z;
     int nlevel;
     int ndepth;
-    int level_start[MAXLEVEL + 1];
-    int level_body[NB];
-    int depth_start[MAXDEPTH + 1];
-    int depth_dof[NV];
-    int body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
-    int body_conadr[NB], body_connum[NB];
-    int body_nchild[NB], body_child[NB][4];
     float body_pos[NB][3], body_mass[NB], body_ipos[NB][3], body_inertia[NB][6];
-    int jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ];
     float jnt_axis[NJ][3], jnt_lo[NJ], jnt_hi[NJ], jnt_margin[NJ];
-    int dof_bodyid[NV], dof_jntid[NV], dof_parentid[NV], dof_depth[NV], dof_Madr[NV], dof_kind[NV];
     float dof_armature[NV], dof_damping[NV], dof_invweight0[NV], dof_gear[NV], dof_ctrl_lo[NV], dof_ctrl_hi[NV];
-    int dof_act[NV];
-    int lim_jnt[NLIM];
-    int M_row[NM], M_col[NM];
-    // factorisation schedule: step k (dof k, leaf to root) owns fac_op[fac_start[k] .. +fac_cnt[k]);
-    // an op holds BYTE offsets into LD: x = target | srcA << 16, y = srcB:  LD[target] -= LD[srcA] / LD[adr(k)] * LD[srcB]
-    int fac_start[NV], fac_cnt[NV];
-    unsigned fac_op[NFAC][2];
-    // contact slots, sorted by body
-    int con_body[NCP], con_kind[NCP], con_sub[NCP], con_geom[NCP];
     float con_gpos[NCP][3], con_gquat[NCP][4], con_size[NCP][3], con_margin[NCP], con_mu[NCP], con_invweight[NCP];
     float qpos0[NQ + 1];
+    // sparse inertia layout: entry e of row i holds M[i, anc_a(i)] at e = dof_Madr[i] + a; anc_adr[e] = dof_Madr[M_col[e]]
+    u16 dof_Madr[NV], anc_adr[NM];
+    u8 M_row[NM], M_col[NM];
+    // elimination ops of the tree-sparse L^T D L, shared by all dofs: op pi of a dof of depth d (pi < d(d+1)/2) updates
+    // row anc_a at offset c - a with (a, c) = (fac_a[pi], fac_c[pi]), 1 <= a <= c <= d
+    u8 fac_a[NFACOP], fac_c[NFACOP];
+    u8 level_start[MAXLEVEL + 1], level_body[NB], depth_start[MAXDEPTH + 1], depth_dof[NV];
+    u8 body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
+    u8 body_conadr[NB], body_connum[NB], body_nchild[NB], body_child[NB][4];
+    u8 jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ];
+    u8 dof_bodyid[NV], dof_jntid[NV], dof_depth[NV], dof_kind[NV];
+    i8 dof_parentid[NV], dof_act[NV];
+    u8 lim_jnt[NLIM];
+    u8 con_body[NCP], con_kind[NCP], con_sub[NCP], con_geom[NCP];
 };
+static_assert(sizeof(DevModel) % 4 == 0, "DevModel is copied to shared memory word by word");
 
 // ---- mimic configuration on the device --------------------------------------------------------
 struct DevMimic {
@@ -222,24 +226,18 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             m.dof_kind[d.jnt_dofadr[j] + k] = d.jnt_type[j] == 0 ? k : DOF_HINGE;
         }
     }
-    {   // elimination schedule (MuJoCo mj_factorI order): for dof k and its a-th ancestor i, row i loses
-        // (L[k,i] / D[k]) * row k from column i on
+    {   // elimination schedule (MuJoCo mj_factorI order): eliminating dof k, its a-th ancestor's row loses
+        // (L[k, anc_a] / D[k]) * L[k, anc_c] at offset c - a for every c >= a; (a, c) enumerated c-major so that a dof of
+        // depth d uses the first d(d+1)/2 ops of one table
+        if (maxdepth * (maxdepth + 1) / 2 > NFACOP) return "dof chains too deep for the elimination table";
         int n = 0;
-        for (int k = 0; k < NV; k++) {
-            int dk = m.dof_depth[k], adr = m.dof_Madr[k];
-            m.fac_start[k] = n;
-            for (int a = 1; a <= dk; a++) {
-                int ia = m.M_col[adr + a];
-                for (int t = 0; t + a <= dk; t++) {
-                    if (n >= NFAC) return "factorisation schedule overflow";
-                    m.fac_op[n][0] = (unsigned)(4 * (m.dof_Madr[ia] + t)) | ((unsigned)(4 * (adr + a)) << 16);
-                    m.fac_op[n][1] = (unsigned)(4 * (adr + a + t));
-                    n++;
-                }
-            }
-            m.fac_cnt[k] = n - m.fac_start[k];
-        }
-        if (n != NFAC) return "factorisation schedule size differs from 1432";
+        for (int c = 1; c <= maxdepth; c++)
+            for (int a = 1; a <= c; a++) { m.fac_a[n] = (u8)a; m.fac_c[n] = (u8)c; n++; }
+        for (; n < NFACOP; n++) { m.fac_a[n] = 1; m.fac_c[n] = 1; }
+        int total = 0;
+        for (int k = 0; k < NV; k++) total += m.dof_depth[k] * (m.dof_depth[k] + 1) / 2;
+        if (total != NFAC) return "factorisation schedule size differs from 1432";
+        for (int e = 0; e < NM; e++) m.anc_adr[e] = m.dof_Madr[m.M_col[e]];
     }
     for (int a = 0; a < NU; a++) {
         int i = d.act_dofadr[a];
