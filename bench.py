@@ -242,7 +242,8 @@ def main():
               status=torch.zeros(n_env, device=dev, dtype=torch.int32), stats=z(8),
               motion_id=torch.from_numpy(motion_id).to(dev), ref_t0=torch.from_numpy(ref_t0).to(dev),
               # processing order: envs of the same clip share a CTA (similar contact work -> balanced phase barriers)
-              env_order=torch.from_numpy(np.argsort(motion_id, kind="stable").astype(np.int32)).to(dev))
+              env_order=torch.from_numpy(np.argsort(motion_id, kind="stable").astype(np.int32)).to(dev),
+              cost=torch.zeros(n_env, device=dev, dtype=torch.int32))
     bufs = L.make_buffers(**st)
     L.check(L.lib().pbrl_reset(M.handle, n_env, 1, ctypes.byref(bufs), L.current_stream_ptr(dev)))  # reference-state init
     torch.cuda.synchronize()
@@ -258,6 +259,8 @@ def main():
         st["stats"].zero_()
         L.check(lib.pbrl_step(M.handle, n_env, N_FRAMES, pd_mode, 1, L._ptr(a), L._ptr(kp), L._ptr(kd), ctypes.c_float(0.002),
                               None, ctypes.c_uint(0x0FFFFFFF), 1, ctypes.byref(bufs), stream))
+        if os.environ.get("PBRL_BENCH_SORT"):
+            st["env_order"].copy_(torch.argsort(st["cost"], descending=True, stable=True).to(torch.int32))
         if world > 1:  # per-step reward/termination statistics all-reduce (32 B, NCCL over NVLink)
             dist.all_reduce(st["stats"])
 
@@ -291,7 +294,7 @@ def main():
         names = {0: "load", 1: "pd_torque", 2: "fk", 3: "com", 4: "crb", 5: "collide", 6: "comvel", 7: "bias", 8: "rows",
                  9: "fsmooth", 10: "free:factor", 11: "free:solve", 12: "newton:init", 13: "newton:grad(JTf)", 14: "newton:hessian",
                  15: "newton:factor", 16: "newton:solve", 17: "newton:Mp,Jp", 18: "newton:linesearch", 19: "newton:update",
-                 20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 26: "cta barrier wait"}
+                 20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 27: "barrier: substep start", 28: "barrier: after position", 29: "barrier: after rows", 30: "barrier: after solver"}
         tot = sum(cyc)
         print(f"stage profile: {tot / (n_env * steps * N_FRAMES):.0f} cycles per env-substep (per warp, incl. stalls)", file=sys.stderr)
         for i in range(64):

@@ -34,4 +34,4 @@ class PbrlBuffers(ctypes.Structure):
     """Mirror of `PbrlBuffers` in include/pbrl.h (device pointers)."""
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics",
-                 "status", "motion_id", "ref_t0", "stats", "env_order")]
+                 "status", "motion_id", "ref_t0", "stats", "env_order", "cost")]

@@ -21,6 +21,7 @@
 // CUDA build and has no CPU path.
 #pragma once
 #include <math.h>
+#include <stddef.h>
 
 #include "pbrl_model.h"
 #include "pbrl_topo_gen.h"
@@ -29,7 +30,6 @@
 #define PB_DEV __device__ __forceinline__
 #define PB_DEVN __device__ __noinline__
 #define PB_MEMBER static __device__ __forceinline__
-#define PB_CX __host__ __device__ constexpr
 #define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
 #define LANE_IF(i, n) for (int i = lane, once_ = 1; once_ && i < (n); once_ = 0)  /* n <= 32: at most one pass */
 #define WSYNC() __syncwarp()
@@ -39,7 +39,6 @@
 #define PB_DEV static inline
 #define PB_DEVN static
 #define PB_MEMBER static inline
-#define PB_CX constexpr
 #define LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
 #define LANE_IF(i, n) for (int i = 0; i < (n); i++)
 #define WSYNC() ((void)0)
@@ -415,77 +414,173 @@ PB_DEV void init_ws_tables(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
-// The dof tree is a compile-time constant (pbrl_topo_gen.h): both routines are unrolled over the dofs so that row
-// addresses, depths and op counts are immediates; only the per-lane op / column tables are read from the model.
-namespace topo {
-PB_CX int depth(int k) { int d = 0; while (PARENT[k] >= 0) { k = PARENT[k]; d++; } return d; }
-PB_CX int madr(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) + 1; return a; }
-PB_CX int fac_total() { int a = 0; for (int i = 0; i < NDOF; i++) a += depth(i) * (depth(i) + 1) / 2; return a; }
-PB_CX int max_depth() { int d = 0; for (int k = 0; k < NDOF; k++) d = depth(k) > d ? depth(k) : d; return d; }
-PB_CX int depth_count(int lv) { int n = 0; for (int k = 0; k < NDOF; k++) n += depth(k) == lv; return n; }
-PB_CX int depth_first(int lv) { int n = 0; for (int l = 0; l < lv; l++) n += depth_count(l); return n; }
-static_assert(NDOF == NV && madr(NDOF - 1) + depth(NDOF - 1) + 1 == NM && fac_total() == NFAC && max_depth() * (max_depth() + 1) / 2 <= NFACOP,
-              "pbrl_topo_gen.h does not match the kernel dimensions");
-}  // namespace topo
-
-template <int K>
-struct FactorStep {  // eliminate dof K: rank-1 update of its ancestors' rows (MuJoCo mj_factorI order, leaf to root)
-    PB_MEMBER void run(const DevModel& m, Ws& w, int lane) {
-        constexpr int d = topo::depth(K), n = d * (d + 1) / 2, adr = topo::madr(K);
-        if constexpr (n > 0) {
-            const float inv = fast_rcp(w.LD[adr]);
-            LANE_LOOP(pi, n) {
-                const int a = m.fac_a[pi], c = m.fac_c[pi];
-                w.LD[m.anc_adr[adr + a] + (c - a)] -= (w.LD[adr + a] * inv) * w.LD[adr + c];
-            }
-            WSYNC();
+// x <- (L^T D L)^-1 x for the tree-sparse matrix in w.LD (row k: k and its ancestors, MuJoCo mj_factorI order).
+// LD is overwritten with the unscaled factor rows LD[adr(k)+a] = L[k, anc_a(k)] * D[k]; w.Dinv[k] = 1/D[k].
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+// Register-resident, shuffle-driven: no shared-memory round trip or warp barrier inside the elimination.
+//   layout A (factor + forward substitution): lane t <-> depth t.  Row k lives in one register R[k]: lane t holds the
+//     entry of k's ancestor at depth t, lane depth(k) the diagonal.  Eliminating k needs, per ancestor row, ONE broadcast
+//     (L[k, anc]) -- the other factor of every rank-1 term is already in the right lane.  The right-hand side rides along
+//     as X[slot] (slot = chain of the dof tree, lane = depth), so the forward substitution costs no extra latency.
+//   layout B (back substitution): lane <-> dof.  Row k sits in lane k's registers, x_k is pushed level by level to all
+//     descendants with one shuffle per level.
+// Dofs are eliminated deepest first, so the five leaf chains of the humanoid interleave and hide each other's latency.
+namespace ldl {
+constexpr unsigned FULL = 0xffffffffu;
+template <int K, int T>
+struct AncRows {  // rows of K's ancestors at depths T-1 .. 0 lose L[K, anc] * row K
+    PB_MEMBER void run(float (&R)[NV], float inv, const float rk) {
+        if constexpr (T > 0) {
+            constexpr int J = topo::anc_at(K, T - 1);
+            const float c = __shfl_sync(FULL, rk, T - 1) * inv;
+            R[J] = fmaf(-c, rk, R[J]);
+            AncRows<K, T - 1>::run(R, inv, rk);
         }
-        if constexpr (K > 1) FactorStep<K - 1>::run(m, w, lane);
     }
 };
-PB_DEVN void ldl_factor(const DevModel& m, Ws& w, int lane) {
-    FactorStep<NV - 1>::run(m, w, lane);
-    LANE_LOOP(i, NV) {
+template <int K, int S>
+struct AncRhs {  // X of K's ancestors (found in slots S-1 .. 0) loses L[K, anc] * D[K] * s
+    PB_MEMBER void run(float (&X)[NSLOT], const float rs, int lane) {
+        if constexpr (S > 0) {
+            constexpr unsigned MK = topo::anc_mask(K, S - 1);
+            if constexpr (MK != 0u) { if ((MK >> lane) & 1u) X[S - 1] -= rs; }
+            AncRhs<K, S - 1>::run(X, rs, lane);
+        }
+    }
+};
+template <int I>
+struct Eliminate {
+    PB_MEMBER void run(float (&R)[NV], float (&X)[NSLOT], float (&DI)[NSLOT], bool& bad, int lane) {
+        constexpr int K = topo::elim_order(I), d = topo::depth(K), S = topo::slot(K);
+        const float rk = R[K];
+        const float diag = __shfl_sync(FULL, rk, d);
+        bad |= !(diag > 0.f);
+        const float inv = fast_rcp(diag);
+        if (lane == d) DI[S] = inv;
+        if constexpr (d > 0) {
+            const float s = __shfl_sync(FULL, X[S], d) * inv;
+            AncRhs<K, NSLOT>::run(X, rk * s, lane);
+            AncRows<K, d>::run(R, inv, rk);
+        }
+        if constexpr (I + 1 < NV) Eliminate<I + 1>::run(R, X, DI, bad, lane);
+    }
+};
+template <int K>
+struct RowIO {
+    PB_MEMBER void load(float (&R)[NV], const float* ld_lane, int lane) {  // ld_lane = LD - lane
+        // unconditional: lanes beyond the diagonal read whatever precedes the row (still inside the workspace) and
+        // carry garbage that is never broadcast, never enters a valid lane and is never stored
+        R[K] = ld_lane[topo::madr(K) + topo::depth(K)];
+        if constexpr (K + 1 < NV) RowIO<K + 1>::load(R, ld_lane, lane);
+    }
+    PB_MEMBER void store(const float (&R)[NV], float* ld_lane, int lane) {
+        constexpr int d = topo::depth(K);
+        if (lane <= d) ld_lane[topo::madr(K) + d] = R[K];
+        if constexpr (K + 1 < NV) RowIO<K + 1>::store(R, ld_lane, lane);
+    }
+};
+template <int S>
+struct SlotIO {
+    PB_MEMBER void load(float (&X)[NSLOT], float (&DI)[NSLOT], const float* x, int lane) {
+        const int t = lane - topo::slot_fd(S);
+        X[S] = (t >= 0 && t < topo::slot_len(S)) ? x[topo::slot_first(S) + t] : 0.f;
+        DI[S] = 0.f;
+        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::load(X, DI, x, lane);
+    }
+    PB_MEMBER void store(const float (&X)[NSLOT], const float (&DI)[NSLOT], float* x, float* dinv, int lane) {
+        const int t = lane - topo::slot_fd(S);
+        if (t >= 0 && t < topo::slot_len(S)) { x[topo::slot_first(S) + t] = X[S] * DI[S]; dinv[topo::slot_first(S) + t] = DI[S]; }
+        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::store(X, DI, x, dinv, lane);
+    }
+};
+template <int T>
+struct BackLevel {  // every dof deeper than T receives L[k, anc_T(k)] * x[anc_T(k)]
+    PB_MEMBER void run(const float (&cl)[MAXANC], const float (&ch)[MAXANC], const unsigned (&sl)[MAXANC / 4],
+                       const unsigned (&sh)[MAXANC / 4], float& xl, float& xh) {
+        if constexpr (T < topo::max_depth()) {
+            const int a_lo = (sl[T / 4] >> (8 * (T % 4))) & 0xffu, a_hi = (sh[T / 4] >> (8 * (T % 4))) & 0xffu;
+            float v_lo = __shfl_sync(FULL, xl, a_lo & 31), v_hi = __shfl_sync(FULL, xl, a_hi & 31);
+            if constexpr (topo::hi_source_at(T)) {
+                const float w_lo = __shfl_sync(FULL, xh, a_lo & 31), w_hi = __shfl_sync(FULL, xh, a_hi & 31);
+                v_lo = a_lo >= 32 ? w_lo : v_lo;
+                v_hi = a_hi >= 32 ? w_hi : v_hi;
+            }
+            xl = fmaf(-cl[T], v_lo, xl);  // cl[T] = 0 when the dof is not deeper than T
+            xh = fmaf(-ch[T], v_hi, xh);
+            BackLevel<T + 1>::run(cl, ch, sl, sh, xl, xh);
+        }
+    }
+};
+}  // namespace ldl
+
+PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
+    static_assert(offsetof(Ws, LD) >= 32 * sizeof(float), "row loads reach up to 31 floats below LD");
+    float R[NV], X[NSLOT], DI[NSLOT];
+    bool bad = false;
+    ldl::RowIO<0>::load(R, w.LD - lane, lane);
+    ldl::SlotIO<0>::load(X, DI, x, lane);
+    ldl::Eliminate<0>::run(R, X, DI, bad, lane);
+    ldl::RowIO<0>::store(R, w.LD - lane, lane);
+    ldl::SlotIO<0>::store(X, DI, x, w.Dinv, lane);  // x <- D^-1 L^-T x
+    if (bad && lane == 0) w.status |= PBRL_STATUS_PIVOT;
+    __syncwarp();
+    // back substitution, lane <-> dof (lanes 0 .. NV-33 also own dof lane + 32)
+    const int klo = lane, khi = lane + 32 < NV ? lane + 32 : lane;
+    const bool has_hi = lane + 32 < NV;
+    const int dlo = m.dof_depth[klo], dhi = has_hi ? m.dof_depth[khi] : 0;
+    const float* rlo = w.LD + m.dof_Madr[klo] + dlo;  // entry of the ancestor at depth t: rlo[-t]
+    const float* rhi = w.LD + m.dof_Madr[khi] + dhi;
+    const float ilo = w.Dinv[klo], ihi = w.Dinv[khi];
+    float cl[MAXANC], ch[MAXANC];
+#pragma unroll
+    for (int t = 0; t < MAXANC; t++) {
+        cl[t] = t < dlo ? rlo[-t] * ilo : 0.f;
+        ch[t] = t < dhi ? rhi[-t] * ihi : 0.f;
+    }
+    unsigned sl[MAXANC / 4], sh[MAXANC / 4];
+#pragma unroll
+    for (int q = 0; q < MAXANC / 4; q++) {
+        sl[q] = reinterpret_cast<const unsigned*>(m.anc_dof[klo])[q];
+        sh[q] = reinterpret_cast<const unsigned*>(m.anc_dof[khi])[q];
+    }
+    float xl = x[klo], xh = has_hi ? x[khi] : 0.f;
+    __syncwarp();
+    ldl::BackLevel<0>::run(cl, ch, sl, sh, xl, xh);
+    x[klo] = xl;
+    if (has_hi) x[khi] = xh;
+    __syncwarp();
+}
+#else
+// host emulation (tests only): the same elimination written as plain loops over the model tables
+PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
+    (void)lane;
+    for (int k = NV - 1; k >= 1; k--) {
+        const int d = m.dof_depth[k], adr = m.dof_Madr[k];
+        const float inv = 1.0f / w.LD[adr];
+        for (int a = 1; a <= d; a++) {
+            const int ia = m.M_col[adr + a];
+            for (int t = 0; t + a <= d; t++) w.LD[m.dof_Madr[ia] + t] -= (w.LD[adr + a] * inv) * w.LD[adr + a + t];
+        }
+    }
+    for (int i = 0; i < NV; i++) {
         const float piv = w.LD[m.dof_Madr[i]];
         if (!(piv > 0.f)) w.status |= PBRL_STATUS_PIVOT;
         w.Dinv[i] = 1.0f / piv;
     }
-    WSYNC();
-}
-
-template <int K>
-struct ForwardStep {  // x <- L^-T x : dof K scatters to its ancestors
-    PB_MEMBER void run(const DevModel& m, Ws& w, float* x, int lane) {
-        constexpr int d = topo::depth(K), adr = topo::madr(K);
-        if constexpr (d > 0) {
-            const float s = x[K] * w.Dinv[K];
-            LANE_IF(a, d) x[m.M_col[adr + 1 + a]] -= w.LD[adr + 1 + a] * s;
-            WSYNC();
-        }
-        if constexpr (K > 1) ForwardStep<K - 1>::run(m, w, x, lane);
+    for (int k = NV - 1; k >= 1; k--) {
+        const int d = m.dof_depth[k], adr = m.dof_Madr[k];
+        const float s = x[k] * w.Dinv[k];
+        for (int a = 1; a <= d; a++) x[m.M_col[adr + a]] -= w.LD[adr + a] * s;
     }
-};
-template <int LV>
-struct BackwardLevel {  // x <- L^-1 x : dofs of equal depth are independent
-    PB_MEMBER void run(const DevModel& m, Ws& w, float* x, int lane) {
-        constexpr int n = topo::depth_count(LV), s0 = topo::depth_first(LV);
-        LANE_IF(q, n) {
-            const int k = m.depth_dof[s0 + q], adr = m.dof_Madr[k];
-            float s = 0.f;
-            for (int a = 1; a <= LV; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
-            x[k] -= s * w.Dinv[k];
-        }
-        WSYNC();
-        if constexpr (LV < topo::max_depth()) BackwardLevel<LV + 1>::run(m, w, x, lane);
+    for (int i = 0; i < NV; i++) x[i] *= w.Dinv[i];
+    for (int k = 1; k < NV; k++) {
+        const int d = m.dof_depth[k], adr = m.dof_Madr[k];
+        float s = 0.f;
+        for (int a = 1; a <= d; a++) s += w.LD[adr + a] * x[m.M_col[adr + a]];
+        x[k] -= s * w.Dinv[k];
     }
-};
-// x <- (L^T D L)^-1 x
-PB_DEVN void ldl_solve(const DevModel& m, Ws& w, float* x, int lane) {
-    ForwardStep<NV - 1>::run(m, w, x, lane);
-    LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
-    WSYNC();
-    BackwardLevel<1>::run(m, w, x, lane);
 }
+#endif
 
 // ---------------------------------------------------------------------------------- tree products
 // V[b] = sum over ancestor dofs of cdof_i x_i  (spatial velocity of body b for generalised velocity x)
@@ -777,9 +872,8 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     if (!constrained) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
         LANE_LOOP(e, NM) w.LD[e] = w.M[e];
         WSYNC();
-        ldl_factor(m, w, lane);
+        ldl_factor_solve(m, w, w.asmooth, lane);
         PROF(10);
-        ldl_solve(m, w, w.asmooth, lane);
         LANE_LOOP(i, NV) { w.qacc[i] = w.asmooth[i]; w.fcon[i] = 0.f; }
         WSYNC();
         PROF(11);
@@ -817,12 +911,10 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         PROF(13);
         assemble_hessian(m, w, lane);
         PROF(14);
-        ldl_factor(m, w, lane);
-        PROF(15);
         LANE_LOOP(i, NV) w.p[i] = -w.grad[i];
         WSYNC();
-        ldl_solve(m, w, w.p, lane);
-        PROF(16);
+        ldl_factor_solve(m, w, w.p, lane);
+        PROF(15);
         tree_vel(m, w, w.p, lane);
         tree_Mx_from_V(m, w, w.p, w.Mp, lane);
         rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
@@ -908,7 +1000,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     const int lock = w.phase_lock;
     if (lock & 1) CTA_SYNC();
-    PROF(26);
+    PROF(27);
     stage_fk(m, w, w.qpos, lane);
     PROF(2);
     stage_com(m, w, lane);
@@ -916,7 +1008,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     stage_crb(m, w, lane);
     PROF(4);
     if (lock & 2) CTA_SYNC();
-    PROF(26);
+    PROF(28);
     stage_collide(m, w, lane);
     PROF(5);
     stage_comvel(m, w, w.qvel, lane);
@@ -926,7 +1018,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     stage_rows(m, w, w.qpos, w.qvel, lane);
     PROF(8);
     if (lock & 4) CTA_SYNC();
-    PROF(26);
+    PROF(29);
     LANE_LOOP(i, NV) {
         float f = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
         int a = m.dof_act[i];
@@ -942,15 +1034,13 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
 PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     forward(m, w, lane);
     if (w.phase_lock & 8) CTA_SYNC();
-    PROF(26);
+    PROF(30);
     float h = m.timestep;
     LANE_LOOP(i, NV) { w.warm[i] = w.qacc[i]; w.p[i] = w.fsmooth[i] + w.fcon[i]; }
     LANE_LOOP(e, NM) w.LD[e] = w.M[e] + ((m.M_row[e] == m.M_col[e]) ? h * m.dof_damping[m.M_row[e]] : 0.f);
     WSYNC();
-    ldl_factor(m, w, lane);
+    ldl_factor_solve(m, w, w.p, lane);
     PROF(21);
-    ldl_solve(m, w, w.p, lane);
-    PROF(22);
     LANE_LOOP(i, NV) w.qvel[i] += h * w.p[i];
     WSYNC();
     LANE_IF(j, NJ) {
@@ -1025,8 +1115,7 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
         w.LD[e] = w.M[e] + ((r == m.M_col[e] && r >= vo) ? kd[r - vo] * pd_dt : 0.f);
     }
     WSYNC();
-    ldl_factor(m, w, lane);
-    ldl_solve(m, w, w.p, lane);
+    ldl_factor_solve(m, w, w.p, lane);
     LANE_IF(a, NU) w.tau[a] = -kp[a] * w.Mp[vo + a] - kd[a] * (w.qvel[vo + a] + w.p[vo + a] * pd_dt);
     WSYNC();
 }
@@ -1092,12 +1181,14 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     LANE_IF(z, 1) w.phase_lock = a.phase_lock;
     WSYNC();
     PROF(1);
+    int cost = 0;
     for (int f = 0; f < a.n_frames; f++) {
         if (f == a.n_frames - 1) {  // the state entering the last forward is what the next PD law evaluates M / bias at
             store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
         }
         substep(m, w, time, lane);
+        cost += w.niter;
     }
     if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
@@ -1108,6 +1199,7 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     LANE_IF(z, 1) {
         B.time[env] = time;
         if (B.status) B.status[env] = w.status | (bad > 0.f ? PBRL_STATUS_NAN : 0);
+        if (B.cost) B.cost[env] = cost;
     }
     PROF(24);
     if (mimic) {
@@ -1222,8 +1314,7 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
     LANE_LOOP(i, NV) w.asmooth[i] = w.fsmooth[i];
     LANE_LOOP(e, NM) w.LD[e] = w.M[e];
     WSYNC();
-    ldl_factor(m, w, lane);
-    ldl_solve(m, w, w.asmooth, lane);
+    ldl_factor_solve(m, w, w.asmooth, lane);
     LANE_LOOP(i, NV) o[PBRL_DBG_QACC_SMOOTH + i] = w.asmooth[i];
     float nact = wsum(lane, NC, [&](int c) { return w.con_on[c] ? 1.f : 0.f; });
     LANE_IF(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }

@@ -24,9 +24,64 @@ constexpr int NLIM = 28;  // limited hinges
 constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
 constexpr int NCP = 32;   // padded
 constexpr int NFAC = 1432;  // rank-1 update operations of one tree-sparse L^T D L factorisation
-constexpr int NFACOP = 96;  // ops of the deepest dof (depth 13: 91), padded to a lane multiple
+constexpr int MAXANC = 12;  // deepest dof chain (ancestors of one dof); checked against the compiled tree below
 constexpr int MAXLEVEL = 8;
 constexpr int MAXDEPTH = 16;
+
+// ---- compile-time view of the dof tree (pbrl_topo_gen.h) ------------------------------------------------------
+// The factorisation / solve code is unrolled over the dofs, so depths, row addresses, ancestor lists and the chain
+// decomposition below are immediates.  A "slot" is a maximal chain of the dof tree (a dof continues its parent's
+// chain iff it is the parent's first child): dofs of one slot have distinct, consecutive depths and consecutive
+// indices, and two dofs of equal depth never share a slot.
+#if defined(__CUDACC__)
+#define PB_CX __host__ __device__ constexpr
+#else
+#define PB_CX constexpr
+#endif
+namespace topo {
+PB_CX int depth(int k) { int d = 0; while (PARENT[k] >= 0) { k = PARENT[k]; d++; } return d; }
+PB_CX int madr(int k) { int a = 0; for (int i = 0; i < k; i++) a += depth(i) + 1; return a; }
+PB_CX int fac_total() { int a = 0; for (int i = 0; i < NDOF; i++) a += depth(i) * (depth(i) + 1) / 2; return a; }
+PB_CX int max_depth() { int d = 0; for (int k = 0; k < NDOF; k++) d = depth(k) > d ? depth(k) : d; return d; }
+PB_CX int depth_count(int lv) { int n = 0; for (int k = 0; k < NDOF; k++) n += depth(k) == lv; return n; }
+PB_CX int depth_first(int lv) { int n = 0; for (int l = 0; l < lv; l++) n += depth_count(l); return n; }
+PB_CX int anc_at(int k, int t) { while (depth(k) > t) k = PARENT[k]; return k; }  // ancestor of k at depth t <= depth(k)
+PB_CX bool first_child(int k) { for (int j = PARENT[k] + 1; j < k; j++) if (PARENT[j] == PARENT[k]) return false; return true; }
+PB_CX int slot(int k) {
+    if (PARENT[k] < 0) return 0;
+    if (first_child(k)) return slot(PARENT[k]);
+    int n = 0;
+    for (int j = 1; j <= k; j++) if (PARENT[j] >= 0 && !first_child(j)) n++;
+    return n;
+}
+PB_CX int nslot() { int n = 0; for (int k = 0; k < NDOF; k++) n = slot(k) + 1 > n ? slot(k) + 1 : n; return n; }
+PB_CX int slot_first(int s) { for (int k = 0; k < NDOF; k++) if (slot(k) == s) return k; return -1; }
+PB_CX int slot_len(int s) { int n = 0; for (int k = 0; k < NDOF; k++) n += slot(k) == s; return n; }
+PB_CX int slot_fd(int s) { return depth(slot_first(s)); }
+PB_CX bool slots_are_chains() {
+    int roots = 0;
+    for (int k = 0; k < NDOF; k++) {
+        roots += PARENT[k] < 0;
+        if (k != slot_first(slot(k)) + depth(k) - slot_fd(slot(k))) return false;
+    }
+    return roots == 1;
+}
+// lanes (= depths) at which the ancestors of k live in slot s
+PB_CX unsigned anc_mask(int k, int s) { unsigned m = 0; for (int t = 0; t < depth(k); t++) if (slot(anc_at(k, t)) == s) m |= 1u << t; return m; }
+// i-th dof in elimination order: deepest first (descendants before ancestors; independent chains interleave)
+PB_CX int elim_order(int i) {
+    int n = 0;
+    for (int d = max_depth(); d >= 0; d--)
+        for (int k = NDOF - 1; k >= 0; k--)
+            if (depth(k) == d) { if (n == i) return k; n++; }
+    return -1;
+}
+PB_CX bool hi_source_at(int t) { for (int k = 0; k < NDOF; k++) if (depth(k) > t && anc_at(k, t) >= 32) return true; return false; }
+static_assert(NDOF == PBRL_NV && madr(NDOF - 1) + depth(NDOF - 1) + 1 == NM && fac_total() == NFAC, "pbrl_topo_gen.h does not match the kernel dimensions");
+static_assert(max_depth() <= MAXANC && max_depth() < 32 && NDOF <= 64, "dof chains too deep for the lane-per-depth factorisation");
+static_assert(slots_are_chains(), "the chain decomposition expects depth-first dof numbering with one root");
+}  // namespace topo
+constexpr int NSLOT = topo::nslot();
 
 enum { DOF_FREE_T0 = 0, DOF_FREE_R0 = 3, DOF_HINGE = 6 };
 enum { CON_SPHERE = 0, CON_CAPSULE = 1, CON_BOX = 3 };
@@ -48,12 +103,10 @@ struct DevModel {
     float dof_armature[NV], dof_damping[NV], dof_invweight0[NV], dof_gear[NV], dof_ctrl_lo[NV], dof_ctrl_hi[NV];
     float con_gpos[NCP][3], con_gquat[NCP][4], con_size[NCP][3], con_margin[NCP], con_mu[NCP], con_invweight[NCP];
     float qpos0[NQ + 1];
-    // sparse inertia layout: entry e of row i holds M[i, anc_a(i)] at e = dof_Madr[i] + a; anc_adr[e] = dof_Madr[M_col[e]]
-    u16 dof_Madr[NV], anc_adr[NM];
+    // sparse inertia layout: entry e of row i holds M[i, anc_a(i)] at e = dof_Madr[i] + a (a = 0: diagonal)
+    u16 dof_Madr[NV];
     u8 M_row[NM], M_col[NM];
-    // elimination ops of the tree-sparse L^T D L, shared by all dofs: op pi of a dof of depth d (pi < d(d+1)/2) updates
-    // row anc_a at offset c - a with (a, c) = (fac_a[pi], fac_c[pi]), 1 <= a <= c <= d
-    u8 fac_a[NFACOP], fac_c[NFACOP];
+    alignas(4) u8 anc_dof[NV][MAXANC];  // anc_dof[k][t]: ancestor of dof k at depth t < depth(k) (back substitution sources)
     u8 level_start[MAXLEVEL + 1], level_body[NB], depth_start[MAXDEPTH + 1], depth_dof[NV];
     u8 body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
     u8 body_conadr[NB], body_connum[NB], body_nchild[NB], body_child[NB][4];
@@ -226,18 +279,10 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             m.dof_kind[d.jnt_dofadr[j] + k] = d.jnt_type[j] == 0 ? k : DOF_HINGE;
         }
     }
-    {   // elimination schedule (MuJoCo mj_factorI order): eliminating dof k, its a-th ancestor's row loses
-        // (L[k, anc_a] / D[k]) * L[k, anc_c] at offset c - a for every c >= a; (a, c) enumerated c-major so that a dof of
-        // depth d uses the first d(d+1)/2 ops of one table
-        if (maxdepth * (maxdepth + 1) / 2 > NFACOP) return "dof chains too deep for the elimination table";
-        int n = 0;
-        for (int c = 1; c <= maxdepth; c++)
-            for (int a = 1; a <= c; a++) { m.fac_a[n] = (u8)a; m.fac_c[n] = (u8)c; n++; }
-        for (; n < NFACOP; n++) { m.fac_a[n] = 1; m.fac_c[n] = 1; }
-        int total = 0;
-        for (int k = 0; k < NV; k++) total += m.dof_depth[k] * (m.dof_depth[k] + 1) / 2;
-        if (total != NFAC) return "factorisation schedule size differs from 1432";
-        for (int e = 0; e < NM; e++) m.anc_adr[e] = m.dof_Madr[m.M_col[e]];
+    for (int k = 0; k < NV; k++) {
+        int chain[MAXDEPTH], n = 0;
+        for (int j = d.dof_parentid[k]; j >= 0; j = d.dof_parentid[j]) chain[n++] = j;  // nearest first
+        for (int t = 0; t < MAXANC; t++) m.anc_dof[k][t] = (u8)(t < n ? chain[n - 1 - t] : 0);
     }
     for (int a = 0; a < NU; a++) {
         int i = d.act_dofadr[a];
