@@ -82,7 +82,8 @@ struct Ws {
         struct { float F[NB * S6], Fsub[NB * S6]; };
     };
     // spatial quantities about the centre of mass, [ang; lin]
-    float cinert[NB * S10], cdof[NV * S6], cvel[NB * S6], buf6[NV * S6];
+    float cinert[NB * S10], cdof[NV * S6], cvel[NB * S6];
+    alignas(16) float buf6[NV * S6];  // also: 14 x 16 staging rows of the factorisation
     union {
         float cacc[NB * S6];  // bias accelerations (com_vel -> rne)
         float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
@@ -427,14 +428,14 @@ PB_DEV void init_ws_tables(const DevModel& m, Ws& w, int lane) {
 // Dofs are eliminated deepest first, so the five leaf chains of the humanoid interleave and hide each other's latency.
 namespace ldl {
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int NSTAGE = 14;  // rotating 16-float staging rows in Ws::buf6 (idle during the factorisation)
 template <int K, int T>
-struct AncRows {  // rows of K's ancestors at depths T-1 .. 0 lose L[K, anc] * row K
-    PB_MEMBER void run(float (&R)[NV], float inv, const float rk) {
+struct AncRows {  // rows of K's ancestors at depths T-1 .. 0 lose L[K, anc] * row K; c[t] = row K's entry at depth t
+    PB_MEMBER void update(float (&R)[NV], const float (&c)[16], const float ninv, const float rk) {
         if constexpr (T > 0) {
             constexpr int J = topo::anc_at(K, T - 1);
-            const float c = __shfl_sync(FULL, rk, T - 1) * inv;
-            R[J] = fmaf(-c, rk, R[J]);
-            AncRows<K, T - 1>::run(R, inv, rk);
+            R[J] = fmaf(c[T - 1] * ninv, rk, R[J]);
+            AncRows<K, T - 1>::update(R, c, ninv, rk);
         }
     }
 };
@@ -450,19 +451,32 @@ struct AncRhs {  // X of K's ancestors (found in slots S-1 .. 0) loses L[K, anc]
 };
 template <int I>
 struct Eliminate {
-    PB_MEMBER void run(float (&R)[NV], float (&X)[NSLOT], float (&DI)[NSLOT], bool& bad, int lane) {
+    // Row K is all-gathered through a 16-float staging row: ONE store, a warp barrier and (depth+1)/4 broadcast vector
+    // loads give every lane the whole row (a chain of per-entry shuffles serialises on the shuffle scoreboard).
+    PB_MEMBER void run(float (&R)[NV], float (&X)[NSLOT], float (&DI)[NSLOT], bool& bad, float* stage, float* ld_lane, int lane) {
         constexpr int K = topo::elim_order(I), d = topo::depth(K), S = topo::slot(K);
         const float rk = R[K];
-        const float diag = __shfl_sync(FULL, rk, d);
+        float4* st = reinterpret_cast<float4*>(stage + 16 * (I % NSTAGE));
+        if (lane < 16) reinterpret_cast<float*>(st)[lane] = rk;
+        if (lane <= d) ld_lane[topo::madr(K) + d] = rk;  // final row K (the back substitution reads it lane-per-dof)
+        float xs = 0.f;
+        if constexpr (d > 0) xs = __shfl_sync(FULL, X[S], d);
+        __syncwarp();
+        float c[16];
+#pragma unroll
+        for (int q = 0; q < (d + 4) / 4; q++) {
+            const float4 v = st[q];
+            c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+        }
+        const float diag = c[d];
         bad |= !(diag > 0.f);
         const float inv = fast_rcp(diag);
         if (lane == d) DI[S] = inv;
         if constexpr (d > 0) {
-            const float s = __shfl_sync(FULL, X[S], d) * inv;
-            AncRhs<K, NSLOT>::run(X, rk * s, lane);
-            AncRows<K, d>::run(R, inv, rk);
+            AncRows<K, d>::update(R, c, -inv, rk);
+            AncRhs<K, NSLOT>::run(X, rk * (xs * inv), lane);
         }
-        if constexpr (I + 1 < NV) Eliminate<I + 1>::run(R, X, DI, bad, lane);
+        if constexpr (I + 1 < NV) Eliminate<I + 1>::run(R, X, DI, bad, stage, ld_lane, lane);
     }
 };
 template <int K>
@@ -515,12 +529,12 @@ struct BackLevel {  // every dof deeper than T receives L[k, anc_T(k)] * x[anc_T
 
 PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
     static_assert(offsetof(Ws, LD) >= 32 * sizeof(float), "row loads reach up to 31 floats below LD");
+    static_assert(sizeof(w.buf6) >= ldl::NSTAGE * 16 * sizeof(float) && offsetof(Ws, buf6) % 16 == 0 && sizeof(Ws) % 16 == 0, "staging rows");
     float R[NV], X[NSLOT], DI[NSLOT];
     bool bad = false;
     ldl::RowIO<0>::load(R, w.LD - lane, lane);
     ldl::SlotIO<0>::load(X, DI, x, lane);
-    ldl::Eliminate<0>::run(R, X, DI, bad, lane);
-    ldl::RowIO<0>::store(R, w.LD - lane, lane);
+    ldl::Eliminate<0>::run(R, X, DI, bad, w.buf6, w.LD - lane, lane);
     ldl::SlotIO<0>::store(X, DI, x, w.Dinv, lane);  // x <- D^-1 L^-T x
     if (bad && lane == 0) w.status |= PBRL_STATUS_PIVOT;
     __syncwarp();

@@ -120,6 +120,32 @@ k_debug_forward(const DevModel* __restrict__ gm, int N, const float* qpos, const
     for (int env = first_env(); env < N; env += env_stride()) env_debug_forward(sm, w, qpos, qvel, ctrl, warm, out, env, lane);
 }
 
+#if defined(PBRL_STAGE_PROF)
+// dev microbenchmark: cycles per ldl_factor_solve with `blockDim.x / 32` warps per CTA looping over resident code
+__global__ void k_bench_ldl(const DevModel* __restrict__ gm, int iters, unsigned long long* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ws& w = *reinterpret_cast<Ws*>(smem_raw + MODEL_SMEM + (size_t)(threadIdx.x >> 5) * sizeof(Ws));
+    const int lane = threadIdx.x & 31;
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
+    LANE_LOOP(i, NQ) w.qpos[i] = sm.qpos0[i];
+    LANE_IF(z, 1) w.status = 0;
+    __syncwarp();
+    smooth_position(sm, w, w.qpos, lane);
+    long long best = 1ll << 60, tot = 0;
+    for (int it = 0; it < iters; it++) {
+        LANE_LOOP(e, NM) w.LD[e] = w.M[e];
+        LANE_LOOP(i, NV) w.p[i] = 1.f + 0.01f * i;
+        __syncwarp();
+        const long long t0 = clock64();
+        ldl_factor_solve(sm, w, w.p, lane);
+        const long long t1 = clock64();
+        if (it > 0) { tot += t1 - t0; best = (t1 - t0) < best ? (t1 - t0) : best; }
+    }
+    if (lane == 0) { atomicAdd(out, (unsigned long long)tot); atomicMin(out + 1, (unsigned long long)best); atomicAdd(out + 2, (unsigned long long)(iters - 1)); }
+}
+#endif
+
 }  // namespace
 
 struct PbrlModel {
@@ -299,6 +325,22 @@ int pbrl_debug_stage_profile(unsigned long long* cycles, unsigned long long* hit
     return fail("not a profiling build (compile with -DPBRL_STAGE_PROF)");
 #endif
 }
+
+#if defined(PBRL_STAGE_PROF)
+int pbrl_debug_bench_ldl(const PbrlModel* m, int warps_per_cta, int ctas, int iters, unsigned long long* out3) {
+    unsigned long long* d = nullptr;
+    unsigned long long init[3] = {0ull, ~0ull, 0ull};
+    CUDA_OK(cudaMalloc(&d, sizeof(init)));
+    CUDA_OK(cudaMemcpy(d, init, sizeof(init), cudaMemcpyHostToDevice));
+    const size_t smem = MODEL_SMEM + sizeof(Ws) * warps_per_cta;
+    CUDA_OK(cudaFuncSetAttribute(k_bench_ldl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bench_ldl<<<ctas, 32 * warps_per_cta, smem>>>(m->dev, iters, d);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(out3, d, sizeof(init), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------ host-buffer layer
 struct PbrlBatch {
