@@ -297,7 +297,8 @@ def main():
                  20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 27: "barrier: substep start", 28: "barrier: after position", 29: "barrier: after rows", 30: "barrier: after solver"}
         tot = sum(cyc)
         print(f"stage profile: {tot / (n_env * steps * N_FRAMES):.0f} cycles per env-substep (per warp, incl. stalls)", file=sys.stderr)
-        for i in range(64):
+        print("  newton iterations per substep: " + " ".join(f"{i - 40}:{hit[i] / (n_env * steps * N_FRAMES):.3f}" for i in range(40, 56) if hit[i]), file=sys.stderr)
+        for i in range(40):
             if hit[i]:
                 print(f"  {i:2d} {names.get(i, '?'):22s} {100.0 * cyc[i] / tot:6.2f}%  hits/substep {hit[i] / (n_env * steps * N_FRAMES):7.3f}  "
                       f"cycles/hit {cyc[i] / hit[i]:9.0f}", file=sys.stderr)

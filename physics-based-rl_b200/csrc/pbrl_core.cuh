@@ -33,7 +33,11 @@
 #define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
 #define LANE_IF(i, n) for (int i = lane, once_ = 1; once_ && i < (n); once_ = 0)  /* n <= 32: at most one pass */
 #define WSYNC() __syncwarp()
-#define CTA_SYNC() __syncthreads()
+// phase-lock barrier: the warps of one lock group (PBRL_LOCK_GROUP consecutive warps of the CTA) meet on a named barrier
+#ifndef PBRL_LOCK_GROUP
+#define PBRL_LOCK_GROUP 8
+#endif
+#define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / PBRL_LOCK_GROUP), "r"(32 * PBRL_LOCK_GROUP) : "memory")
 #define CTA_OR(p) __syncthreads_or(p)
 #else
 #define PB_DEV static inline
@@ -61,7 +65,9 @@ __device__ unsigned long long g_stage_hits[64];
         }                                                                             \
     } while (0)
 #define PROF_START() do { if (lane == 0) w.prof_t = clock64(); } while (0)
+#define PROF_COUNT(id) do { if (lane == 0) atomicAdd(&g_stage_hits[id], 1ull); } while (0)
 #else
+#define PROF_COUNT(id) ((void)0)
 #define PROF(id) ((void)0)
 #define PROF_START() ((void)0)
 #endif
@@ -214,38 +220,60 @@ PB_DEV void cross_force(const float* v, const float* f, float* r) {
 PB_DEV int sym21(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
 
 // ---------------------------------------------------------------------------------- kinematics
+// Flat form: everything that does not depend on the parent pose runs lane-parallel over joints / bodies first (joint
+// rotations, their product per body, the joint axes in the parent-side frame); the level recursion then only composes
+// one quaternion and one offset per body.
 PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
+    float* jq = w.cdof;           // [NJ][4] rotation of each hinge about its axis           (cdof is written by stage_com)
+    float* bq = w.cdof + 4 * NJ;  // [NB][4] product of a body's hinge rotations
+    float* axl = w.buf6;          // [NJ] x S3: joint axis in the body's pre-joint frame here, in the world frame on return
+    static_assert(4 * NJ + 4 * NB <= NV * S6, "fk scratch");
+    LANE_IF(j, NJ) {
+        if (m.jnt_type[j] != 0) {
+            const int qa = m.jnt_qposadr[j];
+            float sn, cs;
+            sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
+            jq[4 * j] = cs; jq[4 * j + 1] = m.jnt_axis[j][0] * sn; jq[4 * j + 2] = m.jnt_axis[j][1] * sn; jq[4 * j + 3] = m.jnt_axis[j][2] * sn;
+        }
+    }
     LANE_IF(z, 1) {
         w.xpos[0] = w.xpos[1] = w.xpos[2] = 0.f;
         w.xquat[0] = 1.f; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0.f;
         for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
     }
     WSYNC();
+    LANE_IF(b, NB) {
+        const int j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
+        if (b > 0 && m.jnt_type[j0] != 0) {
+            float q[4] = {jq[4 * j0], jq[4 * j0 + 1], jq[4 * j0 + 2], jq[4 * j0 + 3]};
+            for (int c = 0; c < 3; c++) axl[S3 * j0 + c] = m.jnt_axis[j0][c];
+            for (int j = j0 + 1; j < j0 + nj; j++) {
+                float qn[4];
+                quat_rotate(q, m.jnt_axis[j], axl + S3 * j);
+                quat_mul(q, jq + 4 * j, qn);
+                for (int c = 0; c < 4; c++) q[c] = qn[c];
+            }
+            for (int c = 0; c < 4; c++) bq[4 * b + c] = q[c];
+        }
+    }
+    WSYNC();
     for (int lv = 1; lv < m.nlevel; lv++) {
         int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
         LANE_IF(k, n) {
-            int b = m.level_body[s + k], p = m.body_parent[b];
-            float pos[3], q[4], t[3];
-            mat_vec(w.xmat + S9 * p, m.body_pos[b], t);
-            for (int c = 0; c < 3; c++) pos[c] = w.xpos[S3 * p + c] + t[c];
-            for (int c = 0; c < 4; c++) q[c] = w.xquat[S4 * p + c];
-            for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
-                int qa = m.jnt_qposadr[j];
-                if (m.jnt_type[j] == 0) {
-                    for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
-                    for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
-                    quat_normalize(q);
-                    w.buf6[S3 * j] = 0.f; w.buf6[S3 * j + 1] = 0.f; w.buf6[S3 * j + 2] = 1.f;
-                } else {
-                    float ql[4], qn[4], sn, cs;
-                    quat_rotate(q, m.jnt_axis[j], w.buf6 + S3 * j);  // world joint axis, parked in buf6 until stage_com
-                    sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
-                    ql[0] = cs; ql[1] = m.jnt_axis[j][0] * sn; ql[2] = m.jnt_axis[j][1] * sn; ql[3] = m.jnt_axis[j][2] * sn;
-                    quat_mul(q, ql, qn);
-                    for (int c = 0; c < 4; c++) q[c] = qn[c];
-                }
+            const int b = m.level_body[s + k], p = m.body_parent[b], j0 = m.body_jntadr[b];
+            float pos[3], q[4];
+            if (m.jnt_type[j0] == 0) {
+                const int qa = m.jnt_qposadr[j0];
+                for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
+                for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
+                quat_normalize(q);  // mj_kinematics normalises the free quaternion before use ...
+            } else {
+                float t[3];
+                mat_vec(w.xmat + S9 * p, m.body_pos[b], t);
+                for (int c = 0; c < 3; c++) pos[c] = w.xpos[S3 * p + c] + t[c];
+                quat_mul(w.xquat + S4 * p, bq + 4 * b, q);
             }
-            quat_normalize(q);
+            quat_normalize(q);      // ... and every body quaternion after its joints
             for (int c = 0; c < 3; c++) w.xpos[S3 * b + c] = pos[c];
             for (int c = 0; c < 4; c++) w.xquat[S4 * b + c] = q[c];
             float R[9];
@@ -254,6 +282,15 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
         }
         WSYNC();
     }
+    // joint axes to the world frame: the pre-joint frame of a hinge body is its parent's frame (body_quat = identity)
+    LANE_IF(j, NJ) {
+        if (m.jnt_type[j] == 0) { axl[S3 * j] = 0.f; axl[S3 * j + 1] = 0.f; axl[S3 * j + 2] = 1.f; }
+        else {
+            float a[3] = {axl[S3 * j], axl[S3 * j + 1], axl[S3 * j + 2]};
+            mat_vec(w.xmat + S9 * m.body_parent[m.jnt_bodyid[j]], a, axl + S3 * j);
+        }
+    }
+    WSYNC();
 }
 
 // com, cinert, cdof  (mjx smooth.com_pos)
@@ -343,43 +380,58 @@ PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
-// body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne)
-PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane) {
-    LANE_IF(z, 1) {
-        for (int c = 0; c < 6; c++) { w.cvel[c] = 0.f; w.cacc[c] = 0.f; }
-        w.cacc[3] = -m.gx; w.cacc[4] = -m.gy; w.cacc[5] = -m.gz;
+// dst[b] = sum of src over b and its ancestors (src[world] must be zero); one table word, four independent loads
+PB_DEV void path_sum6(const DevModel& m, const float* src, float* dst, const float* base6, int lane) {
+    LANE_LOOP(it, NB * 6) {
+        const int b = it / 6, c = it - 6 * b;
+        const u8* an = m.body_anc[b];
+        float s = (src[S6 * an[0] + c] + src[S6 * an[1] + c]) + (src[S6 * an[2] + c] + src[S6 * an[3] + c]);
+        dst[S6 * b + c] = base6 ? s + base6[c] : s;
     }
     WSYNC();
-    for (int lv = 1; lv < m.nlevel; lv++) {
-        int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
-        LANE_IF(k, n) {
-            int b = m.level_body[s + k], p = m.body_parent[b];
-            float v[6], a[6], cdd[6];
-            for (int c = 0; c < 6; c++) { v[c] = w.cvel[S6 * p + c]; a[c] = w.cacc[S6 * p + c]; }
-            for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
-                int da = m.jnt_dofadr[j];
-                if (m.jnt_type[j] == 0) {
-                    for (int i = 0; i < 3; i++) {
-                        for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i];
-                    }
-                    for (int i = 3; i < 6; i++) {
-                        cross_motion(v, w.cdof + S6 * (da + i), cdd);
-                        for (int c = 0; c < 6; c++) a[c] += cdd[c] * qvel[da + i];
-                    }
-                    for (int i = 3; i < 6; i++)
-                        for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * (da + i) + c] * qvel[da + i];
-                } else {
-                    cross_motion(v, w.cdof + S6 * da, cdd);
-                    for (int c = 0; c < 6; c++) {
-                        a[c] += cdd[c] * qvel[da];
-                        v[c] += w.cdof[S6 * da + c] * qvel[da];
-                    }
-                }
-            }
-            for (int c = 0; c < 6; c++) { w.cvel[S6 * b + c] = v[c]; w.cacc[S6 * b + c] = a[c]; }
-        }
-        WSYNC();
+}
+// dst[b] = sum over the dofs of body b of vec6_i * x_i  (x = nullptr: plain sum)
+PB_DEV void body_sum6(const DevModel& m, const float* vec6, const float* x, float* dst, int lane) {
+    LANE_LOOP(it, NB * 6) {
+        const int b = it / 6, c = it - 6 * b, d0 = m.body_dofadr[b], n = m.body_dofnum[b];
+        float s = 0.f;
+        for (int k = 0; k < n; k++) s = x ? fmaf(vec6[S6 * (d0 + k) + c], x[d0 + k], s) : s + vec6[S6 * (d0 + k) + c];
+        dst[S6 * b + c] = s;
     }
+    WSYNC();
+}
+
+// body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne), flat form: per-body
+// partial sums lane-parallel over (body, component), then sums along the (at most 4 bodies long) root path.
+PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane) {
+    float* sb = w.F;   // [NB] x S6 per-body partial sums
+    float* da = w.K;   // [NV] x S6: cdof_dot_i * qvel_i (the Hessian scratch is idle here)
+    static_assert(NV * S6 <= NB * S21, "comvel scratch");
+    body_sum6(m, w.cdof, qvel, sb, lane);
+    path_sum6(m, sb, w.cvel, nullptr, lane);
+    LANE_LOOP(i, NV) {
+        const int kind = m.dof_kind[i];
+        float t[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (kind >= 3) {  // translations of the free joint carry no cdof_dot
+            const int b = m.dof_bodyid[i], p = m.body_parent[b], d0 = m.body_dofadr[b];
+            float v[6];
+            for (int c = 0; c < 6; c++) v[c] = w.cvel[S6 * p + c];
+            // velocity before this dof: parent body + the earlier dofs of the same body (free joint: the translations only)
+            const int nprev = kind < 6 ? 3 : i - d0;
+            for (int k = 0; k < nprev; k++) {
+                const float qd = qvel[d0 + k];
+                for (int c = 0; c < 6; c++) v[c] = fmaf(w.cdof[S6 * (d0 + k) + c], qd, v[c]);
+            }
+            cross_motion(v, w.cdof + S6 * i, t);
+        }
+        const float qd = qvel[i];
+        for (int c = 0; c < 6; c++) da[S6 * i + c] = t[c] * qd;
+    }
+    WSYNC();
+    body_sum6(m, da, nullptr, sb, lane);
+    LANE_IF(c, 6) w.Fsub[c] = c == 3 ? -m.gx : c == 4 ? -m.gy : c == 5 ? -m.gz : 0.f;  // every body inherits -gravity from the world
+    WSYNC();
+    path_sum6(m, sb, w.cacc, w.Fsub, lane);
 }
 
 // leaf-to-root accumulation of 6-vectors as subtree gathers
@@ -599,20 +651,8 @@ PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
 // ---------------------------------------------------------------------------------- tree products
 // V[b] = sum over ancestor dofs of cdof_i x_i  (spatial velocity of body b for generalised velocity x)
 PB_DEVN void tree_vel(const DevModel& m, Ws& w, const float* x, int lane) {
-    LANE_IF(z, 1) for (int c = 0; c < 6; c++) w.V[c] = 0.f;
-    WSYNC();
-    for (int lv = 1; lv < m.nlevel; lv++) {
-        int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
-        LANE_IF(k, n) {
-            int b = m.level_body[s + k], p = m.body_parent[b];
-            float v[6];
-            for (int c = 0; c < 6; c++) v[c] = w.V[S6 * p + c];
-            for (int i = m.body_dofadr[b]; i < m.body_dofadr[b] + m.body_dofnum[b]; i++)
-                for (int c = 0; c < 6; c++) v[c] += w.cdof[S6 * i + c] * x[i];
-            for (int c = 0; c < 6; c++) w.V[S6 * b + c] = v[c];
-        }
-        WSYNC();
-    }
+    body_sum6(m, w.cdof, x, w.F, lane);
+    path_sum6(m, w.F, w.V, nullptr, lane);
 }
 // out = M x using V = tree_vel(x) already in w.V (matrix-free, includes armature)
 PB_DEVN void tree_Mx_from_V(const DevModel& m, Ws& w, const float* x, float* out, int lane) {
@@ -1047,6 +1087,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
 // mjx.step: forward, warmstart <- qacc, Euler with implicit joint damping, integrate
 PB_DEVN void substep(const DevModel& m, Ws& w, float& time, int lane) {
     forward(m, w, lane);
+    PROF_COUNT(40 + (w.niter < 15 ? w.niter : 15));
     if (w.phase_lock & 8) CTA_SYNC();
     PROF(30);
     float h = m.timestep;

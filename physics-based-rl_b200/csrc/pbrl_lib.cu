@@ -24,6 +24,7 @@ namespace {
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
+static_assert(WARPS_PER_CTA % PBRL_LOCK_GROUP == 0, "lock groups tile the CTA");
 
 thread_local std::string g_error;
 int fail(const std::string& msg) { g_error = msg; return -1; }
@@ -64,9 +65,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
         if (slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
         else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
-                for (int k = 0; k < __popc(a.phase_lock & 7); k++) __syncthreads();
+                for (int k = 0; k < __popc(a.phase_lock & 7); k++) CTA_SYNC();
                 if (a.phase_lock & 16) while (__syncthreads_or(0)) {}
-                if (a.phase_lock & 8) __syncthreads();
+                if (a.phase_lock & 8) CTA_SYNC();
             }
         }
     }
@@ -121,25 +122,44 @@ k_debug_forward(const DevModel* __restrict__ gm, int N, const float* qpos, const
 }
 
 #if defined(PBRL_STAGE_PROF)
-// dev microbenchmark: cycles per ldl_factor_solve with `blockDim.x / 32` warps per CTA looping over resident code
-__global__ void k_bench_ldl(const DevModel* __restrict__ gm, int iters, unsigned long long* out) {
+// dev microbenchmark: cycles per call of one stage function, `blockDim.x / 32` warps per CTA looping over resident code
+__global__ void k_bench_stage(const DevModel* __restrict__ gm, int stage, int iters, unsigned long long* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ws& w = *reinterpret_cast<Ws*>(smem_raw + MODEL_SMEM + (size_t)(threadIdx.x >> 5) * sizeof(Ws));
     const int lane = threadIdx.x & 31;
     const DevModel& sm = stage_model(gm);
     init_ws_tables(sm, w, lane);
-    LANE_LOOP(i, NQ) w.qpos[i] = sm.qpos0[i];
-    LANE_IF(z, 1) w.status = 0;
+    LANE_LOOP(i, NQ) w.qpos[i] = sm.qpos0[i] + (i >= 7 ? 0.05f * ((i * 7) % 5 - 2) : 0.f);
+    LANE_LOOP(i, NV) { w.qvel[i] = 0.1f * ((i * 3) % 7 - 3); w.warm[i] = 0.f; }
+    LANE_LOOP(i, NU) w.ctrl[i] = 0.f;
+    LANE_IF(z, 1) { w.status = 0; w.phase_lock = 0; w.qpos[2] = 0.9f; }
     __syncwarp();
-    smooth_position(sm, w, w.qpos, lane);
+    forward(sm, w, lane);  // a consistent workspace (contacts active: the feet touch the floor at z = 0.9)
     long long best = 1ll << 60, tot = 0;
     for (int it = 0; it < iters; it++) {
-        LANE_LOOP(e, NM) w.LD[e] = w.M[e];
-        LANE_LOOP(i, NV) w.p[i] = 1.f + 0.01f * i;
+        if (stage == 0) { LANE_LOOP(e, NM) w.LD[e] = w.M[e]; LANE_LOOP(i, NV) w.p[i] = 1.f + 0.01f * i; }
         __syncwarp();
         const long long t0 = clock64();
-        ldl_factor_solve(sm, w, w.p, lane);
+        switch (stage) {
+            case 0: ldl_factor_solve(sm, w, w.p, lane); break;
+            case 1: stage_fk(sm, w, w.qpos, lane); break;
+            case 2: stage_com(sm, w, lane); break;
+            case 3: stage_crb(sm, w, lane); break;
+            case 4: stage_collide(sm, w, lane); break;
+            case 5: stage_comvel(sm, w, w.qvel, lane); break;
+            case 6: stage_bias(sm, w, lane); break;
+            case 7: stage_rows(sm, w, w.qpos, w.qvel, lane); break;
+            case 8: tree_vel(sm, w, w.qacc, lane); break;
+            case 9: tree_Mx_from_V(sm, w, w.qacc, w.Mp, lane); break;
+            case 10: rows_JTf(sm, w, w.Mp, w.grad, 0, lane); break;
+            case 11: assemble_hessian(sm, w, lane); break;
+            case 12: rows_Jx(sm, w, w.qacc, w.lim_jp, w.con_jp, lane); break;
+            case 13: subtree_sum6(sm, w.F, w.Fsub, lane); break;
+            case 14: path_sum6(sm, w.F, w.V, nullptr, lane); break;
+            case 15: body_sum6(sm, w.cdof, w.qacc, w.F, lane); break;
+        }
         const long long t1 = clock64();
+        if (stage == 1 || stage == 2) { __syncwarp(); }
         if (it > 0) { tot += t1 - t0; best = (t1 - t0) < best ? (t1 - t0) : best; }
     }
     if (lane == 0) { atomicAdd(out, (unsigned long long)tot); atomicMin(out + 1, (unsigned long long)best); atomicAdd(out + 2, (unsigned long long)(iters - 1)); }
@@ -327,14 +347,14 @@ int pbrl_debug_stage_profile(unsigned long long* cycles, unsigned long long* hit
 }
 
 #if defined(PBRL_STAGE_PROF)
-int pbrl_debug_bench_ldl(const PbrlModel* m, int warps_per_cta, int ctas, int iters, unsigned long long* out3) {
+int pbrl_debug_bench_stage(const PbrlModel* m, int stage, int warps_per_cta, int ctas, int iters, unsigned long long* out3) {
     unsigned long long* d = nullptr;
     unsigned long long init[3] = {0ull, ~0ull, 0ull};
     CUDA_OK(cudaMalloc(&d, sizeof(init)));
     CUDA_OK(cudaMemcpy(d, init, sizeof(init), cudaMemcpyHostToDevice));
     const size_t smem = MODEL_SMEM + sizeof(Ws) * warps_per_cta;
-    CUDA_OK(cudaFuncSetAttribute(k_bench_ldl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bench_ldl<<<ctas, 32 * warps_per_cta, smem>>>(m->dev, iters, d);
+    CUDA_OK(cudaFuncSetAttribute(k_bench_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bench_stage<<<ctas, 32 * warps_per_cta, smem>>>(m->dev, stage, iters, d);
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(out3, d, sizeof(init), cudaMemcpyDeviceToHost));
     cudaFree(d);

@@ -110,7 +110,8 @@ struct DevModel {
     u8 level_start[MAXLEVEL + 1], level_body[NB], depth_start[MAXDEPTH + 1], depth_dof[NV];
     u8 body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
     u8 body_conadr[NB], body_connum[NB], body_nchild[NB], body_child[NB][4];
-    u8 jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ];
+    alignas(4) u8 body_anc[NB][4];  // self, parent, grandparent, ... padded with the world body (its partial sums are zero)
+    u8 jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ], jnt_bodyid[NJ];
     u8 dof_bodyid[NV], dof_jntid[NV], dof_depth[NV], dof_kind[NV];
     i8 dof_parentid[NV], dof_act[NV];
     u8 lim_jnt[NLIM];
@@ -212,6 +213,11 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             if (a == b && b != 0) return "bodies must be in depth-first order";
         }
     }
+    for (int b = 0; b < NB; b++) {
+        int a = b;
+        for (int k = 0; k < 4; k++) { m.body_anc[b][k] = (u8)a; a = a > 0 ? d.body_parent[a] : 0; }
+        if (a != 0) return "body tree deeper than 4 levels";
+    }
     for (int b = 1; b < NB; b++) {
         int p = d.body_parent[b];
         if (m.body_nchild[p] >= 4) return "at most 4 children per body";
@@ -230,7 +236,7 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
     int nlim = 0;
     for (int j = 0; j < NJ; j++) {
         m.jnt_type[j] = d.jnt_type[j]; m.jnt_qposadr[j] = d.jnt_qposadr[j]; m.jnt_dofadr[j] = d.jnt_dofadr[j];
-        m.jnt_limited[j] = d.jnt_limited[j];
+        m.jnt_limited[j] = d.jnt_limited[j]; m.jnt_bodyid[j] = d.jnt_bodyid[j];
         for (int k = 0; k < 3; k++) {
             m.jnt_axis[j][k] = (float)d.jnt_axis[3 * j + k];
             if (d.jnt_pos[3 * j + k] != 0.0) return "joint anchors must sit at the body origin (jnt_pos = 0)";
