@@ -35,7 +35,7 @@
 #define WSYNC() __syncwarp()
 // phase-lock barrier: the warps of one lock group (PBRL_LOCK_GROUP consecutive warps of the CTA) meet on a named barrier
 #ifndef PBRL_LOCK_GROUP
-#define PBRL_LOCK_GROUP 8
+#define PBRL_LOCK_GROUP 16
 #endif
 #define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / PBRL_LOCK_GROUP), "r"(32 * PBRL_LOCK_GROUP) : "memory")
 #define CTA_OR(p) __syncthreads_or(p)
@@ -74,7 +74,11 @@ __device__ unsigned long long g_stage_hits[64];
 
 namespace pbrl {
 
-constexpr int S3 = 3, S4 = 5, S6 = 7, S9 = 9, S10 = 11, S21 = 21;  // odd strides: conflict-free lane=row access
+// row strides of the per-body / per-dof arrays: 6-vectors live in 8-float rows, spatial inertias in 12-float rows and
+// symmetric 6x6 blocks in 24-float rows, all 16-byte aligned, so that a lane moves a whole row with a few vector accesses
+constexpr int S3 = 3, S4 = 4, S6 = 8, S9 = 9, S10 = 12, S21 = 24;
+constexpr int SR = 4;        // contact points: float4 rows
+constexpr int NDL = NV - 3;  // "dof lanes": lane l owns dof l + 3; the lane of dof 3 also emits the free translations 0..2
 constexpr int NEWTON_MAXIT = 12;
 constexpr int LS_MAXIT = 24;
 
@@ -82,22 +86,24 @@ struct Ws {
     // state
     float qpos[36], qvel[36], warm[36], ctrl[28];
     // kinematics.  xquat/xmat are dead once the contacts are found; the spatial-force scratch F/Fsub reuses them
-    float xpos[NB * S3], com[4];
+    float xpos[NB * S3], com[4], pad0_[2];
     union {
-        struct { float xquat[NB * S4], xmat[NB * S9]; };
-        struct { float F[NB * S6], Fsub[NB * S6]; };
+        struct { alignas(16) float xquat[NB * S4]; float xmat[NB * S9]; };
+        struct { alignas(16) float F[NB * S6]; float Fsub[NB * S6]; };
     };
     // spatial quantities about the centre of mass, [ang; lin]
-    float cinert[NB * S10], cdof[NV * S6], cvel[NB * S6];
-    alignas(16) float buf6[NV * S6];  // also: 14 x 16 staging rows of the factorisation
+    alignas(16) float cinert[NB * S10];
+    alignas(16) float cdof[NV * S6];
+    alignas(16) float cvel[NB * S6];
+    alignas(16) float buf6[NV * S6];  // stage scratch; also the 14 x 16 staging rows of the factorisation
     union {
-        float cacc[NB * S6];  // bias accelerations (com_vel -> rne)
-        float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
+        alignas(16) float cacc[NB * S6];  // bias accelerations (com_vel -> rne)
+        alignas(16) float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
     };
     // joint-space inertia (tree-sparse), factor, vectors
-    float M[NM], Dinv[36];
+    float M[NM], Dinv[36], pad1_[2];
     union {
-        float LD[NM];                                 // factor workspace
+        alignas(16) float LD[NM];                     // factor workspace
         alignas(16) float fr[2 * PBRL_FRAME_STRIDE];  // mimic: the two reference frames of this env step (cp.async.bulk
     };                                                // target; issued after the last factorisation of the step)
     float fsmooth[36], qacc[36], grad[36], p[36];
@@ -108,13 +114,15 @@ struct Ws {
     // constraint rows: lane l owns limit row l and contact slot l (4 pyramid rows)
     float lim_sign[32], lim_D[32], lim_aref[32], lim_jar[32], lim_jp[32];
     int con_on[NCP], act_bits[32];
-    float con_dist[NCP], con_r[NCP * S3], con_t1[NCP * 2], con_D[NCP];
-    float con_aref[NCP * 4], con_jar[NCP * 4], con_jp[NCP * 4];
+    float con_dist[NCP], con_D[NCP], con_t1[NCP * 2];
+    alignas(16) float con_r[NCP * 4];
+    alignas(16) float con_aref[NCP * 4];
+    alignas(16) float con_jar[NCP * 4];
+    alignas(16) float con_jp[NCP * 4];
     union {
-        struct { float K[NB * S21]; };                                     // Newton Hessian assembly (accumulated in place)
-        struct { float crb[NB * S10]; };                                   // composite inertias (only inside stage_crb)
+        struct { alignas(16) float K[NB * S21]; };                         // Newton Hessian assembly: 6x6 blocks per body
         struct {                                                          // mimic epilogue (after the last substep)
-            float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * S4], rcom[4], ree[12], rerr[8];
+            float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * 5], rcom[4], ree[12], rerr[8];
         };
     };
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
@@ -123,11 +131,16 @@ struct Ws {
     // warp-uniform loop table copied from the model once per kernel
     int lvl_start[MAXLEVEL + 1];
     int status, niter;
-    int phase_lock, pad_;  // CTA barriers at stage-group boundaries keep the CTA's warps inside one I-cache window
+    int phase_lock;  // CTA barriers at stage-group boundaries keep the CTA's warps inside one I-cache window
+    unsigned con_mask;   // contact slots with a constraint row this substep
+    unsigned act_mask;   // ... with at least one active pyramid edge in the current Newton iterate
+    unsigned kbody_mask; // bodies that own such a slot
+    unsigned pad2_[2];
 #if defined(PBRL_STAGE_PROF)
     long long prof_t;
 #endif
 };
+static_assert(sizeof(Ws) % 16 == 0, "workspaces tile shared memory on 16-byte boundaries");
 
 PB_DEV float fast_rcp(float x) {
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
@@ -151,6 +164,47 @@ PB_DEV float wsum(int lane, int n, Fn f) {
     (void)lane;
     return s;
 }
+
+// bit mask of the lanes i < n whose predicate holds
+template <class Fn>
+PB_DEV unsigned wballot(int lane, int n, Fn f) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return __ballot_sync(0xffffffffu, lane < n && f(lane));
+#else
+    unsigned mk = 0;
+    for (int i = 0; i < n; i++) mk |= f(i) ? 1u << i : 0u;
+    (void)lane;
+    return mk;
+#endif
+}
+PB_DEV int first_bit(unsigned mk) {  // index of the lowest set bit (mk != 0)
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return __ffs((int)mk) - 1;
+#else
+    int i = 0;
+    while (!((mk >> i) & 1u)) i++;
+    return i;
+#endif
+}
+
+// ---------------------------------------------------------------------------------- row moves (16-byte aligned rows)
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+PB_DEV void ld4(const float* p, float* r) { const float4 a = *reinterpret_cast<const float4*>(p); r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; }
+PB_DEV void st4(float* p, const float* r) { *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]); }
+PB_DEV void ld2(const float* p, float* r) { const float2 a = *reinterpret_cast<const float2*>(p); r[0] = a.x; r[1] = a.y; }
+PB_DEV void st2(float* p, const float* r) { *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]); }
+#else
+PB_DEV void ld4(const float* p, float* r) { for (int k = 0; k < 4; k++) r[k] = p[k]; }
+PB_DEV void st4(float* p, const float* r) { for (int k = 0; k < 4; k++) p[k] = r[k]; }
+PB_DEV void ld2(const float* p, float* r) { r[0] = p[0]; r[1] = p[1]; }
+PB_DEV void st2(float* p, const float* r) { p[0] = r[0]; p[1] = r[1]; }
+#endif
+PB_DEV void ld6(const float* p, float* r) { ld4(p, r); ld2(p + 4, r + 4); }
+PB_DEV void st6(float* p, const float* r) { st4(p, r); st2(p + 4, r + 4); }
+PB_DEV void ld10(const float* p, float* r) { ld4(p, r); ld4(p + 4, r + 4); ld2(p + 8, r + 8); }
+PB_DEV void st10(float* p, const float* r) { st4(p, r); st4(p + 4, r + 4); st2(p + 8, r + 8); }
+PB_DEV void ld24(const float* p, float* r) { for (int k = 0; k < 6; k++) ld4(p + 4 * k, r + 4 * k); }
+PB_DEV void st24(float* p, const float* r) { for (int k = 0; k < 6; k++) st4(p + 4 * k, r + 4 * k); }
 
 // ---------------------------------------------------------------------------------- small math
 PB_DEV void cross3(const float* a, const float* b, float* r) {
@@ -360,87 +414,134 @@ PB_DEVN void stage_com(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
-// composite inertias + sparse M  (mjx smooth.crb)
+// ---------------------------------------------------------------------------------- dof-lane helpers
+// Lane l < NDL owns dof i = l + 3.  The free-joint translations 0..2 have unit cdofs ([0; e_k]), so whatever they need is
+// a component of a quantity the lane of dof 3 (same body) already holds; that lane emits them.
+struct DofRow {  // the sparse row of dof i: i and its ancestors, nearest ancestor last in `an` order (depth 0 first)
+    int i, d, adr;
+    unsigned an[MAXANC / 4];
+};
+PB_DEV DofRow dof_row(const DevModel& m, int i) {
+    DofRow r;
+    r.i = i; r.d = m.dof_depth[i]; r.adr = m.dof_Madr[i];
+    for (int q = 0; q < MAXANC / 4; q++) r.an[q] = reinterpret_cast<const unsigned*>(m.anc_dof[i])[q];
+    return r;
+}
+PB_DEV int row_anc(const DofRow& r, int t) { return (int)((r.an[t >> 2] >> (8 * (t & 3))) & 0xffu); }  // ancestor at depth t < d
+
+// sum of the 6-vector rows src[c] over the bodies c of the subtree of b (bodies are numbered depth first)
+PB_DEV void subtree_gather6(const DevModel& m, const float* src, int b, float* f) {
+    const int e = m.body_subtree_end[b];
+    ld6(src + S6 * b, f);
+#pragma unroll 4
+    for (int c = b + 1; c < e; c++) {
+        float t[6];
+        ld6(src + S6 * c, t);
+        for (int k = 0; k < 6; k++) f[k] += t[k];
+    }
+}
+// generalised force of the spatial forces F (one per body): out_i = cdof_i . sum_{subtree(body_i)} F  (+ extra per dof)
+template <class Extra>
+PB_DEV void force_to_dofs(const DevModel& m, Ws& w, const float* F, float* out, Extra extra, int lane) {
+    LANE_IF(l, NDL) {
+        const int i = l + 3;
+        float f[6], cd[6];
+        subtree_gather6(m, F, m.dof_bodyid[i], f);
+        ld6(w.cdof + S6 * i, cd);
+        out[i] = dot6(cd, f) + extra(i);
+        if (i == 3) for (int k = 0; k < 3; k++) out[k] = f[3 + k] + extra(k);
+    }
+    WSYNC();
+}
+
+// composite inertias + sparse M  (mjx smooth.crb).  One pass, lane = dof: the composite inertia of the dof's body is
+// gathered over the subtree, applied to the dof's cdof in registers, and dotted with the cdofs of the row's columns.
 PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
-    LANE_LOOP(it, NB * 10) {
-        int b = it / 10, k = it - 10 * b;
-        float s = 0.f;
-        for (int c = b; c < m.body_subtree_end[b]; c++) s += w.cinert[S10 * c + k];
-        w.crb[S10 * b + k] = s;
-    }
-    WSYNC();
-    LANE_LOOP(i, NV) mul_inert(w.crb + S10 * m.dof_bodyid[i], w.cdof + S6 * i, w.buf6 + S6 * i);
-    WSYNC();
-    LANE_LOOP(e, NM) {
-        int r = m.M_row[e], c = m.M_col[e];
-        float v = dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
-        if (r == c) v += m.dof_armature[r];
-        w.M[e] = v;
-    }
-    WSYNC();
-}
-
-// dst[b] = sum of src over b and its ancestors (src[world] must be zero); one table word, four independent loads
-PB_DEV void path_sum6(const DevModel& m, const float* src, float* dst, const float* base6, int lane) {
-    LANE_LOOP(it, NB * 6) {
-        const int b = it / 6, c = it - 6 * b;
-        const u8* an = m.body_anc[b];
-        float s = (src[S6 * an[0] + c] + src[S6 * an[1] + c]) + (src[S6 * an[2] + c] + src[S6 * an[3] + c]);
-        dst[S6 * b + c] = base6 ? s + base6[c] : s;
-    }
-    WSYNC();
-}
-// dst[b] = sum over the dofs of body b of vec6_i * x_i  (x = nullptr: plain sum)
-PB_DEV void body_sum6(const DevModel& m, const float* vec6, const float* x, float* dst, int lane) {
-    LANE_LOOP(it, NB * 6) {
-        const int b = it / 6, c = it - 6 * b, d0 = m.body_dofadr[b], n = m.body_dofnum[b];
-        float s = 0.f;
-        for (int k = 0; k < n; k++) s = x ? fmaf(vec6[S6 * (d0 + k) + c], x[d0 + k], s) : s + vec6[S6 * (d0 + k) + c];
-        dst[S6 * b + c] = s;
+    LANE_IF(l, NDL) {
+        const DofRow r = dof_row(m, l + 3);
+        const int b = m.dof_bodyid[r.i], e = m.body_subtree_end[b];
+        float ci[10], cd[6], f[6];
+        ld10(w.cinert + S10 * b, ci);
+#pragma unroll 4
+        for (int c = b + 1; c < e; c++) {
+            float t[10];
+            ld10(w.cinert + S10 * c, t);
+            for (int k = 0; k < 10; k++) ci[k] += t[k];
+        }
+        ld6(w.cdof + S6 * r.i, cd);
+        mul_inert(ci, cd, f);
+        w.M[r.adr] = dot6(cd, f) + m.dof_armature[r.i];
+#pragma unroll
+        for (int t = 0; t < MAXANC; t++) {
+            if (t < r.d) {
+                float cj[6];
+                ld6(w.cdof + S6 * row_anc(r, t), cj);
+                w.M[r.adr + r.d - t] = dot6(cj, f);
+            }
+        }
+        if (r.i == 3) {  // rows 0..2: cdof = [0; e_k]  ->  M[k][j] = (I_c [0; e_k])_{3+j}: the mass on the diagonal, 0 elsewhere
+            for (int k = 0; k < 3; k++)
+                for (int j = 0; j <= k; j++) w.M[m.dof_Madr[k] + (k - j)] = (j == k ? ci[9] + m.dof_armature[k] : 0.f);
+        }
     }
     WSYNC();
 }
 
-// body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne), flat form: per-body
-// partial sums lane-parallel over (body, component), then sums along the (at most 4 bodies long) root path.
+// V_b = sum over the dofs on the root path of body b of vec6_i * x_i (lane = body; the path is the row of b's last dof)
+PB_DEV void path_product6(const DevModel& m, const float* vec6, const float* x, int b, float* v) {
+    const DofRow r = dof_row(m, m.body_dofadr[b] + m.body_dofnum[b] - 1);
+    float t[6];
+    ld6(vec6 + S6 * r.i, t);
+    const float xi = x ? x[r.i] : 1.f;
+    for (int k = 0; k < 6; k++) v[k] = t[k] * xi;
+#pragma unroll
+    for (int q = 0; q < MAXANC; q++) {
+        if (q < r.d) {
+            const int j = row_anc(r, q);
+            const float xj = x ? x[j] : 1.f;
+            ld6(vec6 + S6 * j, t);
+            for (int k = 0; k < 6; k++) v[k] = fmaf(t[k], xj, v[k]);
+        }
+    }
+}
+
+// body velocities, cdof_dot, bias accelerations  (mjx smooth.com_vel + first half of smooth.rne): three lane-parallel
+// passes (bodies, dofs, bodies), each lane summing along its root path in registers.
 PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane) {
-    float* sb = w.F;   // [NB] x S6 per-body partial sums
-    float* da = w.K;   // [NV] x S6: cdof_dot_i * qvel_i (the Hessian scratch is idle here)
-    static_assert(NV * S6 <= NB * S21, "comvel scratch");
-    body_sum6(m, w.cdof, qvel, sb, lane);
-    path_sum6(m, sb, w.cvel, nullptr, lane);
+    float* da = w.buf6;  // [NV] x S6: cdof_dot_i * qvel_i
+    LANE_IF(b, NB) {
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (b > 0) path_product6(m, w.cdof, qvel, b, v);
+        st6(w.cvel + S6 * b, v);
+    }
+    WSYNC();
     LANE_LOOP(i, NV) {
         const int kind = m.dof_kind[i];
         float t[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (kind >= 3) {  // translations of the free joint carry no cdof_dot
             const int b = m.dof_bodyid[i], p = m.body_parent[b], d0 = m.body_dofadr[b];
-            float v[6];
-            for (int c = 0; c < 6; c++) v[c] = w.cvel[S6 * p + c];
+            float v[6], cd[6];
+            ld6(w.cvel + S6 * p, v);
             // velocity before this dof: parent body + the earlier dofs of the same body (free joint: the translations only)
             const int nprev = kind < 6 ? 3 : i - d0;
             for (int k = 0; k < nprev; k++) {
                 const float qd = qvel[d0 + k];
-                for (int c = 0; c < 6; c++) v[c] = fmaf(w.cdof[S6 * (d0 + k) + c], qd, v[c]);
+                ld6(w.cdof + S6 * (d0 + k), cd);
+                for (int c = 0; c < 6; c++) v[c] = fmaf(cd[c], qd, v[c]);
             }
-            cross_motion(v, w.cdof + S6 * i, t);
+            ld6(w.cdof + S6 * i, cd);
+            cross_motion(v, cd, t);
+            const float qd = qvel[i];
+            for (int c = 0; c < 6; c++) t[c] *= qd;
         }
-        const float qd = qvel[i];
-        for (int c = 0; c < 6; c++) da[S6 * i + c] = t[c] * qd;
+        st6(da + S6 * i, t);
     }
     WSYNC();
-    body_sum6(m, da, nullptr, sb, lane);
-    LANE_IF(c, 6) w.Fsub[c] = c == 3 ? -m.gx : c == 4 ? -m.gy : c == 5 ? -m.gz : 0.f;  // every body inherits -gravity from the world
-    WSYNC();
-    path_sum6(m, sb, w.cacc, w.Fsub, lane);
-}
-
-// leaf-to-root accumulation of 6-vectors as subtree gathers
-PB_DEV void subtree_sum6(const DevModel& m, const float* src, float* dst, int lane) {
-    LANE_LOOP(it, NB * 6) {
-        int b = it / 6, k = it - 6 * b;
-        float s = 0.f;
-        for (int c = b; c < m.body_subtree_end[b]; c++) s += src[S6 * c + k];
-        dst[S6 * b + k] = s;
+    LANE_IF(b, NB) {
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (b > 0) path_product6(m, da, nullptr, b, a);
+        a[3] -= m.gx; a[4] -= m.gy; a[5] -= m.gz;  // every body inherits -gravity from the world
+        st6(w.cacc + S6 * b, a);
     }
     WSYNC();
 }
@@ -448,16 +549,18 @@ PB_DEV void subtree_sum6(const DevModel& m, const float* src, float* dst, int la
 // qfrc_bias  (second half of mjx smooth.rne)
 PB_DEVN void stage_bias(const DevModel& m, Ws& w, int lane) {
     LANE_IF(b, NB) {
-        float t[6], u[6], f[6];
-        mul_inert(w.cinert + S10 * b, w.cacc + S6 * b, t);
-        mul_inert(w.cinert + S10 * b, w.cvel + S6 * b, u);
-        cross_force(w.cvel + S6 * b, u, f);
-        for (int c = 0; c < 6; c++) w.F[S6 * b + c] = (b == 0) ? 0.f : t[c] + f[c];
+        float ci[10], a[6], v[6], t[6], u[6], f[6];
+        ld10(w.cinert + S10 * b, ci);
+        ld6(w.cacc + S6 * b, a);
+        ld6(w.cvel + S6 * b, v);
+        mul_inert(ci, a, t);
+        mul_inert(ci, v, u);
+        cross_force(v, u, f);
+        for (int c = 0; c < 6; c++) f[c] = (b == 0) ? 0.f : t[c] + f[c];
+        st6(w.F + S6 * b, f);
     }
     WSYNC();
-    subtree_sum6(m, w.F, w.Fsub, lane);
-    LANE_LOOP(i, NV) w.bias[i] = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]);
-    WSYNC();
+    force_to_dofs(m, w, w.F, w.bias, [](int) { return 0.f; }, lane);
 }
 
 // ---------------------------------------------------------------------------------- tree-sparse L^T D L
@@ -649,18 +752,21 @@ PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
 #endif
 
 // ---------------------------------------------------------------------------------- tree products
-// V[b] = sum over ancestor dofs of cdof_i x_i  (spatial velocity of body b for generalised velocity x)
-PB_DEVN void tree_vel(const DevModel& m, Ws& w, const float* x, int lane) {
-    body_sum6(m, w.cdof, x, w.F, lane);
-    path_sum6(m, w.F, w.V, nullptr, lane);
-}
-// out = M x using V = tree_vel(x) already in w.V (matrix-free, includes armature)
-PB_DEVN void tree_Mx_from_V(const DevModel& m, Ws& w, const float* x, float* out, int lane) {
-    LANE_IF(b, NB) mul_inert(w.cinert + S10 * b, w.V + S6 * b, w.F + S6 * b);
+// out = M x, matrix-free (includes armature); leaves V[b] = spatial velocity of body b for the generalised velocity x
+PB_DEVN void tree_Mx(const DevModel& m, Ws& w, const float* x, float* out, int lane) {
+    LANE_IF(b, NB) {
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (b > 0) {
+            float ci[10];
+            path_product6(m, w.cdof, x, b, v);
+            ld10(w.cinert + S10 * b, ci);
+            mul_inert(ci, v, f);
+        }
+        st6(w.V + S6 * b, v);
+        st6(w.F + S6 * b, f);
+    }
     WSYNC();
-    subtree_sum6(m, w.F, w.Fsub, lane);
-    LANE_LOOP(i, NV) out[i] = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]) + m.dof_armature[i] * x[i];
-    WSYNC();
+    force_to_dofs(m, w, w.F, out, [&](int i) { return m.dof_armature[i] * x[i]; }, lane);
 }
 
 // ---------------------------------------------------------------------------------- smooth dynamics
@@ -771,7 +877,7 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
             p[0] = gp[0] + t[0]; p[1] = gp[1] + t[1]; p[2] = gp[2] + t[2] - 0.5f * dist;
         }
         w.con_dist[c] = dist;
-        for (int k = 0; k < 3; k++) w.con_r[S3 * c + k] = p[k] - w.com[k];
+        for (int k = 0; k < 3; k++) w.con_r[SR * c + k] = p[k] - w.com[k];
         w.con_t1[2 * c] = t1[0]; w.con_t1[2 * c + 1] = t1[1];  // tangent 1 lies in the floor plane
     }
     WSYNC();
@@ -804,12 +910,15 @@ PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float
                 w.con_on[l] = 1;
                 w.con_D[l] = 1.0f / Rr;
                 for (int e = 0; e < 4; e++) {
-                    contact_j6(w.con_r + S3 * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
+                    contact_j6(w.con_r + SR * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
                     w.con_aref[4 * l + e] = -m.sol_b * dot6(j6, w.cvel + S6 * m.con_body[l]) - m.sol_k * imp * pos;
                 }
             }
         }
     }
+    WSYNC();
+    const unsigned cm = wballot(lane, NC, [&](int c) { return w.con_on[c] != 0; });
+    LANE_IF(z, 1) w.con_mask = cm;
     WSYNC();
 }
 
@@ -820,7 +929,7 @@ PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, fl
         if (l < NC && w.con_on[l]) {
             float j6[6];
             for (int e = 0; e < 4; e++) {
-                contact_j6(w.con_r + S3 * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
+                contact_j6(w.con_r + SR * l, w.con_t1 + 2 * l, m.con_mu[l], e, j6);
                 con_out[4 * l + e] = dot6(j6, w.V + S6 * m.con_body[l]);
             }
         }
@@ -830,88 +939,144 @@ PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, fl
 
 // out[i] -= (J^T f)_i with f_r = -D_r jar_r on active rows (jar<0); i.e. adds the constraint gradient D*jar*J
 // mode 0: out = base - J^T f   (gradient),  mode 1: out = J^T f  (qfrc_constraint)
+// Pass 1 (lane = contact slot): the spatial force of the slot's active pyramid edges.  With w_e = n +- mu t the four
+// edge forces collapse to one force vector, so a slot costs one cross product.  Pass 2 (lane = dof): gather the slots
+// of the dof's subtree (contact slots are sorted by body, a subtree is a bit mask) and project on the dof.
 PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, int mode, int lane) {
-    LANE_IF(b, NB) {
-        float f6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, j6[6];
-        for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
-            if (!w.con_on[c]) continue;
-            for (int e = 0; e < 4; e++) {
-                float jar = w.con_jar[4 * c + e];
-                if (jar < 0.f) {
-                    float f = -w.con_D[c] * jar;
-                    contact_j6(w.con_r + S3 * c, w.con_t1 + 2 * c, m.con_mu[c], e, j6);
-                    for (int k = 0; k < 6; k++) f6[k] += f * j6[k];
-                }
-            }
+    float* Fc = w.K;  // [NCP] x S6 (the Hessian blocks are rebuilt after every gradient)
+    static_assert(NCP * S6 <= NB * S21, "contact force scratch");
+    LANE_IF(c, NC) {
+        if ((w.con_mask >> c) & 1u) {
+            float jar[4], r[4], f6[6];
+            ld4(w.con_jar + 4 * c, jar);
+            ld4(w.con_r + SR * c, r);
+            const float D = w.con_D[c], mu = m.con_mu[c], t1x = w.con_t1[2 * c], t1y = w.con_t1[2 * c + 1];
+            const float f0 = jar[0] < 0.f ? -D * jar[0] : 0.f, f1 = jar[1] < 0.f ? -D * jar[1] : 0.f;
+            const float f2 = jar[2] < 0.f ? -D * jar[2] : 0.f, f3 = jar[3] < 0.f ? -D * jar[3] : 0.f;
+            const float a = mu * (f0 - f1), b = mu * (f2 - f3);
+            f6[3] = a * t1x - b * t1y; f6[4] = a * t1y + b * t1x; f6[5] = (f0 + f1) + (f2 + f3);
+            cross3(r, f6 + 3, f6);
+            st6(Fc + S6 * c, f6);
         }
-        for (int k = 0; k < 6; k++) w.F[S6 * b + k] = f6[k];
     }
     WSYNC();
-    subtree_sum6(m, w.F, w.Fsub, lane);
-    LANE_LOOP(i, NV) {
-        float jtf = dot6(w.cdof + S6 * i, w.Fsub + S6 * m.dof_bodyid[i]);
-        int j = m.dof_jntid[i];
-        if (m.jnt_limited[j]) {
-            int l = i - m.jnt_dofadr[m.lim_jnt[0]];  // limited hinges are contiguous dofs (checked at model creation)
-            if (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) jtf += w.lim_sign[l] * (-w.lim_D[l] * w.lim_jar[l]);
+    const int lim0 = m.jnt_dofadr[m.lim_jnt[0]];  // limited hinges own contiguous dofs (checked at model creation)
+    LANE_IF(l, NDL) {
+        const int i = l + 3;
+        float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cd[6];
+        unsigned mk = w.con_mask & m.body_subconmask[m.dof_bodyid[i]];
+        while (mk) {
+            const int c = first_bit(mk);
+            mk &= mk - 1u;
+            float t[6];
+            ld6(Fc + S6 * c, t);
+            for (int k = 0; k < 6; k++) f[k] += t[k];
+        }
+        ld6(w.cdof + S6 * i, cd);
+        float jtf = dot6(cd, f);
+        if (m.jnt_limited[m.dof_jntid[i]]) {
+            const int r = i - lim0;
+            if (w.lim_sign[r] != 0.f && w.lim_jar[r] < 0.f) jtf += w.lim_sign[r] * (-w.lim_D[r] * w.lim_jar[r]);
         }
         out[i] = mode == 0 ? base[i] - jtf : jtf;
+        if (i == 3) for (int k = 0; k < 3; k++) out[k] = mode == 0 ? base[k] - f[3 + k] : f[3 + k];
     }
     WSYNC();
 }
 
-// LD <- M + J^T D_active J  (tree-sparse, assembled like a composite inertia)
+// LD <- M + J^T D_active J  (tree-sparse, assembled like a composite inertia).
+// Pass 1 (lane = slot): W = sum over active edges of D w w^T, a symmetric 3x3 that has a closed form in the pyramid
+// basis.  Pass 2 (lane = body): the 6x6 block of each body from its slots, K = [r]x W [r]x^T etc.  Pass 3 (lane = dof):
+// gather the blocks of the subtree (bit mask of bodies that carry active contacts), apply to the cdof, fill the row.
 PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
+    float* Wc = w.buf6;  // [NCP] x S6: xx yy zz xy xz yz
+    static_assert(NCP * S6 <= NV * S6, "contact W scratch");
+    const unsigned act = wballot(lane, NC, [&](int c) {
+        return ((w.con_mask >> c) & 1u) && (w.con_jar[4 * c] < 0.f || w.con_jar[4 * c + 1] < 0.f || w.con_jar[4 * c + 2] < 0.f || w.con_jar[4 * c + 3] < 0.f);
+    });
+    LANE_IF(c, NC) {
+        if ((act >> c) & 1u) {
+            float jar[4], W[6];
+            ld4(w.con_jar + 4 * c, jar);
+            const float D = w.con_D[c], mu = m.con_mu[c], cs = w.con_t1[2 * c], sn = w.con_t1[2 * c + 1];
+            const float a0 = jar[0] < 0.f ? D : 0.f, a1 = jar[1] < 0.f ? D : 0.f, a2 = jar[2] < 0.f ? D : 0.f, a3 = jar[3] < 0.f ? D : 0.f;
+            const float B1 = mu * (a0 - a1), B2 = mu * (a2 - a3), C1 = mu * mu * (a0 + a1), C2 = mu * mu * (a2 + a3);
+            W[0] = C1 * cs * cs + C2 * sn * sn; W[1] = C1 * sn * sn + C2 * cs * cs; W[2] = (a0 + a1) + (a2 + a3);
+            W[3] = (C1 - C2) * cs * sn; W[4] = B1 * cs - B2 * sn; W[5] = B1 * sn + B2 * cs;
+            st6(Wc + S6 * c, W);
+        }
+    }
+    WSYNC();
+    const unsigned kb = wballot(lane, NB, [&](int b) { return (act & m.body_conmask[b]) != 0u; });
     LANE_IF(b, NB) {
-        float k21[21], j6[6];
-        for (int q = 0; q < 21; q++) k21[q] = 0.f;
-        for (int c = m.body_conadr[b]; c < m.body_conadr[b] + m.body_connum[b]; c++) {
-            if (!w.con_on[c]) continue;
-            for (int e = 0; e < 4; e++) {
-                if (w.con_jar[4 * c + e] < 0.f) {
-                    contact_j6(w.con_r + S3 * c, w.con_t1 + 2 * c, m.con_mu[c], e, j6);
-                    float D = w.con_D[c];
-                    int q = 0;
-                    for (int r = 0; r < 6; r++)
-                        for (int s = r; s < 6; s++) k21[q++] += D * j6[r] * j6[s];
+        unsigned mk = act & m.body_conmask[b];
+        if (mk) {
+            float k[24];
+            for (int q = 0; q < 24; q++) k[q] = 0.f;
+            while (mk) {
+                const int c = first_bit(mk);
+                mk &= mk - 1u;
+                float W[6], r[4];
+                ld6(Wc + S6 * c, W);
+                ld4(w.con_r + SR * c, r);
+                const float c0[3] = {W[0], W[3], W[4]}, c1[3] = {W[3], W[1], W[5]}, c2[3] = {W[4], W[5], W[2]};
+                float g0[3], g1[3], g2[3];  // columns of G = [r]x W
+                cross3(r, c0, g0); cross3(r, c1, g1); cross3(r, c2, g2);
+                const float r0[3] = {g0[0], g1[0], g2[0]}, r1[3] = {g0[1], g1[1], g2[1]}, r2[3] = {g0[2], g1[2], g2[2]};
+                float h0[3], h1[3], h2[3];  // rows of [r]x W [r]x^T
+                cross3(r, r0, h0); cross3(r, r1, h1); cross3(r, r2, h2);
+                k[0] += h0[0]; k[1] += h0[1]; k[2] += h0[2]; k[6] += h1[1]; k[7] += h1[2]; k[11] += h2[2];
+                k[3] += r0[0]; k[4] += r0[1]; k[5] += r0[2]; k[8] += r1[0]; k[9] += r1[1]; k[10] += r1[2];
+                k[12] += r2[0]; k[13] += r2[1]; k[14] += r2[2];
+                k[15] += W[0]; k[16] += W[3]; k[17] += W[4]; k[18] += W[1]; k[19] += W[5]; k[20] += W[2];
+            }
+            st24(w.K + S21 * b, k);
+        }
+    }
+    WSYNC();
+    const int lim0 = m.jnt_dofadr[m.lim_jnt[0]];
+    LANE_IF(l, NDL) {
+        const DofRow r = dof_row(m, l + 3);
+        unsigned bm = kb & m.body_submask[m.dof_bodyid[r.i]];
+        float diag = 0.f;
+        if (m.jnt_limited[m.dof_jntid[r.i]]) {
+            const int q = r.i - lim0;
+            if (w.lim_sign[q] != 0.f && w.lim_jar[q] < 0.f) diag = w.lim_D[q];
+        }
+        if (bm == 0u) {
+            w.LD[r.adr] = w.M[r.adr] + diag;
+#pragma unroll
+            for (int a = 1; a <= MAXANC; a++) if (a <= r.d) w.LD[r.adr + a] = w.M[r.adr + a];
+            if (r.i == 3) for (int e = 0; e < 6; e++) w.LD[e] = w.M[e];  // rows 0..2 are the first six entries
+        } else {
+            float k[24], cd[6], kc[6];
+            for (int q = 0; q < 24; q++) k[q] = 0.f;
+            while (bm) {
+                const int c = first_bit(bm);
+                bm &= bm - 1u;
+                float t[24];
+                ld24(w.K + S21 * c, t);
+                for (int q = 0; q < 21; q++) k[q] += t[q];
+            }
+            ld6(w.cdof + S6 * r.i, cd);
+            for (int a = 0; a < 6; a++) {
+                float s = 0.f;
+                for (int c = 0; c < 6; c++) s = fmaf(k[sym21(a, c)], cd[c], s);
+                kc[a] = s;
+            }
+            w.LD[r.adr] = w.M[r.adr] + dot6(cd, kc) + diag;
+#pragma unroll
+            for (int t = 0; t < MAXANC; t++) {
+                if (t < r.d) {
+                    float cj[6];
+                    ld6(w.cdof + S6 * row_anc(r, t), cj);
+                    w.LD[r.adr + r.d - t] = w.M[r.adr + r.d - t] + dot6(cj, kc);
                 }
             }
+            if (r.i == 3)  // rows 0..2: cdof = [0; e_k]  ->  the lin-lin block
+                for (int a = 0; a < 3; a++)
+                    for (int j = 0; j <= a; j++) w.LD[m.dof_Madr[a] + (a - j)] = w.M[m.dof_Madr[a] + (a - j)] + k[sym21(3 + j, 3 + a)];
         }
-        for (int q = 0; q < 21; q++) w.K[S21 * b + q] = k21[q];
-    }
-    WSYNC();
-    // leaf-to-root accumulation in place: parents of each level gather their (already complete) children
-    for (int lv = m.nlevel - 2; lv >= 1; lv--) {
-        const int s = w.lvl_start[lv], n = w.lvl_start[lv + 1] - s;
-        LANE_LOOP(it, n * 21) {
-            const int b = m.level_body[s + it / 21], k = it % 21;
-            float acc = w.K[S21 * b + k];
-            for (int c = 0; c < m.body_nchild[b]; c++) acc += w.K[S21 * m.body_child[b][c] + k];
-            w.K[S21 * b + k] = acc;
-        }
-        WSYNC();
-    }
-    // K[b][20] (lin-z, lin-z) sums D over the active rows of the subtree: zero <=> nothing to add for that body's dofs
-    LANE_LOOP(i, NV) {
-        const float* K = w.K + S21 * m.dof_bodyid[i];
-        if (K[20] == 0.f) continue;
-        const float* cd = w.cdof + S6 * i;
-        for (int r = 0; r < 6; r++) {
-            float s = 0.f;
-            for (int c = 0; c < 6; c++) s += K[sym21(r, c)] * cd[c];
-            w.buf6[S6 * i + r] = s;
-        }
-    }
-    WSYNC();
-    LANE_LOOP(e, NM) {
-        int r = m.M_row[e], c = m.M_col[e];
-        float v = w.M[e];
-        if (w.K[S21 * m.dof_bodyid[r] + 20] != 0.f) v += dot6(w.cdof + S6 * c, w.buf6 + S6 * r);
-        if (r == c && m.jnt_limited[m.dof_jntid[r]]) {
-            int l = r - m.jnt_dofadr[m.lim_jnt[0]];
-            if (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) v += w.lim_D[l];
-        }
-        w.LD[e] = v;
     }
     WSYNC();
 }
@@ -937,8 +1102,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         // start from the warm start
         LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
         WSYNC();
-        tree_vel(m, w, w.qacc, lane);
-        tree_Mx_from_V(m, w, w.qacc, w.Ma, lane);
+        tree_Mx(m, w, w.qacc, w.Ma, lane);
         rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
         LANE_IF(l, 32) {
             if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
@@ -969,8 +1133,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         WSYNC();
         ldl_factor_solve(m, w, w.p, lane);
         PROF(15);
-        tree_vel(m, w, w.p, lane);
-        tree_Mx_from_V(m, w, w.p, w.Mp, lane);
+        tree_Mx(m, w, w.p, w.Mp, lane);
         rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
         PROF(17);
         // exact line search on the piecewise-quadratic cost along p (safeguarded Newton on phi')
@@ -1152,8 +1315,7 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
     if (pd_mode == PBRL_PD_FEEDBACK) {
         LANE_LOOP(i, NV) w.p[i] = i < vo ? 0.f : -kp[i - vo] * (w.qpos[qo + i - vo] - w.grad[i - vo]) + (-kd[i - vo] * w.qvel[i]);
         WSYNC();
-        tree_vel(m, w, w.p, lane);
-        tree_Mx_from_V(m, w, w.p, w.Mp, lane);
+        tree_Mx(m, w, w.p, w.Mp, lane);
         LANE_IF(a, NU) w.tau[a] = w.Mp[vo + a] + w.bias[vo + a];
         WSYNC();
         return;
@@ -1375,7 +1537,7 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
     LANE_IF(z, 1) { o[PBRL_DBG_NCON_ACTIVE] = nact; o[PBRL_DBG_NITER] = (float)w.niter; }
     LANE_IF(c, NC) {
         o[PBRL_DBG_CON_DIST + c] = w.con_dist[c];
-        for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_r[S3 * c + k] + w.com[k];
+        for (int k = 0; k < 3; k++) o[PBRL_DBG_CON_POS + 3 * c + k] = w.con_r[SR * c + k] + w.com[k];
         for (int e = 0; e < 4; e++)
             o[PBRL_DBG_CON_FORCE + 4 * c + e] = (w.con_on[c] && w.con_jar[4 * c + e] < 0.f) ? -w.con_D[c] * w.con_jar[4 * c + e] : 0.f;
     }

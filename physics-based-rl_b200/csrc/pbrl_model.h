@@ -110,7 +110,8 @@ struct DevModel {
     u8 level_start[MAXLEVEL + 1], level_body[NB], depth_start[MAXDEPTH + 1], depth_dof[NV];
     u8 body_parent[NB], body_subtree_end[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
     u8 body_conadr[NB], body_connum[NB], body_nchild[NB], body_child[NB][4];
-    alignas(4) u8 body_anc[NB][4];  // self, parent, grandparent, ... padded with the world body (its partial sums are zero)
+    alignas(4) u8 body_anc[NB][4];
+    unsigned body_conmask[NB], body_subconmask[NB], body_submask[NB];  // contact slots of the body / of its subtree; bodies of its subtree  // self, parent, grandparent, ... padded with the world body (its partial sums are zero)
     u8 jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ], jnt_bodyid[NJ];
     u8 dof_bodyid[NV], dof_jntid[NV], dof_depth[NV], dof_kind[NV];
     i8 dof_parentid[NV], dof_act[NV];
@@ -325,6 +326,13 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
         m.body_connum[b] = nc - m.body_conadr[b];
     }
     if (nc != NC) return "expected 29 plane contact slots";
+    for (int b = 0; b < NB; b++) {
+        m.body_conmask[b] = m.body_connum[b] ? (((m.body_connum[b] >= 32 ? 0u : (1u << m.body_connum[b])) - 1u) << m.body_conadr[b]) : 0u;
+        m.body_subconmask[b] = 0u; m.body_submask[b] = 0u;
+    }
+    for (int b = 0; b < NB; b++)
+        for (int c = b; c < m.body_subtree_end[b]; c++) { m.body_subconmask[b] |= m.body_conmask[c]; m.body_submask[b] |= 1u << c; }
+    if (d.jnt_dofadr[0] != 0) return "the free joint must own dofs 0..5";
     for (int i = 0; i < NQ; i++) m.qpos0[i] = (float)d.qpos0[i];
     return "";
 }

@@ -10,7 +10,7 @@ model = mjcf.load_model(ROOT / "physics-based-rl_b200" / "assets" / "final_human
 M = L.Model(model, device=0)
 lib = L.lib()
 NAMES = ["ldl_factor_solve", "stage_fk", "stage_com", "stage_crb", "stage_collide", "stage_comvel", "stage_bias", "stage_rows",
-         "tree_vel", "tree_Mx_from_V", "rows_JTf", "assemble_hessian", "rows_Jx", "subtree_sum6", "path_sum6", "body_sum6"]
+         "tree_Mx", "-", "rows_JTf", "assemble_hessian", "rows_Jx"]
 ids = [int(a) for a in sys.argv[1:]] or range(len(NAMES))
 for s in ids:
     r = []
