@@ -429,15 +429,18 @@ PB_DEV DofRow dof_row(const DevModel& m, int i) {
 }
 PB_DEV int row_anc(const DofRow& r, int t) { return (int)((r.an[t >> 2] >> (8 * (t & 3))) & 0xffu); }  // ancestor at depth t < d
 
-// sum of the 6-vector rows src[c] over the bodies c of the subtree of b (bodies are numbered depth first)
+// sum of the 6-vector rows src[c] over the bodies c of the subtree of b (bodies are numbered depth first).  Branch-free:
+// every lane walks the longest possible subtree with clamped indices and 0/1 weights, so all loads are in flight at once.
 PB_DEV void subtree_gather6(const DevModel& m, const float* src, int b, float* f) {
     const int e = m.body_subtree_end[b];
     ld6(src + S6 * b, f);
-#pragma unroll 4
-    for (int c = b + 1; c < e; c++) {
+#pragma unroll
+    for (int k = 1; k < NB - 1; k++) {
+        const bool on = b + k < e;
         float t[6];
-        ld6(src + S6 * c, t);
-        for (int k = 0; k < 6; k++) f[k] += t[k];
+        ld6(src + S6 * (on ? b + k : b), t);
+        const float wt = on ? 1.f : 0.f;
+        for (int q = 0; q < 6; q++) f[q] = fmaf(wt, t[q], f[q]);
     }
 }
 // generalised force of the spatial forces F (one per body): out_i = cdof_i . sum_{subtree(body_i)} F  (+ extra per dof)
@@ -462,22 +465,24 @@ PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
         const int b = m.dof_bodyid[r.i], e = m.body_subtree_end[b];
         float ci[10], cd[6], f[6];
         ld10(w.cinert + S10 * b, ci);
-#pragma unroll 4
-        for (int c = b + 1; c < e; c++) {
+#pragma unroll
+        for (int k = 1; k < NB - 1; k++) {  // branch-free subtree walk (see subtree_gather6)
+            const bool on = b + k < e;
             float t[10];
-            ld10(w.cinert + S10 * c, t);
-            for (int k = 0; k < 10; k++) ci[k] += t[k];
+            ld10(w.cinert + S10 * (on ? b + k : b), t);
+            const float wt = on ? 1.f : 0.f;
+            for (int q = 0; q < 10; q++) ci[q] = fmaf(wt, t[q], ci[q]);
         }
         ld6(w.cdof + S6 * r.i, cd);
         mul_inert(ci, cd, f);
         w.M[r.adr] = dot6(cd, f) + m.dof_armature[r.i];
 #pragma unroll
         for (int t = 0; t < MAXANC; t++) {
-            if (t < r.d) {
-                float cj[6];
-                ld6(w.cdof + S6 * row_anc(r, t), cj);
-                w.M[r.adr + r.d - t] = dot6(cj, f);
-            }
+            const bool on = t < r.d;
+            float cj[6];
+            ld6(w.cdof + S6 * (on ? row_anc(r, t) : r.i), cj);
+            const float v = dot6(cj, f);
+            if (on) w.M[r.adr + r.d - t] = v;
         }
         if (r.i == 3) {  // rows 0..2: cdof = [0; e_k]  ->  M[k][j] = (I_c [0; e_k])_{3+j}: the mass on the diagonal, 0 elsewhere
             for (int k = 0; k < 3; k++)
@@ -487,21 +492,22 @@ PB_DEVN void stage_crb(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
-// V_b = sum over the dofs on the root path of body b of vec6_i * x_i (lane = body; the path is the row of b's last dof)
+// V_b = sum over the dofs on the root path of body b of vec6_i * x_i (lane = body; the path is the row of b's last dof).
+// Branch-free over the longest path (clamped index, zero weight), so the loads of all terms overlap.
+template <bool HASX>
 PB_DEV void path_product6(const DevModel& m, const float* vec6, const float* x, int b, float* v) {
     const DofRow r = dof_row(m, m.body_dofadr[b] + m.body_dofnum[b] - 1);
     float t[6];
     ld6(vec6 + S6 * r.i, t);
-    const float xi = x ? x[r.i] : 1.f;
+    const float xi = HASX ? x[r.i] : 1.f;
     for (int k = 0; k < 6; k++) v[k] = t[k] * xi;
 #pragma unroll
     for (int q = 0; q < MAXANC; q++) {
-        if (q < r.d) {
-            const int j = row_anc(r, q);
-            const float xj = x ? x[j] : 1.f;
-            ld6(vec6 + S6 * j, t);
-            for (int k = 0; k < 6; k++) v[k] = fmaf(t[k], xj, v[k]);
-        }
+        const bool on = q < r.d;
+        const int j = on ? row_anc(r, q) : r.i;
+        const float xj = on ? (HASX ? x[j] : 1.f) : 0.f;
+        ld6(vec6 + S6 * j, t);
+        for (int k = 0; k < 6; k++) v[k] = fmaf(t[k], xj, v[k]);
     }
 }
 
@@ -511,7 +517,7 @@ PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane)
     float* da = w.buf6;  // [NV] x S6: cdof_dot_i * qvel_i
     LANE_IF(b, NB) {
         float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (b > 0) path_product6(m, w.cdof, qvel, b, v);
+        if (b > 0) path_product6<true>(m, w.cdof, qvel, b, v);
         st6(w.cvel + S6 * b, v);
     }
     WSYNC();
@@ -539,7 +545,7 @@ PB_DEVN void stage_comvel(const DevModel& m, Ws& w, const float* qvel, int lane)
     WSYNC();
     LANE_IF(b, NB) {
         float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (b > 0) path_product6(m, da, nullptr, b, a);
+        if (b > 0) path_product6<false>(m, da, nullptr, b, a);
         a[3] -= m.gx; a[4] -= m.gy; a[5] -= m.gz;  // every body inherits -gravity from the world
         st6(w.cacc + S6 * b, a);
     }
@@ -758,7 +764,7 @@ PB_DEVN void tree_Mx(const DevModel& m, Ws& w, const float* x, float* out, int l
         float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (b > 0) {
             float ci[10];
-            path_product6(m, w.cdof, x, b, v);
+            path_product6<true>(m, w.cdof, x, b, v);
             ld10(w.cinert + S10 * b, ci);
             mul_inert(ci, v, f);
         }
@@ -1067,11 +1073,11 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
             w.LD[r.adr] = w.M[r.adr] + dot6(cd, kc) + diag;
 #pragma unroll
             for (int t = 0; t < MAXANC; t++) {
-                if (t < r.d) {
-                    float cj[6];
-                    ld6(w.cdof + S6 * row_anc(r, t), cj);
-                    w.LD[r.adr + r.d - t] = w.M[r.adr + r.d - t] + dot6(cj, kc);
-                }
+                const bool on = t < r.d;
+                float cj[6];
+                ld6(w.cdof + S6 * (on ? row_anc(r, t) : r.i), cj);
+                const float v = w.M[on ? r.adr + r.d - t : r.adr] + dot6(cj, kc);
+                if (on) w.LD[r.adr + r.d - t] = v;
             }
             if (r.i == 3)  // rows 0..2: cdof = [0; e_k]  ->  the lin-lin block
                 for (int a = 0; a < 3; a++)
