@@ -165,6 +165,21 @@ PB_DEV float wsum(int lane, int n, Fn f) {
     return s;
 }
 
+// two sums at once (the shuffle rounds of the two reductions overlap); f(i, a, b) accumulates item i into a and b
+template <class Fn>
+PB_DEV void wsum2(int lane, int n, Fn f, float& s0, float& s1) {
+    float a = 0.f, b = 0.f;
+    LANE_LOOP(i, n) f(i, a, b);
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        a += ta; b += tb;
+    }
+#endif
+    (void)lane;
+    s0 = a; s1 = b;
+}
 // bit mask of the lanes i < n whose predicate holds
 template <class Fn>
 PB_DEV unsigned wballot(int lane, int n, Fn f) {
@@ -592,11 +607,11 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int NSTAGE = 14;  // rotating 16-float staging rows in Ws::buf6 (idle during the factorisation)
 template <int K, int T>
 struct AncRows {  // rows of K's ancestors at depths T-1 .. 0 lose L[K, anc] * row K; c[t] = row K's entry at depth t
-    PB_MEMBER void update(float (&R)[NV], const float (&c)[16], const float ninv, const float rk) {
+    PB_MEMBER void update(float (&R)[NV], const float (&c)[16], const float rks) {  // rks = -row K / D[K], per lane
         if constexpr (T > 0) {
             constexpr int J = topo::anc_at(K, T - 1);
-            R[J] = fmaf(c[T - 1] * ninv, rk, R[J]);
-            AncRows<K, T - 1>::update(R, c, ninv, rk);
+            R[J] = fmaf(c[T - 1], rks, R[J]);
+            AncRows<K, T - 1>::update(R, c, rks);
         }
     }
 };
@@ -614,7 +629,7 @@ template <int I>
 struct Eliminate {
     // Row K is all-gathered through a 16-float staging row: ONE store, a warp barrier and (depth+1)/4 broadcast vector
     // loads give every lane the whole row (a chain of per-entry shuffles serialises on the shuffle scoreboard).
-    PB_MEMBER void run(float (&R)[NV], float (&X)[NSLOT], float (&DI)[NSLOT], bool& bad, float* stage, float* ld_lane, int lane) {
+    PB_MEMBER void run(float (&R)[NV], float (&X)[NSLOT], bool& bad, float* stage, float* ld_lane, int lane) {
         constexpr int K = topo::elim_order(I), d = topo::depth(K), S = topo::slot(K);
         const float rk = R[K];
         float4* st = reinterpret_cast<float4*>(stage + 16 * (I % NSTAGE));
@@ -631,13 +646,12 @@ struct Eliminate {
         }
         const float diag = c[d];
         bad |= !(diag > 0.f);
-        const float inv = fast_rcp(diag);
-        if (lane == d) DI[S] = inv;
         if constexpr (d > 0) {
-            AncRows<K, d>::update(R, c, -inv, rk);
-            AncRhs<K, NSLOT>::run(X, rk * (xs * inv), lane);
+            const float rks = rk * -fast_rcp(diag);
+            AncRows<K, d>::update(R, c, rks);
+            AncRhs<K, NSLOT>::run(X, -rks * xs, lane);
         }
-        if constexpr (I + 1 < NV) Eliminate<I + 1>::run(R, X, DI, bad, stage, ld_lane, lane);
+        if constexpr (I + 1 < NV) Eliminate<I + 1>::run(R, X, bad, stage, ld_lane, lane);
     }
 };
 template <int K>
@@ -656,16 +670,15 @@ struct RowIO {
 };
 template <int S>
 struct SlotIO {
-    PB_MEMBER void load(float (&X)[NSLOT], float (&DI)[NSLOT], const float* x, int lane) {
+    PB_MEMBER void load(float (&X)[NSLOT], const float* x, int lane) {
         const int t = lane - topo::slot_fd(S);
         X[S] = (t >= 0 && t < topo::slot_len(S)) ? x[topo::slot_first(S) + t] : 0.f;
-        DI[S] = 0.f;
-        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::load(X, DI, x, lane);
+        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::load(X, x, lane);
     }
-    PB_MEMBER void store(const float (&X)[NSLOT], const float (&DI)[NSLOT], float* x, float* dinv, int lane) {
+    PB_MEMBER void store(const float (&X)[NSLOT], float* x, int lane) {
         const int t = lane - topo::slot_fd(S);
-        if (t >= 0 && t < topo::slot_len(S)) { x[topo::slot_first(S) + t] = X[S] * DI[S]; dinv[topo::slot_first(S) + t] = DI[S]; }
-        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::store(X, DI, x, dinv, lane);
+        if (t >= 0 && t < topo::slot_len(S)) x[topo::slot_first(S) + t] = X[S];
+        if constexpr (S + 1 < NSLOT) SlotIO<S + 1>::store(X, x, lane);
     }
 };
 template <int T>
@@ -691,12 +704,12 @@ struct BackLevel {  // every dof deeper than T receives L[k, anc_T(k)] * x[anc_T
 PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
     static_assert(offsetof(Ws, LD) >= 32 * sizeof(float), "row loads reach up to 31 floats below LD");
     static_assert(sizeof(w.buf6) >= ldl::NSTAGE * 16 * sizeof(float) && offsetof(Ws, buf6) % 16 == 0 && sizeof(Ws) % 16 == 0, "staging rows");
-    float R[NV], X[NSLOT], DI[NSLOT];
+    float R[NV], X[NSLOT];
     bool bad = false;
     ldl::RowIO<0>::load(R, w.LD - lane, lane);
-    ldl::SlotIO<0>::load(X, DI, x, lane);
-    ldl::Eliminate<0>::run(R, X, DI, bad, w.buf6, w.LD - lane, lane);
-    ldl::SlotIO<0>::store(X, DI, x, w.Dinv, lane);  // x <- D^-1 L^-T x
+    ldl::SlotIO<0>::load(X, x, lane);
+    ldl::Eliminate<0>::run(R, X, bad, w.buf6, w.LD - lane, lane);
+    ldl::SlotIO<0>::store(X, x, lane);  // x <- L^-T x
     if (bad && lane == 0) w.status |= PBRL_STATUS_PIVOT;
     __syncwarp();
     // back substitution, lane <-> dof (lanes 0 .. NV-33 also own dof lane + 32)
@@ -705,7 +718,9 @@ PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
     const int dlo = m.dof_depth[klo], dhi = has_hi ? m.dof_depth[khi] : 0;
     const float* rlo = w.LD + m.dof_Madr[klo] + dlo;  // entry of the ancestor at depth t: rlo[-t]
     const float* rhi = w.LD + m.dof_Madr[khi] + dhi;
-    const float ilo = w.Dinv[klo], ihi = w.Dinv[khi];
+    const float ilo = fast_rcp(rlo[-dlo]), ihi = fast_rcp(rhi[-dhi]);  // 1 / D[k]: the diagonal sits at offset 0 of the row
+    w.Dinv[klo] = ilo;
+    if (has_hi) w.Dinv[khi] = ihi;
     float cl[MAXANC], ch[MAXANC];
 #pragma unroll
     for (int t = 0; t < MAXANC; t++) {
@@ -718,7 +733,7 @@ PB_DEVN void ldl_factor_solve(const DevModel& m, Ws& w, float* x, int lane) {
         sl[q] = reinterpret_cast<const unsigned*>(m.anc_dof[klo])[q];
         sh[q] = reinterpret_cast<const unsigned*>(m.anc_dof[khi])[q];
     }
-    float xl = x[klo], xh = has_hi ? x[khi] : 0.f;
+    float xl = x[klo] * ilo, xh = has_hi ? x[khi] * ihi : 0.f;  // x <- D^-1 L^-T x
     __syncwarp();
     ldl::BackLevel<0>::run(cl, ch, sl, sh, xl, xh);
     x[klo] = xl;
@@ -799,8 +814,10 @@ PB_DEV float impedance(const DevModel& m, float pos) {
 }
 PB_DEV int argmax_masked(const float* score, const bool* ok, int n) {  // first maximum among ok[]; 0 if none
     int best = -1;
+    float bs = 0.f;  // running best score (no indexed read of score[])
+#pragma unroll
     for (int i = 0; i < n; i++)
-        if (ok[i] && (best < 0 || score[i] > score[best])) best = i;
+        if (ok[i] && (best < 0 || score[i] > bs)) { best = i; bs = score[i]; }
     return best < 0 ? 0 : best;
 }
 // pyramid edge e of a contact: w = n + sg*mu*t, j6 = [r x w ; w]
@@ -833,53 +850,67 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
             dist = ce[2] - m.plane_z - r;
             p[0] = ce[0]; p[1] = ce[1]; p[2] = ce[2] - (r + 0.5f * dist);
         } else {  // box corner manifold (mjx plane_convex + _manifold_points)
-            float Rl[9], Rg[9], vert[8][3], sup[8], sc[16], pl[3], nl[3], d3[3], e3[3], ab[3], ac[3], bc[3], smax;
+            // vertices are generated from their index (bit 2-k of v = sign along axis k): no indexed local arrays
+            const float* sz = m.con_size[c];
+            auto vert = [&](int v, float* o) { o[0] = (v & 4) ? sz[0] : -sz[0]; o[1] = (v & 2) ? sz[1] : -sz[1]; o[2] = (v & 1) ? sz[2] : -sz[2]; };
+            float Rl[9], Rg[9], sup[8], sc[16], pl[3], nl[3], d3[3], e3[3], ab[3], ac[3], bc[3], va[3], vb[3], vc[3], vv[3], smax;
             bool ok[16];
             quat_to_mat(m.con_gquat[c], Rl);
             for (int r = 0; r < 3; r++)
                 for (int q = 0; q < 3; q++) Rg[3 * r + q] = R[3 * r] * Rl[q] + R[3 * r + 1] * Rl[3 + q] + R[3 * r + 2] * Rl[6 + q];
-            for (int v = 0; v < 8; v++)
-                for (int k = 0; k < 3; k++) vert[v][k] = (((v >> (2 - k)) & 1) ? 1.f : -1.f) * m.con_size[c][k];
             d3[0] = -gp[0]; d3[1] = -gp[1]; d3[2] = m.plane_z - gp[2];
             matT_vec(Rg, d3, pl);
             nl[0] = Rg[6]; nl[1] = Rg[7]; nl[2] = Rg[8];
             smax = -1e30f;
+#pragma unroll
             for (int v = 0; v < 8; v++) {
-                for (int k = 0; k < 3; k++) d3[k] = pl[k] - vert[v][k];
+                vert(v, vv);
+                for (int k = 0; k < 3; k++) d3[k] = pl[k] - vv[k];
                 sup[v] = dot3(d3, nl);
                 smax = fmaxf(smax, sup[v]);
             }
             float thr = fmaxf(0.f, smax - 1e-3f);
+#pragma unroll
             for (int v = 0; v < 8; v++) { ok[v] = sup[v] > thr; ok[8 + v] = ok[v]; sc[v] = 0.f; }
             int ia = argmax_masked(sc, ok, 8);
+            vert(ia, va);
+#pragma unroll
             for (int v = 0; v < 8; v++) {
-                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                vert(v, vv);
+                for (int k = 0; k < 3; k++) d3[k] = va[k] - vv[k];
                 sc[v] = dot3(d3, d3);
             }
             int ib = argmax_masked(sc, ok, 8);
-            for (int k = 0; k < 3; k++) e3[k] = vert[ia][k] - vert[ib][k];
+            vert(ib, vb);
+            for (int k = 0; k < 3; k++) e3[k] = va[k] - vb[k];
             cross3(nl, e3, ab);
+#pragma unroll
             for (int v = 0; v < 8; v++) {
-                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                vert(v, vv);
+                for (int k = 0; k < 3; k++) d3[k] = va[k] - vv[k];
                 sc[v] = fabsf(dot3(d3, ab));
             }
             int ic = argmax_masked(sc, ok, 8);
-            for (int k = 0; k < 3; k++) e3[k] = vert[ia][k] - vert[ic][k];
+            vert(ic, vc);
+            for (int k = 0; k < 3; k++) e3[k] = va[k] - vc[k];
             cross3(nl, e3, ac);
-            for (int k = 0; k < 3; k++) e3[k] = vert[ib][k] - vert[ic][k];
+            for (int k = 0; k < 3; k++) e3[k] = vb[k] - vc[k];
             cross3(nl, e3, bc);
+#pragma unroll
             for (int v = 0; v < 8; v++) {
-                for (int k = 0; k < 3; k++) d3[k] = vert[ib][k] - vert[v][k];
+                vert(v, vv);
+                for (int k = 0; k < 3; k++) d3[k] = vb[k] - vv[k];
                 sc[v] = fabsf(dot3(d3, bc));
-                for (int k = 0; k < 3; k++) d3[k] = vert[ia][k] - vert[v][k];
+                for (int k = 0; k < 3; k++) d3[k] = va[k] - vv[k];
                 sc[8 + v] = fabsf(dot3(d3, ac));
             }
             int id = argmax_masked(sc, ok, 16) % 8;
-            int idx[4] = {ia, ib, ic, id}, sub = m.con_sub[c], me = idx[sub];
-            bool uniq = true;
-            for (int q = 0; q < sub; q++) uniq = uniq && (idx[q] != me);
-            dist = uniq ? -sup[me] : 1.f;
-            mat_vec(Rg, vert[me], t);
+            const int sub = m.con_sub[c], me = sub == 0 ? ia : sub == 1 ? ib : sub == 2 ? ic : id;
+            const bool uniq = (sub < 1 || ia != me) && (sub < 2 || ib != me) && (sub < 3 || ic != me);
+            vert(me, vv);
+            for (int k = 0; k < 3; k++) d3[k] = pl[k] - vv[k];
+            dist = uniq ? -dot3(d3, nl) : 1.f;
+            mat_vec(Rg, vv, t);
             p[0] = gp[0] + t[0]; p[1] = gp[1] + t[1]; p[2] = gp[2] + t[2] - 0.5f * dist;
         }
         w.con_dist[c] = dist;
@@ -1090,9 +1121,9 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
 // ---------------------------------------------------------------------------------- Newton solver on qacc
 // minimise 1/2 (a-a_s)^T M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2   
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
-    float nrows = wsum(lane, 32, [&](int l) { return (w.lim_sign[l] != 0.f ? 1.f : 0.f) + (w.con_on[l] ? 1.f : 0.f); });
+    const unsigned lim_rows = wballot(lane, NLIM, [&](int l) { return w.lim_sign[l] != 0.f; });
     w.niter = 0;
-    const bool constrained = nrows > 0.f;
+    const bool constrained = (lim_rows | w.con_mask) != 0u;
     const bool coop = (w.phase_lock & 16) != 0;  // iterate in step with the other warps of the CTA (shared I-cache window)
     if (!constrained) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
         LANE_LOOP(e, NM) w.LD[e] = w.M[e];
@@ -1143,37 +1174,28 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
         PROF(17);
         // exact line search on the piecewise-quadratic cost along p (safeguarded Newton on phi')
-        float g0 = wsum(lane, NV, [&](int i) { return (w.Ma[i] - w.fsmooth[i]) * w.p[i]; });
-        float pMp = wsum(lane, NV, [&](int i) { return w.Mp[i] * w.p[i]; });
+        float g0, pMp;
+        wsum2(lane, NV, [&](int i, float& a, float& b) { const float pi = w.p[i]; a = fmaf(w.Ma[i] - w.fsmooth[i], pi, a); b = fmaf(w.Mp[i], pi, b); }, g0, pMp);
         float alpha = 1.f, lo = 0.f, hi = -1.f;
         float d1_0 = 0.f;
         for (int ls = 0; ls < LS_MAXIT; ls++) {
-            float d1 = wsum(lane, 32, [&](int l) {
-                float s = 0.f;
+            float d1, d2;  // first and second derivative of the row costs at alpha
+            wsum2(lane, 32, [&](int l, float& a, float& b) {
                 if (l < NLIM && w.lim_sign[l] != 0.f) {
-                    float x = w.lim_jar[l] + alpha * w.lim_jp[l];
-                    if (x < 0.f) s += w.lim_D[l] * x * w.lim_jp[l];
+                    const float jp = w.lim_jp[l], x = w.lim_jar[l] + alpha * jp;
+                    if (x < 0.f) { const float dj = w.lim_D[l] * jp; a = fmaf(dj, x, a); b = fmaf(dj, jp, b); }
                 }
-                if (l < NC && w.con_on[l])
+                if (l < NC && w.con_on[l]) {
+                    float jar[4], jp[4];
+                    ld4(w.con_jar + 4 * l, jar);
+                    ld4(w.con_jp + 4 * l, jp);
+                    const float D = w.con_D[l];
                     for (int e = 0; e < 4; e++) {
-                        float x = w.con_jar[4 * l + e] + alpha * w.con_jp[4 * l + e];
-                        if (x < 0.f) s += w.con_D[l] * x * w.con_jp[4 * l + e];
+                        const float x = jar[e] + alpha * jp[e];
+                        if (x < 0.f) { const float dj = D * jp[e]; a = fmaf(dj, x, a); b = fmaf(dj, jp[e], b); }
                     }
-                return s;
-            });
-            float d2 = wsum(lane, 32, [&](int l) {
-                float s = 0.f;
-                if (l < NLIM && w.lim_sign[l] != 0.f) {
-                    float x = w.lim_jar[l] + alpha * w.lim_jp[l];
-                    if (x < 0.f) s += w.lim_D[l] * w.lim_jp[l] * w.lim_jp[l];
                 }
-                if (l < NC && w.con_on[l])
-                    for (int e = 0; e < 4; e++) {
-                        float x = w.con_jar[4 * l + e] + alpha * w.con_jp[4 * l + e];
-                        if (x < 0.f) s += w.con_D[l] * w.con_jp[4 * l + e] * w.con_jp[4 * l + e];
-                    }
-                return s;
-            });
+            }, d1, d2);
             float dphi = g0 + alpha * pMp + d1, ddphi = pMp + d2;
             if (ls == 0) d1_0 = fabsf(g0) + fabsf(pMp) + fabsf(d1);
             if (fabsf(dphi) <= 1e-6f * d1_0) break;
@@ -1186,7 +1208,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         PROF(18);
         // step, refresh residuals, detect active-set change
         LANE_LOOP(i, NV) { w.qacc[i] += alpha * w.p[i]; w.Ma[i] += alpha * w.Mp[i]; }
-        float changed = wsum(lane, 32, [&](int l) {
+        const unsigned changed = wballot(lane, 32, [&](int l) {
             int bits = 0;
             if (l < NLIM && w.lim_sign[l] != 0.f) {
                 w.lim_jar[l] += alpha * w.lim_jp[l];
@@ -1198,14 +1220,14 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
                     bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
                 }
             // act_bits[l] still holds the active set this iteration's Hessian was built from
-            float ch = (bits != w.act_bits[l]) ? 1.f : 0.f;
+            const bool ch = bits != w.act_bits[l];
             w.act_bits[l] = bits;
             return ch;
         });
         WSYNC();
         // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
         it++;
-        if (changed == 0.f) running = false;
+        if (changed == 0u) running = false;
         PROF(19);
     }
     if (!constrained) return;
