@@ -150,6 +150,11 @@ class ModelConst:
     geom_friction: np.ndarray = None
     geom_margin: np.ndarray = None
     geom_gap: np.ndarray = None
+    geom_contype: np.ndarray = None
+    geom_conaffinity: np.ndarray = None
+    # collision candidates (MuJoCo broad-phase filter rules, evaluated once: MJX has no dynamic broad phase)
+    pair_geom1: np.ndarray = None  # geom with the lower mjtGeom type first (MJX dispatch order), then the lower id
+    pair_geom2: np.ndarray = None
     # actuators
     act_names: list = field(default_factory=list)
     act_dofadr: np.ndarray = None
@@ -469,6 +474,8 @@ def compile_mjcf(path) -> ModelConst:
     m.geom_friction = fr
     m.geom_margin = np.array([g["margin"] for g in geoms])
     m.geom_gap = np.array([g["gap"] for g in geoms])
+    m.geom_contype = np.array([g["contype"] for g in geoms], dtype=np.int32)
+    m.geom_conaffinity = np.array([g["conaffinity"] for g in geoms], dtype=np.int32)
 
     # body inertial frames from geoms (inertiafromgeom="true")
     m.body_mass = np.zeros(nb)
@@ -510,6 +517,9 @@ def compile_mjcf(path) -> ModelConst:
     con = root.find("contact")
     if con is not None:
         m.exclude = [[e.get("body1"), e.get("body2")] for e in con.findall("exclude")]
+    pairs = collision_pairs(m)
+    m.pair_geom1 = np.array([p[0] for p in pairs], dtype=np.int32)
+    m.pair_geom2 = np.array([p[1] for p in pairs], dtype=np.int32)
 
     # constants at qpos0 (MuJoCo mj_setConst)
     M0 = mass_matrix(m, m.qpos0)
@@ -529,6 +539,40 @@ def compile_mjcf(path) -> ModelConst:
         m.body_invweight0[b, 0] = np.trace(A[3:6, 3:6]) / 3.0
         m.body_invweight0[b, 1] = np.trace(A[0:3, 0:3]) / 3.0
     return m
+
+
+def collision_pairs(m: ModelConst):
+    """Static collision candidates, SURVEY.md App. A.7 / B.4 (MuJoCo `mj_collision` filters with the MJX rule that
+    every candidate is always evaluated): geoms of different bodies whose contype/conaffinity bits are compatible,
+    not parent and child (a parent that is the world is exempt), not listed under <contact><exclude>.
+    Returns [(g1, g2)] with type(g1) <= type(g2), sorted by (type1, type2, g1, g2)."""
+    excl = {frozenset((m.body_id(a), m.body_id(b))) for a, b in m.exclude}
+    out = []
+    for g1 in range(m.ngeom):
+        for g2 in range(g1 + 1, m.ngeom):
+            b1, b2 = int(m.geom_bodyid[g1]), int(m.geom_bodyid[g2])
+            if b1 == b2:
+                continue
+            if not ((m.geom_contype[g1] & m.geom_conaffinity[g2]) or (m.geom_contype[g2] & m.geom_conaffinity[g1])):
+                continue
+            if (b1 != 0 and m.body_parent[b2] == b1) or (b2 != 0 and m.body_parent[b1] == b2):
+                continue
+            if frozenset((b1, b2)) in excl:
+                continue
+            a, b = (g1, g2) if m.geom_type[g1] <= m.geom_type[g2] else (g2, g1)
+            out.append((a, b))
+    out.sort(key=lambda p: (int(m.geom_type[p[0]]), int(m.geom_type[p[1]]), p[0], p[1]))
+    return out
+
+
+def pair_census(m: ModelConst):
+    """{'SC': 32, ...}: candidate count per geom-type pair (P plane, S sphere, C capsule, B box)."""
+    code = {GEOM_PLANE: "P", GEOM_SPHERE: "S", GEOM_CAPSULE: "C", GEOM_BOX: "B"}
+    out = {}
+    for a, b in zip(m.pair_geom1, m.pair_geom2):
+        k = code[int(m.geom_type[a])] + code[int(m.geom_type[b])]
+        out[k] = out.get(k, 0) + 1
+    return out
 
 
 def load_model(path) -> ModelConst:
