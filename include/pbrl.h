@@ -52,6 +52,7 @@ extern "C" {
 #define PBRL_STATUS_NAN 1
 #define PBRL_STATUS_PIVOT 2
 #define PBRL_STATUS_SOLVER_MAXITER 4
+#define PBRL_STATUS_SELF_OVERFLOW 8 /* more body-vs-body contacts inside the margin than the kernel keeps (8): the extra ones were dropped */
 
 typedef struct PbrlModel PbrlModel;
 
@@ -63,6 +64,7 @@ typedef struct PbrlModel PbrlModel;
 #define PBRL_MAXU 32
 #define PBRL_MAXJNT 32
 #define PBRL_MAXGEOM 20
+#define PBRL_MAXPAIR 128
 #define PBRL_MODEL_FIELDS(I, D)                                                                     \
     I(nbody, 1) I(nq, 1) I(nv, 1) I(nu, 1) I(njnt, 1) I(ngeom, 1) I(iterations, 1)                  \
     I(ls_iterations, 1)                                                                              \
@@ -81,7 +83,8 @@ typedef struct PbrlModel PbrlModel;
     D(geom_pos, PBRL_MAXGEOM * 3) D(geom_quat, PBRL_MAXGEOM * 4) D(geom_friction, PBRL_MAXGEOM * 3) \
     D(geom_margin, PBRL_MAXGEOM) D(geom_gap, PBRL_MAXGEOM)                                           \
     I(act_dofadr, PBRL_MAXU) D(act_gear, PBRL_MAXU) I(act_ctrllimited, PBRL_MAXU)                   \
-    D(act_ctrlrange, PBRL_MAXU * 2)
+    D(act_ctrlrange, PBRL_MAXU * 2)                                                                  \
+    I(npair, 1) I(pair_geom1, PBRL_MAXPAIR) I(pair_geom2, PBRL_MAXPAIR)
 
 typedef struct PbrlModelDesc {
 #define PBRL_I(name, n) int name[n];
@@ -178,7 +181,10 @@ int pbrl_pd_torque(const PbrlModel* model, int N, int pd_mode, int action_cols, 
 #define PBRL_DBG_NITER 1556        /* 1 */
 #define PBRL_DBG_CON_FORCE 1557    /* 32*4 pyramid forces */
 #define PBRL_DBG_LIM_FORCE 1685    /* 28 */
-#define PBRL_DBG_SIZE 1720
+#define PBRL_DBG_NSELF 1713        /* 1: body-vs-body contacts inside the margin */
+#define PBRL_DBG_SELF_DIST 1714    /* 8 */
+#define PBRL_DBG_SELF_FORCE 1722   /* 8*4 pyramid forces */
+#define PBRL_DBG_SIZE 1756
 int pbrl_debug_forward(const PbrlModel* model, int N, const float* qpos, const float* qvel, const float* ctrl,
                        const float* warm, float* out, void* stream);
 

@@ -27,7 +27,10 @@ def build(force=False):
 class Oracle:
     """One precision of the oracle bound to one model."""
 
-    def __init__(self, model, precision="f64", tolerance=None, iterations=None):
+    def __init__(self, model, precision="f64", tolerance=None, iterations=None, self_collision=None):
+        """self_collision: evaluate the body-vs-body candidates (default: the model's `self_collision` switch)."""
+        if self_collision is None:
+            self_collision = bool(getattr(model, "self_collision", 1))
         build()
         self.lib = ctypes.CDLL(str(HERE / f"liboracle_{precision}.so"))
         self.real = np.float64 if precision == "f64" else np.float32
@@ -36,6 +39,10 @@ class Oracle:
         self.nq, self.nv, self.nu, self.nbody = model.nq, model.nv, model.nu, model.nbody
         self._model_buf = np.zeros(self.lib.orc_model_size(), dtype=np.uint8)
         self._fill_model(model, tolerance, iterations)
+        if self_collision and getattr(model, "pair_geom1", None) is not None:
+            self.set_model_field("pair_geom1", model.pair_geom1)
+            self.set_model_field("pair_geom2", model.pair_geom2)
+            self.set_model_field("npair", len(model.pair_geom1))
         self._dsize = self.lib.orc_data_size()
         self._dfields = {}
         for fn in ("orc_reset_data", "orc_forward", "orc_step"):

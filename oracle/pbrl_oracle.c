@@ -288,14 +288,58 @@ static void make_frame(REAL* fr, const REAL* a) { /* rows: a, b, a x b  (mjx mat
     for (int k = 0; k < 3; k++) { b[k] /= n; fr[k] = a[k]; fr[3 + k] = b[k]; }
     cross3(fr + 6, a, b);
 }
-static void add_contact(OrcData* d, int* nc, REAL dist, const REAL* pos, const REAL* frame, int geom, REAL mu, REAL margin) {
+static void add_contact2(OrcData* d, int* nc, REAL dist, const REAL* pos, const REAL* frame, int geom1, int geom, REAL mu, REAL margin) {
     int c = (*nc)++;
+    d->con_geom1[c] = (REAL)geom1;
     d->con_dist[c] = dist;
     memcpy(d->con_pos + 3 * c, pos, 3 * sizeof(REAL));
     memcpy(d->con_frame + 9 * c, frame, 9 * sizeof(REAL));
     d->con_geom[c] = (REAL)geom;
     d->con_mu[c] = mu;
     d->con_includemargin[c] = margin;
+}
+/* ---- sphere / capsule pairs (mjx collision_primitive.py: _sphere_sphere, sphere_capsule, capsule_capsule; math.py:
+ *      normalize_with_norm, closest_segment_point, closest_segment_to_segment_points) */
+static void closest_segment_point(REAL* out, const REAL* a, const REAL* b, const REAL* pt) {
+    REAL ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+    REAL t = dot3(ap, ab) / (dot3(ab, ab) + R(1e-6));
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
+}
+static REAL normalize_with_norm(REAL* n, const REAL* x) {
+    REAL nrm = rsqrt_(dot3(x, x)), den = nrm + (nrm == 0 ? R(1e-6) : 0);
+    for (int k = 0; k < 3; k++) n[k] = x[k] / den;
+    return nrm;
+}
+static void closest_segment_to_segment(REAL* best_a, REAL* best_b, const REAL* a0, const REAL* a1, const REAL* b0, const REAL* b1) {
+    REAL va[3], vb[3], dir_a[3], dir_b[3], a_mid[3], b_mid[3], trans[3], new_a[3], new_b[3], e1[3], e2[3];
+    for (int k = 0; k < 3; k++) { va[k] = a1[k] - a0[k]; vb[k] = b1[k] - b0[k]; }
+    REAL half_a = normalize_with_norm(dir_a, va) * R(0.5), half_b = normalize_with_norm(dir_b, vb) * R(0.5);
+    for (int k = 0; k < 3; k++) { a_mid[k] = a0[k] + dir_a[k] * half_a; b_mid[k] = b0[k] + dir_b[k] * half_b; trans[k] = a_mid[k] - b_mid[k]; }
+    REAL dd = dot3(dir_a, dir_b), dat = dot3(dir_a, trans), dbt = dot3(dir_b, trans), denom = 1 - dd * dd;
+    REAL ta = (-dat + dd * dbt) / (denom + R(1e-6)), tb = dbt + ta * dd;
+    ta = ta < -half_a ? -half_a : (ta > half_a ? half_a : ta);
+    tb = tb < -half_b ? -half_b : (tb > half_b ? half_b : tb);
+    for (int k = 0; k < 3; k++) { best_a[k] = a_mid[k] + dir_a[k] * ta; best_b[k] = b_mid[k] + dir_b[k] * tb; }
+    closest_segment_point(new_a, a0, a1, best_b);
+    closest_segment_point(new_b, b0, b1, best_a);
+    for (int k = 0; k < 3; k++) { e1[k] = new_a[k] - best_b[k]; e2[k] = new_b[k] - best_a[k]; }
+    if (dot3(e1, e1) < dot3(e2, e2)) memcpy(best_a, new_a, 3 * sizeof(REAL)); else memcpy(best_b, new_b, 3 * sizeof(REAL));
+}
+static void sphere_sphere(const REAL* p1, REAL r1, const REAL* p2, REAL r2, REAL* dist, REAL* pos, REAL* frame) {
+    REAL dlt[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, n[3];
+    REAL nrm = normalize_with_norm(n, dlt);
+    if (nrm == 0) { n[0] = 1; n[1] = 0; n[2] = 0; }
+    *dist = nrm - (r1 + r2);
+    for (int k = 0; k < 3; k++) pos[k] = p1[k] + n[k] * (r1 + *dist * R(0.5));
+    make_frame(frame, n);
+}
+static void capsule_ends(const OrcModel* m, const OrcData* d, int g, REAL* e0, REAL* e1) {
+    const REAL* gm = d->geom_xmat + 9 * g;
+    for (int k = 0; k < 3; k++) {
+        REAL s = gm[3 * k + 2] * R(m->geom_size[3 * g + 1]);
+        e0[k] = d->geom_xpos[3 * g + k] - s; e1[k] = d->geom_xpos[3 * g + k] + s;
+    }
 }
 static void plane_sphere(const REAL* n, const REAL* ppos, const REAL* c, REAL r, REAL* dist, REAL* pos) {
     REAL t[3] = {c[0] - ppos[0], c[1] - ppos[1], c[2] - ppos[2]};
@@ -325,7 +369,7 @@ static void collision(const OrcModel* m, OrcData* d) {
                 if (t == GEOM_SPHERE) {
                     make_frame(fr, n);
                     plane_sphere(n, ppos, gp, R(m->geom_size[3 * g]), &dist, pos);
-                    add_contact(d, &nc, dist, pos, fr, g, mu, margin);
+                    add_contact2(d, &nc, dist, pos, fr, p, g, mu, margin);
                 } else if (t == GEOM_CAPSULE) {
                     REAL axis[3] = {gm[2], gm[5], gm[8]}, b[3], bn, na = dot3(n, axis);
                     for (int k = 0; k < 3; k++) b[k] = axis[k] - n[k] * na;
@@ -342,7 +386,7 @@ static void collision(const OrcModel* m, OrcData* d) {
                         REAL sg = s == 0 ? R(1) : R(-1), c[3];
                         for (int k = 0; k < 3; k++) c[k] = gp[k] + sg * axis[k] * R(m->geom_size[3 * g + 1]);
                         plane_sphere(n, ppos, c, R(m->geom_size[3 * g]), &dist, pos);
-                        add_contact(d, &nc, dist, pos, fr, g, mu, margin);
+                        add_contact2(d, &nc, dist, pos, fr, p, g, mu, margin);
                     }
                 } else if (t == GEOM_BOX) {
                     /* mjx plane_convex + _manifold_points on the 8 box corners */
@@ -393,13 +437,40 @@ static void collision(const OrcModel* m, OrcData* d) {
                         dist = unique ? -support[idx[q]] : R(1);
                         mat_vec3(tmp, gm, vert[idx[q]]);
                         for (int k = 0; k < 3; k++) pos[k] = gp[k] + tmp[k] - R(0.5) * dist * n[k];
-                        add_contact(d, &nc, dist, pos, fr, g, mu, margin);
+                        add_contact2(d, &nc, dist, pos, fr, p, g, mu, margin);
                     }
                 }
             }
         }
     }
+    /* self-collision candidates.  MJX evaluates every candidate every step and multiplies
+     * the rows of the distant ones by zero; only the contacts inside the margin get rows here (same optimum).  The
+     * box pairs (sphere/capsule/box vs the foot boxes: mjx collision_convex.py) are not restated yet: they are counted. */
+    int nplane = nc, nbox = 0;
+    for (int q = 0; q < m->npair[0]; q++) {
+        int g1 = m->pair_geom1[q], g2 = m->pair_geom2[q], t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+        if (t1 == GEOM_PLANE) continue;
+        if (t2 == GEOM_BOX) { nbox++; continue; }
+        REAL margin = R(fmax(m->geom_margin[g1], m->geom_margin[g2]) - fmax(m->geom_gap[g1], m->geom_gap[g2]));
+        REAL mu = R(fmax(m->geom_friction[3 * g1], m->geom_friction[3 * g2]));
+        REAL r1 = R(m->geom_size[3 * g1]), r2 = R(m->geom_size[3 * g2]), fr[9], dist, pos[3], a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
+        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) {
+            sphere_sphere(d->geom_xpos + 3 * g1, r1, d->geom_xpos + 3 * g2, r2, &dist, pos, fr);
+        } else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
+            capsule_ends(m, d, g2, b0, b1);
+            closest_segment_point(pb, b0, b1, d->geom_xpos + 3 * g1);
+            sphere_sphere(d->geom_xpos + 3 * g1, r1, pb, r2, &dist, pos, fr);
+        } else {
+            capsule_ends(m, d, g1, a0, a1);
+            capsule_ends(m, d, g2, b0, b1);
+            closest_segment_to_segment(pa, pb, a0, a1, b0, b1);
+            sphere_sphere(pa, r1, pb, r2, &dist, pos, fr);
+        }
+        if (dist - margin < 0 && nc < ORC_MAXCON) add_contact2(d, &nc, dist, pos, fr, g1, g2, mu, margin);
+    }
     d->ncon[0] = (REAL)nc;
+    d->nself[0] = (REAL)(nc - nplane);
+    d->nbox_skipped[0] = (REAL)nbox;
 }
 
 /* ---------------------------------------------------------------- constraints */
@@ -461,15 +532,17 @@ static void make_constraint(const OrcModel* m, OrcData* d) {
     }
     int nc = (int)d->ncon[0];
     for (int c = 0; c < nc; c++) {
-        int g = (int)d->con_geom[c], b2 = m->geom_bodyid[g];
-        REAL jp[3 * NVMAX], jc[3 * NVMAX], mu = d->con_mu[c];
+        int g = (int)d->con_geom[c], b2 = m->geom_bodyid[g], b1 = m->geom_bodyid[(int)d->con_geom1[c]];
+        REAL jp[3 * NVMAX], jp1[3 * NVMAX], jc[3 * NVMAX], mu = d->con_mu[c];
         REAL pos = d->con_dist[c] - d->con_includemargin[c];
-        jac_point(m, d, b2, d->con_pos + 3 * c, jp); /* body1 = world: zero Jacobian */
+        jac_point(m, d, b2, d->con_pos + 3 * c, jp);
+        jac_point(m, d, b1, d->con_pos + 3 * c, jp1); /* zero for the world body (floor contacts) */
+        for (int i = 0; i < 3 * NVMAX; i++) jp[i] -= jp1[i];
         for (int a = 0; a < 3; a++)
             for (int i = 0; i < nv; i++)
                 jc[a * NVMAX + i] = d->con_frame[9 * c + 3 * a] * jp[i] + d->con_frame[9 * c + 3 * a + 1] * jp[NVMAX + i] +
                                     d->con_frame[9 * c + 3 * a + 2] * jp[2 * NVMAX + i];
-        REAL t = R(m->body_invweight0[0]) + R(m->body_invweight0[2 * b2]);
+        REAL t = R(m->body_invweight0[2 * b1]) + R(m->body_invweight0[2 * b2]);
         REAL invweight = (t + mu * mu * t) * 2 * mu * mu / R(m->impratio[0]);
         for (int e = 0; e < 4; e++) {
             int a = 1 + e / 2;

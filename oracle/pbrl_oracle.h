@@ -10,7 +10,9 @@
  * agents_env/agent_env_template.py:88-112, agents_env/agent_replay_motion.py:51-83,
  * agents_env/pds_controllers_agents.py:17-172) and pinned by the notebook goldens T0-T4
  * (tests/golden/mass_traces.npz).  Parity status: contact-free chain pinned by
- * goldens; plane contacts and the mimic reward have no reference known-answer ("parity unpinned").
+ * goldens T1-T4 up to print 10; sphere-capsule self-contact rows (wrist vs thigh) pinned by the same traces
+ * beyond the prints where the hands first touch the thighs (T1 print 15, T2 print 7: tests/test_oracle_golden.py);
+ * plane contacts and the mimic reward have no reference known-answer ("parity unpinned").
  *
  * Compiled twice: -DORC_F32 (REAL=float) and default (REAL=double).
  */
@@ -29,7 +31,8 @@ typedef double REAL;
 #define ORC_MAXU 32
 #define ORC_MAXJNT 32
 #define ORC_MAXGEOM 20
-#define ORC_MAXCON 32
+#define ORC_MAXPAIR 128
+#define ORC_MAXCON 96 /* 29 floor slots + the self-contacts in range (sphere/capsule pairs: at most 64) */
 #define ORC_MAXEFC (ORC_MAXJNT + 4 * ORC_MAXCON)
 
 /* Model: field names equal the attributes of ModelConst (physics-based-rl_b200/mjcf.py). */
@@ -51,7 +54,8 @@ typedef double REAL;
     D(geom_pos, ORC_MAXGEOM * 3) D(geom_quat, ORC_MAXGEOM * 4) D(geom_friction, ORC_MAXGEOM * 3)  \
     D(geom_margin, ORC_MAXGEOM) D(geom_gap, ORC_MAXGEOM)                                           \
     I(act_dofadr, ORC_MAXU) D(act_gear, ORC_MAXU) I(act_ctrllimited, ORC_MAXU)                    \
-    D(act_ctrlrange, ORC_MAXU * 2)
+    D(act_ctrlrange, ORC_MAXU * 2)                                                                 \
+    I(npair, 1) I(pair_geom1, ORC_MAXPAIR) I(pair_geom2, ORC_MAXPAIR)
 
 typedef struct {
 #define ORC_I(name, n) int name[n];
@@ -74,6 +78,7 @@ typedef struct {
     X(qfrc_applied, ORC_MAXV) X(qfrc_smooth, ORC_MAXV) X(qacc_smooth, ORC_MAXV) X(qacc, ORC_MAXV)  \
     X(qfrc_constraint, ORC_MAXV) X(ncon, 1) X(con_dist, ORC_MAXCON) X(con_pos, ORC_MAXCON * 3)     \
     X(con_frame, ORC_MAXCON * 9) X(con_geom, ORC_MAXCON) X(con_mu, ORC_MAXCON)                     \
+    X(con_geom1, ORC_MAXCON) X(nself, 1) X(nbox_skipped, 1)                                        \
     X(con_includemargin, ORC_MAXCON) X(nefc, 1) X(efc_J, ORC_MAXEFC * ORC_MAXV)                    \
     X(efc_pos, ORC_MAXEFC) X(efc_D, ORC_MAXEFC) X(efc_aref, ORC_MAXEFC) X(efc_enabled, ORC_MAXEFC) \
     X(efc_force, ORC_MAXEFC) X(solver_niter, 1) X(com, 3)

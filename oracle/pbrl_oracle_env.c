@@ -320,7 +320,7 @@ static void mimic_epilogue(const OrcModel* m, const PbrlMimicDesc* mm, OrcData* 
     int fall = 0, nc = (int)d->ncon[0];
     if (mm->clip_fall_enabled[clip])
         for (int c = 0; c < nc; c++)
-            if (((mm->fall_geom_mask >> (int)d->con_geom[c]) & 1u) && d->con_dist[c] < 0) fall = 1;
+            if (m->geom_type[(int)d->con_geom1[c]] == 0 /* floor */ && ((mm->fall_geom_mask >> (int)d->con_geom[c]) & 1u) && d->con_dist[c] < 0) fall = 1;
     int end = !mm->clip_wrap[clip] && t >= (REAL)mm->clip_duration[clip];
     *done = (fall || end) ? 1 : 0;
     metrics[0] += 1;

@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stddef.h>
+#include <string.h>
 
 #include "pbrl_model.h"
 #include "pbrl_topo_gen.h"
@@ -35,7 +36,7 @@
 #define WSYNC() __syncwarp()
 // phase-lock barrier: the warps of one lock group (PBRL_LOCK_GROUP consecutive warps of the CTA) meet on a named barrier
 #ifndef PBRL_LOCK_GROUP
-#define PBRL_LOCK_GROUP 16
+#define PBRL_LOCK_GROUP 15
 #endif
 #define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / PBRL_LOCK_GROUP), "r"(32 * PBRL_LOCK_GROUP) : "memory")
 #define CTA_OR(p) __syncthreads_or(p)
@@ -85,11 +86,11 @@ constexpr int LS_MAXIT = 24;
 struct Ws {
     // state
     float qpos[36], qvel[36], warm[36], ctrl[28];
-    // kinematics.  xquat/xmat are dead once the contacts are found; the spatial-force scratch F/Fsub reuses them
+    // kinematics.  xquat/xmat are dead once the contacts are found; the spatial-force scratch F reuses them
     float xpos[NB * S3], com[4], pad0_[2];
     union {
         struct { alignas(16) float xquat[NB * S4]; float xmat[NB * S9]; };
-        struct { alignas(16) float F[NB * S6]; float Fsub[NB * S6]; };
+        struct { alignas(16) float F[NB * S6]; };
     };
     // spatial quantities about the centre of mass, [ang; lin]
     alignas(16) float cinert[NB * S10];
@@ -106,6 +107,12 @@ struct Ws {
         alignas(16) float LD[NM];                     // factor workspace
         alignas(16) float fr[2 * PBRL_FRAME_STRIDE];  // mimic: the two reference frames of this env step (cp.async.bulk
     };                                                // target; issued after the last factorisation of the step)
+    union {  // directly behind LD: the dense Hessian of the body-vs-body path (NHD floats from LD on) covers both
+        struct { alignas(16) float K[NB * S21]; };                         // Newton Hessian assembly: 6x6 blocks per body
+        struct {                                                          // mimic epilogue (after the last substep)
+            float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * 5], rcom[4], ree[12], rerr[8];
+        };
+    };
     float fsmooth[36], qacc[36], grad[36], p[36];
     union { float Ma[36]; float tau[28]; };      // tau: PD law output, consumed before the solver runs
     union { float Mp[36]; float asmooth[36]; };  // asmooth: only formed when no row is active
@@ -119,12 +126,14 @@ struct Ws {
     alignas(16) float con_aref[NCP * 4];
     alignas(16) float con_jar[NCP * 4];
     alignas(16) float con_jp[NCP * 4];
-    union {
-        struct { alignas(16) float K[NB * S21]; };                         // Newton Hessian assembly: 6x6 blocks per body
-        struct {                                                          // mimic epilogue (after the last substep)
-            float rq[9 * 4], rvel[36], rpos[4], rhinge[NB], rxpos[NB * S3], rxquat[NB * 5], rcom[4], ree[12], rerr[8];
-        };
-    };
+    // body-vs-body contacts inside the margin (at most KS): lane l owns pyramid row l & 3 of contact l >> 2
+    alignas(16) float sc_r[KS * 4];     // contact point - com, [3] = D
+    alignas(16) float sc_n[KS * 4];     // normal (geom1 -> geom2), [3] = dist
+    alignas(16) float sc_aref[KS * 4];
+    alignas(16) float sc_jar[KS * 4];
+    alignas(16) float sc_jp[KS * 4];
+    int sc_bb[KS];                      // body1 | body2 << 8
+    int nsc, pad3_[3];
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
     float fr_u, fr_cyc;
     int fr_phase, fr_pad;
@@ -141,6 +150,9 @@ struct Ws {
 #endif
 };
 static_assert(sizeof(Ws) % 16 == 0, "workspaces tile shared memory on 16-byte boundaries");
+constexpr int NHD = NV * (NV + 1) / 2;  // packed lower triangle of the dense Hessian
+static_assert(offsetof(Ws, K) + sizeof(float) * NB * S21 - offsetof(Ws, LD) >= sizeof(float) * NHD, "dense Hessian spans LD + K");
+static_assert(4 * 36 <= NV * S6 && 32 * 8 <= NV * S6 && 8 * NSG <= NB * S21 && NCP * S6 + KS * S6 <= NB * S21, "body-vs-body scratch");
 
 PB_DEV float fast_rcp(float x) {
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
@@ -199,6 +211,28 @@ PB_DEV int first_bit(unsigned mk) {  // index of the lowest set bit (mk != 0)
     int i = 0;
     while (!((mk >> i) & 1u)) i++;
     return i;
+#endif
+}
+
+PB_DEV float __int_as_float_emu(int i) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+PB_DEV int __float_as_int_emu(float f) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+PB_DEV int pop_count(unsigned mk) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return __popc(mk);
+#else
+    return __builtin_popcount(mk);
 #endif
 }
 
@@ -920,6 +954,139 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
+// ---------------------------------------------------------------------------------- body-vs-body contacts
+// Sphere / capsule candidates (mjx collision_primitive.py: _sphere_sphere, sphere_capsule, capsule_capsule with
+// math.closest_segment_point / closest_segment_to_segment_points).  MJX evaluates every candidate
+// every step and keeps a row block per candidate; only contacts inside the margin have non-zero rows, so only those
+// (at most KS) are kept here.  Box candidates are not evaluated (DevModel::nbox_pairs).
+PB_DEV void seg_point(const float* a, const float* b, const float* pt, float* out) {
+    const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+    float t = dot3(ap, ab) / (dot3(ab, ab) + 1e-6f);
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
+}
+PB_DEV float normalize_with_norm(const float* x, float* n) {
+    const float nrm = sqrtf(dot3(x, x)), den = nrm + (nrm == 0.f ? 1e-6f : 0.f);
+    for (int k = 0; k < 3; k++) n[k] = x[k] / den;
+    return nrm;
+}
+PB_DEV void seg_seg(const float* a0, const float* a1, const float* b0, const float* b1, float* best_a, float* best_b) {
+    float va[3], vb[3], da[3], db[3], am[3], bm[3], tr[3], na[3], nb[3], e1[3], e2[3];
+    for (int k = 0; k < 3; k++) { va[k] = a1[k] - a0[k]; vb[k] = b1[k] - b0[k]; }
+    const float ha = 0.5f * normalize_with_norm(va, da), hb = 0.5f * normalize_with_norm(vb, db);
+    for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bm[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bm[k]; }
+    const float dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
+    float ta = (-dat + dd * dbt) / ((1.f - dd * dd) + 1e-6f), tb = dbt + ta * dd;
+    ta = fminf(fmaxf(ta, -ha), ha);
+    tb = fminf(fmaxf(tb, -hb), hb);
+    for (int k = 0; k < 3; k++) { best_a[k] = am[k] + da[k] * ta; best_b[k] = bm[k] + db[k] * tb; }
+    seg_point(a0, a1, best_b, na);
+    seg_point(b0, b1, best_a, nb);
+    for (int k = 0; k < 3; k++) { e1[k] = na[k] - best_b[k]; e2[k] = nb[k] - best_a[k]; }
+    const bool first = dot3(e1, e1) < dot3(e2, e2);
+    for (int k = 0; k < 3; k++) { best_a[k] = first ? na[k] : best_a[k]; best_b[k] = first ? best_b[k] : nb[k]; }
+}
+// tangents of a contact normal (mjx math.make_frame): t1 from the y axis unless the normal is close to it, t2 = n x t1
+PB_DEV void frame_tangents(const float* n, float* t1, float* t2) {
+    float b[3] = {0.f, 0.f, 0.f};
+    if (n[1] > -0.5f && n[1] < 0.5f) b[1] = 1.f; else b[2] = 1.f;
+    const float dt = dot3(n, b);
+    for (int k = 0; k < 3; k++) b[k] -= n[k] * dt;
+    const float inv = 1.0f / sqrtf(dot3(b, b));
+    for (int k = 0; k < 3; k++) t1[k] = b[k] * inv;
+    cross3(n, t1, t2);
+}
+// pyramid row e of body-vs-body contact s: w = n +- mu t, j6 = [r x w ; w]; J x = j6 . (V[body2] - V[body1])
+PB_DEV void self_j6(const Ws& w, float mu, int s, int e, float* j6) {
+    float n[4], r[4], t1[3], t2[3], wv[3];
+    ld4(w.sc_n + 4 * s, n);
+    ld4(w.sc_r + 4 * s, r);
+    frame_tangents(n, t1, t2);
+    const float sg = (e & 1) ? -mu : mu;
+    for (int k = 0; k < 3; k++) wv[k] = n[k] + sg * (e < 2 ? t1[k] : t2[k]);
+    cross3(r, wv, j6);
+    j6[3] = wv[0]; j6[4] = wv[1]; j6[5] = wv[2];
+}
+PB_DEV float self_row_dot(const Ws& w, const float* j6, const float* vec6, int s) {
+    const int bb = w.sc_bb[s];
+    float v1[6], v2[6];
+    ld6(vec6 + S6 * (bb & 0xff), v1);
+    ld6(vec6 + S6 * (bb >> 8), v2);
+    for (int k = 0; k < 6; k++) v2[k] -= v1[k];
+    return dot6(j6, v2);
+}
+
+PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
+    if (m.nsp == 0) {
+        LANE_IF(z, 1) w.nsc = 0;
+        WSYNC();
+        return;
+    }
+    float* gc = w.K;            // [NSG] x 4: world centre of each geom            (K is idle outside the Newton iteration)
+    float* ga = w.K + 4 * NSG;  // [NSG] x 4: world axis x half length (zero for spheres)
+    float* pr = w.buf6;         // [32] x 8: pos(3), dist, normal(3) of the pair a lane evaluated  (buf6 is idle here)
+    LANE_IF(g, NSG) {
+        const int b = m.sg_body[g];
+        const float* R = w.xmat + S9 * b;
+        float t[3], a[3];
+        mat_vec(R, m.sg_pos[g], t);
+        mat_vec(R, m.sg_axis[g], a);
+        for (int k = 0; k < 3; k++) { gc[4 * g + k] = w.xpos[S3 * b + k] + t[k]; ga[4 * g + k] = a[k] * m.sg_hl[g]; }
+    }
+    WSYNC();
+    int total = 0;
+    for (int pass = 0; pass * 32 < m.nsp; pass++) {
+        const unsigned act = wballot(lane, 32, [&](int l) {
+            const int p = l + 32 * pass;
+            if (p >= m.nsp) return false;
+            const int g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+            const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1, *h2 = ga + 4 * g2;
+            float p1[3], p2[3];
+            if (p < m.nsp_sc) {  // sphere - capsule
+                const float b0[3] = {c2[0] - h2[0], c2[1] - h2[1], c2[2] - h2[2]}, b1[3] = {c2[0] + h2[0], c2[1] + h2[1], c2[2] + h2[2]};
+                for (int k = 0; k < 3; k++) p1[k] = c1[k];
+                seg_point(b0, b1, c1, p2);
+            } else if (p < m.nsp_sc + m.nsp_cc) {  // capsule - capsule
+                const float a0[3] = {c1[0] - h1[0], c1[1] - h1[1], c1[2] - h1[2]}, a1[3] = {c1[0] + h1[0], c1[1] + h1[1], c1[2] + h1[2]};
+                const float b0[3] = {c2[0] - h2[0], c2[1] - h2[1], c2[2] - h2[2]}, b1[3] = {c2[0] + h2[0], c2[1] + h2[1], c2[2] + h2[2]};
+                seg_seg(a0, a1, b0, b1, p1, p2);
+            } else {  // sphere - sphere
+                for (int k = 0; k < 3; k++) { p1[k] = c1[k]; p2[k] = c2[k]; }
+            }
+            const float r1 = m.sg_r[g1], r2 = m.sg_r[g2], dl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+            float n[3];
+            const float nrm = normalize_with_norm(dl, n);
+            if (nrm == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
+            const float dist = nrm - (r1 + r2);
+            float* o = pr + 8 * l;
+            for (int k = 0; k < 3; k++) { o[k] = p1[k] + n[k] * (r1 + 0.5f * dist); o[4 + k] = n[k]; }
+            o[3] = dist;
+            o[7] = __int_as_float_emu((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
+            return dist < m.self_margin;
+        });
+        WSYNC();
+        LANE_IF(l, 32) {
+            if ((act >> l) & 1u) {
+                const int slot = total + pop_count(act & ((1u << l) - 1u));
+                if (slot < KS) {
+                    const float* o = pr + 8 * l;
+                    for (int k = 0; k < 3; k++) { w.sc_r[4 * slot + k] = o[k] - w.com[k]; w.sc_n[4 * slot + k] = o[4 + k]; }
+                    w.sc_r[4 * slot + 3] = 0.f;
+                    w.sc_n[4 * slot + 3] = o[3];
+                    w.sc_bb[slot] = __float_as_int_emu(o[7]);
+                }
+            }
+        }
+        total += pop_count(act);
+        WSYNC();
+    }
+    LANE_IF(z, 1) {
+        w.nsc = total < KS ? total : KS;
+        if (total > KS) w.status |= PBRL_STATUS_SELF_OVERFLOW;
+    }
+    WSYNC();
+}
+
 // constraint rows: enabled flags, D, aref  (mjx constraint.make_constraint; needs cvel of the current qvel)
 PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float* qvel, int lane) {
     LANE_IF(l, 32) {
@@ -956,12 +1123,32 @@ PB_DEVN void stage_rows(const DevModel& m, Ws& w, const float* qpos, const float
     WSYNC();
     const unsigned cm = wballot(lane, NC, [&](int c) { return w.con_on[c] != 0; });
     LANE_IF(z, 1) w.con_mask = cm;
+    const int nsc = w.nsc;
+    if (nsc > 0) {  // lane l: pyramid row l & 3 of body-vs-body contact l >> 2
+        LANE_IF(l, 32) {
+            if (l < 4 * nsc) {
+                const int c = l >> 2, bb = w.sc_bb[c];
+                const float pos = w.sc_n[4 * c + 3] - m.self_margin, imp = impedance(m, pos);
+                const float invw = m.self_invw_scale * (m.body_invw[bb & 0xff] + m.body_invw[bb >> 8]);
+                float j6[6];
+                self_j6(w, m.self_mu, c, l & 3, j6);
+                w.sc_aref[l] = -m.sol_b * self_row_dot(w, j6, w.cvel, c) - m.sol_k * imp * pos;
+                // ([3] of the point row: the other three lanes of the contact load the row but use only its xyz)
+                if ((l & 3) == 0) w.sc_r[l + 3] = 1.0f / fmaxf(invw * (1.f - imp) / imp, 1e-15f);
+            }
+        }
+    }
     WSYNC();
 }
 
 // residual-like products for all rows from w.V = tree_vel(x): out = J x (limits into lim_out, contacts into con_out)
-PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, float* con_out, int lane) {
+PB_DEV void rows_Jx(const DevModel& m, Ws& w, const float* x, float* lim_out, float* con_out, float* self_out, int lane) {
     LANE_IF(l, 32) {
+        if (l < 4 * w.nsc) {
+            float j6[6];
+            self_j6(w, m.self_mu, l >> 2, l & 3, j6);
+            self_out[l] = self_row_dot(w, j6, w.V, l >> 2);
+        }
         if (l < NLIM && w.lim_sign[l] != 0.f) lim_out[l] = w.lim_sign[l] * x[m.jnt_dofadr[m.lim_jnt[l]]];
         if (l < NC && w.con_on[l]) {
             float j6[6];
@@ -996,6 +1183,24 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
             st6(Fc + S6 * c, f6);
         }
     }
+    const int nsc = w.nsc;
+    float* Fs = w.K + NCP * S6;  // [KS] x S6: spatial force of each body-vs-body contact on its body2 (body1 gets the opposite)
+    LANE_IF(c, KS) {
+        if (c < nsc) {
+            float jar[4], n[4], r[4], t1[3], t2[3], f6[6];
+            ld4(w.sc_jar + 4 * c, jar);
+            ld4(w.sc_n + 4 * c, n);
+            ld4(w.sc_r + 4 * c, r);
+            frame_tangents(n, t1, t2);
+            const float D = r[3], mu = m.self_mu;
+            const float f0 = jar[0] < 0.f ? -D * jar[0] : 0.f, f1 = jar[1] < 0.f ? -D * jar[1] : 0.f;
+            const float f2 = jar[2] < 0.f ? -D * jar[2] : 0.f, f3 = jar[3] < 0.f ? -D * jar[3] : 0.f;
+            const float fn = (f0 + f1) + (f2 + f3), a = mu * (f0 - f1), b = mu * (f2 - f3);
+            for (int k = 0; k < 3; k++) f6[3 + k] = fn * n[k] + a * t1[k] + b * t2[k];
+            cross3(r, f6 + 3, f6);
+            st6(Fs + S6 * c, f6);
+        }
+    }
     WSYNC();
     const int lim0 = m.jnt_dofadr[m.lim_jnt[0]];  // limited hinges own contiguous dofs (checked at model creation)
     LANE_IF(l, NDL) {
@@ -1008,6 +1213,14 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
             float t[6];
             ld6(Fc + S6 * c, t);
             for (int k = 0; k < 6; k++) f[k] += t[k];
+        }
+        const unsigned sub = m.body_submask[m.dof_bodyid[i]];
+        for (int c = 0; c < nsc; c++) {  // +force where body2 hangs below this dof, -force where body1 does (both: they cancel)
+            const int bb = w.sc_bb[c];
+            const float sg = (float)((int)((sub >> (bb >> 8)) & 1u) - (int)((sub >> (bb & 0xff)) & 1u));
+            float t[6];
+            ld6(Fs + S6 * c, t);
+            for (int k = 0; k < 6; k++) f[k] = fmaf(sg, t[k], f[k]);
         }
         ld6(w.cdof + S6 * i, cd);
         float jtf = dot6(cd, f);
@@ -1118,12 +1331,97 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
     WSYNC();
 }
 
+// ---------------------------------------------------------------------------------- dense Hessian (body-vs-body rows)
+// x <- H^-1 x with H = (tree-sparse matrix in w.LD) + sum over the active body-vs-body rows r of D_r u_r u_r^T, where
+// u_r[i] = +-cdof_i . j6_r for the dofs above body2 (+) / body1 (-) and 0 above both.  H is held as a packed lower
+// triangle across LD + K, factorised as L D L^T column by column (lane = row) with the forward substitution riding along.
+PB_DEV int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* x, int lane) {
+    float* H = w.LD;
+    {
+        float ent[(NM + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < (NM + 31) / 32; k++) ent[k] = 0.f;
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+#pragma unroll
+        for (int k = 0; k < (NM + 31) / 32; k++) { const int e = lane + 32 * k; if (e < NM) ent[k] = w.LD[e]; }
+        WSYNC();
+        LANE_LOOP(i, NHD) H[i] = 0.f;
+        WSYNC();
+#pragma unroll
+        for (int k = 0; k < (NM + 31) / 32; k++) { const int e = lane + 32 * k; if (e < NM) H[tri(m.M_row[e], m.M_col[e])] = ent[k]; }
+#else
+        float tmp[NM];
+        for (int e = 0; e < NM; e++) tmp[e] = w.LD[e];
+        for (int i = 0; i < NHD; i++) H[i] = 0.f;
+        for (int e = 0; e < NM; e++) H[tri(m.M_row[e], m.M_col[e])] = tmp[e];
+        (void)ent;
+#endif
+        WSYNC();
+    }
+    float* U = w.buf6;  // [4] x 36: the four pyramid rows of one contact
+    const int nsc = w.nsc;
+    for (int s = 0; s < nsc; s++) {
+        const unsigned a4 = (sact >> (4 * s)) & 15u;
+        if (a4 == 0u) continue;
+        const int bb = w.sc_bb[s];
+        LANE_LOOP(i, NV) {
+            const unsigned sub = m.body_submask[m.dof_bodyid[i]];
+            const float sg = (float)((int)((sub >> (bb >> 8)) & 1u) - (int)((sub >> (bb & 0xff)) & 1u));
+            float cd[6], j6[6];
+            ld6(w.cdof + S6 * i, cd);
+            for (int e = 0; e < 4; e++) {
+                self_j6(w, m.self_mu, s, e, j6);
+                U[36 * e + i] = sg * dot6(cd, j6);
+            }
+        }
+        WSYNC();
+        const float D = w.sc_r[4 * s + 3];
+        LANE_LOOP(i, NV) {
+            float ui[4];
+            for (int e = 0; e < 4; e++) ui[e] = ((a4 >> e) & 1u) ? D * U[36 * e + i] : 0.f;
+            if (ui[0] != 0.f || ui[1] != 0.f || ui[2] != 0.f || ui[3] != 0.f) {
+                float* row = H + tri(i, 0);
+                for (int j = 0; j <= i; j++)
+                    row[j] += ui[0] * U[j] + ui[1] * U[36 + j] + ui[2] * U[72 + j] + ui[3] * U[108 + j];
+            }
+        }
+        WSYNC();
+    }
+    bool bad = false;
+    for (int k = 0; k < NV; k++) {
+        const float d = H[tri(k, k)], inv = 1.0f / d, xk = x[k];
+        bad |= !(d > 0.f);
+        LANE_LOOP(i, NV) {
+            if (i > k) {
+                float* row = H + tri(i, 0);
+                const float lik = row[k] * inv;  // column k keeps L * D; only the columns right of it are touched
+                for (int j = k + 1; j <= i; j++) row[j] = fmaf(-lik, H[tri(j, k)], row[j]);
+                x[i] = fmaf(-lik, xk, x[i]);
+            }
+        }
+        LANE_IF(z, 1) w.Dinv[k] = inv;
+        WSYNC();
+    }
+    LANE_LOOP(i, NV) x[i] *= w.Dinv[i];
+    WSYNC();
+    for (int k = NV - 1; k > 0; k--) {
+        const float xk = x[k];
+        const float* row = H + tri(k, 0);
+        LANE_LOOP(i, NV) if (i < k) x[i] = fmaf(-row[i] * w.Dinv[i], xk, x[i]);
+        WSYNC();
+    }
+    if (bad) { LANE_IF(z, 1) w.status |= PBRL_STATUS_PIVOT; }
+    WSYNC();
+}
+
 // ---------------------------------------------------------------------------------- Newton solver on qacc
 // minimise 1/2 (a-a_s)^T M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2   
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     const unsigned lim_rows = wballot(lane, NLIM, [&](int l) { return w.lim_sign[l] != 0.f; });
     w.niter = 0;
-    const bool constrained = (lim_rows | w.con_mask) != 0u;
+    const int nsr = 4 * w.nsc;  // body-vs-body pyramid rows (lane l: row l)
+    const bool constrained = (lim_rows | w.con_mask) != 0u || nsr > 0;
     const bool coop = (w.phase_lock & 16) != 0;  // iterate in step with the other warps of the CTA (shared I-cache window)
     if (!constrained) {  // unconstrained: qacc = qacc_smooth = M^-1 qfrc_smooth
         LANE_LOOP(e, NM) w.LD[e] = w.M[e];
@@ -1140,13 +1438,15 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         LANE_LOOP(i, NV) w.qacc[i] = w.warm[i];
         WSYNC();
         tree_Mx(m, w, w.qacc, w.Ma, lane);
-        rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, lane);
+        rows_Jx(m, w, w.qacc, w.lim_jar, w.con_jar, w.sc_jar, lane);
         LANE_IF(l, 32) {
+            if (l < nsr) w.sc_jar[l] -= w.sc_aref[l];
             if (l < NLIM && w.lim_sign[l] != 0.f) w.lim_jar[l] -= w.lim_aref[l];
             if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) w.con_jar[4 * l + e] -= w.con_aref[4 * l + e];
             int bits = 0;
             if (l < NLIM && w.lim_sign[l] != 0.f) bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
             if (l < NC && w.con_on[l]) for (int e = 0; e < 4; e++) bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
+            if (l < nsr) bits |= (w.sc_jar[l] < 0.f) ? 64 : 0;
             w.act_bits[l] = bits;
         }
         WSYNC();
@@ -1168,10 +1468,13 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         PROF(14);
         LANE_LOOP(i, NV) w.p[i] = -w.grad[i];
         WSYNC();
-        ldl_factor_solve(m, w, w.p, lane);
+        // active body-vs-body rows couple two branches of the tree: their Hessian is not tree-sparse -> dense factorisation
+        const unsigned sact = wballot(lane, 32, [&](int l) { return l < nsr && w.sc_jar[l] < 0.f; });
+        if (sact != 0u) dense_factor_solve(m, w, sact, w.p, lane);
+        else ldl_factor_solve(m, w, w.p, lane);
         PROF(15);
         tree_Mx(m, w, w.p, w.Mp, lane);
-        rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, lane);
+        rows_Jx(m, w, w.p, w.lim_jp, w.con_jp, w.sc_jp, lane);
         PROF(17);
         // exact line search on the piecewise-quadratic cost along p (safeguarded Newton on phi')
         float g0, pMp;
@@ -1181,6 +1484,10 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         for (int ls = 0; ls < LS_MAXIT; ls++) {
             float d1, d2;  // first and second derivative of the row costs at alpha
             wsum2(lane, 32, [&](int l, float& a, float& b) {
+                if (l < nsr) {
+                    const float jp = w.sc_jp[l], x = w.sc_jar[l] + alpha * jp;
+                    if (x < 0.f) { const float dj = w.sc_r[(l & ~3) + 3] * jp; a = fmaf(dj, x, a); b = fmaf(dj, jp, b); }
+                }
                 if (l < NLIM && w.lim_sign[l] != 0.f) {
                     const float jp = w.lim_jp[l], x = w.lim_jar[l] + alpha * jp;
                     if (x < 0.f) { const float dj = w.lim_D[l] * jp; a = fmaf(dj, x, a); b = fmaf(dj, jp, b); }
@@ -1210,6 +1517,10 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         LANE_LOOP(i, NV) { w.qacc[i] += alpha * w.p[i]; w.Ma[i] += alpha * w.Mp[i]; }
         const unsigned changed = wballot(lane, 32, [&](int l) {
             int bits = 0;
+            if (l < nsr) {
+                w.sc_jar[l] += alpha * w.sc_jp[l];
+                bits |= (w.sc_jar[l] < 0.f) ? 64 : 0;
+            }
             if (l < NLIM && w.lim_sign[l] != 0.f) {
                 w.lim_jar[l] += alpha * w.lim_jp[l];
                 bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
@@ -1255,6 +1566,7 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     if (lock & 2) CTA_SYNC();
     PROF(28);
     stage_collide(m, w, lane);
+    stage_collide_self(m, w, lane);
     PROF(5);
     stage_comvel(m, w, w.qvel, lane);
     PROF(6);
@@ -1570,6 +1882,13 @@ PB_DEVN void env_debug_forward(const DevModel& m, Ws& w, const float* qpos, cons
             o[PBRL_DBG_CON_FORCE + 4 * c + e] = (w.con_on[c] && w.con_jar[4 * c + e] < 0.f) ? -w.con_D[c] * w.con_jar[4 * c + e] : 0.f;
     }
     LANE_IF(l, NLIM) o[PBRL_DBG_LIM_FORCE + l] = (w.lim_sign[l] != 0.f && w.lim_jar[l] < 0.f) ? -w.lim_D[l] * w.lim_jar[l] : 0.f;
+    LANE_IF(z, 1) o[PBRL_DBG_NSELF] = (float)w.nsc;
+    LANE_IF(l, 32) {
+        if (l < 4 * w.nsc) {
+            if ((l & 3) == 0) o[PBRL_DBG_SELF_DIST + (l >> 2)] = w.sc_n[l + 3];
+            o[PBRL_DBG_SELF_FORCE + l] = w.sc_jar[l] < 0.f ? -w.sc_r[(l & ~3) + 3] * w.sc_jar[l] : 0.f;
+        }
+    }
     WSYNC();
 }
 

@@ -22,7 +22,7 @@ namespace {
 // One CTA of 16 warps per SM, all in one phase-lock group: the kernel is bound by instruction fetch (about 200 KB of
 // straight-line code per substep against a 32 KB L1.5 I-cache), so a single instruction stream per SM wins.
 #ifndef PBRL_WARPS_PER_CTA
-#define PBRL_WARPS_PER_CTA 16
+#define PBRL_WARPS_PER_CTA 15
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;

@@ -155,6 +155,7 @@ class ModelConst:
     # collision candidates (MuJoCo broad-phase filter rules, evaluated once: MJX has no dynamic broad phase)
     pair_geom1: np.ndarray = None  # geom with the lower mjtGeom type first (MJX dispatch order), then the lower id
     pair_geom2: np.ndarray = None
+    self_collision: int = 1  # 0: evaluate the floor pairs only
     # actuators
     act_names: list = field(default_factory=list)
     act_dofadr: np.ndarray = None

@@ -63,8 +63,9 @@ STATE_SHAPES = [("qpos", 35), ("qvel", 34), ("time", 0), ("warm", 34), ("ctrl", 
                 ("obs", 69), ("reward", 3), ("done", 0), ("metrics", 3)]
 DBG = dict(xpos=(0, 42), xquat=(42, 56), com=(98, 3), qM=(101, 1156), bias=(1257, 34), qfrc_smooth=(1291, 34),
            qacc_smooth=(1325, 34), qacc=(1359, 34), qfrc_constraint=(1393, 34), ncon_active=(1427, 1), con_dist=(1428, 32),
-           con_pos=(1460, 96), niter=(1556, 1), con_force=(1557, 128), lim_force=(1685, 28))
-DBG_SIZE = 1720
+           con_pos=(1460, 96), niter=(1556, 1), con_force=(1557, 128), lim_force=(1685, 28), nself=(1713, 1),
+           self_dist=(1714, 8), self_force=(1722, 32))
+DBG_SIZE = 1756
 
 
 class _HostState:
