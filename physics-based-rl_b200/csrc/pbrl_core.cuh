@@ -36,7 +36,7 @@
 #define WSYNC() __syncwarp()
 // phase-lock barrier: the warps of one lock group (PBRL_LOCK_GROUP consecutive warps of the CTA) meet on a named barrier
 #ifndef PBRL_LOCK_GROUP
-#define PBRL_LOCK_GROUP 15
+#define PBRL_LOCK_GROUP 16
 #endif
 #define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / PBRL_LOCK_GROUP), "r"(32 * PBRL_LOCK_GROUP) : "memory")
 #define CTA_OR(p) __syncthreads_or(p)
@@ -119,19 +119,19 @@ struct Ws {
     union { float fcon[36]; float bias[36]; };   // bias is folded into fsmooth before the solver writes fcon
     // PD prologue only: the state of the last forward (qpos_lag / qvel_lag rows) is staged in fsmooth / qacc
     // constraint rows: lane l owns limit row l and contact slot l (4 pyramid rows)
-    float lim_sign[32], lim_D[32], lim_aref[32], lim_jar[32], lim_jp[32];
+    // (aref is consumed when the solver starts: jar = J a - aref; J p of a search direction is formed later -> shared storage)
+    float lim_sign[32], lim_D[32], lim_jar[32];
+    union { float lim_aref[32]; float lim_jp[32]; };
     int con_on[NCP], act_bits[32];
     float con_dist[NCP], con_D[NCP], con_t1[NCP * 2];
     alignas(16) float con_r[NCP * 4];
-    alignas(16) float con_aref[NCP * 4];
+    union { alignas(16) float con_aref[NCP * 4]; alignas(16) float con_jp[NCP * 4]; };
     alignas(16) float con_jar[NCP * 4];
-    alignas(16) float con_jp[NCP * 4];
     // body-vs-body contacts inside the margin (at most KS): lane l owns pyramid row l & 3 of contact l >> 2
     alignas(16) float sc_r[KS * 4];     // contact point - com, [3] = D
     alignas(16) float sc_n[KS * 4];     // normal (geom1 -> geom2), [3] = dist
-    alignas(16) float sc_aref[KS * 4];
+    union { alignas(16) float sc_aref[KS * 4]; alignas(16) float sc_jp[KS * 4]; };
     alignas(16) float sc_jar[KS * 4];
-    alignas(16) float sc_jp[KS * 4];
     int sc_bb[KS];                      // body1 | body2 << 8
     int nsc, pad3_[3];
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
@@ -161,6 +161,14 @@ PB_DEV float fast_rcp(float x) {
     return r;
 #else
     return 1.0f / x;
+#endif
+}
+
+PB_DEV float fast_rsqrt(float x) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    return rsqrtf(x);  // MUFU.RSQ, 2 ulp
+#else
+    return 1.0f / sqrtf(x);
 #endif
 }
 
@@ -961,13 +969,13 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
 // (at most KS) are kept here.  Box candidates are not evaluated (DevModel::nbox_pairs).
 PB_DEV void seg_point(const float* a, const float* b, const float* pt, float* out) {
     const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
-    float t = dot3(ap, ab) / (dot3(ab, ab) + 1e-6f);
+    float t = dot3(ap, ab) * fast_rcp(dot3(ab, ab) + 1e-6f);
     t = fminf(fmaxf(t, 0.f), 1.f);
     for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
 }
 PB_DEV float normalize_with_norm(const float* x, float* n) {
-    const float nrm = sqrtf(dot3(x, x)), den = nrm + (nrm == 0.f ? 1e-6f : 0.f);
-    for (int k = 0; k < 3; k++) n[k] = x[k] / den;
+    const float ss = dot3(x, x), nrm = ss > 0.f ? ss * fast_rsqrt(ss) : 0.f, inv = fast_rcp(nrm + (nrm == 0.f ? 1e-6f : 0.f));
+    for (int k = 0; k < 3; k++) n[k] = x[k] * inv;
     return nrm;
 }
 PB_DEV void seg_seg(const float* a0, const float* a1, const float* b0, const float* b1, float* best_a, float* best_b) {
@@ -976,7 +984,7 @@ PB_DEV void seg_seg(const float* a0, const float* a1, const float* b0, const flo
     const float ha = 0.5f * normalize_with_norm(va, da), hb = 0.5f * normalize_with_norm(vb, db);
     for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bm[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bm[k]; }
     const float dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
-    float ta = (-dat + dd * dbt) / ((1.f - dd * dd) + 1e-6f), tb = dbt + ta * dd;
+    float ta = (-dat + dd * dbt) * fast_rcp((1.f - dd * dd) + 1e-6f), tb = dbt + ta * dd;
     ta = fminf(fmaxf(ta, -ha), ha);
     tb = fminf(fmaxf(tb, -hb), hb);
     for (int k = 0; k < 3; k++) { best_a[k] = am[k] + da[k] * ta; best_b[k] = bm[k] + db[k] * tb; }
@@ -992,7 +1000,7 @@ PB_DEV void frame_tangents(const float* n, float* t1, float* t2) {
     if (n[1] > -0.5f && n[1] < 0.5f) b[1] = 1.f; else b[2] = 1.f;
     const float dt = dot3(n, b);
     for (int k = 0; k < 3; k++) b[k] -= n[k] * dt;
-    const float inv = 1.0f / sqrtf(dot3(b, b));
+    const float inv = fast_rsqrt(dot3(b, b));
     for (int k = 0; k < 3; k++) t1[k] = b[k] * inv;
     cross3(n, t1, t2);
 }
@@ -1333,9 +1341,175 @@ PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
 
 // ---------------------------------------------------------------------------------- dense Hessian (body-vs-body rows)
 // x <- H^-1 x with H = (tree-sparse matrix in w.LD) + sum over the active body-vs-body rows r of D_r u_r u_r^T, where
-// u_r[i] = +-cdof_i . j6_r for the dofs above body2 (+) / body1 (-) and 0 above both.  H is held as a packed lower
-// triangle across LD + K, factorised as L D L^T column by column (lane = row) with the forward substitution riding along.
+// u_r[i] = +-cdof_i . j6_r for the dofs above body2 (+) / body1 (-) and 0 above both.
 PB_DEV int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+// the four pyramid rows of contact s over the dofs: U[36 e + i]
+PB_DEV void self_rows_dense(const DevModel& m, Ws& w, int s, float* U, int lane) {
+    const int bb = w.sc_bb[s];
+    float n[4], r[4], t1[3], t2[3], jn[6], j1[6], j2[6];
+    ld4(w.sc_n + 4 * s, n);
+    ld4(w.sc_r + 4 * s, r);
+    frame_tangents(n, t1, t2);
+    cross3(r, n, jn); cross3(r, t1, j1); cross3(r, t2, j2);
+    for (int k = 0; k < 3; k++) { jn[3 + k] = n[k]; j1[3 + k] = t1[k]; j2[3 + k] = t2[k]; }
+    LANE_LOOP(i, NV) {
+        const unsigned sub = m.body_submask[m.dof_bodyid[i]];
+        const float sg = (float)((int)((sub >> (bb >> 8)) & 1u) - (int)((sub >> (bb & 0xff)) & 1u));
+        float cd[6];
+        ld6(w.cdof + S6 * i, cd);
+        const float an = sg * dot6(cd, jn), a1 = sg * m.self_mu * dot6(cd, j1), a2 = sg * m.self_mu * dot6(cd, j2);
+        U[i] = an + a1; U[36 + i] = an - a1; U[72 + i] = an + a2; U[108 + i] = an - a2;
+    }
+    LANE_IF(z, 2) for (int e = 0; e < 4; e++) U[36 * e + NV + z] = 0.f;  // pad columns 34, 35 (vector loads read them)
+    WSYNC();
+}
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+// Register-resident L^T D L (MuJoCo's elimination order, last dof first): lane i holds row i < 32 of the lower triangle in
+// registers, rows 32 and 33 stay in shared memory (they are eliminated first and never touched again).  Each step
+// broadcasts the pivot row through a 32-float staging row (double buffered); the right-hand side rides along (lane = dof),
+// and the back substitution pushes x_i to the rows below with one shuffle per dof.
+namespace dense {
+constexpr unsigned FULL = 0xffffffffu;
+template <int K>
+struct Step {
+    PB_MEMBER void run(float (&R)[32], float& xl, float& dinv_own, bool& bad, float* stage, int lane) {
+        float* st = stage + 32 * (K & 1);
+        if (lane == K) {
+#pragma unroll
+            for (int q = 0; q < (K + 4) / 4; q++) reinterpret_cast<float4*>(st)[q] = make_float4(R[4 * q], R[4 * q + 1], R[4 * q + 2], R[4 * q + 3]);
+        }
+        const float xk = __shfl_sync(FULL, xl, K);
+        __syncwarp();
+        float c[32];
+#pragma unroll
+        for (int q = 0; q < (K + 4) / 4; q++) {
+            const float4 v = reinterpret_cast<const float4*>(st)[q];
+            c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+        }
+        const float d = c[K], inv = fast_rcp(d);
+        bad |= !(d > 0.f);
+        if (lane == K) dinv_own = inv;
+        if constexpr (K > 0) {
+            const float li = lane < K ? st[lane] * inv : 0.f;  // L[K, lane]
+#pragma unroll
+            for (int j = 0; j < K; j++) R[j] = fmaf(-li, c[j], R[j]);  // entries right of the diagonal of a row are never read
+            xl = fmaf(-li, xk, xl);
+            Step<K - 1>::run(R, xl, dinv_own, bad, stage, lane);
+        }
+    }
+};
+template <int I>
+struct Back {  // x_I is final: every row below receives L[k, I] x_I
+    PB_MEMBER void run(const float (&R)[32], float& xl, float dinv_own, int lane) {
+        if constexpr (I < 31) {
+            const float xi = __shfl_sync(FULL, xl, I);
+            if (lane > I) xl = fmaf(-R[I] * dinv_own, xi, xl);
+            Back<I + 1>::run(R, xl, dinv_own, lane);
+        }
+    }
+};
+}  // namespace dense
+
+PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* x, int lane) {
+    static_assert(NV == 34, "rows 32 and 33 are handled outside the register tile");
+    float* H = w.LD;  // packed lower triangle across LD + K (scatter target; rows 32, 33 stay here)
+    {
+        float ent[(NM + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < (NM + 31) / 32; k++) { const int e = lane + 32 * k; ent[k] = e < NM ? w.LD[e] : 0.f; }
+        __syncwarp();
+        for (int i = lane; i < NHD; i += 32) H[i] = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < (NM + 31) / 32; k++) { const int e = lane + 32 * k; if (e < NM) H[tri(m.M_row[e], m.M_col[e])] = ent[k]; }
+        __syncwarp();
+    }
+    float R[32];
+    {
+        const float* row = H + tri(lane, 0);
+#pragma unroll
+        for (int j = 0; j < 32; j++) R[j] = j <= lane ? row[j] : 0.f;
+    }
+    float* H32 = H + tri(32, 0);  // 33 entries
+    float* H33 = H + tri(33, 0);  // 34 entries
+    float* U = w.buf6;            // [4] x 36: the four pyramid rows of one contact; the staging rows of the factorisation later
+    const int nsc = w.nsc;
+    for (int s = 0; s < nsc; s++) {
+        const unsigned a4 = (sact >> (4 * s)) & 15u;
+        if (a4 == 0u) continue;
+        __syncwarp();
+        self_rows_dense(m, w, s, U, lane);
+        const float D = w.sc_r[4 * s + 3];
+        float ui[4], u32[4], u33[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float a = ((a4 >> e) & 1u) ? D : 0.f;
+            ui[e] = a * U[36 * e + lane]; u32[e] = a * U[36 * e + 32]; u33[e] = a * U[36 * e + 33];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float4 v = reinterpret_cast<const float4*>(U + 36 * e)[q];
+                acc[0] = fmaf(ui[e], v.x, acc[0]); acc[1] = fmaf(ui[e], v.y, acc[1]); acc[2] = fmaf(ui[e], v.z, acc[2]); acc[3] = fmaf(ui[e], v.w, acc[3]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) R[4 * q + t] += acc[t];
+        }
+        for (int j = lane; j < NV; j += 32) {  // rows 32 / 33 in shared memory: column j
+            float a32 = 0.f, a33 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float uj = U[36 * e + j]; a32 = fmaf(u32[e], uj, a32); a33 = fmaf(u33[e], uj, a33); }
+            if (j <= 32) H32[j] += a32;
+            H33[j] += a33;
+        }
+    }
+    __syncwarp();
+    // eliminate dof 33, then dof 32 (rows in shared memory), then the register rows 31 .. 0
+    bool bad = false;
+    float xl = x[lane];
+    float x32 = x[32];
+    const float x33 = x[33];
+    const float d33 = H33[33], inv33 = fast_rcp(d33);
+    bad |= !(d33 > 0.f);
+    {
+        const float li = H33[lane] * inv33;
+#pragma unroll
+        for (int j = 0; j < 32; j++) R[j] = fmaf(-li, H33[j], R[j]);
+        xl = fmaf(-li, x33, xl);
+        const float l32 = H33[32] * inv33;
+        x32 = fmaf(-l32, x33, x32);
+        __syncwarp();
+        for (int j = lane; j <= 32; j += 32) H32[j] = fmaf(-l32, H33[j], H32[j]);
+        __syncwarp();
+    }
+    const float d32 = H32[32], inv32 = fast_rcp(d32);
+    bad |= !(d32 > 0.f);
+    {
+        const float li = H32[lane] * inv32;
+#pragma unroll
+        for (int j = 0; j < 32; j++) R[j] = fmaf(-li, H32[j], R[j]);
+        xl = fmaf(-li, x32, xl);
+    }
+    float dinv_own = 0.f;
+    __syncwarp();
+    dense::Step<31>::run(R, xl, dinv_own, bad, U, lane);
+    // x <- D^-1 x, then L x = z from dof 0 upwards
+    xl *= dinv_own;
+    dense::Back<0>::run(R, xl, dinv_own, lane);
+    float s32 = H32[lane] * xl, s33 = H33[lane] * xl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s32 += __shfl_xor_sync(0xffffffffu, s32, o); s33 += __shfl_xor_sync(0xffffffffu, s33, o); }
+    const float y32 = (x32 - s32) * inv32;                      // x32 holds L^-T b; z = D^-1 y; minus the rows above
+    const float y33 = (x33 - s33 - H33[32] * y32) * inv33;
+    __syncwarp();
+    x[lane] = xl;
+    if (lane == 0) { x[32] = y32; x[33] = y33; if (bad) w.status |= PBRL_STATUS_PIVOT; }
+    __syncwarp();
+}
+#else
+// host emulation (tests only): packed lower triangle, L D L^T column by column with the forward substitution riding along
 PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* x, int lane) {
     float* H = w.LD;
     {
@@ -1364,18 +1538,7 @@ PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* 
     for (int s = 0; s < nsc; s++) {
         const unsigned a4 = (sact >> (4 * s)) & 15u;
         if (a4 == 0u) continue;
-        const int bb = w.sc_bb[s];
-        LANE_LOOP(i, NV) {
-            const unsigned sub = m.body_submask[m.dof_bodyid[i]];
-            const float sg = (float)((int)((sub >> (bb >> 8)) & 1u) - (int)((sub >> (bb & 0xff)) & 1u));
-            float cd[6], j6[6];
-            ld6(w.cdof + S6 * i, cd);
-            for (int e = 0; e < 4; e++) {
-                self_j6(w, m.self_mu, s, e, j6);
-                U[36 * e + i] = sg * dot6(cd, j6);
-            }
-        }
-        WSYNC();
+        self_rows_dense(m, w, s, U, lane);
         const float D = w.sc_r[4 * s + 3];
         LANE_LOOP(i, NV) {
             float ui[4];
@@ -1414,6 +1577,8 @@ PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* 
     if (bad) { LANE_IF(z, 1) w.status |= PBRL_STATUS_PIVOT; }
     WSYNC();
 }
+
+#endif
 
 // ---------------------------------------------------------------------------------- Newton solver on qacc
 // minimise 1/2 (a-a_s)^T M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2   

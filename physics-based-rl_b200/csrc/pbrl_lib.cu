@@ -22,7 +22,7 @@ namespace {
 // One CTA of 16 warps per SM, all in one phase-lock group: the kernel is bound by instruction fetch (about 200 KB of
 // straight-line code per substep against a 32 KB L1.5 I-cache), so a single instruction stream per SM wins.
 #ifndef PBRL_WARPS_PER_CTA
-#define PBRL_WARPS_PER_CTA 15
+#define PBRL_WARPS_PER_CTA 16
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -155,7 +155,7 @@ __global__ void k_bench_stage(const DevModel* __restrict__ gm, int stage, int it
             case 9: break;
             case 10: rows_JTf(sm, w, w.Mp, w.grad, 0, lane); break;
             case 11: assemble_hessian(sm, w, lane); break;
-            case 12: rows_Jx(sm, w, w.qacc, w.lim_jp, w.con_jp, lane); break;
+            case 12: rows_Jx(sm, w, w.qacc, w.lim_jp, w.con_jp, w.sc_jp, lane); break;
         }
         const long long t1 = clock64();
         if (stage == 1 || stage == 2) { __syncwarp(); }
