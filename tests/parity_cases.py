@@ -301,3 +301,44 @@ def check_mimic(backend, model_grav, table, mdesc, N=28, steps=3, seed=23):
             assert abs(s.stats[3] - st_ref[3]) <= max(2, 0.03 * N)       # falls
     # a pose held exactly on the reference with zero velocity error right after reset scores close to the maximum
     return float(env.reward[:, 0].mean())
+
+
+def check_hands_against_thighs(backend, model_nograv, N=16, steps=12, seed=29):
+    """Body-vs-body contacts in the regime a rollout reaches: the arms are driven inwards (shoulder_x targets) so that
+    the wrist spheres press on the thigh capsules.  Per-env parity with the oracle while the contact is shallow, and the
+    contact does its job: the wrists do not sink into the thighs (they do with self_collision = 0)."""
+    orc = _oracle(model_nograv)
+    env = OracleEnv(orc, N)
+    env.reset()
+    s = backend.new_state(N)
+    backend.reset(s)
+    rng = np.random.default_rng(seed)
+    kp, kd = util_data.generate_kp_kd_gains()
+    tgt = np.zeros((N, 28), np.float32)
+    names = model_nograv.jnt_names[1:]
+    tgt[:, names.index("right_shoulder_x")] = rng.uniform(0.15, 0.45, N)    # right arm towards the body
+    tgt[:, names.index("left_shoulder_x")] = -rng.uniform(0.15, 0.45, N)
+    tgt[:, names.index("right_elbow")] = rng.uniform(0.0, 0.3, N)
+    worst, touched = 0.0, np.zeros(N, bool)
+    for k in range(steps):
+        env.step(tgt, kp, kd, pd_mode=1, n_frames=8)
+        backend.step(s, tgt, kp, kd, pd_mode=1, n_frames=8)
+        pen = _self_penetration(model_nograv, env.qpos)
+        touched |= _self_contacts(model_nograv, env.qpos) > 0
+        worst = max(worst, float(row_relerr(s.qpos, env.qpos).max()))
+        assert pen.min() > -5e-3, (k, pen.min())           # soft contact: millimetres of penetration at the impact, then it settles
+    assert touched.mean() >= 0.75, touched.mean()           # the case exercises the rows
+    assert worst <= 2e-4, worst                             # ~100 contact substeps in fp32 vs the float64 oracle
+    assert (s.status & 7 == 0).all()
+    return worst
+
+
+def _self_contacts(model, qpos):
+    orc = _oracle(model)
+    out = np.zeros(len(qpos), int)
+    for e, q in enumerate(qpos):
+        d = orc.new_data()
+        d.qpos[:35] = q
+        orc.forward(d)
+        out[e] = int(d.nself[0])
+    return out

@@ -55,6 +55,11 @@ def test_reset(gpu_nograv, model_nograv):
     pc.check_reset(gpu_nograv, model_nograv)
 
 
+def test_hands_against_thighs(gpu_nograv, model_nograv):
+    """Body-vs-body contacts (sphere / capsule candidates) on the CUDA path, dense Hessian branch included."""
+    pc.check_hands_against_thighs(gpu_nograv, model_nograv, N=48, steps=12)
+
+
 def test_contact_rollout(gpu_grav, model_grav):
     pc.check_contact_rollout(gpu_grav, model_grav, N=64, steps=40)
 
