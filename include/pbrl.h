@@ -149,6 +149,15 @@ void pbrl_model_destroy(PbrlModel* model);
 
 int pbrl_reset(const PbrlModel* model, int N, int reward_mode, const PbrlBuffers* buf, void* stream);
 
+/* Auto-reset (brax.envs.wrappers.training.AutoResetWrapper.step, the `where(done, first_state, state)` part): every
+ * env with done[e] != 0 restarts -- qpos0 / zero velocity in reference mode, the reference pose at clip time
+ * next_ref_t0[e] in mimic mode (NULL: the env's current ref_t0; otherwise ref_t0[e] is overwritten) -- and its obs row
+ * becomes the first observation of the new episode.  reward / done / metrics keep the values of the step that ended the
+ * episode (the trainer reads them).  steps (may be NULL) is zeroed for the restarted envs. */
+int pbrl_autoreset(const PbrlModel* model, int N, int reward_mode, const float* done /* [N] */,
+                   const float* next_ref_t0 /* [N] or NULL */, int* steps /* [N] or NULL */, const PbrlBuffers* buf,
+                   void* stream);
+
 int pbrl_step(const PbrlModel* model, int N, int n_frames, int pd_mode, int action_cols /* 1 or 4 */,
               const float* action /* [N][28][action_cols] */, const float* kp /* [28] */,
               const float* kd /* [28] */, float pd_dt, const float* pd_time /* [N] or NULL = state time */,

@@ -1434,6 +1434,7 @@ PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* 
     float* H33 = H + tri(33, 0);  // 34 entries
     float* U = w.buf6;            // [4] x 36: the four pyramid rows of one contact; the staging rows of the factorisation later
     const int nsc = w.nsc;
+#pragma unroll 1
     for (int s = 0; s < nsc; s++) {
         const unsigned a4 = (sact >> (4 * s)) & 15u;
         if (a4 == 0u) continue;

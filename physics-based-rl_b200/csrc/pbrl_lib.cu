@@ -93,6 +93,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_reset(const DevModel* __restric
     for (int env = first_env(); env < a.N; env += env_stride()) env_reset(sm, w, a, env, lane);
 }
 __global__ void __launch_bounds__(CTA_THREADS)
+k_autoreset(const DevModel* __restrict__ gm, StepArgs a, const float* done, const float* next_ref_t0, int* steps) {
+    Ws& w = my_ws();
+    const int lane = threadIdx.x & 31;
+    const DevModel& sm = stage_model(gm);
+    init_ws_tables(sm, w, lane);
+    frames_init(w, lane);
+    for (int env = first_env(); env < a.N; env += env_stride())
+        if (done[env] != 0.f) env_autoreset(sm, a.mm, a.frames, w, a, next_ref_t0, steps, env, lane);
+}
+__global__ void __launch_bounds__(CTA_THREADS)
 k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float* qvel, float* obs, float* reward,
          float* done, float* xpos, float* xquat) {
     Ws& w = my_ws();
@@ -228,7 +238,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) { delete m; return fail(err); }
     if (prepare_kernel(k_step, m) || prepare_kernel(k_reset, m) || prepare_kernel(k_replay, m) || prepare_kernel(k_pd, m) ||
-        prepare_kernel(k_debug_forward, m)) { delete m; return -1; }
+        prepare_kernel(k_debug_forward, m) || prepare_kernel(k_autoreset, m)) { delete m; return -1; }
     CUDA_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
     CUDA_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
     if (mimic) {
@@ -272,6 +282,23 @@ int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* bu
     return check_launch("pbrl_reset");
 }
 
+int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done, const float* next_ref_t0, int* steps,
+                   const PbrlBuffers* buf, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (check_buffers(buf)) return -1;
+    if (!done) return fail("null done");
+    StepArgs a{};
+    a.N = N; a.reward_mode = reward_mode; a.buf = *buf;
+    if (reward_mode == PBRL_REWARD_MIMIC) {
+        if (!m->has_mimic) return fail("the model was created without a mimic description");
+        if (!buf->motion_id || !buf->ref_t0) return fail("mimic mode needs motion_id and ref_t0");
+        a.frames = m->frames; a.mm = m->mimic;
+    } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
+    k_autoreset<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, done, next_ref_t0, steps);
+    return check_launch("pbrl_autoreset");
+}
+
 int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp,
               const float* kd, float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf,
               void* stream) {
@@ -291,7 +318,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
-    { const char* e = getenv("PBRL_PHASE_LOCK"); a.phase_lock = (e ? atoi(e) : 9) & 31; }
+    { const char* e = getenv("PBRL_PHASE_LOCK"); a.phase_lock = (e ? atoi(e) : 25) & 31; }
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }

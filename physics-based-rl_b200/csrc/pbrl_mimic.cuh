@@ -250,4 +250,23 @@ PB_DEVN void env_reset_mimic(const DevModel& m, const DevMimic& mm, const float*
     WSYNC();
 }
 
+
+// ---- auto-reset of one env whose episode ended (brax AutoResetWrapper): state and obs restart, reward / done / metrics stay
+PB_DEVN void env_autoreset(const DevModel& m, const DevMimic& mm, const float* frames, Ws& w, const StepArgs& a,
+                           const float* next_ref_t0, int* steps, int env, int lane) {
+    StepArgs r = a;
+    r.buf.reward = nullptr; r.buf.done = nullptr; r.buf.metrics = nullptr; r.buf.status = nullptr;
+    if (a.reward_mode == PBRL_REWARD_MIMIC) {
+        if (next_ref_t0) {
+            LANE_IF(z, 1) const_cast<float*>(a.buf.ref_t0)[env] = next_ref_t0[env];
+            WSYNC();
+        }
+        env_reset_mimic(m, mm, frames, w, r.buf, env, lane);
+    } else {
+        env_reset(m, w, r, env, lane);
+    }
+    LANE_IF(z, 1) if (steps) steps[env] = 0;
+    WSYNC();
+}
+
 }  // namespace pbrl

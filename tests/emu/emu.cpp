@@ -49,6 +49,17 @@ int emu_reset(int N, int reward_mode, const PbrlBuffers* buf) {
     }
     return 0;
 }
+int emu_autoreset(int N, int reward_mode, const float* done, const float* next_ref_t0, int* steps, const PbrlBuffers* buf) {
+    std::vector<Ws> ws(1);
+    init_ws_tables(g_model, ws[0], 0);
+    frames_init(ws[0], 0);
+    StepArgs a{};
+    a.N = N; a.buf = *buf; a.reward_mode = reward_mode;
+    if (reward_mode == PBRL_REWARD_MIMIC) { a.frames = g_frames.data(); a.mm = g_mimic; }
+    for (int e = 0; e < N; e++)
+        if (done[e] != 0.f) env_autoreset(g_model, g_mimic, g_frames.data(), ws[0], a, next_ref_t0, steps, e, 0);
+    return 0;
+}
 int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp, const float* kd,
              float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf) {
     std::vector<Ws> ws(1);

@@ -138,6 +138,13 @@ class EmuBackend:
         b = self._bufs(s)
         self.lib.emu_reset(s.N, reward_mode, ctypes.byref(b))
 
+    def autoreset(self, s, done, next_ref_t0=None, steps=None, reward_mode=0):
+        self._select()
+        b = self._bufs(s)
+        done = np.ascontiguousarray(done, np.float32)
+        nxt = None if next_ref_t0 is None else np.ascontiguousarray(next_ref_t0, np.float32)
+        self.lib.emu_autoreset(s.N, reward_mode, self._p(done), self._p(nxt), self._p(steps), ctypes.byref(b))
+
     def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF, reward_mode=0):
         self._select()
         a = np.ascontiguousarray(action, np.float32)
@@ -221,6 +228,18 @@ class GpuBackend:
         self.L.check(self.L.lib().pbrl_reset(self.model.handle, s.N, reward_mode, ctypes.byref(b), self._stream()))
         self.torch.cuda.synchronize()
         self._down(s, d)
+
+    def autoreset(self, s, done, next_ref_t0=None, steps=None, reward_mode=0):
+        d = self._up(s)
+        b = self.L.make_buffers(**d)
+        dn, nx = self._dp(done), self._dp(next_ref_t0)
+        st = None if steps is None else self.torch.from_numpy(steps).to(self.dev)
+        P = self.L._ptr
+        self.L.check(self.L.lib().pbrl_autoreset(self.model.handle, s.N, reward_mode, P(dn), P(nx), P(st), ctypes.byref(b), self._stream()))
+        self.torch.cuda.synchronize()
+        self._down(s, d)
+        if steps is not None:
+            steps[...] = st.cpu().numpy()
 
     def step(self, s, action, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=8, pd_time=None, ctrl_mask=0x0FFFFFFF, reward_mode=0):
         a = np.ascontiguousarray(action, np.float32)

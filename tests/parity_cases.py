@@ -319,16 +319,19 @@ def check_hands_against_thighs(backend, model_nograv, N=16, steps=12, seed=29):
     tgt[:, names.index("right_shoulder_x")] = rng.uniform(0.15, 0.45, N)    # right arm towards the body
     tgt[:, names.index("left_shoulder_x")] = -rng.uniform(0.15, 0.45, N)
     tgt[:, names.index("right_elbow")] = rng.uniform(0.0, 0.3, N)
-    worst, touched = 0.0, np.zeros(N, bool)
+    worst, touched, per_env = 0.0, np.zeros(N, bool), np.zeros(N)
     for k in range(steps):
         env.step(tgt, kp, kd, pd_mode=1, n_frames=8)
         backend.step(s, tgt, kp, kd, pd_mode=1, n_frames=8)
         pen = _self_penetration(model_nograv, env.qpos)
         touched |= _self_contacts(model_nograv, env.qpos) > 0
-        worst = max(worst, float(row_relerr(s.qpos, env.qpos).max()))
+        per_env = np.maximum(per_env, row_relerr(s.qpos, env.qpos))
+        worst = float(per_env.max())
         assert pen.min() > -5e-3, (k, pen.min())           # soft contact: millimetres of penetration at the impact, then it settles
     assert touched.mean() >= 0.75, touched.mean()           # the case exercises the rows
-    assert worst <= 2e-4, worst                             # ~100 contact substeps in fp32 vs the float64 oracle
+    # ~100 contact substeps in fp32 vs the float64 oracle: the 32-substep tolerance of the north star for every env,
+    # a tenth of it for the typical one (the host emulation and the GPU land on the same numbers)
+    assert worst <= TOL_32 and np.median(per_env) <= 1e-4, (worst, np.median(per_env))
     assert (s.status & 7 == 0).all()
     return worst
 
@@ -342,3 +345,47 @@ def _self_contacts(model, qpos):
         orc.forward(d)
         out[e] = int(d.nself[0])
     return out
+
+
+def check_autoreset(backend, model_grav, table, mdesc, N=21, seed=31):
+    """pbrl_autoreset (brax AutoResetWrapper semantics): finished envs restart -- qpos0 in reference mode, the reference
+    pose at the given clip phase in mimic mode -- with the first observation of the new episode in `obs`; the other envs
+    and the terminal reward / done / metrics are untouched; the step count of the restarted envs is zeroed."""
+    rng = np.random.default_rng(seed)
+    kp, kd = util_data.generate_kp_kd_gains()
+    # reference mode
+    s = backend.new_state(N)
+    backend.reset(s)
+    tau = rng.uniform(-0.5, 0.5, (N, 28)).astype(np.float32)
+    backend.step(s, tau, kp, kd, pd_mode=0)
+    before = {k: getattr(s, k).copy() for k in ("qpos", "qvel", "time", "warm", "ctrl", "obs", "reward", "done", "metrics")}
+    done = (np.arange(N) % 3 == 0).astype(np.float32)
+    steps = np.full(N, 7, np.int32)
+    backend.autoreset(s, done, steps=steps)
+    r, k = done != 0, done == 0
+    q0 = model_grav.qpos0.astype(np.float32)
+    assert np.array_equal(s.qpos[r], np.tile(q0, (r.sum(), 1))) and (s.qvel[r] == 0).all() and (s.time[r] == 0).all()
+    assert (s.warm[r] == 0).all() and (s.ctrl[r] == 0).all() and np.array_equal(s.qpos_lag[r], s.qpos[r])
+    assert np.array_equal(s.obs[r], np.concatenate([s.qpos[r], s.qvel[r]], 1))
+    for name in ("qpos", "qvel", "time", "warm", "ctrl", "obs"):
+        assert np.array_equal(getattr(s, name)[k], before[name][k]), name
+    for name in ("reward", "done", "metrics"):
+        assert np.array_equal(getattr(s, name), before[name]), name
+    assert (steps[r] == 0).all() and (steps[k] == 7).all()
+    # mimic mode: restart at a fresh phase == a reset at that phase
+    s = backend.new_state(N)
+    mid = (np.arange(N) % 7).astype(np.int32)
+    s.motion_id[:] = mid
+    s.ref_t0[:] = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    backend.reset(s, reward_mode=1)
+    backend.step(s, s.qpos[:, 7:].copy(), kp, kd, reward_mode=1)
+    rew, met = s.reward.copy(), s.metrics.copy()
+    nxt = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    keep_q = s.qpos.copy()
+    backend.autoreset(s, done, next_ref_t0=nxt, reward_mode=1)
+    fresh = backend.new_state(N)
+    fresh.motion_id[:], fresh.ref_t0[:] = mid, nxt
+    backend.reset(fresh, reward_mode=1)
+    assert np.array_equal(s.qpos[r], fresh.qpos[r]) and np.array_equal(s.qvel[r], fresh.qvel[r])
+    assert np.array_equal(s.ref_t0[r], nxt[r]) and np.array_equal(s.obs[r], fresh.obs[r]) and (s.time[r] == 0).all()
+    assert np.array_equal(s.qpos[k], keep_q[k]) and np.array_equal(s.reward, rew) and np.array_equal(s.metrics, met)

@@ -111,3 +111,43 @@ def test_mimic_env_rollout(mods, model_grav):
     assert (r > 0).all() and (r <= 1.0 + 1e-6).all() and torch.isfinite(state.obs).all()
     assert state.info["stats"][5].item() == 256 and (state.metrics["step_index"] == 4).all()
     assert abs(state.info["stats"][0].item() - r.sum().item()) < 1e-2
+
+
+def test_training_wrappers(mods, model_grav):
+    """wrappers.wrap = brax's EpisodeWrapper + AutoResetWrapper."""
+    torch, envs, _ = mods
+    wrappers = importlib.import_module(PKG + ".wrappers")
+    kp, kd = util_data.generate_kp_kd_gains()
+    N = 64
+    # reference mode: done = 1 every step (agent_mimic.py:72) -> every env restarts from qpos0 every step
+    env = wrappers.wrap(envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=N), episode_length=5, action_repeat=2)
+    state = env.reset(0)
+    assert (state.info["steps"] == 0).all() and (state.info["truncation"] == 0).all()
+    first = state.info["first_obs"].clone()
+    tgt = torch.zeros(N, 28, device="cuda")
+    state = env.step(state, tgt)
+    assert (state.done == 1).all() and torch.equal(state.obs, first) and (state.info["steps"] == 2).all()
+    assert (state.pipeline_state.time == 0).all() and (state.reward == 0).all()
+    state = env.step(state, tgt)
+    assert (state.info["steps"] == 2).all()          # the count restarted with the episode
+    # mimic mode: episodes end by termination or at episode_length; restarted envs sit on their reference pose
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    base = envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=N, reward_mode="mimic", motion_table=table)
+    env = wrappers.wrap(base, episode_length=6)
+    state = env.reset(1)
+    rng = np.random.default_rng(0)
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    ended = torch.zeros(N, dtype=torch.bool, device="cuda")
+    for k in range(6):
+        t0_before = state.info["ref_t0"].clone()
+        state = env.step(state, torch.from_numpy(rng.uniform(lo, hi, (N, 28)).astype(np.float32)).cuda())
+        d = state.done != 0
+        ended |= d
+        assert (state.pipeline_state.time[d] == 0).all() and (state.pipeline_state.qvel_lag[d] == state.pipeline_state.qvel[d]).all()
+        assert torch.equal(state.obs[d][:, :35], state.pipeline_state.qpos[d])
+        assert (state.info["ref_t0"][~d] == t0_before[~d]).all()
+        if d.any():
+            assert (state.info["ref_t0"][d] != t0_before[d]).any()      # a fresh clip phase per restart
+        assert torch.isfinite(state.obs).all() and (state.reward[:, 0] >= 0).all()
+    assert ended.all()                                                   # episode_length = 6 ends the survivors
+    assert (state.info["truncation"][state.info["steps"] >= 6] >= 0).all()

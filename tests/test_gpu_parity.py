@@ -68,3 +68,8 @@ def test_mimic_mode(model_grav):
     table, mdesc, keep = pc.mimic_setup(model_grav)
     b = GpuBackend(model_grav, mimic_desc=mdesc)
     pc.check_mimic(b, model_grav, table, mdesc, N=112)
+
+
+def test_autoreset(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    pc.check_autoreset(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc, N=133)

@@ -63,3 +63,10 @@ def test_mimic_mode(model_grav):
     b = EmuBackend(model_grav)
     b.set_mimic(mdesc)
     pc.check_mimic(b, model_grav, table, mdesc)
+
+
+def test_autoreset(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    b = EmuBackend(model_grav)
+    b.set_mimic(mdesc)
+    pc.check_autoreset(b, model_grav, table, mdesc)
