@@ -46,6 +46,8 @@ def load_assets(workload):
     mimic = importlib.import_module(PKG + ".mimic")
     asset, clips, n_env, pd_mode, descr = WORKLOADS[workload]
     model = mjcf.load_model(ROOT / PKG / "assets" / f"{asset}.model.json")
+    if os.environ.get("PBRL_BENCH_NO_SELF_COLLISION"):  # ablation: floor contacts only (both arms)
+        model.self_collision = 0
     table = mocap.MotionTable.load(ROOT / PKG / "assets" / "motions.npz")
     mdesc, keep = mimic.make_mimic_desc(model, table, clips)
     return model, clips, (table, mdesc, keep), n_env, pd_mode, descr
@@ -354,6 +356,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": args.workload, "description": descr, "envs_per_gpu": n_env, "envs_total": total_envs,
                            "n_frames": N_FRAMES, "pd_mode": "stable", "reward_mode": "mimic", "l2_flush_between_steps": True,
+                           "self_collision": "sphere/capsule pairs (64 of 89 candidates)" if getattr(model, "self_collision", 1) else "off",
                            "parallelism": f"env-sharded x{world}, stats all-reduce per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,
