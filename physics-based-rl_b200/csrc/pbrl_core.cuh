@@ -1911,7 +1911,7 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
         }
         substep(m, w, time, lane);
-        cost += w.niter;
+        cost += w.niter + 2 * w.nsc;  // solver iterations, weighted up when body-vs-body contacts (dense Hessian) are present
     }
     if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });

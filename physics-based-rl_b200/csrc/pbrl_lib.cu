@@ -149,7 +149,7 @@ __global__ void k_bench_stage(const DevModel* __restrict__ gm, int stage, int it
     forward(sm, w, lane);  // a consistent workspace (contacts active: the feet touch the floor at z = 0.9)
     long long best = 1ll << 60, tot = 0;
     for (int it = 0; it < iters; it++) {
-        if (stage == 0) { LANE_LOOP(e, NM) w.LD[e] = w.M[e]; LANE_LOOP(i, NV) w.p[i] = 1.f + 0.01f * i; }
+        if (stage == 0 || stage == 13) { LANE_LOOP(e, NM) w.LD[e] = w.M[e]; LANE_LOOP(i, NV) w.p[i] = 1.f + 0.01f * i; }
         __syncwarp();
         const long long t0 = clock64();
         switch (stage) {
@@ -166,6 +166,8 @@ __global__ void k_bench_stage(const DevModel* __restrict__ gm, int stage, int it
             case 10: rows_JTf(sm, w, w.Mp, w.grad, 0, lane); break;
             case 11: assemble_hessian(sm, w, lane); break;
             case 12: rows_Jx(sm, w, w.qacc, w.lim_jp, w.con_jp, w.sc_jp, lane); break;
+            case 13: dense_factor_solve(sm, w, 0u, w.p, lane); break;
+            case 14: stage_collide_self(sm, w, lane); break;
         }
         const long long t1 = clock64();
         if (stage == 1 || stage == 2) { __syncwarp(); }

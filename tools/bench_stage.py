@@ -10,11 +10,11 @@ model = mjcf.load_model(ROOT / "physics-based-rl_b200" / "assets" / "final_human
 M = L.Model(model, device=0)
 lib = L.lib()
 NAMES = ["ldl_factor_solve", "stage_fk", "stage_com", "stage_crb", "stage_collide", "stage_comvel", "stage_bias", "stage_rows",
-         "tree_Mx", "-", "rows_JTf", "assemble_hessian", "rows_Jx"]
+         "tree_Mx", "-", "rows_JTf", "assemble_hessian", "rows_Jx", "dense_factor_solve", "stage_collide_self"]
 ids = [int(a) for a in sys.argv[1:]] or range(len(NAMES))
 for s in ids:
     r = []
-    for w, c in [(1, 148), (8, 296)]:
+    for w, c in [(1, 148), (16, 148)]:
         out = (ctypes.c_ulonglong * 3)()
         L.check(lib.pbrl_debug_bench_stage(M.handle, s, w, c, 50, out))
         r.append(f"{w * c // 148:2d} warps/SM: avg {out[0] / max(out[2], 1):7.0f} best {out[1]:6d}")
