@@ -310,6 +310,8 @@ def main():
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t_ms = float(t_all.item())
     bad = int((st["status"] & 1).sum().item())
+    maxiter = int(((st["status"] & 4) != 0).sum().item())  # envs whose solver hit the iteration cap in the last step
+    pivots = int(((st["status"] & 2) != 0).sum().item())
     self_overflow = int(((st["status"] & 8) != 0).sum().item())  # envs that had more than 8 body-vs-body contacts at once in the last step
     stats_last = st["stats"].cpu().numpy().tolist()
 
@@ -366,7 +368,7 @@ def main():
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_step",
                              "algorithmic_bytes_per_env_launch": BYTES_PER_ENV_LAUNCH,
                              "note": "the dynamics step is fp32-issue/latency bound (50-300 flop/B); HBM fraction is reported per the tier rule"},
-                "clocks": clocks, "nan_envs": bad, "self_contact_overflow_envs": self_overflow,
+                "clocks": clocks, "nan_envs": bad, "self_contact_overflow_envs": self_overflow, "solver_maxiter_envs": maxiter, "pivot_envs": pivots,
                 "reward_stats_last_step": {"mean_reward": stats_last[0] / max(stats_last[5], 1), "done_frac": stats_last[2] / max(stats_last[5], 1),
                                            "fall_frac": stats_last[3] / max(stats_last[5], 1), "n": stats_last[5]}}
         if not args.no_cpu_baseline:

@@ -1367,7 +1367,9 @@ PB_DEV void self_rows_dense(const DevModel& m, Ws& w, int s, float* U, int lane)
 // Register-resident L^T D L (MuJoCo's elimination order, last dof first): lane i holds row i < 32 of the lower triangle in
 // registers, rows 32 and 33 stay in shared memory (they are eliminated first and never touched again).  Each step
 // broadcasts the pivot row through a 32-float staging row (double buffered); the right-hand side rides along (lane = dof),
-// and the back substitution pushes x_i to the rows below with one shuffle per dof.
+// and the back substitution pushes x_i to the rows below with one shuffle per dof.  (A lane = column variant that
+// broadcasts the pivot row with one shuffle per entry instead of the staging row measured 30 % slower: 10.2k vs 7.7k
+// cycles per call for a lone warp -- shuffles serialise on their scoreboard.)
 namespace dense {
 constexpr unsigned FULL = 0xffffffffu;
 template <int K>
