@@ -168,6 +168,14 @@ int pbrl_replay(const PbrlModel* model, int N, const float* qpos, const float* q
                 float* reward, float* done, float* xpos /* [N][14][3] or NULL */,
                 float* xquat /* [N][14][4] or NULL */, void* stream);
 
+/* Kinematic replay of a frame sequence in one launch: HumanoidReplay.step in the loop the reference's notebooks run
+ * (testing_forward_env.ipynb cell 10: for every frame write data_pos[i] / data_vel[i] into the state, then step).
+ * Env e replays frame (frame0[e] + k) mod F at step k = 0 .. K-1 (frame0 NULL: frame0[e] = e).  data_pos [F][35] and
+ * data_vel [F][34] are device arrays.  Outputs are step-major: obs [K][N][69], reward [K][N][3] (zeros), done [K][N] (ones),
+ * xpos [K][N][14][3], xquat [K][N][14][4]; any of them may be NULL. */
+int pbrl_replay_rollout(const PbrlModel* model, int N, int K, const float* data_pos, const float* data_vel, int F,
+                        const int* frame0, float* obs, float* reward, float* done, float* xpos, float* xquat, void* stream);
+
 int pbrl_pd_torque(const PbrlModel* model, int N, int pd_mode, int action_cols, const float* action,
                    const float* qpos, const float* qvel, const float* qpos_lag, const float* qvel_lag,
                    const float* kp, const float* kd, const float* time, float pd_dt, float* tau /* [N][28] */,

@@ -222,14 +222,14 @@ PB_DEV int first_bit(unsigned mk) {  // index of the lowest set bit (mk != 0)
 #endif
 }
 
-PB_DEV float __int_as_float_emu(int i) {
+PB_DEV float int_bits_as_float(int i) {
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
     return __int_as_float(i);
 #else
     float f; memcpy(&f, &i, 4); return f;
 #endif
 }
-PB_DEV int __float_as_int_emu(float f) {
+PB_DEV int float_bits_as_int(float f) {
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
     return __float_as_int(f);
 #else
@@ -1069,7 +1069,7 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
             float* o = pr + 8 * l;
             for (int k = 0; k < 3; k++) { o[k] = p1[k] + n[k] * (r1 + 0.5f * dist); o[4 + k] = n[k]; }
             o[3] = dist;
-            o[7] = __int_as_float_emu((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
+            o[7] = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
             return dist < m.self_margin;
         });
         WSYNC();
@@ -1081,7 +1081,7 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
                     for (int k = 0; k < 3; k++) { w.sc_r[4 * slot + k] = o[k] - w.com[k]; w.sc_n[4 * slot + k] = o[4 + k]; }
                     w.sc_r[4 * slot + 3] = 0.f;
                     w.sc_n[4 * slot + 3] = o[3];
-                    w.sc_bb[slot] = __float_as_int_emu(o[7]);
+                    w.sc_bb[slot] = float_bits_as_int(o[7]);
                 }
             }
         }
@@ -1968,6 +1968,41 @@ PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float
     if (xpos) LANE_LOOP(i, NB * 3) xpos[(size_t)env * NB * 3 + i] = w.xpos[i];
     if (xquat) LANE_LOOP(i, NB * 4) xquat[(size_t)env * NB * 4 + i] = w.xquat[S4 * (i / 4) + (i & 3)];
     WSYNC();
+}
+
+// Kinematic replay of one (env, frame) item by ONE thread (k_replay_rollout): the same kinematics as stage_fk, walked body by
+// body in parents-first order; poses are written to / read back from the item's own row (xpos: 14 x 3, xquat: 14 x 4).
+PB_DEV void replay_item_fk(const DevModel& m, const float* qpos, float* xpos, float* xquat) {
+    xpos[0] = xpos[1] = xpos[2] = 0.f;
+    xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
+    for (int b = 1; b < NB; b++) {
+        const int p = m.body_parent[b], j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
+        float pos[3], q[4];
+        if (m.jnt_type[j0] == 0) {
+            const int qa = m.jnt_qposadr[j0];
+            for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
+            for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
+            quat_normalize(q);
+        } else {
+            float pq[4], R[9], t[3], ql[4];
+            for (int c = 0; c < 4; c++) pq[c] = xquat[4 * p + c];
+            quat_to_mat(pq, R);
+            mat_vec(R, m.body_pos[b], t);
+            for (int c = 0; c < 3; c++) pos[c] = xpos[3 * p + c] + t[c];
+            for (int j = j0; j < j0 + nj; j++) {
+                const int qa = m.jnt_qposadr[j];
+                float sn, cs, jq[4], qn[4];
+                sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
+                jq[0] = cs; jq[1] = m.jnt_axis[j][0] * sn; jq[2] = m.jnt_axis[j][1] * sn; jq[3] = m.jnt_axis[j][2] * sn;
+                if (j == j0) { for (int c = 0; c < 4; c++) ql[c] = jq[c]; }
+                else { quat_mul(ql, jq, qn); for (int c = 0; c < 4; c++) ql[c] = qn[c]; }
+            }
+            quat_mul(pq, ql, q);
+        }
+        quat_normalize(q);
+        for (int c = 0; c < 3; c++) xpos[3 * b + c] = pos[c];
+        for (int c = 0; c < 4; c++) xquat[4 * b + c] = q[c];
+    }
 }
 
 // separate-controller path (testing_pds_env3.ipynb cell 21): tau, and optionally dense qM / qfrc_bias

@@ -112,6 +112,71 @@ k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float*
     for (int env = first_env(); env < N; env += env_stride())
         env_replay(sm, w, qpos, qvel, obs, reward, done, xpos, xquat, env, lane);
 }
+// Replay rollout: HBM-bound (944 B out per (env, frame) item against ~70 warp instructions), so the mapping is the
+// opposite of the dynamics kernels: one THREAD per item.  The item's body poses (xpos 42 | xquat 56 floats) are staged in a
+// shared-memory tile with an odd row stride (conflict-free column access) and written out by the whole CTA as contiguous
+// 16-byte vectors (the rows of RR_ITEMS consecutive items are contiguous in every output array); the observation rows are
+// copied straight from the clip (a few KB, L1-resident).  The model tables are read through L1 with warp-uniform loads:
+// no per-CTA model copy, so four CTAs (16 warps) fit an SM and hide the latency of the per-thread kinematic chain.
+constexpr int RR_ITEMS = 128;              // items (= threads) per CTA
+constexpr int RR_ROW = NB * 3 + NB * 4 + 1;  // 99 floats, odd
+static_assert(RR_ROW % 2 == 1, "odd row stride keeps per-thread rows on distinct banks");
+constexpr size_t RR_SMEM = sizeof(float) * RR_ITEMS * RR_ROW + sizeof(int) * RR_ITEMS;
+__device__ __forceinline__ void rr_store(float* __restrict__ out, const float* tile, long long g0, int nitems, int width, int col0) {
+    if (!out) return;
+    float* dst = out + g0 * width;                       // 16-byte aligned: g0 is a multiple of RR_ITEMS
+    const int total = nitems * width, nvec = total / 4;
+    for (int v = threadIdx.x; v < nvec; v += RR_ITEMS) {
+        float r[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { const int i = 4 * v + t; r[t] = tile[(i / width) * RR_ROW + col0 + i % width]; }
+        __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(r[0], r[1], r[2], r[3]));   // streaming: written once, never re-read
+    }
+    for (int i = 4 * nvec + threadIdx.x; i < total; i += RR_ITEMS) dst[i] = tile[(i / width) * RR_ROW + col0 + i % width];
+}
+__global__ void __launch_bounds__(RR_ITEMS, 4)
+k_replay_rollout(const DevModel* __restrict__ gm, int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel,
+                 int F, const int* __restrict__ frame0, float* obs, float* reward, float* done, float* xpos, float* xquat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    int* frame = reinterpret_cast<int*>(smem_raw + sizeof(float) * RR_ITEMS * RR_ROW);
+    const DevModel& m = *gm;
+    const long long total = (long long)N * K;
+    for (long long g0 = (long long)blockIdx.x * RR_ITEMS; g0 < total; g0 += (long long)gridDim.x * RR_ITEMS) {
+        const long long g = g0 + threadIdx.x;
+        const int nitems = total - g0 < RR_ITEMS ? (int)(total - g0) : RR_ITEMS;
+        if (g < total) {
+            const int k = (int)(g / N), e = (int)(g - (long long)k * N);
+            const int f = ((frame0 ? frame0[e] : e) + k) % F;
+            frame[threadIdx.x] = f;
+            float* row = tile + threadIdx.x * RR_ROW;
+            if (xpos || xquat) replay_item_fk(m, data_pos + (size_t)f * NQ, row, row + NB * 3);
+        }
+        __syncthreads();
+        if (obs) {  // obs = [qpos, qvel] of the item's frame (agent_env_template.py:151-155)
+            float* dst = obs + g0 * PBRL_OBS;
+            const int tot = nitems * PBRL_OBS, nvec = tot / 4;
+            for (int v = threadIdx.x; v < nvec; v += RR_ITEMS) {
+                float r[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int i = 4 * v + t, it = i / PBRL_OBS, c = i - it * PBRL_OBS, f = frame[it];
+                    r[t] = c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
+                }
+                __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(r[0], r[1], r[2], r[3]));
+            }
+            for (int i = 4 * nvec + threadIdx.x; i < tot; i += RR_ITEMS) {
+                const int it = i / PBRL_OBS, c = i - it * PBRL_OBS, f = frame[it];
+                dst[i] = c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
+            }
+        }
+        rr_store(xpos, tile, g0, nitems, NB * 3, 0);
+        rr_store(xquat, tile, g0, nitems, NB * 4, NB * 3);
+        if (reward) for (int i = threadIdx.x; i < nitems * 3; i += RR_ITEMS) reward[g0 * 3 + i] = 0.f;   // agent_replay_motion.py: zeros(3)
+        if (done && threadIdx.x < nitems) done[g0 + threadIdx.x] = 1.0f;
+        __syncthreads();
+    }
+}
 __global__ void __launch_bounds__(CTA_THREADS)
 k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
      const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
@@ -183,6 +248,8 @@ struct PbrlModel {
     int device = 0;
     int sm_count = 0;
     int ctas_per_sm = 1;
+    int rr_ctas_per_sm = 1;
+    int phase_lock = 25;  // CTA barrier mask of k_step (pbrl_core.cuh: forward); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
     DevModel host{};
     DevModel* dev = nullptr;
     DevMimic mimic{};
@@ -237,10 +304,18 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     m->device = device;
     m->sm_count = prop.multiProcessorCount;
     m->ctas_per_sm = 0;
+    { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 31; }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) { delete m; return fail(err); }
     if (prepare_kernel(k_step, m) || prepare_kernel(k_reset, m) || prepare_kernel(k_replay, m) || prepare_kernel(k_pd, m) ||
         prepare_kernel(k_debug_forward, m) || prepare_kernel(k_autoreset, m)) { delete m; return -1; }
+    {
+        CUDA_OK(cudaFuncSetAttribute(k_replay_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+        int nb = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay_rollout, RR_ITEMS, RR_SMEM));
+        if (nb < 1) { delete m; return fail("k_replay_rollout does not fit on an SM"); }
+        m->rr_ctas_per_sm = nb;
+    }
     CUDA_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
     CUDA_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
     if (mimic) {
@@ -320,7 +395,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     } else if (reward_mode != PBRL_REWARD_REFERENCE) return fail("unknown reward_mode");
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
-    { const char* e = getenv("PBRL_PHASE_LOCK"); a.phase_lock = (e ? atoi(e) : 25) & 31; }
+    a.phase_lock = m->phase_lock;
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }
@@ -332,6 +407,18 @@ int pbrl_replay(const PbrlModel* m, int N, const float* qpos, const float* qvel,
     if (!qpos || !qvel) return fail("null qpos/qvel");
     k_replay<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, obs, reward, done, xpos, xquat);
     return check_launch("pbrl_replay");
+}
+
+int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos, const float* data_vel, int F, const int* frame0,
+                        float* obs, float* reward, float* done, float* xpos, float* xquat, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0 || K <= 0) return 0;
+    if (!data_pos || !data_vel || F <= 0) return fail("null frame data");
+    const long long ctas = ((long long)N * K + RR_ITEMS - 1) / RR_ITEMS;
+    const long long cap = (long long)m->sm_count * m->rr_ctas_per_sm;
+    k_replay_rollout<<<(unsigned)(ctas < cap ? ctas : cap), RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(
+        m->dev, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+    return check_launch("pbrl_replay_rollout");
 }
 
 int pbrl_pd_torque(const PbrlModel* m, int N, int pd_mode, int action_cols, const float* action, const float* qpos,

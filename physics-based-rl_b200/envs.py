@@ -282,6 +282,30 @@ class HumanoidReplay(HumanoidDiff):
         return state
 
 
+    def rollout(self, frame0=None, num_steps=None, want_poses=True):
+        """The replay loop of the reference's notebooks (testing_forward_env.ipynb cell 10: write frame i of the reference
+        trajectory into the state, step, next frame) as ONE launch: env e shows frame (frame0[e] + k) mod F at step k.
+        Returns step-major tensors: obs (K, N, 69), reward (K, N, 3) zeros, done (K, N) ones and, with want_poses,
+        xpos (K, N, 14, 3), xquat (K, N, 14, 4)."""
+        if getattr(self, "_traj_dev", None) is None:
+            qp = torch.as_tensor(np.asarray(self.reference_trajectory_qpos), dtype=torch.float32, device=self.device).contiguous()
+            qv = torch.as_tensor(np.asarray(self.reference_trajectory_qvel), dtype=torch.float32, device=self.device).contiguous()
+            self._traj_dev = (qp, qv)
+        qp, qv = self._traj_dev
+        F, N = int(qp.shape[0]), self.num_envs
+        K = F if num_steps is None else int(num_steps)
+        f0 = None if frame0 is None else torch.as_tensor(frame0, dtype=torch.int32, device=self.device).contiguous()
+        e = lambda *s: torch.empty(s, device=self.device, dtype=torch.float32)
+        out = dict(obs=e(K, N, 69), reward=e(K, N, 3), done=e(K, N))
+        if want_poses:
+            out.update(xpos=e(K, N, 14, 3), xquat=e(K, N, 14, 4))
+        _lib.check(_lib.lib().pbrl_replay_rollout(self.model.handle, ctypes.c_int(N), ctypes.c_int(K), _lib._ptr(qp), _lib._ptr(qv),
+                                                  ctypes.c_int(F), _lib._ptr(f0), _lib._ptr(out["obs"]), _lib._ptr(out["reward"]),
+                                                  _lib._ptr(out["done"]), _lib._ptr(out.get("xpos")), _lib._ptr(out.get("xquat")),
+                                                  self._stream()))
+        return out
+
+
 _REGISTRY = {}
 
 

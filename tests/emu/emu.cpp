@@ -80,6 +80,10 @@ int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* r
     for (int e = 0; e < N; e++) env_replay(g_model, ws[0], qpos, qvel, obs, reward, done, xpos, xquat, e, 0);
     return 0;
 }
+int emu_replay_item_fk(const float* qpos, float* xpos, float* xquat) {
+    replay_item_fk(g_model, qpos, xpos, xquat);
+    return 0;
+}
 int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, const float* qpos, const float* qvel,
                   const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd, const float* time,
                   float pd_dt, float* tau, float* qM, float* bias) {

@@ -176,6 +176,15 @@ class EmuBackend:
                                self._p(qM), self._p(bias))
         return (tau, qM, bias) if want_qM else tau
 
+    def replay_item_fk(self, qpos):
+        """The per-item kinematics of the replay-rollout kernel (one thread per item on the GPU)."""
+        self._select()
+        qpos = np.ascontiguousarray(qpos, np.float32)
+        xpos, xquat = np.zeros((qpos.shape[0], 14, 3), np.float32), np.zeros((qpos.shape[0], 14, 4), np.float32)
+        for i in range(qpos.shape[0]):
+            self.lib.emu_replay_item_fk(self._p(qpos[i]), self._p(xpos[i]), self._p(xquat[i]))
+        return xpos, xquat
+
     def replay(self, qpos, qvel, want_poses=True):
         self._select()
         qpos, qvel = np.ascontiguousarray(qpos, np.float32), np.ascontiguousarray(qvel, np.float32)
@@ -276,6 +285,17 @@ class GpuBackend:
                                                  ctypes.c_float(pd_dt), P(tau), P(qM), P(bias), self._stream()))
         t.cuda.synchronize()
         return (tau.cpu().numpy(), qM.cpu().numpy(), bias.cpu().numpy()) if want_qM else tau.cpu().numpy()
+
+    def replay_rollout(self, data_pos, data_vel, frame0, N, K):
+        t = self.torch
+        dp, dv, f0 = self._dp(data_pos), self._dp(data_vel), self._dp(frame0, np.int32)
+        z = lambda *s_: t.full(s_, -7.0, device=self.dev)
+        out = dict(obs=z(K, N, 69), reward=z(K, N, 3), done=z(K, N), xpos=z(K, N, 14, 3), xquat=z(K, N, 14, 4))
+        P = self.L._ptr
+        self.L.check(self.L.lib().pbrl_replay_rollout(self.model.handle, N, K, P(dp), P(dv), dp.shape[0], P(f0), P(out["obs"]),
+                                                      P(out["reward"]), P(out["done"]), P(out["xpos"]), P(out["xquat"]), self._stream()))
+        t.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
 
     def replay(self, qpos, qvel, want_poses=True):
         t = self.torch

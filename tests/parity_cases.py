@@ -389,3 +389,23 @@ def check_autoreset(backend, model_grav, table, mdesc, N=21, seed=31):
     assert np.array_equal(s.qpos[r], fresh.qpos[r]) and np.array_equal(s.qvel[r], fresh.qvel[r])
     assert np.array_equal(s.ref_t0[r], nxt[r]) and np.array_equal(s.obs[r], fresh.obs[r]) and (s.time[r] == 0).all()
     assert np.array_equal(s.qpos[k], keep_q[k]) and np.array_equal(s.reward, rew) and np.array_equal(s.metrics, met)
+
+
+def check_replay_rollout(backend, model, F=39, N=50, K=7, seed=37):
+    """pbrl_replay_rollout: env e shows frame (frame0[e] + k) mod F at step k; every (step, env) item equals
+    HumanoidReplay.step at that frame (obs bit-exact echo, zeros / ones, body poses vs the oracle's FK)."""
+    rng = np.random.default_rng(seed)
+    qpos, qvel = random_states(model, F, seed, vel_scale=1.0, joint_frac=0.9)
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    frame0 = rng.integers(0, F, N).astype(np.int32)
+    out = backend.replay_rollout(q32, v32, frame0, N, K)
+    env = OracleEnv(_oracle(model), F)
+    _, _, _, xpos_r, xquat_r = env.replay(q32, v32, want_poses=True)
+    for k in range(K):
+        f = (frame0 + k) % F
+        assert np.array_equal(out["obs"][k], np.concatenate([q32[f], v32[f]], 1))
+        assert relerr(out["xpos"][k], xpos_r[f]) <= 2e-6 and relerr(out["xquat"][k], xquat_r[f]) <= 2e-6
+    assert (out["reward"] == 0).all() and (out["done"] == 1).all()
+    out2 = backend.replay_rollout(q32, v32, None, N, K)   # frame0 = env id
+    k2 = min(2, K - 1)
+    assert np.array_equal(out2["obs"][k2][:, :35], q32[(np.arange(N) + k2) % F])

@@ -126,3 +126,9 @@ def test_edge_sizes_and_full_size_batch_invariance(gpu_grav, model_grav):
     assert np.allclose(np.linalg.norm(s.qpos[:, 3:7], axis=1), 1.0, atol=1e-5)
     sp = run(N, order=np.random.default_rng(5).permutation(N))
     assert np.array_equal(sp.qpos, s.qpos) and np.array_equal(sp.qvel, s.qvel) and np.array_equal(sp.warm, s.warm)
+
+
+def test_replay_rollout(gpu_nograv, model_nograv):
+    pc.check_replay_rollout(gpu_nograv, model_nograv)
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=227, N=4096, K=3, seed=38)   # several CTAs per step, ragged tail
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=1, K=1, seed=39)

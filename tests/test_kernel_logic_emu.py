@@ -70,3 +70,15 @@ def test_autoreset(model_grav):
     b = EmuBackend(model_grav)
     b.set_mimic(mdesc)
     pc.check_autoreset(b, model_grav, table, mdesc)
+
+
+def test_replay_item_kinematics(emu_nograv, model_nograv):
+    """The thread-serial FK of the replay-rollout kernel against the oracle (same poses as stage_fk)."""
+    import numpy as np
+    from helpers import Oracle, OracleEnv, random_states, relerr
+    qpos, qvel = random_states(model_nograv, 40, 37, vel_scale=1.0, joint_frac=0.9)
+    qpos[0, 3:7] *= 0.99
+    q32 = qpos.astype(np.float32)
+    xpos, xquat = emu_nograv.replay_item_fk(q32)
+    _, _, _, xpos_r, xquat_r = OracleEnv(Oracle(model_nograv, "f64"), 40).replay(q32, qvel.astype(np.float32), want_poses=True)
+    assert relerr(xpos, xpos_r) <= 2e-6 and relerr(xquat, xquat_r) <= 2e-6
