@@ -1972,37 +1972,77 @@ PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float
 
 // Kinematic replay of one (env, frame) item by ONE thread (k_replay_rollout): the same kinematics as stage_fk, walked body by
 // body in parents-first order; poses are written to / read back from the item's own row (xpos: 14 x 3, xquat: 14 x 4).
-PB_DEV void replay_item_fk(const DevModel& m, const float* qpos, float* xpos, float* xquat) {
-    xpos[0] = xpos[1] = xpos[2] = 0.f;
-    xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
-    for (int b = 1; b < NB; b++) {
-        const int p = m.body_parent[b], j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
-        float pos[3], q[4];
-        if (m.jnt_type[j0] == 0) {
-            const int qa = m.jnt_qposadr[j0];
-            for (int c = 0; c < 3; c++) pos[c] = qpos[qa + c];
-            for (int c = 0; c < 4; c++) q[c] = qpos[qa + 3 + c];
-            quat_normalize(q);
+// Thread-serial, so the scalar cost matters: half-angle sine / cosine by odd / even polynomials on |x| <= 1.7 (hinge ranges
+// are within +-3.14; error < 1e-7, library call beyond), reciprocal square roots for the normalisations, vectors rotated by
+// the quaternion directly (v + w t + u x t, t = 2 u x v) instead of through a rotation matrix.
+PB_DEV void sincos_half_angle(float x, float* sn, float* cs) {
+    if (fabsf(x) > 1.7f) { sincosf(x, sn, cs); return; }
+    const float z = x * x;
+    float s = fmaf(z, -2.5052108e-8f, 2.7557319e-6f);   // Taylor to x^13 / x^12: truncation below 2e-8 on the interval
+    s = fmaf(s, z, -1.9841270e-4f); s = fmaf(s, z, 8.3333333e-3f); s = fmaf(s, z, -1.6666667e-1f);
+    *sn = fmaf(x * z, s, x);
+    float c = fmaf(z, 2.0876757e-9f, -2.7557319e-7f);
+    c = fmaf(c, z, 2.4801587e-5f); c = fmaf(c, z, -1.3888889e-3f); c = fmaf(c, z, 4.1666667e-2f); c = fmaf(c, z, -0.5f);
+    *cs = fmaf(c, z, 1.0f);
+}
+PB_DEV void quat_normalize_fast(float* q) {
+    const float ss = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (ss < 1e-30f) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+    const float inv = fast_rsqrt(ss);
+    q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+// The float tables the item kinematics read.  k_replay_rollout receives them as a kernel parameter (constant bank, uniform
+// loads: no L1 traffic); the body tree itself is compile-time (pbrl_topo_gen.h), so the walk is fully unrolled, every qpos
+// load has an immediate offset and the poses of the ancestors live in registers.
+struct ReplayTables {
+    float body_pos[NB][3], jnt_axis[NJ][3], qpos0[NQ + 1];
+};
+inline void replay_tables_from(const DevModel& m, ReplayTables& t) {  // host side
+    for (int b = 0; b < NB; b++) for (int c = 0; c < 3; c++) t.body_pos[b][c] = m.body_pos[b][c];
+    for (int j = 0; j < NJ; j++) for (int c = 0; c < 3; c++) t.jnt_axis[j][c] = m.jnt_axis[j][c];
+    for (int i = 0; i <= NQ; i++) t.qpos0[i] = m.qpos0[i];
+}
+namespace replay {
+template <int B>
+struct Body {
+    PB_MEMBER void run(const ReplayTables& T, const float* qpos, float (&xp)[NB][3], float (&xq)[NB][4], float* xpos, float* xquat) {
+        constexpr int P = topo::BODY_PARENT[B], J0 = topo::BODY_JNTADR[B], NJB = topo::BODY_JNTNUM[B];
+        float q[4];
+        if constexpr (J0 == 0) {  // the free joint
+            for (int c = 0; c < 3; c++) xp[B][c] = qpos[c];
+            for (int c = 0; c < 4; c++) q[c] = qpos[3 + c];
         } else {
-            float pq[4], R[9], t[3], ql[4];
-            for (int c = 0; c < 4; c++) pq[c] = xquat[4 * p + c];
-            quat_to_mat(pq, R);
-            mat_vec(R, m.body_pos[b], t);
-            for (int c = 0; c < 3; c++) pos[c] = xpos[3 * p + c] + t[c];
-            for (int j = j0; j < j0 + nj; j++) {
-                const int qa = m.jnt_qposadr[j];
+            float t[3], ut[3], ql[4];
+            const float* v = T.body_pos[B];
+            cross3(xq[P] + 1, v, t);
+            for (int c = 0; c < 3; c++) t[c] *= 2.f;
+            cross3(xq[P] + 1, t, ut);
+            for (int c = 0; c < 3; c++) xp[B][c] = xp[P][c] + (v[c] + xq[P][0] * t[c] + ut[c]);
+#pragma unroll
+            for (int j = J0; j < J0 + NJB; j++) {
                 float sn, cs, jq[4], qn[4];
-                sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
-                jq[0] = cs; jq[1] = m.jnt_axis[j][0] * sn; jq[2] = m.jnt_axis[j][1] * sn; jq[3] = m.jnt_axis[j][2] * sn;
-                if (j == j0) { for (int c = 0; c < 4; c++) ql[c] = jq[c]; }
+                sincos_half_angle(0.5f * (qpos[6 + j] - T.qpos0[6 + j]), &sn, &cs);
+                jq[0] = cs; jq[1] = T.jnt_axis[j][0] * sn; jq[2] = T.jnt_axis[j][1] * sn; jq[3] = T.jnt_axis[j][2] * sn;
+                if (j == J0) { for (int c = 0; c < 4; c++) ql[c] = jq[c]; }
                 else { quat_mul(ql, jq, qn); for (int c = 0; c < 4; c++) ql[c] = qn[c]; }
             }
-            quat_mul(pq, ql, q);
+            quat_mul(xq[P], ql, q);
         }
-        quat_normalize(q);
-        for (int c = 0; c < 3; c++) xpos[3 * b + c] = pos[c];
-        for (int c = 0; c < 4; c++) xquat[4 * b + c] = q[c];
+        quat_normalize_fast(q);
+        for (int c = 0; c < 4; c++) xq[B][c] = q[c];
+        for (int c = 0; c < 3; c++) xpos[3 * B + c] = xp[B][c];
+        for (int c = 0; c < 4; c++) xquat[4 * B + c] = q[c];
+        if constexpr (B + 1 < NB) Body<B + 1>::run(T, qpos, xp, xq, xpos, xquat);
     }
+};
+}  // namespace replay
+PB_DEV void replay_item_fk(const ReplayTables& T, const float* qpos, float* xpos, float* xquat) {
+    float xp[NB][3], xq[NB][4];
+    xp[0][0] = xp[0][1] = xp[0][2] = 0.f;
+    xq[0][0] = 1.f; xq[0][1] = xq[0][2] = xq[0][3] = 0.f;
+    for (int c = 0; c < 3; c++) xpos[c] = 0.f;
+    xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
+    replay::Body<1>::run(T, qpos, xp, xq, xpos, xquat);
 }
 
 // separate-controller path (testing_pds_env3.ipynb cell 21): tau, and optionally dense qM / qfrc_bias

@@ -122,25 +122,27 @@ constexpr int RR_ITEMS = 128;              // items (= threads) per CTA
 constexpr int RR_ROW = NB * 3 + NB * 4 + 1;  // 99 floats, odd
 static_assert(RR_ROW % 2 == 1, "odd row stride keeps per-thread rows on distinct banks");
 constexpr size_t RR_SMEM = sizeof(float) * RR_ITEMS * RR_ROW + sizeof(int) * RR_ITEMS;
-__device__ __forceinline__ void rr_store(float* __restrict__ out, const float* tile, long long g0, int nitems, int width, int col0) {
+// tile columns [col0, col0 + W) of `nitems` rows -> out rows of width W starting at item g0, as VEC-float vectors
+// (W % VEC == 0: a vector never straddles two rows; the division by the constant W / VEC is a multiply-shift)
+template <int W, int VEC>
+__device__ __forceinline__ void rr_store(float* __restrict__ out, const float* tile, long long g0, int nitems, int col0) {
+    static_assert(W % VEC == 0 && (VEC == 2 || VEC == 4), "vector width");
     if (!out) return;
-    float* dst = out + g0 * width;                       // 16-byte aligned: g0 is a multiple of RR_ITEMS
-    const int total = nitems * width, nvec = total / 4;
-    for (int v = threadIdx.x; v < nvec; v += RR_ITEMS) {
-        float r[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) { const int i = 4 * v + t; r[t] = tile[(i / width) * RR_ROW + col0 + i % width]; }
-        __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(r[0], r[1], r[2], r[3]));   // streaming: written once, never re-read
+    constexpr int PER_ROW = W / VEC;
+    float* dst = out + g0 * W;  // 16-byte aligned: g0 is a multiple of RR_ITEMS
+    for (int v = threadIdx.x; v < nitems * PER_ROW; v += RR_ITEMS) {
+        const int row = v / PER_ROW, s = v - row * PER_ROW;
+        const float* src = tile + row * RR_ROW + col0 + VEC * s;
+        if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(src[0], src[1], src[2], src[3]));  // streaming: never re-read
+        else __stcs(reinterpret_cast<float2*>(dst) + v, make_float2(src[0], src[1]));
     }
-    for (int i = 4 * nvec + threadIdx.x; i < total; i += RR_ITEMS) dst[i] = tile[(i / width) * RR_ROW + col0 + i % width];
 }
 __global__ void __launch_bounds__(RR_ITEMS, 4)
-k_replay_rollout(const DevModel* __restrict__ gm, int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel,
+k_replay_rollout(const __grid_constant__ ReplayTables T, int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel,
                  int F, const int* __restrict__ frame0, float* obs, float* reward, float* done, float* xpos, float* xquat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     int* frame = reinterpret_cast<int*>(smem_raw + sizeof(float) * RR_ITEMS * RR_ROW);
-    const DevModel& m = *gm;
     const long long total = (long long)N * K;
     for (long long g0 = (long long)blockIdx.x * RR_ITEMS; g0 < total; g0 += (long long)gridDim.x * RR_ITEMS) {
         const long long g = g0 + threadIdx.x;
@@ -150,28 +152,30 @@ k_replay_rollout(const DevModel* __restrict__ gm, int N, int K, const float* __r
             const int f = ((frame0 ? frame0[e] : e) + k) % F;
             frame[threadIdx.x] = f;
             float* row = tile + threadIdx.x * RR_ROW;
-            if (xpos || xquat) replay_item_fk(m, data_pos + (size_t)f * NQ, row, row + NB * 3);
+            if (xpos || xquat) replay_item_fk(T, data_pos + (size_t)f * NQ, row, row + NB * 3);
         }
         __syncthreads();
-        if (obs) {  // obs = [qpos, qvel] of the item's frame (agent_env_template.py:151-155)
+        if (obs) {  // obs = [qpos, qvel] of the item's frame (agent_env_template.py:151-155), 16-byte vectors over the block
             float* dst = obs + g0 * PBRL_OBS;
             const int tot = nitems * PBRL_OBS, nvec = tot / 4;
+            int row = (4 * threadIdx.x) / PBRL_OBS, col = 4 * threadIdx.x - row * PBRL_OBS;   // of the vector's first element
+            constexpr int DROW = (4 * RR_ITEMS) / PBRL_OBS, DCOL = 4 * RR_ITEMS - DROW * PBRL_OBS;  // advance per iteration
+            auto elem = [&](int r, int c) {
+                const int f = frame[r];
+                return c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
+            };
             for (int v = threadIdx.x; v < nvec; v += RR_ITEMS) {
                 float r[4];
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int i = 4 * v + t, it = i / PBRL_OBS, c = i - it * PBRL_OBS, f = frame[it];
-                    r[t] = c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
-                }
+                for (int t = 0; t < 4; t++) { const bool wrap = col + t >= PBRL_OBS; r[t] = elem(wrap ? row + 1 : row, wrap ? col + t - PBRL_OBS : col + t); }
                 __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(r[0], r[1], r[2], r[3]));
+                row += DROW; col += DCOL;
+                if (col >= PBRL_OBS) { col -= PBRL_OBS; row++; }
             }
-            for (int i = 4 * nvec + threadIdx.x; i < tot; i += RR_ITEMS) {
-                const int it = i / PBRL_OBS, c = i - it * PBRL_OBS, f = frame[it];
-                dst[i] = c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
-            }
+            for (int i = 4 * nvec + threadIdx.x; i < tot; i += RR_ITEMS) { const int it = i / PBRL_OBS; dst[i] = elem(it, i - it * PBRL_OBS); }
         }
-        rr_store(xpos, tile, g0, nitems, NB * 3, 0);
-        rr_store(xquat, tile, g0, nitems, NB * 4, NB * 3);
+        rr_store<NB * 3, 2>(xpos, tile, g0, nitems, 0);
+        rr_store<NB * 4, 4>(xquat, tile, g0, nitems, NB * 3);
         if (reward) for (int i = threadIdx.x; i < nitems * 3; i += RR_ITEMS) reward[g0 * 3 + i] = 0.f;   // agent_replay_motion.py: zeros(3)
         if (done && threadIdx.x < nitems) done[g0 + threadIdx.x] = 1.0f;
         __syncthreads();
@@ -416,8 +420,10 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
     if (!data_pos || !data_vel || F <= 0) return fail("null frame data");
     const long long ctas = ((long long)N * K + RR_ITEMS - 1) / RR_ITEMS;
     const long long cap = (long long)m->sm_count * m->rr_ctas_per_sm;
+    ReplayTables T;
+    replay_tables_from(m->host, T);
     k_replay_rollout<<<(unsigned)(ctas < cap ? ctas : cap), RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(
-        m->dev, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+        T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
     return check_launch("pbrl_replay_rollout");
 }
 

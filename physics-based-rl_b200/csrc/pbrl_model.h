@@ -283,6 +283,10 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
     if (madr != NM) return "sparse inertia layout size differs from 310";
     for (int i = 0; i < NV; i++)
         if (d.dof_parentid[i] != topo::PARENT[i]) return "the dof tree differs from the one the kernels were compiled for (csrc/pbrl_topo_gen.h)";
+    for (int b = 1; b < NB; b++)
+        if (d.body_parent[b] != topo::BODY_PARENT[b] || d.body_jntadr[b] != topo::BODY_JNTADR[b] || d.body_jntnum[b] != topo::BODY_JNTNUM[b])
+            return "the body tree differs from the one the kernels were compiled for (csrc/pbrl_topo_gen.h)";
+    for (int j = 1; j < NJ; j++) if (d.jnt_qposadr[j] != 6 + j || d.jnt_type[j] != 3) return "joints 1.. must be hinges reading qpos[6 + j]";
     if (maxdepth + 1 > MAXDEPTH) return "dof chains too deep";
     m.ndepth = maxdepth + 1;
     pos = 0;

@@ -81,7 +81,9 @@ int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* r
     return 0;
 }
 int emu_replay_item_fk(const float* qpos, float* xpos, float* xquat) {
-    replay_item_fk(g_model, qpos, xpos, xquat);
+    ReplayTables T;
+    replay_tables_from(g_model, T);
+    replay_item_fk(T, qpos, xpos, xquat);
     return 0;
 }
 int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, const float* qpos, const float* qvel,
