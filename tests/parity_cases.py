@@ -409,3 +409,40 @@ def check_replay_rollout(backend, model, F=39, N=50, K=7, seed=37):
     out2 = backend.replay_rollout(q32, v32, None, N, K)   # frame0 = env id
     k2 = min(2, K - 1)
     assert np.array_equal(out2["obs"][k2][:, :35], q32[(np.arange(N) + k2) % F])
+
+
+def check_contact_rich_statistics(backend, model_grav, table, mdesc, N=1024, steps=24, seed=43):
+    """North star: 'contact-rich rollouts are additionally checked by matching termination steps and reward statistics'.
+    The bench workload (reference-state init over all clips, random target angles, stable PD, mimic reward) on the back end
+    and on the oracle (fp32 build, all host threads): per-step mean reward, termination-step histogram, fall fraction."""
+    orc = Oracle(model_grav, "f32")
+    env = OracleEnv(orc, N)
+    rng = np.random.default_rng(seed)
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    env.reset_mimic(mdesc, mid, t0)
+    s = backend.new_state(N)
+    s.motion_id[:], s.ref_t0[:] = mid, t0
+    backend.reset(s, reward_mode=1)
+    kp, kd = util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    first_ref, first = np.full(N, steps), np.full(N, steps)
+    rew_ref, rew = [], []
+    for k in range(steps):
+        tgt = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
+        env.step_mimic(tgt, kp, kd)
+        s.stats[:] = 0
+        backend.step(s, tgt, kp, kd, reward_mode=1)
+        rew_ref.append(env.reward[:, 0].mean())
+        rew.append(s.reward[:, 0].mean())
+        first_ref = np.where((first_ref == steps) & (env.done != 0), k, first_ref)
+        first = np.where((first == steps) & (s.done != 0), k, first)
+    rew_ref, rew = np.array(rew_ref), np.array(rew)
+    assert np.isfinite(s.qpos).all() and (s.status & 1 == 0).all()
+    assert np.abs(rew - rew_ref).max() <= 0.01 + 0.05 * rew_ref.max(), (rew, rew_ref)
+    h_ref = np.bincount(first_ref, minlength=steps + 1) / N
+    h = np.bincount(first, minlength=steps + 1) / N
+    assert np.abs(np.cumsum(h) - np.cumsum(h_ref)).max() <= 0.04, (np.cumsum(h), np.cumsum(h_ref))   # termination-step CDF
+    assert abs((first < steps).mean() - (first_ref < steps).mean()) <= 0.03
+    assert (first == first_ref).mean() >= 0.8, (first == first_ref).mean()                               # per env: same termination step for most
+    return float(np.abs(rew - rew_ref).max()), float((first == first_ref).mean())

@@ -132,3 +132,8 @@ def test_replay_rollout(gpu_nograv, model_nograv):
     pc.check_replay_rollout(gpu_nograv, model_nograv)
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=227, N=4096, K=3, seed=38)   # several CTAs per step, ragged tail
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=1, K=1, seed=39)
+
+
+def test_contact_rich_statistics(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    pc.check_contact_rich_statistics(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc)

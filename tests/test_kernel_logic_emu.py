@@ -82,3 +82,10 @@ def test_replay_item_kinematics(emu_nograv, model_nograv):
     xpos, xquat = emu_nograv.replay_item_fk(q32)
     _, _, _, xpos_r, xquat_r = OracleEnv(Oracle(model_nograv, "f64"), 40).replay(q32, qvel.astype(np.float32), want_poses=True)
     assert relerr(xpos, xpos_r) <= 2e-6 and relerr(xquat, xquat_r) <= 2e-6
+
+
+def test_contact_rich_statistics_small(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    b = EmuBackend(model_grav)
+    b.set_mimic(mdesc)
+    pc.check_contact_rich_statistics(b, model_grav, table, mdesc, N=70, steps=10)

@@ -37,6 +37,21 @@ wr = get("dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum
     "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "algorithmic_bytes_per_launch": 16384 * 1248,
     "source": f"ncu --set full --clock-control none, one k_step launch (profiles/{name}_k_step_ncu_full_summary.csv)"}, indent=1))
 
+# the replay-rollout kernel (HBM-bound)
+rrep = G / f"prof_replay_{tag}.ncu-rep"
+if rrep.exists():
+    raw2 = subprocess.run(["ncu", "-i", str(rrep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r2 = list(csv.reader(io.StringIO(raw2)))
+    h2, u2, v2 = r2[0], r2[1], r2[2]
+    st2 = sorted(h for h in h2 if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"))
+    with open(P / f"{name}_k_replay_rollout_ncu_full_summary.csv", "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_replay_rollout -s 3 -c 1: python bench.py --workload replay --steps 4 --warmup 3 ({rrep.name})\n")
+        f.write("metric,unit,value\n")
+        for h in WANT + ["l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"] + st2:
+            if h in h2:
+                i = h2.index(h)
+                f.write(f"{h},{u2[i]},{v2[i]}\n")
+
 # launch list
 lines = [l for l in (G / f"launches_{tag}.csv").read_text().splitlines() if l.startswith('"')]
 (P / f"{name}_launches_ncu.csv").write_text("\n".join(lines) + "\n")
