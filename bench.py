@@ -296,8 +296,8 @@ def main():
         st["stats"].zero_()
         L.check(lib.pbrl_step(M.handle, n_env, N_FRAMES, pd_mode, 1, L._ptr(a), L._ptr(kp), L._ptr(kd), ctypes.c_float(0.002),
                               None, ctypes.c_uint(0x0FFFFFFF), 1, ctypes.byref(bufs), stream))
-        if os.environ.get("PBRL_BENCH_SORT"):
-            st["env_order"].copy_(torch.argsort(st["cost"], descending=True, stable=True).to(torch.int32))
+        if not os.environ.get("PBRL_BENCH_NO_BALANCE"):  # processing order of the next step from this step's work estimates
+            L.check(lib.pbrl_balance_order(M.handle, n_env, L._ptr(st["cost"]), L._ptr(st["env_order"]), stream))
         if world > 1:  # per-step reward/termination statistics all-reduce (32 B, NCCL over NVLink)
             dist.all_reduce(st["stats"])
 
@@ -398,7 +398,7 @@ def main():
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,
                         "steps": e2e_steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)"},
-                "gpu_launches": steps + e2e_steps + 3 + warmup,
+                "gpu_launches": (steps + warmup) * (1 if os.environ.get("PBRL_BENCH_NO_BALANCE") else 2) + e2e_steps + 3,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_step",
                              "algorithmic_bytes_per_env_launch": BYTES_PER_ENV_LAUNCH,

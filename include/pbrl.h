@@ -135,7 +135,7 @@ typedef struct PbrlBuffers {
                              neighbours in this order share a CTA; grouping envs of similar cost (e.g. by clip)
                              balances the CTA-wide phase barriers of pbrl_step.  Results do not depend on it. */
     int* cost;       /* [N] out, may be NULL: work estimate of the env step just taken (constraint-solver iterations summed
-                        over the substeps); the input of pbrl_balance_order */
+                        over the substeps, weighted up by the body-vs-body contacts); the input of pbrl_balance_order */
 } PbrlBuffers;
 
 int pbrl_model_desc_size(void);
@@ -148,6 +148,12 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic /* m
 void pbrl_model_destroy(PbrlModel* model);
 
 int pbrl_reset(const PbrlModel* model, int N, int reward_mode, const PbrlBuffers* buf, void* stream);
+
+/* Processing order for the next pbrl_step from the work estimates of the last one (PbrlBuffers.cost): envs sorted by
+ * decreasing cost, so that the 16 envs that share a CTA (and its phase barriers) need similar numbers of solver iterations
+ * and the expensive groups start first.  A counting sort on the device (one small launch); results of pbrl_step do not
+ * depend on the order. */
+int pbrl_balance_order(const PbrlModel* model, int N, const int* cost /* [N] */, int* env_order /* [N] out */, void* stream);
 
 /* Auto-reset (brax.envs.wrappers.training.AutoResetWrapper.step, the `where(done, first_state, state)` part): every
  * env with done[e] != 0 restarts -- qpos0 / zero velocity in reference mode, the reference pose at clip time

@@ -92,6 +92,21 @@ __global__ void __launch_bounds__(CTA_THREADS) k_reset(const DevModel* __restric
     }
     for (int env = first_env(); env < a.N; env += env_stride()) env_reset(sm, w, a, env, lane);
 }
+// counting sort of the env ids by decreasing work estimate (one CTA; N <= a few 100k)
+constexpr int BO_THREADS = 1024, BO_BINS = 256;
+__global__ void __launch_bounds__(BO_THREADS) k_balance_order(int N, const int* __restrict__ cost, int* __restrict__ order) {
+    __shared__ int hist[BO_BINS], start[BO_BINS];
+    for (int b = threadIdx.x; b < BO_BINS; b += BO_THREADS) hist[b] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < N; e += BO_THREADS) atomicAdd(&hist[min(max(cost[e], 0), BO_BINS - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // 256 bins: a serial scan is a few hundred cycles
+        int acc = 0;
+        for (int b = BO_BINS - 1; b >= 0; b--) { start[b] = acc; acc += hist[b]; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N; e += BO_THREADS) order[atomicAdd(&start[min(max(cost[e], 0), BO_BINS - 1)], 1)] = e;
+}
 __global__ void __launch_bounds__(CTA_THREADS)
 k_autoreset(const DevModel* __restrict__ gm, StepArgs a, const float* done, const float* next_ref_t0, int* steps) {
     Ws& w = my_ws();
@@ -363,6 +378,14 @@ int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* bu
     return check_launch("pbrl_reset");
 }
 
+int pbrl_balance_order(const PbrlModel* m, int N, const int* cost, int* env_order, void* stream) {
+    if (!m) return fail("null model");
+    if (N <= 0) return 0;
+    if (!cost || !env_order) return fail("null argument");
+    k_balance_order<<<1, BO_THREADS, 0, (cudaStream_t)stream>>>(N, cost, env_order);
+    return check_launch("pbrl_balance_order");
+}
+
 int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done, const float* next_ref_t0, int* steps,
                    const PbrlBuffers* buf, void* stream) {
     if (!m) return fail("null model");
@@ -493,6 +516,7 @@ struct PbrlBatch {
     float* gains;      // device, kp[28] kd[28]
     int* motion_id;
     float* ref_t0;
+    int* order;        // device, processing order of the next step (pbrl_balance_order)
     std::vector<void*> allocs;
 };
 
@@ -514,10 +538,18 @@ int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
     B.ctrl = alloc((size_t)N * NU); B.qpos_lag = alloc((size_t)N * NQ); B.qvel_lag = alloc((size_t)N * NV);
     B.obs = alloc((size_t)N * PBRL_OBS); B.reward = alloc((size_t)N * 3); B.done = alloc(N); B.metrics = alloc((size_t)N * 3);
     B.status = (int*)alloc(N); B.stats = alloc(8);
+    B.cost = (int*)alloc(N); b->order = (int*)alloc(N);
     b->motion_id = (int*)alloc(N); b->ref_t0 = alloc(N);
     B.motion_id = nullptr; B.ref_t0 = nullptr;
     b->action = alloc((size_t)N * NU * 4); b->gains = alloc(2 * NU);
     for (void* p : b->allocs) if (!p) { pbrl_batch_destroy(b); return fail("cudaMalloc failed"); }
+    {
+        std::vector<int> iota(N);
+        for (int i = 0; i < N; i++) iota[i] = i;
+        CUDA_OK(cudaMemcpyAsync(b->order, iota.data(), N * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        CUDA_OK(cudaStreamSynchronize(b->stream));
+        B.env_order = b->order;
+    }
     *out = b;
     return 0;
 }
@@ -554,6 +586,7 @@ int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_col
     if (stats_out) CUDA_OK(cudaMemsetAsync(b->buf.stats, 0, 8 * sizeof(float), b->stream));
     if (pbrl_step(b->model, N, n_frames, pd_mode, action_cols, b->action, b->gains, b->gains + NU, pd_dt, nullptr, 0x0FFFFFFFu,
                   reward_mode, &b->buf, b->stream)) return -1;
+    if (pbrl_balance_order(b->model, N, b->buf.cost, b->order, b->stream)) return -1;  // next step's processing order
     if (obs_out) CUDA_OK(cudaMemcpyAsync(obs_out, b->buf.obs, (size_t)N * PBRL_OBS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (reward_out) CUDA_OK(cudaMemcpyAsync(reward_out, b->buf.reward, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (done_out) CUDA_OK(cudaMemcpyAsync(done_out, b->buf.done, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, b->stream));

@@ -145,6 +145,9 @@ class HumanoidDiff:
         st = State(ps, z(N, 69), z(N, 3), z(N), {}, {})
         st.info["_metrics"] = metrics
         st.info["status"] = torch.zeros(N, device=d, dtype=torch.int32)
+        # scheduling hints of pbrl_step: work estimate of the last step and the processing order derived from it
+        st.info["cost"] = torch.zeros(N, device=d, dtype=torch.int32)
+        st.info["env_order"] = torch.arange(N, device=d, dtype=torch.int32)
         if self.reward_mode == 1:
             st.info["motion_id"] = torch.zeros(N, device=d, dtype=torch.int32)
             st.info["ref_t0"] = z(N)
@@ -162,7 +165,8 @@ class HumanoidDiff:
         return _lib.make_buffers(qpos=ps.qpos, qvel=ps.qvel, time=ps.time, warm=ps.qacc_warmstart, ctrl=ps.ctrl,
                                  qpos_lag=ps.qpos_lag, qvel_lag=ps.qvel_lag, obs=st.obs, reward=st.reward, done=st.done,
                                  metrics=st.info["_metrics"], status=st.info["status"], motion_id=st.info.get("motion_id"),
-                                 ref_t0=st.info.get("ref_t0"), stats=st.info.get("stats"))
+                                 ref_t0=st.info.get("ref_t0"), stats=st.info.get("stats"), cost=st.info.get("cost"),
+                                 env_order=st.info.get("env_order"))
 
     def _stream(self):
         return _lib.current_stream_ptr(self.device)
@@ -206,6 +210,9 @@ class HumanoidDiff:
             self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(self.n_frames), ctypes.c_int(pd_mode),
             ctypes.c_int(cols), _lib._ptr(action), _lib._ptr(kp), _lib._ptr(kd), ctypes.c_float(pd_dt),
             _lib._ptr(pd_time), ctypes.c_uint(ctrl_mask), ctypes.c_int(self.reward_mode), ctypes.byref(b), self._stream()))
+        if st.info.get("cost") is not None and st.info.get("env_order") is not None:  # next step: similar-cost envs share a CTA
+            _lib.check(_lib.lib().pbrl_balance_order(self.model.handle, ctypes.c_int(self.num_envs), _lib._ptr(st.info["cost"]),
+                                                     _lib._ptr(st.info["env_order"]), self._stream()))
         return st
 
 

@@ -69,7 +69,7 @@ with open(P / f"{name}_launch_summary.csv", "w") as f:
 
 # bench lines of the same call
 with open(P / f"{name}_bench_lines.jsonl", "w") as f:
-    for w in ("n1", "ref", "contact_free", "contact_rich", "cpu64", "replay", "sorted", "noself"):
+    for w in ("n1", "ref", "contact_free", "contact_rich", "cpu64", "replay", "nobalance", "noself"):
         p = G / f"bench_{tag}_{w}.json"
         if p.exists() and p.read_text().strip():
             f.write(p.read_text().strip().splitlines()[-1] + "\n")
