@@ -403,6 +403,14 @@ def main():
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_step",
                              "algorithmic_bytes_per_env_launch": BYTES_PER_ENV_LAUNCH,
                              "note": "the dynamics step is fp32-issue/latency bound (50-300 flop/B); HBM fraction is reported per the tier rule"},
+                # what actually bounds k_step: warp-instruction issue (ncu instruction count of the committed capture x live rate
+                # against 4 issue slots per SM-cycle at the sampled SM clock)
+                "sm_issue": None if not (tr and tr.get("warp_instructions_per_env_substep") and clocks and clocks.get("sm_mhz")) else {
+                    "warp_instructions_per_env_substep": tr["warp_instructions_per_env_substep"],
+                    "achieved_Ginst_per_s": tr["warp_instructions_per_env_substep"] * value / world / 1e9,
+                    "peak_Ginst_per_s": 148 * 4 * clocks["sm_mhz"] * 1e6 / 1e9,
+                    "frac": tr["warp_instructions_per_env_substep"] * value / world / (148 * 4 * clocks["sm_mhz"] * 1e6),
+                    "source": "profiles/r1_traffic.json (ncu smsp__inst_executed.sum of one launch)"},
                 "clocks": clocks, "nan_envs": bad, "self_contact_overflow_envs": self_overflow, "solver_maxiter_envs": maxiter, "pivot_envs": pivots,
                 "reward_stats_last_step": {"mean_reward": stats_last[0] / max(stats_last[5], 1), "done_frac": stats_last[2] / max(stats_last[5], 1),
                                            "fall_frac": stats_last[3] / max(stats_last[5], 1), "n": stats_last[5]}}

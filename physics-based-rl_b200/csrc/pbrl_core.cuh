@@ -845,10 +845,16 @@ PB_DEVN void smooth_velocity(const DevModel& m, Ws& w, const float* qvel, int la
 
 // ---------------------------------------------------------------------------------- collision with the floor plane
 // impedance of a row at penetration `pos` (mjx constraint._kbi)
+// general solimp power: kept out of line (one copy of the powf code), MuJoCo's default power 2 takes the squares below
+PB_DEVN float impedance_y_general(float x, float mid, float power) {
+    if (x < mid) return (1.0f / powf(mid, power - 1.f)) * powf(x, power);
+    return 1.f - (1.0f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+}
 PB_DEV float impedance(const DevModel& m, float pos) {
     float x = fabsf(pos) / m.sol_width, y;
-    if (x < m.sol_mid) y = (1.0f / powf(m.sol_mid, m.sol_power - 1.f)) * powf(x, m.sol_power);
-    else y = 1.f - (1.0f / powf(1.f - m.sol_mid, m.sol_power - 1.f)) * powf(1.f - x, m.sol_power);
+    if (m.sol_power != 2.f) y = impedance_y_general(x, m.sol_mid, m.sol_power);
+    else if (x < m.sol_mid) y = (1.0f / m.sol_mid) * (x * x);
+    else y = 1.f - (1.0f / (1.f - m.sol_mid)) * ((1.f - x) * (1.f - x));
     float imp = m.sol_dmin + y * (m.sol_dmax - m.sol_dmin);
     imp = fminf(fmaxf(imp, m.sol_dmin), m.sol_dmax);
     if (x > 1.f) imp = m.sol_dmax;

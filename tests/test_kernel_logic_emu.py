@@ -89,3 +89,12 @@ def test_contact_rich_statistics_small(model_grav):
     b = EmuBackend(model_grav)
     b.set_mimic(mdesc)
     pc.check_contact_rich_statistics(b, model_grav, table, mdesc, N=70, steps=10)
+
+
+def test_forward_stages_general_solimp_power(model_grav):
+    """A solimp power other than MuJoCo's default 2 takes the out-of-line powf path of the impedance."""
+    import copy
+    import numpy as np
+    m = copy.copy(model_grav)
+    m.solimp = np.array([0.9, 0.95, 0.001, 0.4, 3.0])
+    pc.check_forward_stages(EmuBackend(m), m, gravity=True, N=12, seed=9)

@@ -35,6 +35,7 @@ wr = get("dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum
 (P / "r1_traffic.json").write_text(json.dumps({
     "kernel": "k_step", "workload": "mimic_mixed", "envs_per_gpu": 16384, "dram_bytes_per_launch": int(rd + wr),
     "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "algorithmic_bytes_per_launch": 16384 * 1248,
+    "warp_instructions_per_launch": int(get("smsp__inst_executed.sum")), "warp_instructions_per_env_substep": get("smsp__inst_executed.sum") / (16384 * 8),
     "source": f"ncu --set full --clock-control none, one k_step launch (profiles/{name}_k_step_ncu_full_summary.csv)"}, indent=1))
 
 # the replay-rollout kernel (HBM-bound)
