@@ -134,8 +134,8 @@ typedef struct PbrlBuffers {
     const int* env_order; /* [N] optional processing order (a permutation of 0..N-1), may be NULL.  Envs that are
                              neighbours in this order share a CTA; grouping envs of similar cost (e.g. by clip)
                              balances the CTA-wide phase barriers of pbrl_step.  Results do not depend on it. */
-    int* cost;       /* [N] out, may be NULL: work estimate of the env step just taken (constraint-solver iterations summed
-                        over the substeps, weighted up by the body-vs-body contacts); the input of pbrl_balance_order */
+    int* cost;       /* [N] out, may be NULL: work estimate of the env step just taken (constraint-solver iterations of its most
+                        expensive substep, dense-Hessian iterations weighted up); the input of pbrl_balance_order */
 } PbrlBuffers;
 
 int pbrl_model_desc_size(void);

@@ -73,6 +73,10 @@ __device__ unsigned long long g_stage_hits[64];
 #define PROF_START() ((void)0)
 #endif
 
+#ifndef PBRL_DENSE_WEIGHT
+#define PBRL_DENSE_WEIGHT 3  // a Newton iteration with the dense Hessian, in units of a tree-sparse one (work estimate only)
+#endif
+
 namespace pbrl {
 
 // row strides of the per-body / per-dof arrays: 6-vectors live in 8-float rows, spatial inertias in 12-float rows and
@@ -133,7 +137,7 @@ struct Ws {
     union { alignas(16) float sc_aref[KS * 4]; alignas(16) float sc_jp[KS * 4]; };
     alignas(16) float sc_jar[KS * 4];
     int sc_bb[KS];                      // body1 | body2 << 8
-    int nsc, pad3_[3];
+    int nsc, work, pad3_[2];   // work: solver work estimate of the substep (input of pbrl_balance_order)
     alignas(8) unsigned long long fr_bar;        // mbarrier the bulk copy completes on
     float fr_u, fr_cyc;
     int fr_phase, fr_pad;
@@ -1594,6 +1598,7 @@ PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* 
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     const unsigned lim_rows = wballot(lane, NLIM, [&](int l) { return w.lim_sign[l] != 0.f; });
     w.niter = 0;
+    w.work = 0;
     const int nsr = 4 * w.nsc;  // body-vs-body pyramid rows (lane l: row l)
     const bool constrained = (lim_rows | w.con_mask) != 0u || nsr > 0;
     const bool coop = (w.phase_lock & 16) != 0;  // iterate in step with the other warps of the CTA (shared I-cache window)
@@ -1626,7 +1631,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         WSYNC();
         PROF(12);
     }
-    int it = 0;
+    int it = 0, ndense = 0;
     bool running = constrained;
     for (;;) {
         const bool go = running && it < NEWTON_MAXIT;
@@ -1644,7 +1649,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         WSYNC();
         // active body-vs-body rows couple two branches of the tree: their Hessian is not tree-sparse -> dense factorisation
         const unsigned sact = wballot(lane, 32, [&](int l) { return l < nsr && w.sc_jar[l] < 0.f; });
-        if (sact != 0u) dense_factor_solve(m, w, sact, w.p, lane);
+        if (sact != 0u) { dense_factor_solve(m, w, sact, w.p, lane); ndense++; }
         else ldl_factor_solve(m, w, w.p, lane);
         PROF(15);
         tree_Mx(m, w, w.p, w.Mp, lane);
@@ -1718,6 +1723,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     if (!constrained) return;
     if (it >= NEWTON_MAXIT) w.status |= PBRL_STATUS_SOLVER_MAXITER;
     w.niter = it;
+    w.work = it + PBRL_DENSE_WEIGHT * ndense;  // work estimate: an iteration with the dense Hessian counts more
     rows_JTf(m, w, w.Mp, w.fcon, 1, lane);
     PROF(20);
 }
@@ -1919,7 +1925,7 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
         }
         substep(m, w, time, lane);
-        cost += w.niter + 2 * w.nsc;  // solver iterations, weighted up when body-vs-body contacts (dense Hessian) are present
+        cost = cost > w.work ? cost : w.work;  // the most expensive substep decides how long the CTA's barriers wait for this env
     }
     if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
