@@ -393,7 +393,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": args.workload, "description": descr, "envs_per_gpu": n_env, "envs_total": total_envs,
                            "n_frames": N_FRAMES, "pd_mode": "stable", "reward_mode": "mimic", "l2_flush_between_steps": True,
-                           "self_collision": "sphere/capsule pairs (64 of 89 candidates)" if getattr(model, "self_collision", 1) else "off",
+                           "self_collision": "sphere/capsule/sphere-box pairs (74 of 89 candidates)" if getattr(model, "self_collision", 1) else "off",
                            "parallelism": f"env-sharded x{world}, stats all-reduce per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,

@@ -334,6 +334,33 @@ static void sphere_sphere(const REAL* p1, REAL r1, const REAL* p2, REAL r2, REAL
     for (int k = 0; k < 3; k++) pos[k] = p1[k] + n[k] * (r1 + *dist * R(0.5));
     make_frame(frame, n);
 }
+/* sphere vs box: mjx collision_convex.py _sphere_convex on the box's six faces -- among the faces whose plane the sphere's
+ * deepest point is behind (support < 0) take the one of least penetration, then the closest point of that face polygon to
+ * the sphere centre (projection, or the nearest edge / corner when the projection falls outside) [M] */
+static void sphere_box(const REAL* sp, REAL r, const REAL* bp, const REAL* bm, const double* half, REAL* dist, REAL* pos, REAL* frame) {
+    REAL dlt[3] = {sp[0] - bp[0], sp[1] - bp[1], sp[2] - bp[2]}, p[3], pt[3], e[3], n[3], nw[3], pl[3], best = R(-1e12);
+    int bk = 0, bs = 1;
+    matT_vec3(p, bm, dlt);
+    for (int k = 0; k < 3; k++)
+        for (int sg = 1; sg >= -1; sg -= 2) {
+            REAL sup = (REAL)sg * p[k] - R(half[k]) - r;
+            if (sup >= 0) sup = R(-1e12);
+            if (sup > best) { best = sup; bk = k; bs = sg; }
+        }
+    for (int k = 0; k < 3; k++) {
+        REAL h = R(half[k]);
+        pt[k] = p[k] < -h ? -h : (p[k] > h ? h : p[k]);
+    }
+    pt[bk] = (REAL)bs * R(half[bk]);
+    for (int k = 0; k < 3; k++) e[k] = pt[k] - p[k];
+    REAL nrm = normalize_with_norm(n, e);
+    *dist = nrm - r;
+    for (int k = 0; k < 3; k++) pl[k] = R(0.5) * (pt[k] + p[k] + n[k] * r);
+    mat_vec3(nw, bm, n);
+    mat_vec3(pos, bm, pl);
+    for (int k = 0; k < 3; k++) pos[k] += bp[k];
+    make_frame(frame, nw);
+}
 static void capsule_ends(const OrcModel* m, const OrcData* d, int g, REAL* e0, REAL* e1) {
     const REAL* gm = d->geom_xmat + 9 * g;
     for (int k = 0; k < 3; k++) {
@@ -445,16 +472,18 @@ static void collision(const OrcModel* m, OrcData* d) {
     }
     /* self-collision candidates.  MJX evaluates every candidate every step and multiplies
      * the rows of the distant ones by zero; only the contacts inside the margin get rows here (same optimum).  The
-     * box pairs (sphere/capsule/box vs the foot boxes: mjx collision_convex.py) are not restated yet: they are counted. */
+     * capsule-box and box-box pairs (mjx collision_convex.py capsule_convex / convex_convex) are not restated yet: they are counted. */
     int nplane = nc, nbox = 0;
     for (int q = 0; q < m->npair[0]; q++) {
         int g1 = m->pair_geom1[q], g2 = m->pair_geom2[q], t1 = m->geom_type[g1], t2 = m->geom_type[g2];
         if (t1 == GEOM_PLANE) continue;
-        if (t2 == GEOM_BOX) { nbox++; continue; }
+        if (t2 == GEOM_BOX && t1 != GEOM_SPHERE) { nbox++; continue; } /* capsule-box, box-box: not restated */
         REAL margin = R(fmax(m->geom_margin[g1], m->geom_margin[g2]) - fmax(m->geom_gap[g1], m->geom_gap[g2]));
         REAL mu = R(fmax(m->geom_friction[3 * g1], m->geom_friction[3 * g2]));
         REAL r1 = R(m->geom_size[3 * g1]), r2 = R(m->geom_size[3 * g2]), fr[9], dist, pos[3], a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
-        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) {
+        if (t2 == GEOM_BOX) {
+            sphere_box(d->geom_xpos + 3 * g1, r1, d->geom_xpos + 3 * g2, d->geom_xmat + 9 * g2, m->geom_size + 3 * g2, &dist, pos, fr);
+        } else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) {
             sphere_sphere(d->geom_xpos + 3 * g1, r1, d->geom_xpos + 3 * g2, r2, &dist, pos, fr);
         } else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
             capsule_ends(m, d, g2, b0, b1);
@@ -704,6 +733,11 @@ static void solve_constraints(const OrcModel* m, OrcData* d) {
             for (int i = 0; i < nv; i++) d->qfrc_constraint[i] += d->efc_J[r * NVMAX + i] * d->efc_force[r];
         }
     }
+}
+
+/* test hook: the sphere-box distance function on its own (tests/test_self_collision.py) */
+void orc_test_sphere_box(const REAL* sp, REAL r, const REAL* bp, const REAL* bm, const double* half, REAL* dist, REAL* pos, REAL* frame) {
+    sphere_box(sp, r, bp, bm, half, dist, pos, frame);
 }
 
 /* ---------------------------------------------------------------- public: forward / step */

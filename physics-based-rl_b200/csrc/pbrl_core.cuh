@@ -974,9 +974,10 @@ PB_DEVN void stage_collide(const DevModel& m, Ws& w, int lane) {
 
 // ---------------------------------------------------------------------------------- body-vs-body contacts
 // Sphere / capsule candidates (mjx collision_primitive.py: _sphere_sphere, sphere_capsule, capsule_capsule with
-// math.closest_segment_point / closest_segment_to_segment_points).  MJX evaluates every candidate
+// math.closest_segment_point / closest_segment_to_segment_points) and sphere-box candidates
+// (collision_convex.py: _sphere_convex).  MJX evaluates every candidate
 // every step and keeps a row block per candidate; only contacts inside the margin have non-zero rows, so only those
-// (at most KS) are kept here.  Box candidates are not evaluated (DevModel::nbox_pairs).
+// (at most KS) are kept here.  Capsule-box and box-box candidates are not evaluated (DevModel::nbox_pairs).
 PB_DEV void seg_point(const float* a, const float* b, const float* pt, float* out) {
     const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
     float t = dot3(ap, ab) * fast_rcp(dot3(ab, ab) + 1e-6f);
@@ -1068,10 +1069,27 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
                 const float a0[3] = {c1[0] - h1[0], c1[1] - h1[1], c1[2] - h1[2]}, a1[3] = {c1[0] + h1[0], c1[1] + h1[1], c1[2] + h1[2]};
                 const float b0[3] = {c2[0] - h2[0], c2[1] - h2[1], c2[2] - h2[2]}, b1[3] = {c2[0] + h2[0], c2[1] + h2[1], c2[2] + h2[2]};
                 seg_seg(a0, a1, b0, b1, p1, p2);
-            } else {  // sphere - sphere
+            } else if (p < m.nsp_sc + m.nsp_cc + m.nsp_ss) {  // sphere - sphere
                 for (int k = 0; k < 3; k++) { p1[k] = c1[k]; p2[k] = c2[k]; }
+            } else {  // sphere - box (mjx _sphere_convex on the six faces): p2 = closest point of the chosen face, as a zero-radius geom
+                const float* R = w.xmat + S9 * m.sg_body[g2];
+                const float* half = m.sg_axis[g2];
+                const float dl0[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]}, r = m.sg_r[g1];
+                float q[3], pt[3], best = -1e12f;
+                int bk = 0;
+                float bsgn = 1.f;
+                matT_vec(R, dl0, q);
+                for (int k = 0; k < 3; k++) {
+                    const float sp = q[k] - half[k] - r, sm = -q[k] - half[k] - r;   // support of the +k / -k face
+                    if (sp < 0.f && sp > best) { best = sp; bk = k; bsgn = 1.f; }
+                    if (sm < 0.f && sm > best) { best = sm; bk = k; bsgn = -1.f; }
+                }
+                for (int k = 0; k < 3; k++) pt[k] = fminf(fmaxf(q[k], -half[k]), half[k]);
+                for (int k = 0; k < 3; k++) if (k == bk) pt[k] = bsgn * half[k];
+                mat_vec(R, pt, p2);
+                for (int k = 0; k < 3; k++) { p1[k] = c1[k]; p2[k] += c2[k]; }
             }
-            const float r1 = m.sg_r[g1], r2 = m.sg_r[g2], dl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+            const float r1 = m.sg_r[g1], r2 = p < m.nsp_sc + m.nsp_cc + m.nsp_ss ? m.sg_r[g2] : 0.f, dl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
             float n[3];
             const float nrm = normalize_with_norm(dl, n);
             if (nrm == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }

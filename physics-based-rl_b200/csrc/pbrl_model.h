@@ -24,7 +24,7 @@ constexpr int NLIM = 28;  // limited hinges
 constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
 constexpr int NCP = 32;   // padded
 constexpr int NSG = 15;   // geoms that can touch each other (everything but the floor)
-constexpr int NSP = 64;   // sphere / capsule candidate pairs between bodies (SC 32 + CC 24 + SS 8)
+constexpr int NSP = 80;   // candidate pairs between bodies that are evaluated (SC 32 + CC 24 + SS 8 + SB 10 = 74)
 constexpr int KS = 8;     // body-vs-body contacts kept per env and substep (inside the margin at the same time)
 constexpr int NFAC = 1432;  // rank-1 update operations of one tree-sparse L^T D L factorisation
 constexpr int MAXANC = 12;  // deepest dof chain (ancestors of one dof); checked against the compiled tree below
@@ -120,13 +120,13 @@ struct DevModel {
     i8 dof_parentid[NV], dof_act[NV];
     u8 lim_jnt[NLIM];
     u8 con_body[NCP], con_kind[NCP], con_sub[NCP], con_geom[NCP];
-    // body-vs-body candidates (sphere / capsule geoms): geom table + pair list ordered [sphere-capsule][capsule-capsule]
-    // [sphere-sphere] so that the 32 lanes of a pass run the same distance function
-    int nsp, nsp_sc, nsp_cc;           // pairs in total / sphere-capsule / capsule-capsule (0 pairs: self-collision off)
-    int nbox_pairs;                    // candidates that involve a box: not evaluated
+    // body-vs-body candidates: geom table + pair list ordered [sphere-capsule][capsule-capsule][sphere-sphere][sphere-box]
+    // so that the 32 lanes of a pass run (mostly) the same distance function
+    int nsp, nsp_sc, nsp_cc, nsp_ss;   // pairs in total / sphere-capsule / capsule-capsule / sphere-sphere (0 pairs: self-collision off)
+    int nbox_pairs;                    // capsule-box and box-box candidates: not evaluated
     float self_margin, self_mu, self_invw_scale;  // includemargin, sliding friction, (1 + mu^2) 2 mu^2 / impratio
     float body_invw[NB];               // body_invweight0[:, 0]
-    float sg_pos[NSG][3], sg_axis[NSG][3], sg_r[NSG], sg_hl[NSG];
+    float sg_pos[NSG][3], sg_axis[NSG][3], sg_r[NSG], sg_hl[NSG];  // (boxes: sg_axis holds the half sizes, the box frame is the body frame)
     u8 sg_body[NSG], pad_sg_;
     u8 sp_g1[NSP], sp_g2[NSP];
 };
@@ -362,23 +362,27 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             const double* q = d.geom_quat + 4 * g;  // local z axis of the geom frame
             const double ax[3] = {2 * (q[1] * q[3] + q[0] * q[2]), 2 * (q[2] * q[3] - q[0] * q[1]), q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3]};
             for (int k = 0; k < 3; k++) { m.sg_pos[nsg][k] = (float)d.geom_pos[3 * g + k]; m.sg_axis[nsg][k] = (float)ax[k]; }
+            if (d.geom_type[g] == 6) {
+                if (q[0] != 1.0) return "box geoms must be aligned with their body frame";
+                for (int k = 0; k < 3; k++) m.sg_axis[nsg][k] = (float)d.geom_size[3 * g + k];
+            }
             nsg++;
         }
         for (int b = 0; b < NB; b++) m.body_invw[b] = (float)d.body_invweight0[2 * b];
         int np = d.npair[0];
         if (np < 0 || np > PBRL_MAXPAIR) return "bad npair";
         bool first = true;
-        for (int pass = 0; pass < 3; pass++) {  // 0: sphere-capsule, 1: capsule-capsule, 2: sphere-sphere
+        for (int pass = 0; pass < 4; pass++) {  // 0: sphere-capsule, 1: capsule-capsule, 2: sphere-sphere, 3: sphere-box
             for (int q = 0; q < np; q++) {
                 const int g1 = d.pair_geom1[q], g2 = d.pair_geom2[q];
                 if (g1 < 0 || g2 < 0 || g1 >= NG || g2 >= NG) return "pair geom out of range";
                 const int t1 = d.geom_type[g1], t2 = d.geom_type[g2];
                 if (g1 == plane || g2 == plane) continue;  // floor pairs are the contact slots above
-                if (t1 == 6 || t2 == 6) { if (pass == 0) m.nbox_pairs++; continue; }
-                const int kind = (t1 == 2 && t2 == 3) ? 0 : (t1 == 3 && t2 == 3) ? 1 : (t1 == 2 && t2 == 2) ? 2 : -1;
+                if (t1 == 6 || (t2 == 6 && t1 != 2)) { if (pass == 0) m.nbox_pairs++; continue; }
+                const int kind = (t1 == 2 && t2 == 3) ? 0 : (t1 == 3 && t2 == 3) ? 1 : (t1 == 2 && t2 == 2) ? 2 : (t1 == 2 && t2 == 6) ? 3 : -1;
                 if (kind < 0) return "pair geoms must be ordered by type (sphere before capsule)";
                 if (kind != pass) continue;
-                if (m.nsp >= NSP) return "too many sphere / capsule pairs";
+                if (m.nsp >= NSP) return "too many body-vs-body pairs";
                 const double mu = std::fmax(d.geom_friction[3 * g1], d.geom_friction[3 * g2]);
                 const double margin = std::fmax(d.geom_margin[g1], d.geom_margin[g2]) - std::fmax(d.geom_gap[g1], d.geom_gap[g2]);
                 if (first) { m.self_mu = (float)mu; m.self_margin = (float)margin; first = false; }
@@ -388,6 +392,7 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             }
             if (pass == 0) m.nsp_sc = m.nsp;
             if (pass == 1) m.nsp_cc = m.nsp - m.nsp_sc;
+            if (pass == 2) m.nsp_ss = m.nsp - m.nsp_sc - m.nsp_cc;
         }
         m.self_invw_scale = (1.f + m.self_mu * m.self_mu) * 2.f * m.self_mu * m.self_mu / (float)d.impratio[0];
     }

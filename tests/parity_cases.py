@@ -446,3 +446,47 @@ def check_contact_rich_statistics(backend, model_grav, table, mdesc, N=1024, ste
     assert abs((first < steps).mean() - (first_ref < steps).mean()) <= 0.03
     assert (first == first_ref).mean() >= 0.8, (first == first_ref).mean()                               # per env: same termination step for most
     return float(np.abs(rew - rew_ref).max()), float((first == first_ref).mean())
+
+
+def check_sphere_box_contacts(backend, model_grav, want=12):
+    """Sphere-box candidates (torso / wrist spheres against the foot boxes, mjx _sphere_convex): random poses that contain
+    such a contact, found with the oracle; the back end must list the same contacts (distances) and resolve them alike."""
+    orc = _oracle(model_grav)
+    states = []
+    for seed in range(100, 220):
+        qpos, qvel = random_states(model_grav, 64, seed, gravity_heights=True, vel_scale=1.0, joint_frac=1.0)
+        for e in range(64):
+            d = orc.new_data()
+            d.qpos[:35], d.qvel[:34] = qpos[e].astype(np.float32), qvel[e].astype(np.float32)
+            orc.forward(d)
+            nc, ns = int(d.ncon[0]), int(d.nself[0])
+            kinds = [int(model_grav.geom_type[int(d.con_geom[c])]) for c in range(nc - ns, nc)]
+            if 6 in kinds and ns <= 8:
+                states.append((qpos[e], qvel[e]))
+        if len(states) >= want:
+            break
+    assert len(states) >= want
+    q32 = np.array([s[0] for s in states], np.float32)
+    v32 = np.array([s[1] for s in states], np.float32)
+    N = len(states)
+    out = backend.debug_forward(q32, v32, np.zeros((N, 28), np.float32), np.zeros((N, 34), np.float32))
+    nbox, errs = 0, []
+    for e in range(N):
+        d = orc.new_data()
+        d.qpos[:35], d.qvel[:34] = q32[e], v32[e]
+        orc.forward(d)
+        get = lambda k: out[e, DBG[k][0]:DBG[k][0] + DBG[k][1]]
+        nc, ns = int(d.ncon[0]), int(d.nself[0])
+        nf = nc - ns
+        assert int(get("nself")[0]) == ns, (e, get("nself"), ns)
+        assert np.abs(np.sort(get("self_dist")[:ns]) - np.sort(d.con_dist[nf:nc])).max() <= 2e-6
+        f_ref = np.sort(d.efc_force[28 + 4 * nf:28 + 4 * nc].reshape(ns, 4).sum(1))
+        f_got = np.sort(get("self_force")[:4 * ns].reshape(ns, 4).sum(1))
+        assert np.abs(f_got - f_ref).max() <= 2e-3 * max(1.0, np.abs(f_ref).max()), (e, f_got, f_ref)
+        errs.append(relerr(get("qacc"), d.qacc[:34]))
+        nbox += sum(int(model_grav.geom_type[int(d.con_geom[c])]) == 6 for c in range(nf, nc))
+    assert nbox >= want
+    # random poses overlap by centimetres in several places at once: a few are ill-conditioned in fp32 (the fp32 oracle agrees
+    # with the back end to 2e-5 on them); the typical one is at rounding level
+    assert np.median(errs) <= 1e-5 and max(errs) <= 5e-3, (np.median(errs), max(errs))
+    return nbox

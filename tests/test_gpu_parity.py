@@ -137,3 +137,7 @@ def test_replay_rollout(gpu_nograv, model_nograv):
 def test_contact_rich_statistics(model_grav):
     table, mdesc, keep = pc.mimic_setup(model_grav)
     pc.check_contact_rich_statistics(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc)
+
+
+def test_sphere_box_contacts(gpu_grav, model_grav):
+    pc.check_sphere_box_contacts(gpu_grav, model_grav, want=30)

@@ -98,3 +98,7 @@ def test_forward_stages_general_solimp_power(model_grav):
     m = copy.copy(model_grav)
     m.solimp = np.array([0.9, 0.95, 0.001, 0.4, 3.0])
     pc.check_forward_stages(EmuBackend(m), m, gravity=True, N=12, seed=9)
+
+
+def test_sphere_box_contacts(emu_grav, model_grav):
+    pc.check_sphere_box_contacts(emu_grav, model_grav)

@@ -1,4 +1,4 @@
-"""Body-vs-body contacts (sphere / capsule candidates): the candidate census of the model
+"""Body-vs-body contacts (sphere / capsule / sphere-box candidates): the candidate census of the model
 compiler, the distance functions of the oracle against closed forms, Newton's third law, the kernel logic (host emulation)
 against the oracle, and what the reference's own golden traces say about these contacts."""
 import numpy as np
@@ -135,3 +135,41 @@ def test_golden_traces_show_the_contact_event(model_nograv):
     assert first_touch == 13                                          # first substep with the pair inside the margin: env step 13
     assert errs["on"][15] < 0.5 * errs["off"][15]                     # the restated contact moves the trace the right way
     assert max(errs["on"][:14]) <= 1e-5
+
+
+def test_sphere_box_distance_closed_forms():
+    """The oracle's sphere-box function on hand-computable placements (box half sizes .0885 x .045 x .0275, axis aligned):
+    above a face, beyond an edge, beyond a corner, centre inside."""
+    import ctypes
+    from oracle.oracle import HERE
+    lib = ctypes.CDLL(str(HERE / "liboracle_f64.so"))
+    if not hasattr(lib, "orc_test_sphere_box"):
+        pytest.skip("oracle built without the test hook")
+    half = np.array([0.0885, 0.045, 0.0275])
+    eye = np.eye(3).ravel().copy()
+    bp = np.zeros(3)
+
+    def run(c, r):
+        c = np.asarray(c, float)
+        dist, pos, fr = ctypes.c_double(), np.zeros(3), np.zeros(9)
+        lib.orc_test_sphere_box(c.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(r), bp.ctypes.data_as(ctypes.c_void_p),
+                                eye.ctypes.data_as(ctypes.c_void_p), half.ctypes.data_as(ctypes.c_void_p), ctypes.byref(dist),
+                                pos.ctypes.data_as(ctypes.c_void_p), fr.ctypes.data_as(ctypes.c_void_p))
+        return dist.value, pos, fr[:3]
+    r = 0.04
+    # touching the top face from above (penetrating 1 mm): normal points from the sphere down into the box
+    d, pos, n = run([0.02, 0.01, 0.0275 + r - 0.001], r)
+    assert abs(d + 0.001) < 1e-12 and np.allclose(n, [0, 0, -1]) and np.allclose(pos, [0.02, 0.01, 0.0275 - 0.0005])
+    # beyond the +x edge of the top face: closest point on the edge
+    c = np.array([0.0885 + 0.02, 0.0, 0.0275 + 0.02])
+    d, pos, n = run(c, r)
+    want = np.hypot(0.02, 0.02) - r
+    assert abs(d - want) < 1e-12 and np.allclose(n, np.array([-0.02, 0, -0.02]) / np.hypot(0.02, 0.02))
+    # beyond a corner
+    c = half + 0.02
+    d, pos, n = run(c, r)
+    assert abs(d - (np.sqrt(3) * 0.02 - r)) < 1e-12
+    # hovering 0.5 mm above the middle of the top face: the face itself has support >= 0 and is skipped (MJX rule), so the
+    # reported distance comes from a side face's edge and is larger than the gap -> no row inside the margin
+    d, pos, n = run([0.0, 0.0, 0.0275 + r + 0.0005], r)
+    assert d > 0.001
