@@ -151,3 +151,35 @@ def test_training_wrappers(mods, model_grav):
         assert torch.isfinite(state.obs).all() and (state.reward[:, 0] >= 0).all()
     assert ended.all()                                                   # episode_length = 6 ends the survivors
     assert (state.info["truncation"][state.info["steps"] >= 6] >= 0).all()
+
+
+def test_long_wrapped_rollout_stays_finite(mods, model_grav):
+    """2 048 envs x 150 env steps (1 200 substeps) of random actions through the training wrappers: every state stays finite,
+    no factorisation fails, episodes end and restart, and the reward statistics stay in range."""
+    torch, envs, _ = mods
+    wrappers = importlib.import_module(PKG + ".wrappers")
+    kp, kd = util_data.generate_kp_kd_gains()
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    N = 2048
+    env = wrappers.wrap(envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=N, reward_mode="mimic", motion_table=table),
+                        episode_length=60)
+    state = env.reset(5)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    lo = torch.from_numpy(model_grav.jnt_range[1:, 0].astype(np.float32)).cuda()
+    hi = torch.from_numpy(model_grav.jnt_range[1:, 1].astype(np.float32)).cuda()
+    restarts = torch.zeros(N, device="cuda")
+    flags = torch.zeros(N, dtype=torch.int32, device="cuda")
+    rsum = 0.0
+    for k in range(150):
+        act = lo + (hi - lo) * torch.rand(N, 28, generator=g, device="cuda")
+        state = env.step(state, act)
+        restarts += state.done
+        flags |= state.info["status"]
+        rsum += float(state.reward[:, 0].mean())
+    torch.cuda.synchronize()
+    assert torch.isfinite(state.obs).all() and torch.isfinite(state.pipeline_state.qacc_warmstart).all()
+    assert int((flags & 3).max()) == 0                      # never a non-finite state or a non-positive pivot
+    assert (restarts >= 2).all()                            # episode_length 60 alone ends every env at least twice
+    assert 0.0 < rsum / 150 < 1.0
+    assert (state.info["steps"] <= 60).all()
