@@ -2002,18 +2002,23 @@ PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float
 
 // Kinematic replay of one (env, frame) item by ONE thread (k_replay_rollout): the same kinematics as stage_fk, walked body by
 // body in parents-first order; poses are written to / read back from the item's own row (xpos: 14 x 3, xquat: 14 x 4).
-// Thread-serial, so the scalar cost matters: half-angle sine / cosine by odd / even polynomials on |x| <= 1.7 (hinge ranges
-// are within +-3.14; error < 1e-7, library call beyond), reciprocal square roots for the normalisations, vectors rotated by
+// Thread-serial, so the scalar cost matters: half-angle sine / cosine by odd / even polynomials after a reduction to
+// |r| <= pi / 2 (error < 1e-7), reciprocal square roots for the normalisations, vectors rotated by
 // the quaternion directly (v + w t + u x t, t = 2 u x v) instead of through a rotation matrix.
 PB_DEV void sincos_half_angle(float x, float* sn, float* cs) {
-    if (fabsf(x) > 1.7f) { sincosf(x, sn, cs); return; }
-    const float z = x * x;
-    float s = fmaf(z, -2.5052108e-8f, 2.7557319e-6f);   // Taylor to x^13 / x^12: truncation below 2e-8 on the interval
+    // x = k pi + r, |r| <= pi / 2 (two-term Cody-Waite: exact enough for the |x| < ~100 a joint angle can reach), then
+    // sin x = (-1)^k sin r, cos x = (-1)^k cos r: branch-free, no library fallback to inline at each of the 28 hinges
+    const float k = rintf(x * 0.31830988618f);
+    float r = fmaf(k, -3.14159274101f, x);
+    r = fmaf(k, 8.74227766e-8f, r);   // pi = 3.14159274101 (fp32) - 8.74227766e-8
+    const float sgn = ((int)k & 1) ? -1.f : 1.f;
+    const float z = r * r;
+    float s = fmaf(z, -2.5052108e-8f, 2.7557319e-6f);   // Taylor to r^13 / r^12: truncation below 1e-8 on the interval
     s = fmaf(s, z, -1.9841270e-4f); s = fmaf(s, z, 8.3333333e-3f); s = fmaf(s, z, -1.6666667e-1f);
-    *sn = fmaf(x * z, s, x);
+    *sn = sgn * fmaf(r * z, s, r);
     float c = fmaf(z, 2.0876757e-9f, -2.7557319e-7f);
     c = fmaf(c, z, 2.4801587e-5f); c = fmaf(c, z, -1.3888889e-3f); c = fmaf(c, z, 4.1666667e-2f); c = fmaf(c, z, -0.5f);
-    *cs = fmaf(c, z, 1.0f);
+    *cs = sgn * fmaf(c, z, 1.0f);
 }
 PB_DEV void quat_normalize_fast(float* q) {
     const float ss = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
