@@ -10,9 +10,9 @@
  * agents_env/agent_env_template.py:88-112, agents_env/agent_replay_motion.py:51-83,
  * agents_env/pds_controllers_agents.py:17-172) and pinned by the notebook goldens T0-T4
  * (tests/golden/mass_traces.npz).  Parity status: contact-free chain pinned by
- * goldens T1-T4 up to print 10; sphere-capsule self-contact rows (wrist vs thigh) pinned by the same traces
- * beyond the prints where the hands first touch the thighs (T1 print 15, T2 print 7: tests/test_oracle_golden.py);
- * plane contacts and the mimic reward have no reference known-answer ("parity unpinned").
+ * goldens T1-T4 up to print 10 (T1: 13); contact rows -- floor and body-vs-body -- and the mimic reward have no
+ * reference known-answer ("parity unpinned"): the hands first touch the thighs at T1 print 14, after the saturated PD
+ * loop has already lost fp32 reproducibility (tests/test_self_collision.py).
  *
  * Compiled twice: -DORC_F32 (REAL=float) and default (REAL=double).
  */

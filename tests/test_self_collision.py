@@ -106,19 +106,21 @@ def test_switch_off_lets_the_hands_through(model_nograv):
     assert depth["on"] > -3e-3 and depth["off"] < -1e-2, depth
 
 
-def test_golden_traces_show_the_contact_event(model_nograv):
-    """What the reference's own artefacts say about body-vs-body contacts (no known answer pins them):
-    the T1 mass-matrix trace follows the contact-free restatement to <= 1e-5 up to print 14 and leaves it at print 15 --
-    exactly when the right wrist first comes within the 1 mm margin of the right thigh.  With the restated contact rows
-    the trace moves towards the golden at print 15 but does not reproduce it to print precision: the rows stay
-    'unvalidated' (DESIGN.md section 4)."""
+def test_golden_trace_cannot_pin_the_contact_rows(model_nograv):
+    """What the reference's own artefacts can say about body-vs-body contacts (no known answer pins them).
+    In the T1 run the right wrist first comes within the 1 mm margin of the right thigh in env step 13, and the golden
+    trace leaves the contact-free restatement at print 15 -- but not because of that contact: the notebook's PD loop runs
+    its motors in saturation and is chaotic in the low-inertia joints, so the fp32 and fp64 builds of the SAME contact-free
+    restatement already differ by > 0.05 rad/s (right ankle) at env step 12, and that difference reaches the printed block
+    at the 1e-5 level from print 14 on.  Up to print 13 the trace is a known answer (with or without the contact rows);
+    beyond, it is not."""
     golden = np.load(GOLDEN / "mass_traces.npz")["T1"]
     kp, kd = util_data.generate_kp_kd_gains()
     coef = start_trajectory()[None]
     idx = [0, 1, 2, 31, 32, 33]
-    errs, first_touch = {}, None
-    for name, sc in (("off", False), ("on", True)):
-        orc = Oracle(model_nograv, "f64", tolerance=1e-14, self_collision=sc)
+    errs, first_touch, qvel12 = {}, None, {}
+    for name, prec, sc in (("off", "f64", False), ("on", "f64", True), ("off32", "f32", False)):
+        orc = Oracle(model_nograv, prec, tolerance=1e-14 if prec == "f64" else None, self_collision=sc)
         env = OracleEnv(orc, 1)
         env.reset()
         e = []
@@ -126,15 +128,20 @@ def test_golden_traces_show_the_contact_event(model_nograv):
             t = np.clip(env.time.astype(np.float32), 1, 3)
             tau, qM, _ = env.pd_torque(coef, kp, kd, 3, 0.016, time=t, want_qM=True)
             e.append(float(np.abs(qM[0][np.ix_(idx, idx)] - golden[k]).max()))
+            if k == 12:
+                assert np.abs(tau).min() > 0.5 or (np.abs(tau) > 0.5).mean() > 0.9   # (nearly) every motor is saturated
             for f in range(8):
                 if name == "on" and first_touch is None and pc._self_contacts(model_nograv, env.qpos)[0] > 0:
                     first_touch = k
                 env.step(tau, kp, kd, pd_mode=0, n_frames=1)
+            if k == 12:
+                qvel12[name] = env.qvel[0].astype(np.float64).copy()
         errs[name] = e
-    assert max(errs["off"][:15]) <= 1e-5 and errs["off"][15] > 5e-5   # the event in the golden trace
-    assert first_touch == 13                                          # first substep with the pair inside the margin: env step 13
-    assert errs["on"][15] < 0.5 * errs["off"][15]                     # the restated contact moves the trace the right way
-    assert max(errs["on"][:14]) <= 1e-5
+    assert first_touch == 13                                          # the reference's run does contain the contact
+    assert max(errs["off"][:14]) <= 1e-5 and max(errs["on"][:14]) <= 1e-5   # known answer up to print 13, contact rows or not
+    assert errs["off"][15] > 5e-5                                     # ... and the trace leaves the restatement at print 15
+    assert np.abs(qvel12["off32"] - qvel12["off"]).max() > 0.05       # chaos: two precisions of one model, before any contact
+    assert max(errs["off32"][:14]) <= 1e-5                            # the printed block is blind to it until print 13
 
 
 def test_sphere_box_distance_closed_forms():
