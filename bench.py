@@ -415,7 +415,7 @@ def main():
                 "clocks": clocks, "nan_envs": bad, "self_contact_overflow_envs": self_overflow, "solver_maxiter_envs": maxiter, "pivot_envs": pivots,
                 "reward_stats_last_step": {"mean_reward": stats_last[0] / max(stats_last[5], 1), "done_frac": stats_last[2] / max(stats_last[5], 1),
                                            "fall_frac": stats_last[3] / max(stats_last[5], 1), "n": stats_last[5]}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU leg runs beside the single-GPU number only
             r = cpu_reference_run(args.workload, 4, 1)
             line["cpu_baseline"] = {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
