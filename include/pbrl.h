@@ -9,6 +9,9 @@
  *   pbrl_step       HumanoidTrain.step + variants /root/reference/agents_env/agent_mimic.py:58-91,94-271
  *                   (PD callback, then PipelineEnv.pipeline_step = n_frames x mjx.step, obs/reward/done)
  *   pbrl_replay     HumanoidReplay.step           /root/reference/agents_env/agent_replay_motion.py:51-83
+ *   pbrl_replay_rollout  the frame loop around it /root/reference/testing_forward_env.ipynb cell 10 (write frame i, step, next)
+ *   pbrl_autoreset  brax AutoResetWrapper.step    brax 0.10.3 envs/wrappers/training.py (imported by agent_mimic.py:14-15 via ppo)
+ *   pbrl_balance_order   no counterpart: a scheduling hint for pbrl_step (which envs share a CTA)
  *   pbrl_pd_torque  standard/feedback/stable PD   /root/reference/agents_env/pds_controllers_agents.py:17-172
  *                   and the *_mjx signature twins /root/reference/agents_env/pds_controllers_mjx.py:17-191
  *   pbrl_debug_forward  fields of brax `pipeline_state` the reference reads back
