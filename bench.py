@@ -53,9 +53,13 @@ def load_assets(workload):
     return model, clips, (table, mdesc, keep), n_env, pd_mode, descr
 
 
+ACTIONS = "random"  # --actions: "random" (north star: random-action rollouts) or "reference" (PD targets track the clip)
+
+
 def synth_inputs(model, clips, mim, n_env, rank, steps, seed=0):
     """Seeded, shard-independent synthetic inputs keyed by the GLOBAL env id: clip = id mod nclip, reference-state
-    init at a uniform phase of the clip, random target-angle actions inside the joint ranges."""
+    init at a uniform phase of the clip, and per env step either random target angles inside the joint ranges or the
+    clip's own joint angles at the end of the step (target = reference joint angles at time + dt)."""
     table, mdesc, _ = mim
     gid = np.arange(rank * n_env, (rank + 1) * n_env)
     motion_id = (gid % len(clips)).astype(np.int32)
@@ -64,6 +68,10 @@ def synth_inputs(model, clips, mim, n_env, rank, steps, seed=0):
     ref_t0 = (phase * dur[motion_id]).astype(np.float32)
     lo, hi = model.jnt_range[1:, 0].astype(np.float32), model.jnt_range[1:, 1].astype(np.float32)
     rs = np.random.default_rng([seed, 1000, rank])
+    if ACTIONS == "reference":  # one batch per step of the rollout (warm-up and timed loops both start from the initial state)
+        n_act = min(steps + 4, 96)
+        actions = np.stack([table.reference_joint_angles(motion_id, ref_t0 + (k + 1) * N_FRAMES * 0.002) for k in range(n_act)]).astype(np.float32)
+        return motion_id, ref_t0, actions
     n_act = min(steps, 16)  # a ring of action batches, reused
     actions = rs.uniform(lo, hi, (n_act, n_env, 28)).astype(np.float32)
     return motion_id, ref_t0, actions
@@ -234,12 +242,16 @@ def main():
     ap.add_argument("--workload", default="mimic_mixed", choices=sorted(WORKLOADS) + ["replay"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--actions", default="random", choices=["random", "reference"],
+                    help="PD targets: random inside the joint ranges (default, the north star's random-action rollouts) or the clip's joint angles at time + dt")
     ap.add_argument("--stage-profile", action="store_true", help="dev: print the per-stage cycle table (needs a -DPBRL_STAGE_PROF library, PBRL_LIB=...)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = args.steps, max(args.warmup, 3)
+    global ACTIONS
+    ACTIONS = args.actions
 
     if args.workload == "replay":
         return replay_bench(args, rank, local_rank, world) if rank == 0 else 0
@@ -392,7 +404,7 @@ def main():
                 "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "description": descr, "envs_per_gpu": n_env, "envs_total": total_envs,
-                           "n_frames": N_FRAMES, "pd_mode": "stable", "reward_mode": "mimic", "l2_flush_between_steps": True,
+                           "n_frames": N_FRAMES, "pd_mode": "stable", "reward_mode": "mimic", "actions": args.actions, "l2_flush_between_steps": True,
                            "self_collision": "sphere/capsule/sphere-box pairs (74 of 89 candidates)" if getattr(model, "self_collision", 1) else "off",
                            "parallelism": f"env-sharded x{world}, stats all-reduce per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,

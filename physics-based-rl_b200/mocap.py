@@ -269,6 +269,46 @@ class MotionTable:
     def clip_index(self, name):
         return self.names.index(name)
 
+    # offsets of the eight 3-dof joints (table order) and of the four 1-dof joints inside qpos[7:35]
+    _SPH_OFFSET = (0, 3, 6, 10, 14, 18, 21, 25)
+    _HINGE_OFFSET = (9, 13, 17, 24)
+
+    def reference_joint_angles(self, clip_ids, t):
+        """Reference joint angles (N, 28) of clip `clip_ids[e]` at clip time `t[e]`, interpolated like the device does
+        (pbrl_mimic.cuh: frame_lookup, slerp of the 3-dof joints then intrinsic-XYZ Euler angles, lerp of the 1-dof joints).
+        Host-side helper: PD targets that track the clip."""
+        clip_ids = np.asarray(clip_ids, dtype=np.int64)
+        t = np.asarray(t, dtype=np.float64)
+        h = self.header[clip_ids]
+        first, nfr, T, wrap, dt = h[:, 0].astype(np.int64), h[:, 1].astype(np.int64), h[:, 2], h[:, 3] > 0, h[:, 4]
+        tc = np.where(wrap, t - np.floor(t / T) * T, np.minimum(t, T))
+        tc = np.maximum(tc, 0.0)
+        fi = np.minimum((tc / dt).astype(np.int64), nfr - 2)
+        u = np.clip(tc / dt - fi, 0.0, 1.0)[:, None]
+        f0, f1 = self.frames[first + fi].astype(np.float64), self.frames[first + fi + 1].astype(np.float64)
+        out = np.zeros((len(t), 28))
+        for o in self._HINGE_OFFSET:
+            out[:, o] = (1 - u[:, 0]) * f0[:, 7 + o] + u[:, 0] * f1[:, 7 + o]
+        for j, o in enumerate(self._SPH_OFFSET):
+            a, b = f0[:, 69 + 4 * j:73 + 4 * j], f1[:, 69 + 4 * j:73 + 4 * j]
+            d = np.sum(a * b, axis=1, keepdims=True)
+            sg = np.where(d < 0, -1.0, 1.0)
+            d = np.abs(d)
+            th = np.arccos(np.minimum(d, 1.0))
+            lin = d > 0.9995
+            sth = np.where(lin, 1.0, np.sin(th))
+            wa = np.where(lin, 1 - u, np.sin((1 - u) * th) / sth)
+            wb = np.where(lin, u, np.sin(u * th) / sth)
+            q = wa * a + sg * wb * b
+            q /= np.linalg.norm(q, axis=1, keepdims=True)
+            w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            m00, m01, m02 = 1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)
+            m12, m22 = 2 * (y * z - x * w), 1 - 2 * (x * x + y * y)
+            out[:, o] = np.arctan2(-m12, m22)
+            out[:, o + 1] = np.arctan2(m02, np.sqrt(m22 * m22 + m12 * m12))
+            out[:, o + 2] = np.arctan2(-m01, m00)
+        return out
+
 
 def load_motion_dir(motion_dir, names=MOTION_NAMES):
     clips = []
