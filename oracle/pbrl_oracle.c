@@ -735,7 +735,17 @@ static void solve_constraints(const OrcModel* m, OrcData* d) {
     }
 }
 
-/* test hook: the sphere-box distance function on its own (tests/test_self_collision.py) */
+/* test hooks: the distance functions on their own (tests/test_self_collision.py) */
+void orc_test_capsule_capsule(const REAL* a0, const REAL* a1, REAL r1, const REAL* b0, const REAL* b1, REAL r2, REAL* dist, REAL* pos, REAL* frame) {
+    REAL pa[3], pb[3];
+    closest_segment_to_segment(pa, pb, a0, a1, b0, b1);
+    sphere_sphere(pa, r1, pb, r2, dist, pos, frame);
+}
+void orc_test_sphere_capsule(const REAL* c, REAL r1, const REAL* b0, const REAL* b1, REAL r2, REAL* dist, REAL* pos, REAL* frame) {
+    REAL pb[3];
+    closest_segment_point(pb, b0, b1, c);
+    sphere_sphere(c, r1, pb, r2, dist, pos, frame);
+}
 void orc_test_sphere_box(const REAL* sp, REAL r, const REAL* bp, const REAL* bm, const double* half, REAL* dist, REAL* pos, REAL* frame) {
     sphere_box(sp, r, bp, bm, half, dist, pos, frame);
 }

@@ -180,3 +180,51 @@ def test_sphere_box_distance_closed_forms():
     # reported distance comes from a side face's edge and is larger than the gap -> no row inside the margin
     d, pos, n = run([0.0, 0.0, 0.0275 + r + 0.0005], r)
     assert d > 0.001
+
+
+def _hook(name):
+    import ctypes
+    from oracle.oracle import HERE
+    lib = ctypes.CDLL(str(HERE / "liboracle_f64.so"))
+    if not hasattr(lib, name):
+        pytest.skip("oracle built without the test hooks")
+    return lib, ctypes
+
+
+def test_segment_distances_against_brute_force():
+    """The restated closest-point functions (mjx math.closest_segment_point / closest_segment_to_segment_points) against a
+    brute-force minimisation over both segments, on random capsule pairs including near-parallel and crossing ones."""
+    lib, ctypes = _hook("orc_test_capsule_capsule")
+    rng = np.random.default_rng(7)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    s = np.linspace(0, 1, 401)
+    worst = 0.0
+    for case in range(200):
+        a0, a1, b0 = rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3)
+        if case % 4 == 0:      # near-parallel
+            b1 = b0 + (a1 - a0) * rng.uniform(0.5, 1.5) + 1e-3 * rng.normal(size=3)
+        elif case % 4 == 1:    # crossing lines
+            mid = a0 + 0.5 * (a1 - a0)
+            d = rng.normal(size=3)
+            b0, b1 = mid - 0.2 * d + 1e-3 * rng.normal(size=3), mid + 0.2 * d
+        else:
+            b1 = rng.uniform(-0.3, 0.3, 3)
+        r1, r2 = 0.04, 0.055
+        dist, pos, fr = ctypes.c_double(), np.zeros(3), np.zeros(9)
+        lib.orc_test_capsule_capsule(P(a0), P(a1), ctypes.c_double(r1), P(b0), P(b1), ctypes.c_double(r2), ctypes.byref(dist), P(pos), P(fr))
+        pa = a0[None, :] + s[:, None] * (a1 - a0)
+        pb = b0[None, :] + s[:, None] * (b1 - b0)
+        dmin = np.sqrt(((pa[:, None, :] - pb[None, :, :]) ** 2).sum(-1)).min() - r1 - r2
+        # the restatement is exact up to its 1e-6 regularisers; the grid over-estimates by at most its spacing
+        assert dist.value <= dmin + 1e-6 and dist.value >= dmin - 2e-3, (case, dist.value, dmin)
+        worst = max(worst, abs(dist.value - dmin))
+        n = fr[:3]
+        assert abs(np.linalg.norm(n) - 1) < 1e-9
+    # sphere against segment
+    for case in range(100):
+        c, b0, b1 = rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3)
+        dist, pos, fr = ctypes.c_double(), np.zeros(3), np.zeros(9)
+        lib.orc_test_sphere_capsule(P(c), ctypes.c_double(0.04), P(b0), P(b1), ctypes.c_double(0.055), ctypes.byref(dist), P(pos), P(fr))
+        pb = b0[None, :] + np.linspace(0, 1, 20001)[:, None] * (b1 - b0)
+        dmin = np.sqrt(((pb - c) ** 2).sum(-1)).min() - 0.095
+        assert abs(dist.value - dmin) < 2e-5, (case, dist.value, dmin)
