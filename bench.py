@@ -409,7 +409,8 @@ def main():
                            "parallelism": f"env-sharded x{world}, stats all-reduce per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total_envs * N_FRAMES * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,
-                        "steps": e2e_steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)"},
+                        "steps": e2e_steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)",
+                        "note": "wall clock around back-to-back host calls; no L2 flush between them (state stays L2-resident), which is why it can exceed the flushed, event-timed value"},
                 # k_step (+ k_balance_order) per step of the timed loop and of the host-buffer loop, one k_reset each
                 "gpu_launches": (steps + warmup) * (1 if os.environ.get("PBRL_BENCH_NO_BALANCE") else 2) + 2 * (e2e_steps + 3) + 2,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
