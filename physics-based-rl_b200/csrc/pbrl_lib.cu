@@ -268,7 +268,8 @@ struct PbrlModel {
     int sm_count = 0;
     int ctas_per_sm = 1;
     int rr_ctas_per_sm = 1;
-    int phase_lock = 25;  // CTA barrier mask of k_step (pbrl_core.cuh: forward); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int phase_lock = 16;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per
+                          // iteration is the only CTA-wide sync; PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
     DevModel host{};
     DevModel* dev = nullptr;
     DevMimic mimic{};
