@@ -55,7 +55,7 @@ extern "C" {
 #define PBRL_STATUS_NAN 1
 #define PBRL_STATUS_PIVOT 2
 #define PBRL_STATUS_SOLVER_MAXITER 4
-#define PBRL_STATUS_SELF_OVERFLOW 8 /* more body-vs-body contacts inside the margin than the kernel keeps (8): the extra ones were dropped */
+#define PBRL_STATUS_SELF_OVERFLOW 8 /* more body-vs-body contacts inside the margin than the kernel keeps (8): the deepest 8 were kept */
 
 typedef struct PbrlModel PbrlModel;
 

@@ -1113,6 +1113,23 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
                 }
             }
         }
+        WSYNC();
+        if (total + pop_count(act) > KS) {  // (warp-uniform, rare) list full: a deeper contact replaces the shallowest one kept
+            LANE_IF(z, 1) {
+                int skip = KS > total ? KS - total : 0;  // the first `skip` contacts of this pass got slots above
+                for (unsigned rest = act; rest != 0u; rest &= rest - 1u) {
+                    if (skip > 0) { skip--; continue; }
+                    const float* o = pr + 8 * first_bit(rest);
+                    int worst = 0;
+                    for (int c = 1; c < KS; c++) if (w.sc_n[4 * c + 3] > w.sc_n[4 * worst + 3]) worst = c;
+                    if (o[3] < w.sc_n[4 * worst + 3]) {
+                        for (int k = 0; k < 3; k++) { w.sc_r[4 * worst + k] = o[k] - w.com[k]; w.sc_n[4 * worst + k] = o[4 + k]; }
+                        w.sc_n[4 * worst + 3] = o[3];
+                        w.sc_bb[worst] = float_bits_as_int(o[7]);
+                    }
+                }
+            }
+        }
         total += pop_count(act);
         WSYNC();
     }

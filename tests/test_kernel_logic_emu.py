@@ -102,3 +102,29 @@ def test_forward_stages_general_solimp_power(model_grav):
 
 def test_sphere_box_contacts(emu_grav, model_grav):
     pc.check_sphere_box_contacts(emu_grav, model_grav)
+
+
+def test_contact_list_overflow_keeps_the_deepest(model_grav):
+    """More than 8 body-vs-body contacts at once (absurdly folded random poses): the 8 deepest are kept and the status says so."""
+    import numpy as np
+    from helpers import DBG, Oracle, random_states
+    orc = Oracle(model_grav, "f64")
+    be = EmuBackend(model_grav)
+    found = 0
+    for seed in range(300, 340):
+        qpos, qvel = random_states(model_grav, 32, seed, gravity_heights=True, vel_scale=0.0, joint_frac=1.0)
+        for e in range(32):
+            d = orc.new_data()
+            d.qpos[:35] = qpos[e].astype(np.float32)
+            orc.forward(d)
+            nc, ns = int(d.ncon[0]), int(d.nself[0])
+            if ns <= 8:
+                continue
+            out = be.debug_forward(qpos[e:e + 1].astype(np.float32), np.zeros((1, 34), np.float32), np.zeros((1, 28), np.float32), np.zeros((1, 34), np.float32))
+            kept = np.sort(out[0, DBG["self_dist"][0]:DBG["self_dist"][0] + 8])
+            want = np.sort(d.con_dist[nc - ns:nc])[:8]
+            assert int(out[0, DBG["nself"][0]]) == 8 and np.abs(kept - want).max() <= 2e-6, (seed, e, kept, want)
+            found += 1
+        if found >= 3:
+            break
+    assert found >= 2
