@@ -39,7 +39,17 @@
 #define PBRL_LOCK_GROUP 16
 #endif
 #define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / PBRL_LOCK_GROUP), "r"(32 * PBRL_LOCK_GROUP) : "memory")
-#define CTA_OR(p) __syncthreads_or(p)
+// Newton vote: OR of a predicate over the warps that iterate in step (PBRL_VOTE_GROUP consecutive warps; default: the CTA)
+#ifndef PBRL_VOTE_GROUP
+#define PBRL_VOTE_GROUP 16
+#endif
+__device__ __forceinline__ int vote_group_or(int p) {
+    int r;
+    asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.b32 q, %1, 0;\n\tbarrier.cta.red.or.pred r, %2, %3, q;\n\tselp.b32 %0, 1, 0, r;\n\t}"
+                 : "=r"(r) : "r"(p), "r"(8 + (int)(threadIdx.x >> 5) / PBRL_VOTE_GROUP), "r"(32 * PBRL_VOTE_GROUP) : "memory");
+    return r;
+}
+#define CTA_OR(p) vote_group_or(p)
 #else
 #define PB_DEV static inline
 #define PB_DEVN static
@@ -79,9 +89,12 @@ __device__ unsigned long long g_stage_hits[64];
 
 namespace pbrl {
 
-// row strides of the per-body / per-dof arrays: 6-vectors live in 8-float rows, spatial inertias in 12-float rows and
-// symmetric 6x6 blocks in 24-float rows, all 16-byte aligned, so that a lane moves a whole row with a few vector accesses
-constexpr int S3 = 3, S4 = 4, S6 = 8, S9 = 9, S10 = 12, S21 = 24;
+// row strides of the per-body / per-dof arrays.  6-vectors are packed (24-byte rows moved as three 8-byte accesses: with
+// consecutive rows in consecutive lanes a 64-bit access touches every bank pair once per half warp, where 8-float rows
+// moved as 16 + 8 bytes replayed 2x / 4x on bank conflicts); spatial inertias live in 12-float rows (48 bytes: conflict-free
+// for 128-bit accesses) and symmetric 6x6 blocks in 24-float rows.
+constexpr int S3 = 3, S4 = 4, S6 = 6, S9 = 9, S10 = 12, S21 = 24;
+constexpr int NBUF6 = 256;  // floats of stage scratch: 32 x 8 pair results of the narrow phase is the largest user
 constexpr int SR = 4;        // contact points: float4 rows
 constexpr int NDL = NV - 3;  // "dof lanes": lane l owns dof l + 3; the lane of dof 3 also emits the free translations 0..2
 constexpr int NEWTON_MAXIT = 12;
@@ -100,7 +113,7 @@ struct Ws {
     alignas(16) float cinert[NB * S10];
     alignas(16) float cdof[NV * S6];
     alignas(16) float cvel[NB * S6];
-    alignas(16) float buf6[NV * S6];  // stage scratch; also the 14 x 16 staging rows of the factorisation
+    alignas(16) float buf6[NBUF6];    // stage scratch; also the 14 x 16 staging rows of the factorisation
     union {
         alignas(16) float cacc[NB * S6];  // bias accelerations (com_vel -> rne)
         alignas(16) float V[NB * S6];     // body velocities of a generalised vector (solver, feedback PD)
@@ -156,7 +169,7 @@ struct Ws {
 static_assert(sizeof(Ws) % 16 == 0, "workspaces tile shared memory on 16-byte boundaries");
 constexpr int NHD = NV * (NV + 1) / 2;  // packed lower triangle of the dense Hessian
 static_assert(offsetof(Ws, K) + sizeof(float) * NB * S21 - offsetof(Ws, LD) >= sizeof(float) * NHD, "dense Hessian spans LD + K");
-static_assert(4 * 36 <= NV * S6 && 32 * 8 <= NV * S6 && 8 * NSG <= NB * S21 && NCP * S6 + KS * S6 <= NB * S21, "body-vs-body scratch");
+static_assert(4 * 36 <= NBUF6 && 32 * 8 <= NBUF6 && NV * S6 <= NBUF6 && 8 * NSG <= NB * S21 && NCP * S6 + KS * S6 <= NB * S21, "body-vs-body scratch");
 
 PB_DEV float fast_rcp(float x) {
 #if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
@@ -260,8 +273,8 @@ PB_DEV void st4(float* p, const float* r) { for (int k = 0; k < 4; k++) p[k] = r
 PB_DEV void ld2(const float* p, float* r) { r[0] = p[0]; r[1] = p[1]; }
 PB_DEV void st2(float* p, const float* r) { p[0] = r[0]; p[1] = r[1]; }
 #endif
-PB_DEV void ld6(const float* p, float* r) { ld4(p, r); ld2(p + 4, r + 4); }
-PB_DEV void st6(float* p, const float* r) { st4(p, r); st2(p + 4, r + 4); }
+PB_DEV void ld6(const float* p, float* r) { ld2(p, r); ld2(p + 2, r + 2); ld2(p + 4, r + 4); }   // 8-byte aligned rows (S6)
+PB_DEV void st6(float* p, const float* r) { st2(p, r); st2(p + 2, r + 2); st2(p + 4, r + 4); }
 PB_DEV void ld10(const float* p, float* r) { ld4(p, r); ld4(p + 4, r + 4); ld2(p + 8, r + 8); }
 PB_DEV void st10(float* p, const float* r) { st4(p, r); st4(p + 4, r + 4); st2(p + 8, r + 8); }
 PB_DEV void ld24(const float* p, float* r) { for (int k = 0; k < 6; k++) ld4(p + 4 * k, r + 4 * k); }
@@ -342,7 +355,7 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
     float* jq = w.cdof;           // [NJ][4] rotation of each hinge about its axis           (cdof is written by stage_com)
     float* bq = w.cdof + 4 * NJ;  // [NB][4] product of a body's hinge rotations
     float* axl = w.buf6;          // [NJ] x S3: joint axis in the body's pre-joint frame here, in the world frame on return
-    static_assert(4 * NJ + 4 * NB <= NV * S6, "fk scratch");
+    static_assert(4 * NJ + 4 * NB <= NV * S6 && S3 * NJ <= NBUF6, "fk scratch");
     LANE_IF(j, NJ) {
         if (m.jnt_type[j] != 0) {
             const int qa = m.jnt_qposadr[j];
@@ -1293,7 +1306,7 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
 // gather the blocks of the subtree (bit mask of bodies that carry active contacts), apply to the cdof, fill the row.
 PB_DEVN void assemble_hessian(const DevModel& m, Ws& w, int lane) {
     float* Wc = w.buf6;  // [NCP] x S6: xx yy zz xy xz yz
-    static_assert(NCP * S6 <= NV * S6, "contact W scratch");
+    static_assert(NCP * S6 <= NBUF6, "contact W scratch");
     const unsigned act = wballot(lane, NC, [&](int c) {
         return ((w.con_mask >> c) & 1u) && (w.con_jar[4 * c] < 0.f || w.con_jar[4 * c + 1] < 0.f || w.con_jar[4 * c + 2] < 0.f || w.con_jar[4 * c + 3] < 0.f);
     });
@@ -1670,6 +1683,8 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     bool running = constrained;
     for (;;) {
         const bool go = running && it < NEWTON_MAXIT;
+        PROF_COUNT(60);
+        if (go) PROF_COUNT(61);
         if (coop) { if (!CTA_OR(go ? 1 : 0)) break; }
         else if (!go) break;
         if (!go) continue;
@@ -1903,6 +1918,7 @@ namespace pbrl {
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
+    int cost_mode;   // work estimate written to buf.cost: 0 most expensive substep, 1 sum over the substeps, 2 last substep
     const float *action, *kp, *kd, *pd_time;
     float pd_dt;
     unsigned ctrl_mask;
@@ -1953,7 +1969,7 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     LANE_IF(z, 1) w.phase_lock = a.phase_lock;
     WSYNC();
     PROF(1);
-    int cost = 0;
+    int cost = 0, cost_sum = 0;
     for (int f = 0; f < a.n_frames; f++) {
         if (f == a.n_frames - 1) {  // the state entering the last forward is what the next PD law evaluates M / bias at
             store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
@@ -1961,7 +1977,10 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
         }
         substep(m, w, time, lane);
         cost = cost > w.work ? cost : w.work;  // the most expensive substep decides how long the CTA's barriers wait for this env
+        cost_sum += w.work;
     }
+    if (a.cost_mode == 1) cost = cost_sum;
+    else if (a.cost_mode == 2) cost = w.work;
     if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
     store_row(B.qpos + (size_t)env * NQ, w.qpos, NQ, lane);

@@ -36,6 +36,21 @@ int fail(const std::string& msg) { g_error = msg; return -1; }
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
 
+// Entry points launch on the model's device whatever the caller's current device is, and leave the caller's device as
+// they found it (torch streams of device k are usable only while device k is current).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true, changed = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device) { changed = true; if (cudaSetDevice(device) != cudaSuccess) ok = false; }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(m)                                                  \
+    DeviceGuard guard_((m)->device);                                  \
+    if (!guard_.ok) return fail("cannot select the model's CUDA device")
+
 // dynamic shared memory of a CTA: [DevModel copy][Ws x WARPS_PER_CTA]
 constexpr size_t MODEL_SMEM = (sizeof(DevModel) + 15) / 16 * 16;
 __device__ __forceinline__ Ws& my_ws() {
@@ -68,7 +83,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
         else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 7); k++) CTA_SYNC();
-                if (a.phase_lock & 16) while (__syncthreads_or(0)) {}
+                if (a.phase_lock & 16) while (CTA_OR(0)) {}
                 if (a.phase_lock & 8) CTA_SYNC();
             }
         }
@@ -270,6 +285,7 @@ struct PbrlModel {
     int rr_ctas_per_sm = 1;
     int phase_lock = 16;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per
                           // iteration is the only CTA-wide sync; PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
     DevModel* dev = nullptr;
     DevMimic mimic{};
@@ -313,46 +329,57 @@ int pbrl_device_count(void) {
 
 int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int device, PbrlModel** out) {
     if (!desc || !out) return fail("null argument");
+    *out = nullptr;
     int ndev = pbrl_device_count();
     if (ndev <= 0) return fail("no CUDA device: this library has no CPU path");
     if (device < 0 || device >= ndev) return fail("bad device index");
-    CUDA_OK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail("cannot select the CUDA device");
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("libpbrl is built for sm_100a (B200) only");
     PbrlModel* m = new PbrlModel();
+    // every failure below releases the handle and whatever it owns (pbrl_model_destroy frees dev / frames if set)
+    auto bail = [&](const std::string& msg) { pbrl_model_destroy(m); return fail(msg); };
+#define CREATE_OK(call)                                                                                      \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
     m->device = device;
     m->sm_count = prop.multiProcessorCount;
     m->ctas_per_sm = 0;
     { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 31; }
+    { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
-    if (!err.empty()) { delete m; return fail(err); }
+    if (!err.empty()) return bail(err);
     if (prepare_kernel(k_step, m) || prepare_kernel(k_reset, m) || prepare_kernel(k_replay, m) || prepare_kernel(k_pd, m) ||
-        prepare_kernel(k_debug_forward, m) || prepare_kernel(k_autoreset, m)) { delete m; return -1; }
+        prepare_kernel(k_debug_forward, m) || prepare_kernel(k_autoreset, m)) { const std::string keep = g_error; return bail(keep); }
     {
-        CUDA_OK(cudaFuncSetAttribute(k_replay_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+        CREATE_OK(cudaFuncSetAttribute(k_replay_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
         int nb = 0;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay_rollout, RR_ITEMS, RR_SMEM));
-        if (nb < 1) { delete m; return fail("k_replay_rollout does not fit on an SM"); }
+        CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay_rollout, RR_ITEMS, RR_SMEM));
+        if (nb < 1) return bail("k_replay_rollout does not fit on an SM");
         m->rr_ctas_per_sm = nb;
     }
-    CUDA_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
-    CUDA_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
+    CREATE_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
+    CREATE_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
     if (mimic) {
         std::string merr = build_dev_mimic(*mimic, m->host, m->mimic);
-        if (!merr.empty()) { pbrl_model_destroy(m); return fail(merr); }
+        if (!merr.empty()) return bail(merr);
         size_t bytes = (size_t)mimic->nframes_total * PBRL_FRAME_STRIDE * sizeof(float);
-        CUDA_OK(cudaMalloc(&m->frames, bytes));
-        CUDA_OK(cudaMemcpy(m->frames, mimic->frames, bytes, cudaMemcpyHostToDevice));
+        CREATE_OK(cudaMalloc(&m->frames, bytes));
+        CREATE_OK(cudaMemcpy(m->frames, mimic->frames, bytes, cudaMemcpyHostToDevice));
         m->has_mimic = true;
     }
+#undef CREATE_OK
     *out = m;
     return 0;
 }
 
 void pbrl_model_destroy(PbrlModel* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     if (m->dev) cudaFree(m->dev);
     if (m->frames) cudaFree(m->frames);
     delete m;
@@ -366,6 +393,7 @@ static int check_buffers(const PbrlBuffers* b) {
 
 int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* buf, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (check_buffers(buf)) return -1;
     StepArgs a{};
@@ -381,6 +409,7 @@ int pbrl_reset(const PbrlModel* m, int N, int reward_mode, const PbrlBuffers* bu
 
 int pbrl_balance_order(const PbrlModel* m, int N, const int* cost, int* env_order, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (!cost || !env_order) return fail("null argument");
     k_balance_order<<<1, BO_THREADS, 0, (cudaStream_t)stream>>>(N, cost, env_order);
@@ -390,6 +419,7 @@ int pbrl_balance_order(const PbrlModel* m, int N, const int* cost, int* env_orde
 int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done, const float* next_ref_t0, int* steps,
                    const PbrlBuffers* buf, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (check_buffers(buf)) return -1;
     if (!done) return fail("null done");
@@ -408,6 +438,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
               const float* kd, float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf,
               void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (check_buffers(buf)) return -1;
     if (!action) return fail("null action");
@@ -424,6 +455,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     a.N = N; a.n_frames = n_frames; a.pd_mode = pd_mode; a.action_cols = action_cols; a.reward_mode = reward_mode;
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
     a.phase_lock = m->phase_lock;
+    a.cost_mode = m->cost_mode;
     k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
     return check_launch("pbrl_step");
 }
@@ -431,6 +463,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
 int pbrl_replay(const PbrlModel* m, int N, const float* qpos, const float* qvel, float* obs, float* reward, float* done,
                 float* xpos, float* xquat, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (!qpos || !qvel) return fail("null qpos/qvel");
     k_replay<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, obs, reward, done, xpos, xquat);
@@ -440,6 +473,7 @@ int pbrl_replay(const PbrlModel* m, int N, const float* qpos, const float* qvel,
 int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos, const float* data_vel, int F, const int* frame0,
                         float* obs, float* reward, float* done, float* xpos, float* xquat, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0 || K <= 0) return 0;
     if (!data_pos || !data_vel || F <= 0) return fail("null frame data");
     const long long ctas = ((long long)N * K + RR_ITEMS - 1) / RR_ITEMS;
@@ -455,6 +489,7 @@ int pbrl_pd_torque(const PbrlModel* m, int N, int pd_mode, int action_cols, cons
                    const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
                    const float* time, float pd_dt, float* tau, float* qM, float* bias, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (!action || !qpos || !qvel || !qpos_lag || !qvel_lag || !kp || !kd || !time || !tau) return fail("null argument");
     if (pd_mode < 0 || pd_mode > 3) return fail("pd_mode must be 0..3");
@@ -467,6 +502,7 @@ int pbrl_pd_torque(const PbrlModel* m, int N, int pd_mode, int action_cols, cons
 int pbrl_debug_forward(const PbrlModel* m, int N, const float* qpos, const float* qvel, const float* ctrl, const float* warm,
                        float* out, void* stream) {
     if (!m) return fail("null model");
+    ON_DEVICE(m);
     if (N <= 0) return 0;
     if (!qpos || !qvel || !ctrl || !warm || !out) return fail("null argument");
     k_debug_forward<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, warm, out);
@@ -523,13 +559,14 @@ struct PbrlBatch {
 
 int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
     if (!m || !out || N <= 0) return fail("bad argument");
-    CUDA_OK(cudaSetDevice(m->device));
+    ON_DEVICE(m);
     PbrlBatch* b = new PbrlBatch();
     b->model = m; b->N = N;
-    CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return fail("cudaStreamCreate failed"); }
+    bool failed = false;
     auto alloc = [&](size_t n) -> float* {
         void* p = nullptr;
-        if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) { cudaGetLastError(); failed = true; return nullptr; }
         cudaMemsetAsync(p, 0, n * sizeof(float), b->stream);
         b->allocs.push_back(p);
         return (float*)p;
@@ -543,12 +580,12 @@ int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
     b->motion_id = (int*)alloc(N); b->ref_t0 = alloc(N);
     B.motion_id = nullptr; B.ref_t0 = nullptr;
     b->action = alloc((size_t)N * NU * 4); b->gains = alloc(2 * NU);
-    for (void* p : b->allocs) if (!p) { pbrl_batch_destroy(b); return fail("cudaMalloc failed"); }
+    if (failed) { pbrl_batch_destroy(b); return fail("cudaMalloc failed"); }
     {
         std::vector<int> iota(N);
         for (int i = 0; i < N; i++) iota[i] = i;
-        CUDA_OK(cudaMemcpyAsync(b->order, iota.data(), N * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-        CUDA_OK(cudaStreamSynchronize(b->stream));
+        if (cudaMemcpyAsync(b->order, iota.data(), N * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+            cudaStreamSynchronize(b->stream) != cudaSuccess) { pbrl_batch_destroy(b); return fail("pbrl_batch_create: upload failed"); }
         B.env_order = b->order;
     }
     *out = b;
@@ -556,7 +593,7 @@ int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
 }
 void pbrl_batch_destroy(PbrlBatch* b) {
     if (!b) return;
-    cudaSetDevice(b->model->device);
+    DeviceGuard guard(b->model->device);
     cudaStreamSynchronize(b->stream);
     for (void* p : b->allocs) if (p) cudaFree(p);
     cudaStreamDestroy(b->stream);
@@ -564,7 +601,7 @@ void pbrl_batch_destroy(PbrlBatch* b) {
 }
 int pbrl_batch_reset_host(PbrlBatch* b, int reward_mode, const int* motion_id, const float* ref_t0, float* obs_out) {
     if (!b) return fail("null batch");
-    CUDA_OK(cudaSetDevice(b->model->device));
+    ON_DEVICE(b->model);
     if (motion_id) { CUDA_OK(cudaMemcpyAsync(b->motion_id, motion_id, b->N * sizeof(int), cudaMemcpyHostToDevice, b->stream)); b->buf.motion_id = b->motion_id; }
     if (ref_t0) { CUDA_OK(cudaMemcpyAsync(b->ref_t0, ref_t0, b->N * sizeof(float), cudaMemcpyHostToDevice, b->stream)); b->buf.ref_t0 = b->ref_t0; }
     if (pbrl_reset(b->model, b->N, reward_mode, &b->buf, b->stream)) return -1;
@@ -577,7 +614,7 @@ int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_col
                          float* stats_out) {
     if (!b || !action) return fail("null argument");
     if (action_cols != 1 && action_cols != 4) return fail("action_cols must be 1 or 4");
-    CUDA_OK(cudaSetDevice(b->model->device));
+    ON_DEVICE(b->model);
     const int N = b->N;
     CUDA_OK(cudaMemcpyAsync(b->action, action, (size_t)N * NU * action_cols * sizeof(float), cudaMemcpyHostToDevice, b->stream));
     if (kp && kd) {
@@ -597,7 +634,7 @@ int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_col
 }
 int pbrl_batch_get_state_host(PbrlBatch* b, float* qpos, float* qvel, float* time) {
     if (!b) return fail("null batch");
-    CUDA_OK(cudaSetDevice(b->model->device));
+    ON_DEVICE(b->model);
     if (qpos) CUDA_OK(cudaMemcpyAsync(qpos, b->buf.qpos, (size_t)b->N * NQ * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (qvel) CUDA_OK(cudaMemcpyAsync(qvel, b->buf.qvel, (size_t)b->N * NV * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (time) CUDA_OK(cudaMemcpyAsync(time, b->buf.time, (size_t)b->N * sizeof(float), cudaMemcpyDeviceToHost, b->stream));

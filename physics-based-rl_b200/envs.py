@@ -89,8 +89,16 @@ class State:
         return State(**d)
 
     def clone(self):
-        return State(self.pipeline_state.clone(), self.obs.clone(), self.reward.clone(), self.done.clone(),
-                     {k: v.clone() for k, v in self.metrics.items()}, dict(self.info))
+        """An independent copy: every tensor (state, info buffers the kernels write -- metrics, status, cost, env_order,
+        motion_id, ref_t0, stats, the wrappers' step counters) is duplicated, and `metrics` is re-bound to views of the
+        copy's own metrics buffer, so stepping either state leaves the other untouched."""
+        info = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.info.items()}
+        st = State(self.pipeline_state.clone(), self.obs.clone(), self.reward.clone(), self.done.clone(), {}, info)
+        if "_metrics" in info:
+            HumanoidDiff._bind_metrics(st)
+        else:
+            st.metrics = {k: v.clone() for k, v in self.metrics.items()}
+        return st
 
 
 class HumanoidDiff:
@@ -198,13 +206,34 @@ class HumanoidDiff:
     def _get_obs(self, data: PipelineState, action=None):
         return torch.cat([data.qpos, data.qvel], dim=-1)  # agent_env_template.py:151-155
 
+    def _check_state(self, st: State):
+        """The kernels read N rows of every state buffer through raw pointers: refuse a state of another batch size."""
+        ps, N = st.pipeline_state, self.num_envs
+        for name, t, w in (("qpos", ps.qpos, (35,)), ("qvel", ps.qvel, (34,)), ("time", ps.time, ()), ("qacc_warmstart", ps.qacc_warmstart, (34,)),
+                           ("ctrl", ps.ctrl, (28,)), ("qpos_lag", ps.qpos_lag, (35,)), ("qvel_lag", ps.qvel_lag, (34,)),
+                           ("obs", st.obs, (69,)), ("reward", st.reward, (3,)), ("done", st.done, ())):
+            if tuple(t.shape) != (N, *w) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"state.{name}: expected a contiguous float32 tensor of shape {(N, *w)} on {self.device}, got {tuple(t.shape)} {t.dtype} on {t.device}")
+
     def _launch_step(self, st: State, action, pd_mode, pd_dt, pd_time=None, ctrl_mask=0x0FFFFFFF, kp=None, kd=None):
-        action = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
-        if action.dim() == 1 or (action.dim() == 2 and action.shape == (28, 4)):
-            action = action.expand(self.num_envs, *action.shape).contiguous()
-        cols = 1 if action.dim() == 2 else int(action.shape[2])
+        N = self.num_envs
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if tuple(action.shape) in ((28,), (28, 4)):  # one action for every env (the reference's unbatched call)
+            action = action.expand(N, *action.shape)
+        if tuple(action.shape) not in ((N, 28), (N, 28, 4)):
+            raise ValueError(f"action: expected shape ({N}, 28) [targets / torques] or ({N}, 28, 4) [cubic coefficients], got {tuple(action.shape)}")
+        action = action.contiguous()
+        cols = 1 if action.dim() == 2 else 4
+        if pd_mode != PD_TORQUE:
+            for name, g in (("kp", kp), ("kd", kd)):
+                if g is None or g.numel() != 28 or g.dtype != torch.float32 or g.device != self.device:
+                    raise ValueError(f"{name}: expected 28 float32 gains on {self.device}")
         if pd_time is not None:
-            pd_time = torch.as_tensor(pd_time, dtype=torch.float32, device=self.device).expand(self.num_envs).contiguous()
+            pd_time = torch.as_tensor(pd_time, dtype=torch.float32, device=self.device)
+            if pd_time.numel() not in (1, N):
+                raise ValueError(f"time: expected a scalar or {N} values, got {tuple(pd_time.shape)}")
+            pd_time = pd_time.reshape(-1).expand(N).contiguous()
+        self._check_state(st)
         b = self._buffers(st)
         _lib.check(_lib.lib().pbrl_step(
             self.model.handle, ctypes.c_int(self.num_envs), ctypes.c_int(self.n_frames), ctypes.c_int(pd_mode),

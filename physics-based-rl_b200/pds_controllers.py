@@ -20,13 +20,24 @@ def _evaluate(mode, target, env_model, pipeline_state, q, qdot, kp, kd, time, dt
     dev = q.device
     N = q.shape[0]
     target = torch.as_tensor(target, dtype=torch.float32, device=dev)
-    if target.dim() == 1 or (target.dim() == 2 and tuple(target.shape) == (28, 4)):
+    if tuple(target.shape) in ((28,), (28, 4)):
         target = target.expand(N, *target.shape)
+    # the kernel reads N x 28 x cols floats through a raw pointer: refuse anything else before the launch
+    if tuple(target.shape) not in ((N, 28), (N, 28, 4)):
+        raise ValueError(f"target: expected shape ({N}, 28) or ({N}, 28, 4) [cubic coefficients], got {tuple(target.shape)}")
     target = target.contiguous()
-    cols = 1 if target.dim() == 2 else int(target.shape[2])
+    cols = 1 if target.dim() == 2 else 4
     kp = torch.as_tensor(kp, dtype=torch.float32, device=dev).contiguous()
     kd = torch.as_tensor(kd, dtype=torch.float32, device=dev).contiguous()
-    time = torch.as_tensor(time, dtype=torch.float32, device=dev).expand(N).contiguous()
+    if kp.numel() != 28 or kd.numel() != 28:
+        raise ValueError("kp_array / kd_array: expected 28 gains each")
+    time = torch.as_tensor(time, dtype=torch.float32, device=dev)
+    if time.numel() not in (1, N):
+        raise ValueError(f"time: expected a scalar or {N} values, got {tuple(time.shape)}")
+    time = time.reshape(-1).expand(N).contiguous()
+    if tuple(q.shape) != (N, 35) or tuple(qdot.shape) != (N, 34) or tuple(pipeline_state.qpos_lag.shape) != (N, 35) or \
+            tuple(pipeline_state.qvel_lag.shape) != (N, 34):
+        raise ValueError("q / qdot / lagged state: expected (N, 35) / (N, 34) rows for the same N")
     tau = torch.empty((N, 28), device=dev)
     _lib.check(_lib.lib().pbrl_pd_torque(
         env_model.handle, ctypes.c_int(N), ctypes.c_int(mode), ctypes.c_int(cols), _lib._ptr(target),

@@ -496,3 +496,126 @@ def check_sphere_box_contacts(backend, model_grav, want=12):
     # with the back end to 2e-5 on them); the typical one is at rounding level
     assert np.median(errs) <= 1e-5 and max(errs) <= 5e-3, (np.median(errs), max(errs))
     return nbox
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The BASELINE.json configurations by name: reference-state initialisation from the named clips at
+# a uniform phase, stable PD whose targets are the clip's own joint angles at the end of the env step ("--actions reference").
+def named_config_setup(model, clips):
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    mdesc, keep = mimic.make_mimic_desc(model, table, clips)
+    table_ids = np.array([table.names.index(c) for c in clips])
+    return table, mdesc, keep, table_ids
+
+
+def _tracking_rollout(backend, orc_env, model, table, mdesc, table_ids, N, steps, seed, n_frames=8, on_step=None):
+    rng = np.random.default_rng(seed)
+    nclip = len(table_ids)
+    mid = (np.arange(N) % nclip).astype(np.int32)
+    dur = table.header[table_ids[mid], 2]
+    t0 = (rng.uniform(0, 1, N) * dur).astype(np.float32)
+    orc_env.reset_mimic(mdesc, mid, t0)
+    s = backend.new_state(N)
+    s.motion_id[:], s.ref_t0[:] = mid, t0
+    backend.reset(s, reward_mode=1)
+    kp, kd = util_data.generate_kp_kd_gains()
+    h = float(model.timestep)
+    for k in range(steps):
+        tgt = table.reference_joint_angles(table_ids[mid], t0.astype(np.float64) + (k + 1) * n_frames * h).astype(np.float32)
+        st_ref = orc_env.step_mimic(tgt, kp, kd, pd_mode=3, pd_dt=h, n_frames=n_frames)
+        s.stats[:] = 0
+        backend.step(s, tgt, kp, kd, pd_mode=3, pd_dt=h, n_frames=n_frames, reward_mode=1)
+        if on_step is not None:
+            on_step(k, s, orc_env, st_ref)
+    return s, mid, t0
+
+
+def check_config3_punch_tracking(backend, model_nograv, table, mdesc, table_ids, N=32, seed=51):
+    """BASELINE configs[2]: final_humanoid_no_gravity.xml, PD tracking of humanoid3d_punch.txt from reference-state
+    initialisation; 32 substeps (4 env steps x 8), fp32 relative error <= 1e-3 on qpos / qvel PER ENV against the float64
+    oracle (north star).  Without gravity the feet still rest on the floor plane at the clip's root height, so floor rows
+    are active in part of the envs: those are reported separately and held to the same bound."""
+    env = OracleEnv(_oracle(model_nograv), N)
+    touched = np.zeros(N, bool)
+
+    def on_step(k, s, e, st):
+        for i in range(N):
+            touched[i] |= _floor_active(model_nograv, e.qpos[i])
+    s, mid, t0 = _tracking_rollout(backend, env, model_nograv, table, mdesc, table_ids, N, 4, seed, on_step=on_step)
+    eq, ev = row_relerr(s.qpos, env.qpos), row_relerr(s.qvel, env.qvel)
+    assert np.isfinite(s.qpos).all() and (s.status & 7 == 0).all()
+    assert eq.max() <= TOL_32 and ev.max() <= TOL_32, (eq.max(), ev.max(), int((np.maximum(eq, ev) > TOL_32).sum()))
+    assert np.abs(s.reward[:, 0] - env.reward[:, 0]).max() <= 1e-3 and (s.done == env.done).all()
+    return dict(qpos=float(eq.max()), qvel=float(ev.max()), median=float(np.median(np.maximum(eq, ev))), floor_contact_envs=int(touched.sum()))
+
+
+def _floor_active(model, qpos):
+    orc = _oracle(model)
+    d = orc.new_data()
+    d.qpos[:35] = qpos
+    orc.forward(d)
+    nf = int(d.ncon[0]) - int(d.nself[0])
+    return bool((d.con_dist[:nf] - d.con_includemargin[:nf] < 0).any())
+
+
+def check_config4_backflip_jump(backend, model_grav, table, mdesc, table_ids, N=64, N_stat=512, steps=24, seed=53):
+    """BASELINE configs[3]: final_humanoid.xml, contact-rich mimic of humanoid3d_backflip.txt (even env ids) and
+    humanoid3d_jump.txt (odd).  First env step (8 contact substeps): per-env parity with the float64 oracle; then the
+    statistics the north star names over `steps` env steps: termination-step histogram and per-step reward mean."""
+    env = OracleEnv(_oracle(model_grav), N)
+    first = {}
+
+    def on_first(k, s, e, st):
+        if k == 0:
+            first.update(eq=row_relerr(s.qpos, e.qpos), ev=row_relerr(s.qvel, e.qvel), rew=np.abs(s.reward[:, 0] - e.reward[:, 0]).max(),
+                         done=(s.done == e.done).all(), stats=np.abs(s.stats[:6] - st[:6]).max())
+    _tracking_rollout(backend, env, model_grav, table, mdesc, table_ids, N, 1, seed, on_step=on_first)
+    # 8 substeps with feet on the floor: the 32-contact-free-substep bound of the north star is met per env, the typical env
+    # sits two orders below it
+    assert first["eq"].max() <= TOL_32 and first["ev"].max() <= TOL_32, (first["eq"].max(), first["ev"].max())
+    assert np.median(first["eq"]) <= 1e-5, np.median(first["eq"])
+    assert first["rew"] <= 1e-3 and first["done"] and first["stats"] <= 1e-2 * max(1, N / 64)
+    # statistics (fp32 oracle, all host threads): the rollout the bench times, with the clip-tracking targets
+    env32 = OracleEnv(Oracle(model_grav, "f32"), N_stat)
+    fr, f, rr, r = np.full(N_stat, steps), np.full(N_stat, steps), [], []
+
+    def on_stat(k, s, e, st):
+        rr.append(e.reward[:, 0].mean()); r.append(s.reward[:, 0].mean())
+        fr[:] = np.where((fr == steps) & (e.done != 0), k, fr)
+        f[:] = np.where((f == steps) & (s.done != 0), k, f)
+    s, _, _ = _tracking_rollout(backend, env32, model_grav, table, mdesc, table_ids, N_stat, steps, seed + 1, on_step=on_stat)
+    rr, r = np.array(rr), np.array(r)
+    assert np.isfinite(s.qpos).all() and (s.status & 1 == 0).all()
+    assert np.abs(r - rr).max() <= 0.01 + 0.05 * rr.max(), (r, rr)
+    h_ref, h = np.bincount(fr, minlength=steps + 1) / N_stat, np.bincount(f, minlength=steps + 1) / N_stat
+    assert np.abs(np.cumsum(h) - np.cumsum(h_ref)).max() <= 0.04, (np.cumsum(h), np.cumsum(h_ref))
+    assert (f == fr).mean() >= 0.8, (f == fr).mean()
+    return dict(first_qpos=float(first["eq"].max()), first_qvel=float(first["ev"].max()), reward=float(np.abs(r - rr).max()),
+                same_termination_step=float((f == fr).mean()))
+
+
+def check_alt_rate(backend_factory, model_nograv_or_grav, N=16, seed=57):
+    """The reference's second rate configuration (agents_env/agent_env_template2.py:49-58: timestep = 1/1200, n_frames = 40,
+    env.dt = 1/30): one env step (40 substeps, stable PD with pd_dt = sys.dt) against the float64 oracle."""
+    import copy
+    m = copy.copy(model_nograv_or_grav)
+    m.timestep = 1.0 / 1200.0
+    backend = backend_factory(m)
+    env = OracleEnv(_oracle(m), N)
+    qpos, qvel = random_states(m, N, seed, gravity_heights=False)
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    env.set_state(q32, v32)
+    s = backend.new_state(N)
+    s.set_state(q32, v32)
+    rng = np.random.default_rng(seed)
+    kp, kd = util_data.generate_kp_kd_gains()
+    lo, hi = m.jnt_range[1:, 0], m.jnt_range[1:, 1]
+    tgt = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
+    h = np.float32(1.0 / 1200.0)
+    env.step(tgt, kp, kd, pd_mode=3, pd_dt=float(h), n_frames=40)
+    backend.step(s, tgt, kp, kd, pd_mode=3, pd_dt=float(h), n_frames=40)
+    eq, ev = row_relerr(s.qpos, env.qpos), row_relerr(s.qvel, env.qvel)
+    assert np.allclose(s.time, 40 * h, rtol=1e-5) and np.allclose(s.time, env.time, rtol=1e-5)
+    assert eq.max() <= TOL_32 and ev.max() <= TOL_32, (eq.max(), ev.max())   # 40 contact-free substeps
+    assert (s.status & 7 == 0).all()
+    return float(eq.max()), float(ev.max())

@@ -183,3 +183,57 @@ def test_long_wrapped_rollout_stays_finite(mods, model_grav):
     assert (restarts >= 2).all()                            # episode_length 60 alone ends every env at least twice
     assert 0.0 < rsum / 150 < 1.0
     assert (state.info["steps"] <= 60).all()
+
+
+def test_state_clone_is_independent(mods, model_grav):
+    """State.clone() keeps a copy: stepping the original must not touch the clone's state, metrics, status or clip phase
+    (and the clone's metrics stay bound to its own buffer)."""
+    torch, envs, _ = mods
+    kp, kd = util_data.generate_kp_kd_gains()
+    table = mocap.MotionTable.load(ASSETS / "motions.npz")
+    env = envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=40, reward_mode="mimic", motion_table=table)
+    state = env.reset(2)
+    state = env.step(state, state.pipeline_state.qpos[:, 7:].clone())
+    torch.cuda.synchronize()
+    keep = state.clone()
+    snap = {k: v.clone() for k, v in keep.info.items() if torch.is_tensor(v)}
+    snap_q, snap_m = keep.pipeline_state.qpos.clone(), {k: v.clone() for k, v in keep.metrics.items()}
+    for k in range(3):
+        state = env.step(state, state.pipeline_state.qpos[:, 7:].clone())
+    torch.cuda.synchronize()
+    assert torch.equal(keep.pipeline_state.qpos, snap_q) and not torch.equal(state.pipeline_state.qpos, snap_q)
+    for k, v in snap.items():
+        assert torch.equal(keep.info[k], v), k
+        assert keep.info[k].data_ptr() != state.info[k].data_ptr(), k
+    for k, v in snap_m.items():
+        assert torch.equal(keep.metrics[k], v), k
+    assert (state.metrics["step_index"] == 4).all() and (keep.metrics["step_index"] == 1).all()
+    # the clone steps on its own buffers: its metrics are views of its own _metrics
+    keep = env.step(keep, keep.pipeline_state.qpos[:, 7:].clone())
+    torch.cuda.synchronize()
+    assert (keep.metrics["step_index"] == 2).all() and (state.metrics["step_index"] == 4).all()
+
+
+def test_step_rejects_malformed_inputs(mods, model_grav):
+    """Raw pointers go to the kernel: wrong shapes must raise before the launch instead of reading out of bounds."""
+    torch, envs, pdc = mods
+    kp, kd = util_data.generate_kp_kd_gains()
+    env = envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=8)
+    state = env.reset(0)
+    good = torch.zeros(8, 28, device="cuda")
+    for bad in (torch.zeros(7, 28, device="cuda"), torch.zeros(8, 27, device="cuda"), torch.zeros(8, 28, 3, device="cuda"), torch.zeros(8, 28, 4, 1, device="cuda")):
+        with pytest.raises(ValueError):
+            env.step(state, bad)
+    with pytest.raises(ValueError):
+        env.step_custom_target(state, None, good, torch.zeros(5, device="cuda"))
+    other = envs.HumanoidTrain(None, None, 0.0, {}, model_grav, kp, kd, num_envs=4).reset(0)
+    with pytest.raises(ValueError):
+        env.step(other, good)
+    with pytest.raises(ValueError):
+        pdc.stable_pd_controller_custom_trajectory(torch.zeros(3, 28, device="cuda"), env.sys, state, state.pipeline_state.q, state.pipeline_state.qd,
+                                                   kp, kd, state.pipeline_state.time, 0.002)
+    state = env.step(state, good)                       # the well-formed call still works: (28,) and (28, 4) broadcast
+    state = env.step(state, torch.zeros(28, device="cuda"))
+    state = env.step(state, torch.zeros(28, 4, device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.isfinite(state.obs).all()

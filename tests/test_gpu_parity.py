@@ -141,3 +141,100 @@ def test_contact_rich_statistics(model_grav):
 
 def test_sphere_box_contacts(gpu_grav, model_grav):
     pc.check_sphere_box_contacts(gpu_grav, model_grav, want=30)
+
+
+def test_config3_punch_tracking(model_nograv):
+    """BASELINE configs[2] as named: final_humanoid_no_gravity.xml, punch clip reference-state init, PD targets that track the
+    clip (bench.py --workload contact_free --actions reference), 32 substeps <= 1e-3 per env vs the float64 oracle."""
+    table, mdesc, keep, ids = pc.named_config_setup(model_nograv, ["punch"])
+    out = pc.check_config3_punch_tracking(GpuBackend(model_nograv, mimic_desc=mdesc), model_nograv, table, mdesc, ids, N=256)
+    print("config3", out)
+
+
+def test_config4_backflip_jump(model_grav):
+    """BASELINE configs[3] as named: backflip (even env ids) + jump (odd): first env step per env, then 24-step statistics."""
+    table, mdesc, keep, ids = pc.named_config_setup(model_grav, ["backflip", "jump"])
+    out = pc.check_config4_backflip_jump(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc, ids, N=256, N_stat=1024, steps=24)
+    print("config4", out)
+
+
+def test_alt_rate_1200hz_40_frames(model_nograv, model_grav):
+    """The reference's second rate configuration (agent_env_template2.py:49-58): timestep 1/1200, n_frames 40."""
+    pc.check_alt_rate(lambda m: GpuBackend(m), model_nograv, N=64)
+    pc.check_alt_rate(lambda m: GpuBackend(m), model_grav, N=64)
+
+
+def test_balance_order_is_a_permutation(gpu_grav):
+    """pbrl_balance_order: every env id exactly once (a duplicate would silently skip an env in k_step), sorted by
+    decreasing clamped cost, for costs beyond the 256 bins and negative ones, N in {1, 17, 65536}."""
+    import numpy as np
+    import torch
+    be = gpu_grav
+    L = be.L
+    rng = np.random.default_rng(61)
+    for N in (1, 17, 2368, 65536):
+        for kind in ("small", "wide", "const"):
+            cost = {"small": rng.integers(0, 12, N), "wide": rng.integers(-5, 2000, N), "const": np.full(N, 3)}[kind].astype(np.int32)
+            c = torch.from_numpy(cost).to(be.dev)
+            order = torch.full((N,), -1, dtype=torch.int32, device=be.dev)
+            L.check(L.lib().pbrl_balance_order(be.model.handle, N, L._ptr(c), L._ptr(order), be._stream()))
+            torch.cuda.synchronize()
+            o = order.cpu().numpy()
+            assert np.array_equal(np.sort(o), np.arange(N)), (N, kind)
+            key = np.clip(cost, 0, 255)[o]
+            assert (np.diff(key) <= 0).all(), (N, kind)
+
+
+def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav):
+    """pbrl_batch_reset_host / pbrl_batch_step_host / pbrl_batch_get_state_host (the API bench.py's e2e number flows through)
+    against pbrl_reset / pbrl_step (+ pbrl_balance_order) on device buffers: identical obs / reward / done / stats and
+    state, bit for bit, over several env steps in mimic mode and in reference mode."""
+    import ctypes
+    import numpy as np
+    import torch
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    be = GpuBackend(model_grav, mimic_desc=mdesc)
+    L, lib = be.L, be.L.lib()
+    N = 2500                                     # more than one wave of 148 x 16 slots, ragged tail
+    rng = np.random.default_rng(67)
+    kp, kd = pc.util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for reward_mode in (1, 0):
+        batch = ctypes.c_void_p()
+        L.check(lib.pbrl_batch_create(be.model.handle, N, ctypes.byref(batch)))
+        h_obs, h_rew, h_done, h_stats = np.zeros((N, 69), np.float32), np.zeros((N, 3), np.float32), np.zeros(N, np.float32), np.zeros(8, np.float32)
+        L.check(lib.pbrl_batch_reset_host(batch, reward_mode, vp(mid) if reward_mode else None, vp(t0) if reward_mode else None, vp(h_obs)))
+        # the same on device buffers
+        z = lambda *s: torch.zeros(s, device=be.dev)
+        d = dict(qpos=z(N, 35), qvel=z(N, 34), time=z(N), warm=z(N, 34), ctrl=z(N, 28), qpos_lag=z(N, 35), qvel_lag=z(N, 34), obs=z(N, 69),
+                 reward=z(N, 3), done=z(N), metrics=z(N, 3), status=torch.zeros(N, dtype=torch.int32, device=be.dev), stats=z(8),
+                 cost=torch.zeros(N, dtype=torch.int32, device=be.dev), env_order=torch.arange(N, dtype=torch.int32, device=be.dev))
+        if reward_mode:
+            d["motion_id"], d["ref_t0"] = torch.from_numpy(mid).to(be.dev), torch.from_numpy(t0).to(be.dev)
+        b = L.make_buffers(**d)
+        L.check(lib.pbrl_reset(be.model.handle, N, reward_mode, ctypes.byref(b), be._stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(h_obs, d["obs"].cpu().numpy())
+        kpd, kdd = be._dp(kp), be._dp(kd)
+        for k in range(3):
+            act = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
+            L.check(lib.pbrl_batch_step_host(batch, 8, 3, 1, vp(act), vp(kp), vp(kd), ctypes.c_float(0.002), reward_mode, vp(h_obs), vp(h_rew),
+                                             vp(h_done), vp(h_stats)))
+            a = torch.from_numpy(act).to(be.dev)
+            d["stats"].zero_()
+            L.check(lib.pbrl_step(be.model.handle, N, 8, 3, 1, L._ptr(a), L._ptr(kpd), L._ptr(kdd), ctypes.c_float(0.002), None,
+                                  ctypes.c_uint(0x0FFFFFFF), reward_mode, ctypes.byref(b), be._stream()))
+            L.check(lib.pbrl_balance_order(be.model.handle, N, L._ptr(d["cost"]), L._ptr(d["env_order"]), be._stream()))
+            torch.cuda.synchronize()
+            assert np.array_equal(h_obs, d["obs"].cpu().numpy()), (reward_mode, k)
+            assert np.array_equal(h_rew, d["reward"].cpu().numpy()) and np.array_equal(h_done, d["done"].cpu().numpy()), (reward_mode, k)
+            if reward_mode:   # the statistics are float atomics over warps: same addends, order may differ
+                assert np.allclose(h_stats[:6], d["stats"].cpu().numpy()[:6], rtol=1e-5, atol=1e-3) and h_stats[5] == N
+        q, v, t = np.zeros((N, 35), np.float32), np.zeros((N, 34), np.float32), np.zeros(N, np.float32)
+        L.check(lib.pbrl_batch_get_state_host(batch, vp(q), vp(v), vp(t)))
+        assert np.array_equal(q, d["qpos"].cpu().numpy()) and np.array_equal(v, d["qvel"].cpu().numpy()) and np.array_equal(t, d["time"].cpu().numpy())
+        assert np.array_equal(h_obs, np.concatenate([q, v], 1))
+        lib.pbrl_batch_destroy(batch)

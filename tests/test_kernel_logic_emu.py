@@ -128,3 +128,25 @@ def test_contact_list_overflow_keeps_the_deepest(model_grav):
         if found >= 3:
             break
     assert found >= 2
+
+
+def test_config3_punch_tracking_small(model_nograv):
+    """BASELINE configs[2] by name (no-gravity model, punch clip, clip-tracking PD targets), small batch on the host emulation."""
+    table, mdesc, keep, ids = pc.named_config_setup(model_nograv, ["punch"])
+    b = EmuBackend(model_nograv)
+    b.set_mimic(mdesc)
+    pc.check_config3_punch_tracking(b, model_nograv, table, mdesc, ids, N=12)
+
+
+def test_config4_backflip_jump_small(model_grav):
+    """BASELINE configs[3] by name (backflip on even env ids, jump on odd ones), small batch on the host emulation."""
+    table, mdesc, keep, ids = pc.named_config_setup(model_grav, ["backflip", "jump"])
+    b = EmuBackend(model_grav)
+    b.set_mimic(mdesc)
+    pc.check_config4_backflip_jump(b, model_grav, table, mdesc, ids, N=12, N_stat=48, steps=8)
+
+
+def test_alt_rate_1200hz_40_frames(model_nograv, model_grav):
+    """agents_env/agent_env_template2.py:49-58: timestep 1/1200, n_frames 40."""
+    pc.check_alt_rate(lambda m: EmuBackend(m), model_nograv, N=6)
+    pc.check_alt_rate(lambda m: EmuBackend(m), model_grav, N=6)

@@ -30,6 +30,7 @@ rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr, data = rows[hi], rows[hi + 1:]
 ia, iex, ith, ismp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
+iwf, iwx = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 base = int(data[0][ia], 16)
 agg = {}
@@ -37,16 +38,18 @@ for r in data:
     if len(r) < len(hdr):
         continue
     k = bisect.bisect_right(offs, int(r[ia], 16) - base) - 1
-    a = agg.setdefault(labels[k][0], [0, 0, 0, 0, {}])
-    a[0] += 1; a[1] += int(r[iex]); a[2] += int(r[ith]); a[3] += int(r[ismp])
+    a = agg.setdefault(labels[k][0], [0, 0, 0, 0, {}, 0, 0])
+    a[0] += 1; a[1] += int(r[iex]); a[2] += int(r[ith]); a[3] += int(r[ismp]); a[5] += int(r[iwf]); a[6] += int(r[iwx])
     for i in stall:
         a[4][hdr[i]] = a[4].get(hdr[i], 0) + int(r[i])
 tex, ts = sum(a[1] for a in agg.values()), sum(a[3] for a in agg.values())
 print("total warp inst %.3e  per env-substep %.0f" % (tex, tex / (envs * nf)))
-print(f"{'function':20s} {'sass':>6s} {'exec%':>6s} {'inst/substep':>12s} {'thr/inst':>8s} {'time%':>6s} {'cyc/inst(rel)':>8s}  top stalls (share of the function's samples)")
+twf = sum(a[5] for a in agg.values())
+print("shared-memory wavefronts per env-substep %.0f (excessive %.0f)" % (twf / (envs * nf), sum(a[6] for a in agg.values()) / (envs * nf)))
+print(f"{'function':20s} {'sass':>6s} {'exec%':>6s} {'inst/substep':>12s} {'thr/inst':>8s} {'time%':>6s} {'cyc/inst(rel)':>8s} {'smem wf/substep':>15s} {'excess':>7s}  top stalls (share of the function's samples)")
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][3]):
     if a[1] == 0:
         continue
     top = sorted(a[4].items(), key=lambda kv: -kv[1])[:6]
-    print(f"{n:20s} {a[0]:6d} {100*a[1]/tex:6.2f} {a[1]/(envs*nf):12.0f} {a[2]/max(a[1],1):8.1f} {100*a[3]/ts:6.2f} {a[3]/max(a[1],1)*tex/ts:8.2f}  "
+    print(f"{n:20s} {a[0]:6d} {100*a[1]/tex:6.2f} {a[1]/(envs*nf):12.0f} {a[2]/max(a[1],1):8.1f} {100*a[3]/ts:6.2f} {a[3]/max(a[1],1)*tex/ts:8.2f} {a[5]/(envs*nf):15.0f} {a[6]/(envs*nf):7.0f}  "
           + " ".join(f"{k[6:]}={v/max(a[3],1):.2f}" for k, v in top))
