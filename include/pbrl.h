@@ -70,7 +70,7 @@ typedef struct PbrlModel PbrlModel;
 #define PBRL_MAXPAIR 128
 #define PBRL_MODEL_FIELDS(I, D)                                                                     \
     I(nbody, 1) I(nq, 1) I(nv, 1) I(nu, 1) I(njnt, 1) I(ngeom, 1) I(iterations, 1)                  \
-    I(ls_iterations, 1)                                                                              \
+    I(ls_iterations, 1) I(solver_rule, 1)                                                            \
     D(timestep, 1) D(gravity, 3) D(solref, 2) D(solimp, 5) D(impratio, 1) D(tolerance, 1)           \
     D(ls_tolerance, 1) D(meaninertia, 1)                                                             \
     I(body_parent, PBRL_MAXBODY) D(body_pos, PBRL_MAXBODY * 3) D(body_mass, PBRL_MAXBODY)           \
@@ -88,6 +88,19 @@ typedef struct PbrlModel PbrlModel;
     I(act_dofadr, PBRL_MAXU) D(act_gear, PBRL_MAXU) I(act_ctrllimited, PBRL_MAXU)                   \
     D(act_ctrlrange, PBRL_MAXU * 2)                                                                  \
     I(npair, 1) I(pair_geom1, PBRL_MAXPAIR) I(pair_geom2, PBRL_MAXPAIR)
+
+/* Constraint-solver options (mjOption: iterations, tolerance, ls_iterations, ls_tolerance) and
+ * `solver_rule`, which selects how the primal Newton iteration on qacc stops:
+ *   PBRL_SOLVER_EXACT (0, default)  iterate until a full Newton step with exact line search leaves the active set of the
+ *       piecewise-quadratic cost unchanged -- the minimiser is then reached exactly; at most min(iterations, 12) iterations
+ *       (PBRL_STATUS_SOLVER_MAXITER reports the cap); the line search runs to fp32 resolution.  `tolerance`, `ls_iterations`
+ *       and `ls_tolerance` are not used.
+ *   PBRL_SOLVER_MJX (1)             MuJoCo / MJX's rule: stop when tolerance > improvement / (meaninertia * max(1, nv)) or
+ *       tolerance > |gradient| / (meaninertia * max(1, nv)), at most `iterations` iterations; the line search stops at
+ *       |phi'| < tolerance * ls_tolerance * |search| * meaninertia * max(1, nv) or after `ls_iterations` iterations.
+ * Both rules converge to the same (unique) minimiser; they differ in the stopping point. */
+#define PBRL_SOLVER_EXACT 0
+#define PBRL_SOLVER_MJX 1
 
 typedef struct PbrlModelDesc {
 #define PBRL_I(name, n) int name[n];

@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 
 MODEL_SCALARS = ["nbody", "nq", "nv", "nu", "njnt", "ngeom", "iterations", "ls_iterations", "timestep",
-                 "impratio", "tolerance", "ls_tolerance", "meaninertia", "npair"]
+                 "impratio", "tolerance", "ls_tolerance", "meaninertia", "npair", "solver_rule"]
 MODEL_ARRAYS = ["gravity", "solref", "solimp", "body_parent", "body_pos", "body_mass", "body_ipos",
                 "body_inertia", "body_jntadr", "body_jntnum", "body_dofadr", "body_dofnum", "body_invweight0",
                 "jnt_type", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "jnt_axis", "jnt_pos", "jnt_limited",
@@ -28,6 +28,8 @@ def build_model_desc(model, size_fn, field_fn):
         elif name in ("pair_geom1", "pair_geom2"):
             val = getattr(model, name, None)
             val = np.zeros(0, np.int32) if val is None else val
+        elif name == "solver_rule":  # 0 exact active set (default), 1 MuJoCo / MJX tolerance rule (include/pbrl.h)
+            val = int(getattr(model, "solver_rule", 0))
         else:
             val = getattr(model, name)
         v = np.asarray(val, dtype=dt).ravel()

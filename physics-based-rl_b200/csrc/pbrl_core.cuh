@@ -97,8 +97,8 @@ constexpr int S3 = 3, S4 = 4, S6 = 6, S9 = 9, S10 = 12, S21 = 24;
 constexpr int NBUF6 = 256;  // floats of stage scratch: 32 x 8 pair results of the narrow phase is the largest user
 constexpr int SR = 4;        // contact points: float4 rows
 constexpr int NDL = NV - 3;  // "dof lanes": lane l owns dof l + 3; the lane of dof 3 also emits the free translations 0..2
-constexpr int NEWTON_MAXIT = 12;
-constexpr int LS_MAXIT = 24;
+constexpr int NEWTON_MAXIT = 12;  // iteration cap of the exact-active-set rule (it needs <= 6 in practice; guards against fp32 cycling)
+constexpr int LS_MAXIT = 24;      // line-search cap of the exact-active-set rule
 
 struct Ws {
     // state
@@ -216,6 +216,14 @@ PB_DEV void wsum2(int lane, int n, Fn f, float& s0, float& s1) {
 #endif
     (void)lane;
     s0 = a; s1 = b;
+}
+// sum of one value per lane
+PB_DEV float wreduce(float s) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#endif
+    return s;  // (host emulation: the lane loop already accumulated into one variable)
 }
 // bit mask of the lanes i < n whose predicate holds
 template <class Fn>
@@ -1681,8 +1689,12 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     }
     int it = 0, ndense = 0;
     bool running = constrained;
+    // stop rule (include/pbrl.h: solver_rule): exact active set (default) or MuJoCo / MJX's tolerance-scaled improvement / gradient
+    const bool mjx_rule = m.solver_rule == PBRL_SOLVER_MJX;
+    const int maxit = mjx_rule ? m.solver_iterations : (m.solver_iterations < NEWTON_MAXIT ? m.solver_iterations : NEWTON_MAXIT);
+    const int ls_maxit = mjx_rule ? m.ls_iterations : LS_MAXIT;
     for (;;) {
-        const bool go = running && it < NEWTON_MAXIT;
+        const bool go = running && it < maxit;
         PROF_COUNT(60);
         if (go) PROF_COUNT(61);
         if (coop) { if (!CTA_OR(go ? 1 : 0)) break; }
@@ -1693,6 +1705,10 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         WSYNC();
         rows_JTf(m, w, w.Mp, w.grad, 0, lane);
         PROF(13);
+        if (mjx_rule) {  // mjx solver.solve cond: gradient / (meaninertia * max(1, nv)) < tolerance -> converged (also before the first iteration)
+            const float g2 = wsum(lane, NV, [&](int i) { return w.grad[i] * w.grad[i]; });
+            if (sqrtf(g2) < m.solver_tol) { running = false; continue; }
+        }
         assemble_hessian(m, w, lane);
         PROF(14);
         LANE_LOOP(i, NV) w.p[i] = -w.grad[i];
@@ -1709,8 +1725,9 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         float g0, pMp;
         wsum2(lane, NV, [&](int i, float& a, float& b) { const float pi = w.p[i]; a = fmaf(w.Ma[i] - w.fsmooth[i], pi, a); b = fmaf(w.Mp[i], pi, b); }, g0, pMp);
         float alpha = 1.f, lo = 0.f, hi = -1.f;
-        float d1_0 = 0.f;
-        for (int ls = 0; ls < LS_MAXIT; ls++) {
+        float d1_0 = 0.f, gtol = 0.f;
+        if (mjx_rule) gtol = m.ls_gtol * sqrtf(wsum(lane, NV, [&](int i) { return w.p[i] * w.p[i]; }));
+        for (int ls = 0; ls < ls_maxit; ls++) {
             float d1, d2;  // first and second derivative of the row costs at alpha
             wsum2(lane, 32, [&](int l, float& a, float& b) {
                 if (l < nsr) {
@@ -1734,7 +1751,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
             }, d1, d2);
             float dphi = g0 + alpha * pMp + d1, ddphi = pMp + d2;
             if (ls == 0) d1_0 = fabsf(g0) + fabsf(pMp) + fabsf(d1);
-            if (fabsf(dphi) <= 1e-6f * d1_0) break;
+            if (mjx_rule ? fabsf(dphi) < gtol : fabsf(dphi) <= 1e-6f * d1_0) break;
             if (dphi < 0.f) lo = alpha; else hi = alpha;
             float an = alpha - dphi / ddphi;
             if (!(an > lo) || (hi > 0.f && !(an < hi))) an = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha;
@@ -1744,20 +1761,28 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         PROF(18);
         // step, refresh residuals, detect active-set change
         LANE_LOOP(i, NV) { w.qacc[i] += alpha * w.p[i]; w.Ma[i] += alpha * w.Mp[i]; }
+        float drow = 0.f;  // change of the row costs 1/2 D min(0, jar)^2 along the step (rule 1: cost improvement)
+        auto row_cost = [](float D, float x0, float x1) { const float a = fminf(x0, 0.f), b = fminf(x1, 0.f); return 0.5f * D * (b * b - a * a); };
         const unsigned changed = wballot(lane, 32, [&](int l) {
             int bits = 0;
             if (l < nsr) {
-                w.sc_jar[l] += alpha * w.sc_jp[l];
-                bits |= (w.sc_jar[l] < 0.f) ? 64 : 0;
+                const float x0 = w.sc_jar[l], x1 = x0 + alpha * w.sc_jp[l];
+                w.sc_jar[l] = x1;
+                drow += row_cost(w.sc_r[(l & ~3) + 3], x0, x1);
+                bits |= (x1 < 0.f) ? 64 : 0;
             }
             if (l < NLIM && w.lim_sign[l] != 0.f) {
-                w.lim_jar[l] += alpha * w.lim_jp[l];
-                bits |= (w.lim_jar[l] < 0.f) ? 1 : 0;
+                const float x0 = w.lim_jar[l], x1 = x0 + alpha * w.lim_jp[l];
+                w.lim_jar[l] = x1;
+                drow += row_cost(w.lim_D[l], x0, x1);
+                bits |= (x1 < 0.f) ? 1 : 0;
             }
             if (l < NC && w.con_on[l])
                 for (int e = 0; e < 4; e++) {
-                    w.con_jar[4 * l + e] += alpha * w.con_jp[4 * l + e];
-                    bits |= (w.con_jar[4 * l + e] < 0.f) ? (2 << e) : 0;
+                    const float x0 = w.con_jar[4 * l + e], x1 = x0 + alpha * w.con_jp[4 * l + e];
+                    w.con_jar[4 * l + e] = x1;
+                    drow += row_cost(w.con_D[l], x0, x1);
+                    bits |= (x1 < 0.f) ? (2 << e) : 0;
                 }
             // act_bits[l] still holds the active set this iteration's Hessian was built from
             const bool ch = bits != w.act_bits[l];
@@ -1765,13 +1790,15 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
             return ch;
         });
         WSYNC();
-        // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
         it++;
-        if (changed == 0u) running = false;
+        if (mjx_rule) {  // improvement = cost(a) - cost(a + alpha p) = -(alpha g0 + alpha^2 pMp / 2 + change of the row costs)
+            const float improvement = -(alpha * g0 + 0.5f * alpha * alpha * pMp + wreduce(drow));
+            if (improvement < m.solver_tol) running = false;
+        } else if (changed == 0u) running = false;  // unchanged active set: the Newton step minimised the exact quadratic, i.e. the optimum is reached
         PROF(19);
     }
     if (!constrained) return;
-    if (it >= NEWTON_MAXIT) w.status |= PBRL_STATUS_SOLVER_MAXITER;
+    if (it >= maxit && running) w.status |= PBRL_STATUS_SOLVER_MAXITER;
     w.niter = it;
     w.work = it + PBRL_DENSE_WEIGHT * ndense;  // work estimate: an iteration with the dense Hessian counts more
     rows_JTf(m, w, w.Mp, w.fcon, 1, lane);

@@ -99,6 +99,10 @@ struct DevModel {
     float timestep, gx, gy, gz;
     float sol_k, sol_b, sol_dmin, sol_dmax, sol_width, sol_mid, sol_power, meaninertia;
     float total_mass, plane_z;
+    // constraint-solver options (include/pbrl.h: solver_rule)
+    int solver_rule, solver_iterations, ls_iterations;
+    float solver_tol;   // tolerance * meaninertia * max(1, nv): bound on the cost improvement and on |gradient| (rule 1)
+    float ls_gtol;      // tolerance * ls_tolerance * meaninertia * max(1, nv): bound on |phi'| / |search| (rule 1)
     int nlevel;
     int ndepth;
     float body_pos[NB][3], body_mass[NB], body_ipos[NB][3], body_inertia[NB][6];
@@ -193,6 +197,13 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
         m.sol_power = (float)std::fmax(1.0, d.solimp[4]);
     }
     m.meaninertia = (float)d.meaninertia[0];
+    if (d.solver_rule[0] != PBRL_SOLVER_EXACT && d.solver_rule[0] != PBRL_SOLVER_MJX) return "solver_rule must be 0 (exact active set) or 1 (MJX tolerance rule)";
+    if (d.iterations[0] < 1 || d.ls_iterations[0] < 1) return "iterations and ls_iterations must be >= 1";
+    m.solver_rule = d.solver_rule[0];
+    m.solver_iterations = d.iterations[0];
+    m.ls_iterations = d.ls_iterations[0];
+    m.solver_tol = (float)(d.tolerance[0] * d.meaninertia[0] * (NV > 1 ? NV : 1));
+    m.ls_gtol = (float)(d.tolerance[0] * d.ls_tolerance[0] * d.meaninertia[0] * (NV > 1 ? NV : 1));
     int level[NB] = {0};
     for (int b = 0; b < NB; b++) {
         m.body_parent[b] = d.body_parent[b];

@@ -103,6 +103,7 @@ class ModelConst:
     iterations: int = 100
     ls_iterations: int = 50
     ls_tolerance: float = 0.01
+    solver_rule: int = 0  # how the Newton solver stops: 0 exact active set, 1 MuJoCo / MJX tolerance rule (include/pbrl.h)
     # bodies
     body_names: list = field(default_factory=list)
     body_parent: np.ndarray = None

@@ -238,3 +238,10 @@ def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav):
         assert np.array_equal(q, d["qpos"].cpu().numpy()) and np.array_equal(v, d["qvel"].cpu().numpy()) and np.array_equal(t, d["time"].cpu().numpy())
         assert np.array_equal(h_obs, np.concatenate([q, v], 1))
         lib.pbrl_batch_destroy(batch)
+
+
+def test_solver_rule_mjx_and_options(model_grav):
+    """solver_rule = 1: MuJoCo / MJX's tolerance rule with the model's iterations / tolerance / ls_* options, vs the oracle under
+    the same options; and the distance between the two rules' answers on contact-rich states."""
+    out = pc.check_solver_rule(lambda m: GpuBackend(m), model_grav, N=128, seed=72)
+    print("solver_rule", out)

@@ -150,3 +150,8 @@ def test_alt_rate_1200hz_40_frames(model_nograv, model_grav):
     """agents_env/agent_env_template2.py:49-58: timestep 1/1200, n_frames 40."""
     pc.check_alt_rate(lambda m: EmuBackend(m), model_nograv, N=6)
     pc.check_alt_rate(lambda m: EmuBackend(m), model_grav, N=6)
+
+
+def test_solver_rule_mjx_and_options(model_grav):
+    """PbrlModelDesc.iterations / tolerance / ls_iterations / ls_tolerance are honoured under solver_rule = 1 (MJX's stop rule)."""
+    pc.check_solver_rule(lambda m: EmuBackend(m), model_grav, N=32)
