@@ -62,7 +62,7 @@ def load_assets(workload):
 def self_collision_label(model):
     if not getattr(model, "self_collision", 1):
         return "off"
-    n_eval = int(getattr(model, "n_self_pairs_evaluated", 74))
+    n_eval = int(getattr(model, "n_self_pairs_evaluated", 89))
     return f"{n_eval} of 89 body-vs-body candidates evaluated"
 
 

@@ -361,6 +361,247 @@ static void sphere_box(const REAL* sp, REAL r, const REAL* bp, const REAL* bm, c
     for (int k = 0; k < 3; k++) pos[k] += bp[k];
     make_frame(frame, nw);
 }
+static int argmax_(const REAL* v, int n) { int b = 0; for (int i = 1; i < n; i++) if (v[i] > v[b]) b = i; return b; }
+/* ---- capsule / box against a box (mjx collision_convex.py: capsule_convex, convex_convex through _create_contact_manifold,
+ *      _clip, _clip_edge_to_planes, _closest_segment_point_plane, _project_pt_onto_plane, _manifold_points) [M: restated from the
+ *      published algorithm, mujoco-mjx 3.1.x; no golden exists for these rows -- parity unpinned].  Conventions of this
+ *      restatement where the source could not be consulted: box faces are listed +x, -x, +y, -y, +z, -z with their corners
+ *      counter-clockwise seen from outside; the first maximum / minimum wins every argmax / argmin; contact positions lie
+ *      midway between the two surfaces; manifold picks that coincide with an earlier pick (within 10 microns) are switched off
+ *      (dist = 1), as plane_convex does for repeated indices. */
+static void box_face(const double* half, int f, REAL v[4][3], REAL* n) {
+    int k = f / 2, a = (k + 1) % 3, b = (k + 2) % 3;
+    REAL sg = (f & 1) ? R(-1) : R(1);
+    static const int ccw[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+    for (int i = 0; i < 4; i++) {
+        int j = (f & 1) ? (4 - i) % 4 : i; /* reversed order for the negative face: still counter-clockwise from outside */
+        v[i][k] = sg * R(half[k]); v[i][a] = (REAL)ccw[j][0] * R(half[a]); v[i][b] = (REAL)ccw[j][1] * R(half[b]);
+    }
+    n[0] = n[1] = n[2] = 0; n[k] = sg;
+}
+static void project_pt_onto_plane(REAL* out, const REAL* pt, const REAL* plane_pt, const REAL* n) {
+    REAL t[3] = {pt[0] - plane_pt[0], pt[1] - plane_pt[1], pt[2] - plane_pt[2]}, dd = dot3(t, n);
+    for (int k = 0; k < 3; k++) out[k] = pt[k] - dd * n[k];
+}
+static void closest_segment_point_plane(REAL* out, const REAL* a, const REAL* b, const REAL* p0, const REAL* n) {
+    REAL ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, dd = dot3(p0, n), denom = dot3(n, ab);
+    REAL t = (dd - dot3(n, a)) / (denom + (denom == 0 ? R(1e-6) : 0));
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
+}
+/* clips the edge (e0, e1) against `np` planes (point, outward normal); returns the mask of the clipped edge */
+static int clip_edge_to_planes(const REAL* e0, const REAL* e1, REAL (*ppt)[3], REAL (*pn)[3], int np, REAL out[2][3]) {
+    REAL cand[8][3], best0 = 0, best1 = 0, n0[3], n1[3], e01[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]}, e10[3] = {-e01[0], -e01[1], -e01[2]};
+    int in0[8], in1[8], both = 0;
+    for (int k = 0; k < np; k++) {
+        REAL t0[3] = {e0[0] - ppt[k][0], e0[1] - ppt[k][1], e0[2] - ppt[k][2]}, t1[3] = {e1[0] - ppt[k][0], e1[1] - ppt[k][1], e1[2] - ppt[k][2]};
+        in0[k] = dot3(t0, pn[k]) > R(1e-6);
+        in1[k] = dot3(t1, pn[k]) > R(1e-6);
+        both |= in0[k] && in1[k];
+        closest_segment_point_plane(cand[k], e0, e1, ppt[k], pn[k]);
+    }
+    for (int k = 0; k < np; k++) { /* the clipped point that lies farthest along the edge direction (the end point itself if nothing clips) */
+        const REAL* q0 = in0[k] ? cand[k] : e0;
+        const REAL* q1 = in1[k] ? cand[k] : e1;
+        REAL t0[3] = {q0[0] - e0[0], q0[1] - e0[1], q0[2] - e0[2]}, t1[3] = {q1[0] - e1[0], q1[1] - e1[1], q1[2] - e1[2]};
+        REAL d0 = dot3(t0, e01), d1 = dot3(t1, e10);
+        if (k == 0 || d0 > best0) { best0 = d0; memcpy(n0, q0, sizeof(n0)); }
+        if (k == 0 || d1 > best1) { best1 = d1; memcpy(n1, q1, sizeof(n1)); }
+    }
+    int mask = !both;
+    if (!mask) { memcpy(n0, e0, sizeof(n0)); memcpy(n1, e1, sizeof(n1)); }
+    memcpy(out[0], n0, sizeof(n0));
+    memcpy(out[1], n1, sizeof(n1));
+    REAL dn[3] = {n0[0] - n1[0], n0[1] - n1[1], n0[2] - n1[2]};
+    if (dot3(e10, dn) < 0) mask = 0; /* the clipped end points crossed */
+    return mask;
+}
+/* mjx _manifold_points: four well-spread points among the masked candidates */
+static void manifold_points(REAL (*pt)[3], const int* mask, int n, const REAL* nrm, int idx[4]) {
+    REAL sc[32], ab[3], ac[3], bc[3], e[3], t[3];
+    for (int i = 0; i < n; i++) sc[i] = mask[i] ? 0 : R(-1e6);
+    int a = argmax_(sc, n);
+    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = dot3(t, t) + (mask[i] ? 0 : R(-1e6)); }
+    int b = argmax_(sc, n);
+    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[b][k];
+    cross3(ab, nrm, e);
+    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = R(fabs((double)dot3(t, ab))) + (mask[i] ? 0 : R(-1e6)); }
+    int c = argmax_(sc, n);
+    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[c][k];
+    cross3(ac, nrm, e);
+    for (int k = 0; k < 3; k++) e[k] = pt[b][k] - pt[c][k];
+    cross3(bc, nrm, e);
+    for (int i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) t[k] = pt[b][k] - pt[i][k];
+        sc[i] = R(fabs((double)dot3(t, bc))) + (mask[i] ? 0 : R(-1e6));
+    }
+    int d1 = argmax_(sc, n);
+    REAL s1 = sc[d1];
+    for (int i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k];
+        sc[i] = R(fabs((double)dot3(t, ac))) + (mask[i] ? 0 : R(-1e6));
+    }
+    int d2 = argmax_(sc, n);
+    idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = sc[d2] > s1 ? d2 : d1;
+}
+/* capsule (world centre cpos, frame cmat, radius r, half length hl) against a box: two contacts, normal from the capsule to the box */
+static void capsule_box(const REAL* cpos, const REAL* cmat, REAL r, REAL hl, const REAL* bpos, const REAL* bmat, const double* half,
+                        REAL dist[2], REAL pos[2][3], REAL nrm[2][3]) {
+    REAL dl[3] = {cpos[0] - bpos[0], cpos[1] - bpos[1], cpos[2] - bpos[2]}, axw[3] = {cmat[2], cmat[5], cmat[8]}, cp[3], ax[3], p0[3], p1[3];
+    matT_vec3(cp, bmat, dl);
+    matT_vec3(ax, bmat, axw);
+    for (int k = 0; k < 3; k++) { p0[k] = cp[k] - ax[k] * hl; p1[k] = cp[k] + ax[k] * hl; }
+    /* the face of least penetration among those the (inflated) segment reaches behind */
+    REAL best = 0, fv[4][3], fn[3];
+    int bf = 0, separated = 0; /* a face whose plane the inflated segment does not reach behind separates the two geoms: no face contact */
+    for (int f = 0; f < 6; f++) {
+        box_face(half, f, fv, fn);
+        REAL a[3] = {p0[0] - fn[0] * r - fv[0][0], p0[1] - fn[1] * r - fv[0][1], p0[2] - fn[2] * r - fv[0][2]};
+        REAL b[3] = {p1[0] - fn[0] * r - fv[0][0], p1[1] - fn[1] * r - fv[0][1], p1[2] - fn[2] * r - fv[0][2]};
+        REAL sa = dot3(a, fn), sb = dot3(b, fn), sup = sa < sb ? sa : sb;
+        if (sup >= 0) { sup = R(-1e12); separated = 1; }
+        if (f == 0 || sup > best) { best = sup; bf = f; }
+    }
+    box_face(half, bf, fv, fn);
+    REAL ep0[4][3], ep1[4][3], en[4][3], cl[2][3], lp[2][3], ln[2][3], pen[2];
+    for (int i = 0; i < 4; i++) {
+        REAL e[3];
+        memcpy(ep0[i], fv[(i + 3) % 4], sizeof(ep0[i]));
+        memcpy(ep1[i], fv[i], sizeof(ep1[i]));
+        for (int k = 0; k < 3; k++) e[k] = ep1[i][k] - ep0[i][k];
+        cross3(en[i], e, fn);
+    }
+    int mask = clip_edge_to_planes(p0, p1, ep0, en, 4, cl) && !separated;
+    for (int i = 0; i < 2; i++) {
+        REAL fp[3], t[3];
+        for (int k = 0; k < 3; k++) cl[i][k] -= fn[k] * r;
+        project_pt_onto_plane(fp, cl[i], fv[0], fn);
+        for (int k = 0; k < 3; k++) { lp[i][k] = R(0.5) * (cl[i][k] + fp[k]); ln[i][k] = -fn[k]; t[k] = fp[k] - cl[i][k]; }
+        pen[i] = mask ? dot3(t, fn) : R(-1);
+    }
+    /* a potential edge contact: the edge of that face closest to the capsule's segment */
+    REAL bd = 0, ec[3], cc[3];
+    for (int i = 0; i < 4; i++) {
+        REAL e_[3], c_[3], t[3];
+        closest_segment_to_segment(e_, c_, ep0[i], ep1[i], p0, p1);
+        for (int k = 0; k < 3; k++) t[k] = e_[k] - c_[k];
+        REAL dd = dot3(t, t);
+        if (i == 0 || dd < bd) { bd = dd; memcpy(ec, e_, sizeof(ec)); memcpy(cc, c_, sizeof(cc)); }
+    }
+    REAL ea[3] = {cc[0] - ec[0], cc[1] - ec[1], cc[2] - ec[2]}, eax[3];
+    REAL ed = normalize_with_norm(eax, ea);
+    if (r - ed > 0 && ed > 0) {
+        for (int k = 0; k < 3; k++) { lp[0][k] = R(0.5) * (ec[k] + (cc[k] - eax[k] * r)); ln[0][k] = -eax[k]; }
+        pen[0] = r - ed;
+        pen[1] = R(-1);
+    }
+    for (int i = 0; i < 2; i++) {
+        dist[i] = -pen[i];
+        mat_vec3(pos[i], bmat, lp[i]);
+        for (int k = 0; k < 3; k++) pos[i][k] += bpos[k];
+        mat_vec3(nrm[i], bmat, ln[i]);
+    }
+}
+/* box against box: separating-axis test over the 6 face normals and the 9 edge cross products, then the face manifold
+ * (reference face clipped against the incident one, four well-spread points) or the single edge-edge contact.
+ * Up to four contacts, normal from box 1 to box 2; returns the number of contact slots filled (always 4). */
+static void box_box(const REAL* c1, const REAL* m1, const double* h1, const REAL* c2, const REAL* m2, const double* h2,
+                    REAL dist[4], REAL pos[4][3], REAL nrm[4][3]) {
+    REAL ax[15][3], bestd = 0, bestax[3] = {1, 0, 0}, dc[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+    int besti = -1;
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { ax[i][k] = m1[3 * k + i]; ax[3 + i][k] = m2[3 * k + i]; }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) cross3(ax[6 + 3 * i + j], ax[i], ax[3 + j]);
+    for (int a = 0; a < 15; a++) {
+        REAL L[3], nn = rsqrt_(dot3(ax[a], ax[a]));
+        int degenerate = nn < R(1e-6);
+        for (int k = 0; k < 3; k++) L[k] = degenerate ? ax[a][k] : ax[a][k] / nn;
+        REAL r1 = 0, r2 = 0;
+        for (int i = 0; i < 3; i++) { r1 += R(h1[i]) * R(fabs((double)dot3(ax[i], L))); r2 += R(h2[i]) * R(fabs((double)dot3(ax[3 + i], L))); }
+        REAL pc = dot3(dc, L), d1 = r1 + r2 - pc, d2 = r1 + r2 + pc; /* overlap if box 2 lies on the +L / -L side of box 1 */
+        REAL dd = d1 < d2 ? d1 : d2, sg = d1 > d2 ? R(-1) : R(1);
+        if (degenerate) dd = R(1e6);
+        if (besti < 0 || dd < bestd) { bestd = dd; besti = a; for (int k = 0; k < 3; k++) bestax[k] = sg * L[k]; }
+    }
+    for (int q = 0; q < 4; q++) { dist[q] = 1; for (int k = 0; k < 3; k++) { pos[q][k] = R(0.5) * (c1[k] + c2[k]); nrm[q][k] = bestax[k]; } }
+    if (besti >= 6) { /* edge-edge: the edge of each box that faces the other one, closest points between them */
+        int i = (besti - 6) / 3, j = (besti - 6) % 3;
+        REAL a0[3], a1[3], b0[3], b1[3], pa[3], pb[3], t[3];
+        for (int k = 0; k < 3; k++) { a0[k] = c1[k]; b0[k] = c2[k]; }
+        for (int q = 0; q < 3; q++) {
+            if (q != i) { REAL s = dot3(ax[q], bestax) > 0 ? R(1) : R(-1); for (int k = 0; k < 3; k++) a0[k] += s * R(h1[q]) * ax[q][k]; }
+            if (q != j) { REAL s = dot3(ax[3 + q], bestax) > 0 ? R(-1) : R(1); for (int k = 0; k < 3; k++) b0[k] += s * R(h2[q]) * ax[3 + q][k]; }
+        }
+        for (int k = 0; k < 3; k++) { a1[k] = a0[k] + R(h1[i]) * ax[i][k]; a0[k] -= R(h1[i]) * ax[i][k]; b1[k] = b0[k] + R(h2[j]) * ax[3 + j][k]; b0[k] -= R(h2[j]) * ax[3 + j][k]; }
+        closest_segment_to_segment(pa, pb, a0, a1, b0, b1);
+        for (int k = 0; k < 3; k++) { t[k] = pb[k] - pa[k]; pos[0][k] = R(0.5) * (pa[k] + pb[k]); }
+        dist[0] = dot3(t, bestax);
+        return;
+    }
+    /* face contact: reference face = the face most aligned with the axis (of box 1 towards +axis, of box 2 towards -axis) */
+    REAL amax = 0, bmin = 0;
+    int af = 0, bfc = 0;
+    for (int f = 0; f < 6; f++) {
+        REAL sg = (f & 1) ? R(-1) : R(1), da = sg * dot3(ax[f / 2], bestax), db = sg * dot3(ax[3 + f / 2], bestax);
+        if (f == 0 || da > amax) { amax = da; af = f; }
+        if (f == 0 || db < bmin) { bmin = db; bfc = f; }
+    }
+    int ref1 = amax >= -bmin; /* 1: the reference face belongs to box 1 */
+    const REAL *rc = ref1 ? c1 : c2, *rm = ref1 ? m1 : m2, *ic = ref1 ? c2 : c1, *im = ref1 ? m2 : m1;
+    const double *rh = ref1 ? h1 : h2, *ih = ref1 ? h2 : h1;
+    REAL rv[4][3], rn[3], iv[4][3], in_[3], lv[4][3], ln[3];
+    box_face(rh, ref1 ? af : bfc, lv, ln);
+    for (int q = 0; q < 4; q++) { mat_vec3(rv[q], rm, lv[q]); for (int k = 0; k < 3; k++) rv[q][k] += rc[k]; }
+    mat_vec3(rn, rm, ln);
+    box_face(ih, ref1 ? bfc : af, lv, ln);
+    for (int q = 0; q < 4; q++) { mat_vec3(iv[q], im, lv[q]); for (int k = 0; k < 3; k++) iv[q][k] += ic[k]; }
+    mat_vec3(in_, im, ln);
+    /* mjx _clip: incident edges against the reference side planes, then the (projected) reference edges against the incident side planes */
+    REAL rp0[4][3], rpn[4][3], ip0[4][3], ipn[4][3], cand[16][3], out2[2][3], e[3];
+    int cmask[16];
+    for (int q = 0; q < 4; q++) {
+        memcpy(rp0[q], rv[(q + 3) % 4], sizeof(rp0[q]));
+        for (int k = 0; k < 3; k++) e[k] = rv[q][k] - rp0[q][k];
+        cross3(rpn[q], e, rn);
+        memcpy(ip0[q], iv[(q + 3) % 4], sizeof(ip0[q]));
+        for (int k = 0; k < 3; k++) e[k] = iv[q][k] - ip0[q][k];
+        cross3(ipn[q], e, in_);
+    }
+    for (int q = 0; q < 4; q++) {
+        int mk = clip_edge_to_planes(ip0[q], iv[q], rp0, rpn, 4, out2);
+        memcpy(cand[2 * q], out2[0], sizeof(out2[0])); memcpy(cand[2 * q + 1], out2[1], sizeof(out2[1]));
+        cmask[2 * q] = cmask[2 * q + 1] = mk;
+    }
+    REAL rproj[4][3], dpl = dot3(iv[0], in_), den = dot3(rn, in_);
+    for (int q = 0; q < 4; q++) { /* reference corners moved onto the incident plane along the reference normal */
+        REAL t = (dpl - dot3(rv[q], in_)) / (den + (den == 0 ? R(1e-6) : 0));
+        for (int k = 0; k < 3; k++) rproj[q][k] = rv[q][k] + t * rn[k];
+    }
+    for (int q = 0; q < 4; q++) {
+        int mk = clip_edge_to_planes(rproj[(q + 3) % 4], rproj[q], ip0, ipn, 4, out2);
+        memcpy(cand[8 + 2 * q], out2[0], sizeof(out2[0])); memcpy(cand[8 + 2 * q + 1], out2[1], sizeof(out2[1]));
+        cmask[8 + 2 * q] = cmask[8 + 2 * q + 1] = mk;
+    }
+    REAL onref[16][3];
+    for (int q = 0; q < 16; q++) {
+        REAL t[3] = {cand[q][0] - rv[0][0], cand[q][1] - rv[0][1], cand[q][2] - rv[0][2]};
+        project_pt_onto_plane(onref[q], cand[q], rv[0], rn);
+        cmask[q] = cmask[q] && (-dot3(t, rn) > R(1e-6)); /* behind the reference face */
+    }
+    int idx[4];
+    manifold_points(onref, cmask, 16, rn, idx);
+    for (int q = 0; q < 4; q++) {
+        int unique = 1, p = idx[q];
+        for (int r2 = 0; r2 < q; r2++) { /* a pick that coincides with an earlier one (same candidate, or the shared corner of two clipped edges) is switched off */
+            REAL u[3] = {onref[p][0] - onref[idx[r2]][0], onref[p][1] - onref[idx[r2]][1], onref[p][2] - onref[idx[r2]][2]};
+            if (dot3(u, u) < R(1e-10)) unique = 0;
+        }
+        REAL t[3] = {cand[p][0] - onref[p][0], cand[p][1] - onref[p][1], cand[p][2] - onref[p][2]};
+        REAL pen = -dot3(t, rn);
+        dist[q] = (cmask[p] && unique) ? -pen : R(1);
+        for (int k = 0; k < 3; k++) pos[q][k] = R(0.5) * (cand[p][k] + onref[p][k]);
+    }
+}
 static void capsule_ends(const OrcModel* m, const OrcData* d, int g, REAL* e0, REAL* e1) {
     const REAL* gm = d->geom_xmat + 9 * g;
     for (int k = 0; k < 3; k++) {
@@ -373,7 +614,6 @@ static void plane_sphere(const REAL* n, const REAL* ppos, const REAL* c, REAL r,
     *dist = dot3(t, n) - r;
     for (int k = 0; k < 3; k++) pos[k] = c[k] - n[k] * (r + R(0.5) * (*dist));
 }
-static int argmax_(const REAL* v, int n) { int b = 0; for (int i = 1; i < n; i++) if (v[i] > v[b]) b = i; return b; }
 
 static void collision(const OrcModel* m, OrcData* d) {
     int nc = 0, ng = m->ngeom[0];
@@ -477,7 +717,20 @@ static void collision(const OrcModel* m, OrcData* d) {
     for (int q = 0; q < m->npair[0]; q++) {
         int g1 = m->pair_geom1[q], g2 = m->pair_geom2[q], t1 = m->geom_type[g1], t2 = m->geom_type[g2];
         if (t1 == GEOM_PLANE) continue;
-        if (t2 == GEOM_BOX && t1 != GEOM_SPHERE) { nbox++; continue; } /* capsule-box, box-box: not restated */
+        if (t2 == GEOM_BOX && t1 != GEOM_SPHERE) { /* capsule-box: 2 contact slots, box-box: 4 */
+            REAL margin2 = R(fmax(m->geom_margin[g1], m->geom_margin[g2]) - fmax(m->geom_gap[g1], m->geom_gap[g2]));
+            REAL mu2 = R(fmax(m->geom_friction[3 * g1], m->geom_friction[3 * g2])), dd[4], pp[4][3], nn[4][3], fr2[9];
+            int nslot = t1 == GEOM_CAPSULE ? 2 : 4;
+            if (t1 == GEOM_CAPSULE)
+                capsule_box(d->geom_xpos + 3 * g1, d->geom_xmat + 9 * g1, R(m->geom_size[3 * g1]), R(m->geom_size[3 * g1 + 1]), d->geom_xpos + 3 * g2,
+                            d->geom_xmat + 9 * g2, m->geom_size + 3 * g2, dd, pp, nn);
+            else
+                box_box(d->geom_xpos + 3 * g1, d->geom_xmat + 9 * g1, m->geom_size + 3 * g1, d->geom_xpos + 3 * g2, d->geom_xmat + 9 * g2,
+                        m->geom_size + 3 * g2, dd, pp, nn);
+            for (int q2 = 0; q2 < nslot; q2++)
+                if (dd[q2] - margin2 < 0 && nc < ORC_MAXCON) { make_frame(fr2, nn[q2]); add_contact2(d, &nc, dd[q2], pp[q2], fr2, g1, g2, mu2, margin2); }
+            continue;
+        }
         REAL margin = R(fmax(m->geom_margin[g1], m->geom_margin[g2]) - fmax(m->geom_gap[g1], m->geom_gap[g2]));
         REAL mu = R(fmax(m->geom_friction[3 * g1], m->geom_friction[3 * g2]));
         REAL r1 = R(m->geom_size[3 * g1]), r2 = R(m->geom_size[3 * g2]), fr[9], dist, pos[3], a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
@@ -736,6 +989,17 @@ static void solve_constraints(const OrcModel* m, OrcData* d) {
 }
 
 /* test hooks: the distance functions on their own (tests/test_self_collision.py) */
+void orc_test_capsule_box(const REAL* cpos, const REAL* cmat, REAL r, REAL hl, const REAL* bpos, const REAL* bmat, const double* half,
+                          REAL* dist, REAL* pos, REAL* nrm) {
+    REAL dd[2], pp[2][3], nn[2][3];
+    capsule_box(cpos, cmat, r, hl, bpos, bmat, half, dd, pp, nn);
+    for (int i = 0; i < 2; i++) { dist[i] = dd[i]; for (int k = 0; k < 3; k++) { pos[3 * i + k] = pp[i][k]; nrm[3 * i + k] = nn[i][k]; } }
+}
+void orc_test_box_box(const REAL* c1, const REAL* m1, const double* h1, const REAL* c2, const REAL* m2, const double* h2, REAL* dist, REAL* pos, REAL* nrm) {
+    REAL dd[4], pp[4][3], nn[4][3];
+    box_box(c1, m1, h1, c2, m2, h2, dd, pp, nn);
+    for (int i = 0; i < 4; i++) { dist[i] = dd[i]; for (int k = 0; k < 3; k++) { pos[3 * i + k] = pp[i][k]; nrm[3 * i + k] = nn[i][k]; } }
+}
 void orc_test_capsule_capsule(const REAL* a0, const REAL* a1, REAL r1, const REAL* b0, const REAL* b1, REAL r2, REAL* dist, REAL* pos, REAL* frame) {
     REAL pa[3], pb[3];
     closest_segment_to_segment(pa, pb, a0, a1, b0, b1);

@@ -32,7 +32,7 @@ typedef double REAL;
 #define ORC_MAXJNT 32
 #define ORC_MAXGEOM 20
 #define ORC_MAXPAIR 128
-#define ORC_MAXCON 104 /* 29 floor slots + the self-contacts in range (sphere / capsule / sphere-box pairs: at most 74) */
+#define ORC_MAXCON 136 /* 29 floor slots + the body-vs-body contacts in range: 74 one-contact pairs, 14 capsule-box pairs x 2, 1 box-box pair x 4 (135 slots) */
 #define ORC_MAXEFC (ORC_MAXJNT + 4 * ORC_MAXCON)
 
 /* Model: field names equal the attributes of ModelConst (physics-based-rl_b200/mjcf.py). */

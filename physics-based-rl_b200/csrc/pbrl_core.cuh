@@ -1056,6 +1056,239 @@ PB_DEV float self_row_dot(const Ws& w, const float* j6, const float* vec6, int s
     return dot6(j6, v2);
 }
 
+// ---- capsule / box against a box (mjx collision_convex.py: capsule_convex, convex_convex with _create_contact_manifold, _clip,
+// _clip_edge_to_planes, _manifold_points.  Conventions where the published algorithm leaves a choice: box faces listed +x, -x, +y,
+// -y, +z, -z with corners counter-clockwise seen from outside, the first maximum wins, contact positions midway between the two
+// surfaces, manifold picks that coincide with an earlier one switched off like plane_convex does for repeated indices).  These candidates (14 capsule-box,
+// 1 box-box) are far apart in almost every pose: a lane runs the out-of-line functions below only when its pair passes a
+// bounding-volume test, and the warp skips them when no lane does.
+PB_DEV void box_face_dev(const float* half, int f, float (*v)[3], float* n) {
+    const int k = f >> 1, a = k == 2 ? 0 : k + 1, b = a == 2 ? 0 : a + 1;
+    const float sg = (f & 1) ? -1.f : 1.f;
+    for (int i = 0; i < 4; i++) {
+        const int j = (f & 1) ? ((4 - i) & 3) : i;  // reversed order for the negative face: counter-clockwise seen from outside
+        const float su = (j == 1 || j == 2) ? 1.f : -1.f, sv = (j >= 2) ? 1.f : -1.f;
+        v[i][k] = sg * half[k]; v[i][a] = su * half[a]; v[i][b] = sv * half[b];
+    }
+    n[0] = n[1] = n[2] = 0.f; n[k] = sg;
+}
+PB_DEV void project_on_plane(const float* pt, const float* plane_pt, const float* n, float* out) {
+    const float t[3] = {pt[0] - plane_pt[0], pt[1] - plane_pt[1], pt[2] - plane_pt[2]}, dd = dot3(t, n);
+    for (int k = 0; k < 3; k++) out[k] = pt[k] - dd * n[k];
+}
+PB_DEV void seg_plane_point(const float* a, const float* b, const float* p0, const float* n, float* out) {
+    const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, dd = dot3(p0, n), denom = dot3(n, ab);
+    float t = (dd - dot3(n, a)) / (denom + (denom == 0.f ? 1e-6f : 0.f));
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
+}
+// clips the edge (e0, e1) against four planes (point, outward normal); returns the mask of the clipped edge
+PB_DEV bool clip_edge_4(const float* e0, const float* e1, const float (*ppt)[3], const float (*pn)[3], float (*out)[3]) {
+    float best0 = 0.f, best1 = 0.f, n0[3] = {0.f, 0.f, 0.f}, n1[3] = {0.f, 0.f, 0.f};
+    const float e01[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]}, e10[3] = {-e01[0], -e01[1], -e01[2]};
+    bool both = false;
+    for (int k = 0; k < 4; k++) {
+        const float t0[3] = {e0[0] - ppt[k][0], e0[1] - ppt[k][1], e0[2] - ppt[k][2]}, t1[3] = {e1[0] - ppt[k][0], e1[1] - ppt[k][1], e1[2] - ppt[k][2]};
+        const bool in0 = dot3(t0, pn[k]) > 1e-6f, in1 = dot3(t1, pn[k]) > 1e-6f;
+        both |= in0 && in1;
+        float cand[3], q0[3], q1[3];
+        seg_plane_point(e0, e1, ppt[k], pn[k], cand);
+        for (int c = 0; c < 3; c++) { q0[c] = in0 ? cand[c] : e0[c]; q1[c] = in1 ? cand[c] : e1[c]; }
+        const float u0[3] = {q0[0] - e0[0], q0[1] - e0[1], q0[2] - e0[2]}, u1[3] = {q1[0] - e1[0], q1[1] - e1[1], q1[2] - e1[2]};
+        const float d0 = dot3(u0, e01), d1 = dot3(u1, e10);
+        if (k == 0 || d0 > best0) { best0 = d0; for (int c = 0; c < 3; c++) n0[c] = q0[c]; }
+        if (k == 0 || d1 > best1) { best1 = d1; for (int c = 0; c < 3; c++) n1[c] = q1[c]; }
+    }
+    bool mask = !both;
+    for (int c = 0; c < 3; c++) { out[0][c] = mask ? n0[c] : e0[c]; out[1][c] = mask ? n1[c] : e1[c]; }
+    const float dn[3] = {out[0][0] - out[1][0], out[0][1] - out[1][1], out[0][2] - out[1][2]};
+    if (dot3(e10, dn) < 0.f) mask = false;  // the clipped end points crossed
+    return mask;
+}
+// capsule (world centre c, axis x half length a, radius r) against a box (world centre bc, frame R, half sizes): two contact
+// slots, written as [pos(3), dist, normal(3)] rows; the normal points from the capsule to the box
+PB_DEVN void capsule_box_dev(const float* c, const float* a, float r, const float* bc, const float* R, const float* half, float* out) {
+    const float dl[3] = {c[0] - bc[0], c[1] - bc[1], c[2] - bc[2]};
+    float cp[3], ax[3], p0[3], p1[3];
+    matT_vec(R, dl, cp);
+    matT_vec(R, a, ax);
+    for (int k = 0; k < 3; k++) { p0[k] = cp[k] - ax[k]; p1[k] = cp[k] + ax[k]; }
+    float best = 0.f, fv[4][3], fn[3];
+    int bf = 0;
+    bool separated = false;
+    for (int f = 0; f < 6; f++) {  // support of face f: the lower end of the inflated segment against the face plane
+        const int k = f >> 1;
+        const float sg = (f & 1) ? -1.f : 1.f;
+        float sup = fminf(sg * p0[k], sg * p1[k]) - r - half[k];
+        if (sup >= 0.f) { sup = -1e12f; separated = true; }
+        if (f == 0 || sup > best) { best = sup; bf = f; }
+    }
+    box_face_dev(half, bf, fv, fn);
+    float ep0[4][3], en[4][3], cl[2][3], lp[2][3], ln[2][3], pen[2];
+    for (int i = 0; i < 4; i++) {
+        float e[3];
+        for (int k = 0; k < 3; k++) { ep0[i][k] = fv[(i + 3) & 3][k]; e[k] = fv[i][k] - ep0[i][k]; }
+        cross3(e, fn, en[i]);
+    }
+    const bool mask = clip_edge_4(p0, p1, ep0, en, cl) && !separated;
+    for (int i = 0; i < 2; i++) {
+        float fp[3], t[3];
+        for (int k = 0; k < 3; k++) cl[i][k] -= fn[k] * r;
+        project_on_plane(cl[i], fv[0], fn, fp);
+        for (int k = 0; k < 3; k++) { lp[i][k] = 0.5f * (cl[i][k] + fp[k]); ln[i][k] = -fn[k]; t[k] = fp[k] - cl[i][k]; }
+        pen[i] = mask ? dot3(t, fn) : -1.f;
+    }
+    float bd = 0.f, ec[3] = {0.f, 0.f, 0.f}, cc[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < 4; i++) {  // the edge of that face closest to the capsule's segment
+        float e_[3], c_[3];
+        seg_seg(ep0[i], fv[i], p0, p1, e_, c_);
+        const float t[3] = {e_[0] - c_[0], e_[1] - c_[1], e_[2] - c_[2]}, dd = dot3(t, t);
+        if (i == 0 || dd < bd) { bd = dd; for (int k = 0; k < 3; k++) { ec[k] = e_[k]; cc[k] = c_[k]; } }
+    }
+    const float ea[3] = {cc[0] - ec[0], cc[1] - ec[1], cc[2] - ec[2]};
+    float eax[3];
+    const float ed = normalize_with_norm(ea, eax);
+    if (r - ed > 0.f && ed > 0.f) {
+        for (int k = 0; k < 3; k++) { lp[0][k] = 0.5f * (ec[k] + (cc[k] - eax[k] * r)); ln[0][k] = -eax[k]; }
+        pen[0] = r - ed;
+        pen[1] = -1.f;
+    }
+    for (int i = 0; i < 2; i++) {
+        float pw[3], nw[3];
+        mat_vec(R, lp[i], pw);
+        mat_vec(R, ln[i], nw);
+        for (int k = 0; k < 3; k++) { out[8 * i + k] = pw[k] + bc[k]; out[8 * i + 4 + k] = nw[k]; }
+        out[8 * i + 3] = -pen[i];
+    }
+}
+// mjx _manifold_points over 16 candidates
+PB_DEV void manifold_points_16(const float (*pt)[3], const bool* mask, const float* nrm, int* idx) {
+    float t[3], e[3], ab[3], ac[3], bc[3];
+    int a = 0;
+    for (int i = 15; i >= 0; i--) if (mask[i]) a = i;  // first masked candidate (0 if none)
+    auto pick = [&](auto score) {  // first maximum of score(i) + (mask ? 0 : -1e6)
+        int b = 0;
+        float bs = 0.f;
+        for (int i = 0; i < 16; i++) { const float sc = score(i) + (mask[i] ? 0.f : -1e6f); if (i == 0 || sc > bs) { bs = sc; b = i; } }
+        return b;
+    };
+    const int b = pick([&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return dot3(t, t); });
+    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[b][k];
+    cross3(nrm, e, ab);
+    const int c = pick([&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return fabsf(dot3(t, ab)); });
+    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[c][k];
+    cross3(nrm, e, ac);
+    for (int k = 0; k < 3; k++) e[k] = pt[b][k] - pt[c][k];
+    cross3(nrm, e, bc);
+    auto sbp = [&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[b][k] - pt[i][k]; return fabsf(dot3(t, bc)); };
+    auto sap = [&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return fabsf(dot3(t, ac)); };
+    const int d1 = pick(sbp), d2 = pick(sap);
+    const float s1 = sbp(d1) + (mask[d1] ? 0.f : -1e6f), s2 = sap(d2) + (mask[d2] ? 0.f : -1e6f);
+    idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = s2 > s1 ? d2 : d1;
+}
+// box against box: four contact slots [pos(3), dist, normal(3)], normal from box 1 to box 2
+PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out) {
+    float ax[15][3], bestd = 0.f, bestax[3] = {1.f, 0.f, 0.f};
+    const float dc[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+    int besti = -1;
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { ax[i][k] = R1[3 * k + i]; ax[3 + i][k] = R2[3 * k + i]; }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) cross3(ax[i], ax[3 + j], ax[6 + 3 * i + j]);
+    for (int a = 0; a < 15; a++) {
+        const float nn = sqrtf(dot3(ax[a], ax[a]));
+        const bool degenerate = nn < 1e-6f;
+        float L[3];
+        for (int k = 0; k < 3; k++) L[k] = degenerate ? ax[a][k] : ax[a][k] / nn;
+        float r1 = 0.f, r2 = 0.f;
+        for (int i = 0; i < 3; i++) { r1 += h1[i] * fabsf(dot3(ax[i], L)); r2 += h2[i] * fabsf(dot3(ax[3 + i], L)); }
+        const float pc = dot3(dc, L), d1 = r1 + r2 - pc, d2 = r1 + r2 + pc;
+        float dd = fminf(d1, d2);
+        const float sg = d1 > d2 ? -1.f : 1.f;
+        if (degenerate) dd = 1e6f;
+        if (besti < 0 || dd < bestd) { bestd = dd; besti = a; for (int k = 0; k < 3; k++) bestax[k] = sg * L[k]; }
+    }
+    for (int q = 0; q < 4; q++) {
+        for (int k = 0; k < 3; k++) { out[8 * q + k] = 0.5f * (c1[k] + c2[k]); out[8 * q + 4 + k] = bestax[k]; }
+        out[8 * q + 3] = 1.f;
+    }
+    if (besti >= 6) {  // edge against edge
+        const int i = (besti - 6) / 3, j = (besti - 6) % 3;
+        float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
+        for (int k = 0; k < 3; k++) { a0[k] = c1[k]; b0[k] = c2[k]; }
+        for (int q = 0; q < 3; q++) {
+            if (q != i) { const float sq = dot3(ax[q], bestax) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) a0[k] += sq * h1[q] * ax[q][k]; }
+            if (q != j) { const float sq = dot3(ax[3 + q], bestax) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) b0[k] += sq * h2[q] * ax[3 + q][k]; }
+        }
+        for (int k = 0; k < 3; k++) {
+            a1[k] = a0[k] + h1[i] * ax[i][k]; a0[k] -= h1[i] * ax[i][k];
+            b1[k] = b0[k] + h2[j] * ax[3 + j][k]; b0[k] -= h2[j] * ax[3 + j][k];
+        }
+        seg_seg(a0, a1, b0, b1, pa, pb);
+        const float t[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        for (int k = 0; k < 3; k++) out[k] = 0.5f * (pa[k] + pb[k]);
+        out[3] = dot3(t, bestax);
+        return;
+    }
+    float amax = 0.f, bmin = 0.f;
+    int af = 0, bfc = 0;
+    for (int f = 0; f < 6; f++) {
+        const float sg = (f & 1) ? -1.f : 1.f, da = sg * dot3(ax[f >> 1], bestax), db = sg * dot3(ax[3 + (f >> 1)], bestax);
+        if (f == 0 || da > amax) { amax = da; af = f; }
+        if (f == 0 || db < bmin) { bmin = db; bfc = f; }
+    }
+    const bool ref1 = amax >= -bmin;  // the reference face belongs to box 1
+    const float *rc = ref1 ? c1 : c2, *rm = ref1 ? R1 : R2, *ic = ref1 ? c2 : c1, *im = ref1 ? R2 : R1, *rh = ref1 ? h1 : h2, *ih = ref1 ? h2 : h1;
+    float rv[4][3], rn[3], iv[4][3], inn[3], lv[4][3], ln[3];
+    box_face_dev(rh, ref1 ? af : bfc, lv, ln);
+    for (int q = 0; q < 4; q++) { mat_vec(rm, lv[q], rv[q]); for (int k = 0; k < 3; k++) rv[q][k] += rc[k]; }
+    mat_vec(rm, ln, rn);
+    box_face_dev(ih, ref1 ? bfc : af, lv, ln);
+    for (int q = 0; q < 4; q++) { mat_vec(im, lv[q], iv[q]); for (int k = 0; k < 3; k++) iv[q][k] += ic[k]; }
+    mat_vec(im, ln, inn);
+    float rp0[4][3], rpn[4][3], ip0[4][3], ipn[4][3], cand[16][3], out2[2][3], e[3];
+    bool cmask[16];
+    for (int q = 0; q < 4; q++) {
+        for (int k = 0; k < 3; k++) { rp0[q][k] = rv[(q + 3) & 3][k]; e[k] = rv[q][k] - rp0[q][k]; }
+        cross3(e, rn, rpn[q]);
+        for (int k = 0; k < 3; k++) { ip0[q][k] = iv[(q + 3) & 3][k]; e[k] = iv[q][k] - ip0[q][k]; }
+        cross3(e, inn, ipn[q]);
+    }
+    for (int q = 0; q < 4; q++) {  // incident edges against the reference side planes
+        const bool mk = clip_edge_4(ip0[q], iv[q], rp0, rpn, out2);
+        for (int k = 0; k < 3; k++) { cand[2 * q][k] = out2[0][k]; cand[2 * q + 1][k] = out2[1][k]; }
+        cmask[2 * q] = cmask[2 * q + 1] = mk;
+    }
+    float rproj[4][3];
+    const float dpl = dot3(iv[0], inn), den = dot3(rn, inn);
+    for (int q = 0; q < 4; q++) {  // reference corners moved onto the incident plane along the reference normal
+        const float t = (dpl - dot3(rv[q], inn)) / (den + (den == 0.f ? 1e-6f : 0.f));
+        for (int k = 0; k < 3; k++) rproj[q][k] = rv[q][k] + t * rn[k];
+    }
+    for (int q = 0; q < 4; q++) {  // ... and their edges against the incident side planes
+        const bool mk = clip_edge_4(rproj[(q + 3) & 3], rproj[q], ip0, ipn, out2);
+        for (int k = 0; k < 3; k++) { cand[8 + 2 * q][k] = out2[0][k]; cand[8 + 2 * q + 1][k] = out2[1][k]; }
+        cmask[8 + 2 * q] = cmask[8 + 2 * q + 1] = mk;
+    }
+    float onref[16][3];
+    for (int q = 0; q < 16; q++) {
+        const float t[3] = {cand[q][0] - rv[0][0], cand[q][1] - rv[0][1], cand[q][2] - rv[0][2]};
+        project_on_plane(cand[q], rv[0], rn, onref[q]);
+        cmask[q] = cmask[q] && (-dot3(t, rn) > 1e-6f);  // behind the reference face
+    }
+    int idx[4];
+    manifold_points_16(onref, cmask, rn, idx);
+    for (int q = 0; q < 4; q++) {
+        const int p = idx[q];
+        bool unique = true;
+        for (int r2 = 0; r2 < q; r2++) {  // a pick that coincides with an earlier one (within 10 microns) is switched off
+            const float u[3] = {onref[p][0] - onref[idx[r2]][0], onref[p][1] - onref[idx[r2]][1], onref[p][2] - onref[idx[r2]][2]};
+            unique = unique && !(dot3(u, u) < 1e-10f);
+        }
+        const float t[3] = {cand[p][0] - onref[p][0], cand[p][1] - onref[p][1], cand[p][2] - onref[p][2]};
+        out[8 * q + 3] = (cmask[p] && unique) ? dot3(t, rn) : 1.f;   // dist = -penetration = (incident - reference) . n_ref
+        for (int k = 0; k < 3; k++) out[8 * q + k] = 0.5f * (cand[p][k] + onref[p][k]);
+    }
+}
+
 PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
     if (m.nsp == 0) {
         LANE_IF(z, 1) w.nsc = 0;
@@ -1065,6 +1298,11 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
     float* gc = w.K;            // [NSG] x 4: world centre of each geom            (K is idle outside the Newton iteration)
     float* ga = w.K + 4 * NSG;  // [NSG] x 4: world axis x half length (zero for spheres)
     float* pr = w.buf6;         // [32] x 8: pos(3), dist, normal(3) of the pair a lane evaluated  (buf6 is idle here)
+    float* px = w.K + 8 * NSG;  // [NXROW] x 8: the further contact slots of the capsule-box (1 each) / box-box (3 each) pairs
+    constexpr int NXROW = 24;
+    static_assert(8 * NSG + 8 * NXROW <= NB * S21, "narrow-phase scratch");
+    // row of slot q >= 1 of convex pair e (counted from the first capsule-box pair)
+    auto xrow = [&](int e, int q) { return e < m.nsp_cb ? e : m.nsp_cb + 3 * (e - m.nsp_cb) + (q - 1); };
     LANE_IF(g, NSG) {
         const int b = m.sg_body[g];
         const float* R = w.xmat + S9 * b;
@@ -1074,13 +1312,82 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
         for (int k = 0; k < 3; k++) { gc[4 * g + k] = w.xpos[S3 * b + k] + t[k]; ga[4 * g + k] = a[k] * m.sg_hl[g]; }
     }
     WSYNC();
+    const int n_one = m.nsp_sc + m.nsp_cc + m.nsp_ss + m.nsp_sb;  // pairs with one contact slot; then capsule-box (2), box-box (4)
     int total = 0;
+    // contacts of this round (one row per lane in `pr`, lanes of `act`) join the list; a full list keeps the deepest KS
+    auto commit = [&](unsigned act) {
+        LANE_IF(l, 32) {
+            if ((act >> l) & 1u) {
+                const int slot = total + pop_count(act & ((1u << l) - 1u));
+                if (slot < KS) {
+                    const float* o = pr + 8 * l;
+                    for (int k = 0; k < 3; k++) { w.sc_r[4 * slot + k] = o[k] - w.com[k]; w.sc_n[4 * slot + k] = o[4 + k]; }
+                    w.sc_r[4 * slot + 3] = 0.f;
+                    w.sc_n[4 * slot + 3] = o[3];
+                    w.sc_bb[slot] = float_bits_as_int(o[7]);
+                }
+            }
+        }
+        WSYNC();
+        if (total + pop_count(act) > KS) {  // (warp-uniform, rare) list full: a deeper contact replaces the shallowest one kept
+            LANE_IF(z, 1) {
+                int skip = KS > total ? KS - total : 0;  // the first `skip` contacts of this round got slots above
+                for (unsigned rest = act; rest != 0u; rest &= rest - 1u) {
+                    if (skip > 0) { skip--; continue; }
+                    const float* o = pr + 8 * first_bit(rest);
+                    int worst = 0;
+                    for (int c = 1; c < KS; c++) if (w.sc_n[4 * c + 3] > w.sc_n[4 * worst + 3]) worst = c;
+                    if (o[3] < w.sc_n[4 * worst + 3]) {
+                        for (int k = 0; k < 3; k++) { w.sc_r[4 * worst + k] = o[k] - w.com[k]; w.sc_n[4 * worst + k] = o[4 + k]; }
+                        w.sc_n[4 * worst + 3] = o[3];
+                        w.sc_bb[worst] = float_bits_as_int(o[7]);
+                    }
+                }
+            }
+        }
+        total += pop_count(act);
+        WSYNC();
+    };
     for (int pass = 0; pass * 32 < m.nsp; pass++) {
+        // bounding-volume test of the capsule-box / box-box pairs of this pass: does any lane have to run the convex functions?
+        const unsigned need_convex = wballot(lane, 32, [&](int l) {
+            const int p = l + 32 * pass;
+            if (p < n_one || p >= m.nsp) return false;
+            const int g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+            const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2;
+            if (p < n_one + m.nsp_cb) {  // box centre against the capsule's segment
+                const float *h1 = ga + 4 * g1;
+                const float a0[3] = {c1[0] - h1[0], c1[1] - h1[1], c1[2] - h1[2]}, a1[3] = {c1[0] + h1[0], c1[1] + h1[1], c1[2] + h1[2]};
+                float q[3];
+                seg_point(a0, a1, c2, q);
+                const float d[3] = {q[0] - c2[0], q[1] - c2[1], q[2] - c2[2]}, reach = m.sg_r[g1] + m.box_bound[g2] + m.self_margin;
+                return dot3(d, d) <= reach * reach;
+            }
+            const float d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]}, reach = m.box_bound[g1] + m.box_bound[g2] + m.self_margin;
+            return dot3(d, d) <= reach * reach;
+        });
         const unsigned act = wballot(lane, 32, [&](int l) {
             const int p = l + 32 * pass;
             if (p >= m.nsp) return false;
             const int g1 = m.sp_g1[p], g2 = m.sp_g2[p];
             const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1, *h2 = ga + 4 * g2;
+            float* o = pr + 8 * l;
+            const float bodies = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
+            if (p >= n_one) {  // capsule-box (2 slots) / box-box (4 slots)
+                if (!((need_convex >> l) & 1u)) return false;
+                float res[32];
+                const int nslot = p < n_one + m.nsp_cb ? 2 : 4;
+                if (nslot == 2) capsule_box_dev(c1, h1, m.sg_r[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
+                else box_box_dev(c1, w.xmat + S9 * m.sg_body[g1], m.sg_axis[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
+                for (int k = 0; k < 7; k++) o[k] = res[k];
+                o[7] = bodies;
+                for (int q = 1; q < nslot; q++) {
+                    float* x = px + 8 * xrow(p - n_one, q);
+                    for (int k = 0; k < 7; k++) x[k] = res[8 * q + k];
+                    x[7] = bodies;
+                }
+                return res[3] < m.self_margin;
+            }
             float p1[3], p2[3];
             if (p < m.nsp_sc) {  // sphere - capsule
                 const float b0[3] = {c2[0] - h2[0], c2[1] - h2[1], c2[2] - h2[2]}, b1[3] = {c2[0] + h2[0], c2[1] + h2[1], c2[2] + h2[2]};
@@ -1115,44 +1422,28 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
             const float nrm = normalize_with_norm(dl, n);
             if (nrm == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
             const float dist = nrm - (r1 + r2);
-            float* o = pr + 8 * l;
             for (int k = 0; k < 3; k++) { o[k] = p1[k] + n[k] * (r1 + 0.5f * dist); o[4 + k] = n[k]; }
             o[3] = dist;
-            o[7] = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
+            o[7] = bodies;
             return dist < m.self_margin;
         });
         WSYNC();
-        LANE_IF(l, 32) {
-            if ((act >> l) & 1u) {
-                const int slot = total + pop_count(act & ((1u << l) - 1u));
-                if (slot < KS) {
-                    const float* o = pr + 8 * l;
-                    for (int k = 0; k < 3; k++) { w.sc_r[4 * slot + k] = o[k] - w.com[k]; w.sc_n[4 * slot + k] = o[4 + k]; }
-                    w.sc_r[4 * slot + 3] = 0.f;
-                    w.sc_n[4 * slot + 3] = o[3];
-                    w.sc_bb[slot] = float_bits_as_int(o[7]);
-                }
+        commit(act);
+        if (need_convex != 0u) {  // (warp-uniform, rare) the further slots of the capsule-box / box-box pairs, one round per slot
+            for (int q = 1; q < 4; q++) {
+                const unsigned more = wballot(lane, 32, [&](int l) {
+                    const int p = l + 32 * pass;
+                    if (!((need_convex >> l) & 1u) || q >= (p < n_one + m.nsp_cb ? 2 : 4)) return false;
+                    const float* x = px + 8 * xrow(p - n_one, q);
+                    if (!(x[3] < m.self_margin)) return false;
+                    float* o = pr + 8 * l;
+                    for (int k = 0; k < 8; k++) o[k] = x[k];
+                    return true;
+                });
+                WSYNC();
+                if (more != 0u) commit(more);
             }
         }
-        WSYNC();
-        if (total + pop_count(act) > KS) {  // (warp-uniform, rare) list full: a deeper contact replaces the shallowest one kept
-            LANE_IF(z, 1) {
-                int skip = KS > total ? KS - total : 0;  // the first `skip` contacts of this pass got slots above
-                for (unsigned rest = act; rest != 0u; rest &= rest - 1u) {
-                    if (skip > 0) { skip--; continue; }
-                    const float* o = pr + 8 * first_bit(rest);
-                    int worst = 0;
-                    for (int c = 1; c < KS; c++) if (w.sc_n[4 * c + 3] > w.sc_n[4 * worst + 3]) worst = c;
-                    if (o[3] < w.sc_n[4 * worst + 3]) {
-                        for (int k = 0; k < 3; k++) { w.sc_r[4 * worst + k] = o[k] - w.com[k]; w.sc_n[4 * worst + k] = o[4 + k]; }
-                        w.sc_n[4 * worst + 3] = o[3];
-                        w.sc_bb[worst] = float_bits_as_int(o[7]);
-                    }
-                }
-            }
-        }
-        total += pop_count(act);
-        WSYNC();
     }
     LANE_IF(z, 1) {
         w.nsc = total < KS ? total : KS;
@@ -2101,7 +2392,39 @@ inline void replay_tables_from(const DevModel& m, ReplayTables& t) {  // host si
     for (int i = 0; i <= NQ; i++) t.qpos0[i] = m.qpos0[i];
 }
 namespace replay {
-template <int B>
+// q <- q (x) rot(axis K, half-angle cosine c, sine s), K = 1 / 2 / 3: a coordinate axis (the sign of the axis is folded into s)
+template <int K>
+PB_DEV void quat_mul_axis(float (&q)[4], float c, float s) {
+    const float w = q[0], x = q[1], y = q[2], z = q[3];
+    if constexpr (K == 1) { q[0] = w * c - x * s; q[1] = w * s + x * c; q[2] = y * c + z * s; q[3] = z * c - y * s; }
+    else if constexpr (K == 2) { q[0] = w * c - y * s; q[1] = x * c - z * s; q[2] = w * s + y * c; q[3] = z * c + x * s; }
+    else { q[0] = w * c - z * s; q[1] = x * c + y * s; q[2] = y * c - x * s; q[3] = w * s + z * c; }
+}
+// ql <- product of the rotations of hinges J .. JEND-1 of a body (J0: its first hinge).
+// AXSPEC: the model's hinge axes equal topo::JNT_AXIS_KIND (checked at model creation) -> axis-aligned hinges compose cheaply
+template <int J, int J0, int JEND, bool AXSPEC>
+struct Hinges {
+    PB_MEMBER void run(const ReplayTables& T, const float* qpos, float (&ql)[4]) {
+        if constexpr (J < JEND) {
+            float sn, cs;
+            sincos_half_angle(0.5f * (qpos[6 + J] - T.qpos0[6 + J]), &sn, &cs);
+            constexpr int kind = AXSPEC ? topo::JNT_AXIS_KIND[J] : 0;
+            if constexpr (kind != 0) {
+                constexpr int k = kind > 0 ? kind : -kind;
+                const float s = kind > 0 ? sn : -sn;
+                if constexpr (J == J0) { ql[0] = cs; ql[1] = k == 1 ? s : 0.f; ql[2] = k == 2 ? s : 0.f; ql[3] = k == 3 ? s : 0.f; }
+                else quat_mul_axis<k>(ql, cs, s);
+            } else {
+                float jq[4], qn[4];
+                jq[0] = cs; jq[1] = T.jnt_axis[J][0] * sn; jq[2] = T.jnt_axis[J][1] * sn; jq[3] = T.jnt_axis[J][2] * sn;
+                if constexpr (J == J0) { for (int c = 0; c < 4; c++) ql[c] = jq[c]; }
+                else { quat_mul(ql, jq, qn); for (int c = 0; c < 4; c++) ql[c] = qn[c]; }
+            }
+            Hinges<J + 1, J0, JEND, AXSPEC>::run(T, qpos, ql);
+        }
+    }
+};
+template <int B, bool AXSPEC>
 struct Body {
     PB_MEMBER void run(const ReplayTables& T, const float* qpos, float (&xp)[NB][3], float (&xq)[NB][4], float* xpos, float* xquat) {
         constexpr int P = topo::BODY_PARENT[B], J0 = topo::BODY_JNTADR[B], NJB = topo::BODY_JNTNUM[B];
@@ -2116,31 +2439,25 @@ struct Body {
             for (int c = 0; c < 3; c++) t[c] *= 2.f;
             cross3(xq[P] + 1, t, ut);
             for (int c = 0; c < 3; c++) xp[B][c] = xp[P][c] + (v[c] + xq[P][0] * t[c] + ut[c]);
-#pragma unroll
-            for (int j = J0; j < J0 + NJB; j++) {
-                float sn, cs, jq[4], qn[4];
-                sincos_half_angle(0.5f * (qpos[6 + j] - T.qpos0[6 + j]), &sn, &cs);
-                jq[0] = cs; jq[1] = T.jnt_axis[j][0] * sn; jq[2] = T.jnt_axis[j][1] * sn; jq[3] = T.jnt_axis[j][2] * sn;
-                if (j == J0) { for (int c = 0; c < 4; c++) ql[c] = jq[c]; }
-                else { quat_mul(ql, jq, qn); for (int c = 0; c < 4; c++) ql[c] = qn[c]; }
-            }
+            Hinges<J0, J0, J0 + NJB, AXSPEC>::run(T, qpos, ql);
             quat_mul(xq[P], ql, q);
         }
         quat_normalize_fast(q);
         for (int c = 0; c < 4; c++) xq[B][c] = q[c];
         for (int c = 0; c < 3; c++) xpos[3 * B + c] = xp[B][c];
         for (int c = 0; c < 4; c++) xquat[4 * B + c] = q[c];
-        if constexpr (B + 1 < NB) Body<B + 1>::run(T, qpos, xp, xq, xpos, xquat);
+        if constexpr (B + 1 < NB) Body<B + 1, AXSPEC>::run(T, qpos, xp, xq, xpos, xquat);
     }
 };
 }  // namespace replay
+template <bool AXSPEC>
 PB_DEV void replay_item_fk(const ReplayTables& T, const float* qpos, float* xpos, float* xquat) {
     float xp[NB][3], xq[NB][4];
     xp[0][0] = xp[0][1] = xp[0][2] = 0.f;
     xq[0][0] = 1.f; xq[0][1] = xq[0][2] = xq[0][3] = 0.f;
     for (int c = 0; c < 3; c++) xpos[c] = 0.f;
     xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
-    replay::Body<1>::run(T, qpos, xp, xq, xpos, xquat);
+    replay::Body<1, AXSPEC>::run(T, qpos, xp, xq, xpos, xquat);
 }
 
 // separate-controller path (testing_pds_env3.ipynb cell 21): tau, and optionally dense qM / qfrc_bias

@@ -148,7 +148,10 @@ k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float*
 // 16-byte vectors (the rows of RR_ITEMS consecutive items are contiguous in every output array); the observation rows are
 // copied straight from the clip (a few KB, L1-resident).  The model tables are read through L1 with warp-uniform loads:
 // no per-CTA model copy, so four CTAs (16 warps) fit an SM and hide the latency of the per-thread kinematic chain.
-constexpr int RR_ITEMS = 128;              // items (= threads) per CTA
+#ifndef PBRL_RR_ITEMS
+#define PBRL_RR_ITEMS 128
+#endif
+constexpr int RR_ITEMS = PBRL_RR_ITEMS;    // items (= threads) per CTA
 constexpr int RR_ROW = NB * 3 + NB * 4 + 1;  // 99 floats, odd
 static_assert(RR_ROW % 2 == 1, "odd row stride keeps per-thread rows on distinct banks");
 constexpr size_t RR_SMEM = sizeof(float) * RR_ITEMS * RR_ROW + sizeof(int) * RR_ITEMS;
@@ -167,13 +170,21 @@ __device__ __forceinline__ void rr_store(float* __restrict__ out, const float* t
         else __stcs(reinterpret_cast<float2*>(dst) + v, make_float2(src[0], src[1]));
     }
 }
-__global__ void __launch_bounds__(RR_ITEMS, 4)
+template <bool AXSPEC>
+__global__ void __launch_bounds__(RR_ITEMS, 512 / RR_ITEMS)
 k_replay_rollout(const __grid_constant__ ReplayTables T, int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel,
                  int F, const int* __restrict__ frame0, float* obs, float* reward, float* done, float* xpos, float* xquat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     int* frame = reinterpret_cast<int*>(smem_raw + sizeof(float) * RR_ITEMS * RR_ROW);
     const long long total = (long long)N * K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-lane source columns of an observation row [qpos 35 | qvel 34] (byte pointers into frame 0; a frame adds f * row bytes)
+    const char* src_a = reinterpret_cast<const char*>(data_pos + lane);
+    const bool b_in_qpos = lane < NQ - 32;
+    const char* src_b = b_in_qpos ? reinterpret_cast<const char*>(data_pos + 32 + lane) : reinterpret_cast<const char*>(data_vel + lane - (NQ - 32));
+    const unsigned stride_b = b_in_qpos ? NQ * 4 : NV * 4;
+    const char* src_c = reinterpret_cast<const char*>(data_vel + 64 - NQ + lane);
     for (long long g0 = (long long)blockIdx.x * RR_ITEMS; g0 < total; g0 += (long long)gridDim.x * RR_ITEMS) {
         const long long g = g0 + threadIdx.x;
         const int nitems = total - g0 < RR_ITEMS ? (int)(total - g0) : RR_ITEMS;
@@ -182,27 +193,26 @@ k_replay_rollout(const __grid_constant__ ReplayTables T, int N, int K, const flo
             const int f = ((frame0 ? frame0[e] : e) + k) % F;
             frame[threadIdx.x] = f;
             float* row = tile + threadIdx.x * RR_ROW;
-            if (xpos || xquat) replay_item_fk(T, data_pos + (size_t)f * NQ, row, row + NB * 3);
+            if (xpos || xquat) replay_item_fk<AXSPEC>(T, data_pos + (size_t)f * NQ, row, row + NB * 3);
         }
         __syncthreads();
-        if (obs) {  // obs = [qpos, qvel] of the item's frame (agent_env_template.py:151-155), 16-byte vectors over the block
-            float* dst = obs + g0 * PBRL_OBS;
-            const int tot = nitems * PBRL_OBS, nvec = tot / 4;
-            int row = (4 * threadIdx.x) / PBRL_OBS, col = 4 * threadIdx.x - row * PBRL_OBS;   // of the vector's first element
-            constexpr int DROW = (4 * RR_ITEMS) / PBRL_OBS, DCOL = 4 * RR_ITEMS - DROW * PBRL_OBS;  // advance per iteration
-            auto elem = [&](int r, int c) {
+        if (obs) {
+            // obs = [qpos, qvel] of the item's frame (agent_env_template.py:151-155).  One warp per row: the frame index and the two
+            // source rows are warp-uniform, a lane's column is fixed, so a row costs three loads (the clip is L1-resident) and
+            // three 128-byte streaming stores; consecutive rows are contiguous in the output.
+            static_assert(NQ == 35 && NV == 34 && PBRL_OBS == 69, "column split of the three 32-lane chunks");
+            float* dst = obs + (g0 + warp) * PBRL_OBS + lane;
+#pragma unroll 4
+            for (int r = warp; r < nitems; r += RR_ITEMS / 32, dst += (RR_ITEMS / 32) * PBRL_OBS) {
                 const int f = frame[r];
-                return c < NQ ? __ldg(data_pos + (size_t)f * NQ + c) : __ldg(data_vel + (size_t)f * NV + (c - NQ));
-            };
-            for (int v = threadIdx.x; v < nvec; v += RR_ITEMS) {
-                float r[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) { const bool wrap = col + t >= PBRL_OBS; r[t] = elem(wrap ? row + 1 : row, wrap ? col + t - PBRL_OBS : col + t); }
-                __stcs(reinterpret_cast<float4*>(dst) + v, make_float4(r[0], r[1], r[2], r[3]));
-                row += DROW; col += DCOL;
-                if (col >= PBRL_OBS) { col -= PBRL_OBS; row++; }
+                const float a = __ldg(reinterpret_cast<const float*>(src_a + (size_t)f * (NQ * 4)));      // columns 0..31
+                const float b = __ldg(reinterpret_cast<const float*>(src_b + (size_t)f * stride_b));      // columns 32..63: qpos 32..34, qvel 0..28
+                float c = 0.f;
+                if (lane < PBRL_OBS - 64) c = __ldg(reinterpret_cast<const float*>(src_c + (size_t)f * (NV * 4)));  // columns 64..68: qvel 29..33
+                __stcs(dst, a);
+                __stcs(dst + 32, b);
+                if (lane < PBRL_OBS - 64) __stcs(dst + 64, c);
             }
-            for (int i = 4 * nvec + threadIdx.x; i < tot; i += RR_ITEMS) { const int it = i / PBRL_OBS; dst[i] = elem(it, i - it * PBRL_OBS); }
         }
         rr_store<NB * 3, 2>(xpos, tile, g0, nitems, 0);
         rr_store<NB * 4, 4>(xquat, tile, g0, nitems, NB * 3);
@@ -283,6 +293,7 @@ struct PbrlModel {
     int sm_count = 0;
     int ctas_per_sm = 1;
     int rr_ctas_per_sm = 1;
+    bool axes_match = false;  // the model's hinge axes equal the compiled table topo::JNT_AXIS_KIND (replay kinematics specialisation)
     int phase_lock = 16;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per
                           // iteration is the only CTA-wide sync; PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
@@ -356,11 +367,22 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     if (prepare_kernel(k_step, m) || prepare_kernel(k_reset, m) || prepare_kernel(k_replay, m) || prepare_kernel(k_pd, m) ||
         prepare_kernel(k_debug_forward, m) || prepare_kernel(k_autoreset, m)) { const std::string keep = g_error; return bail(keep); }
     {
-        CREATE_OK(cudaFuncSetAttribute(k_replay_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
-        int nb = 0;
-        CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay_rollout, RR_ITEMS, RR_SMEM));
-        if (nb < 1) return bail("k_replay_rollout does not fit on an SM");
-        m->rr_ctas_per_sm = nb;
+        CREATE_OK(cudaFuncSetAttribute(k_replay_rollout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+        CREATE_OK(cudaFuncSetAttribute(k_replay_rollout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+        int nb = 0, nb2 = 0;
+        CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay_rollout<true>, RR_ITEMS, RR_SMEM));
+        CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_replay_rollout<false>, RR_ITEMS, RR_SMEM));
+        if (nb < 1 || nb2 < 1) return bail("k_replay_rollout does not fit on an SM");
+        m->rr_ctas_per_sm = nb < nb2 ? nb : nb2;
+        m->axes_match = true;
+        for (int j = 0; j < NJ; j++) {
+            const int kind = topo::JNT_AXIS_KIND[j];
+            if (kind == 0) continue;
+            for (int c = 0; c < 3; c++) {
+                const float want = (c + 1 == (kind > 0 ? kind : -kind)) ? (kind > 0 ? 1.f : -1.f) : 0.f;
+                if (m->host.jnt_axis[j][c] != want) m->axes_match = false;
+            }
+        }
     }
     CREATE_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
     CREATE_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
@@ -480,8 +502,9 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
     const long long cap = (long long)m->sm_count * m->rr_ctas_per_sm;
     ReplayTables T;
     replay_tables_from(m->host, T);
-    k_replay_rollout<<<(unsigned)(ctas < cap ? ctas : cap), RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(
-        T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+    if (m->axes_match) k_replay_rollout<true><<<grid, RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+    else k_replay_rollout<false><<<grid, RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
     return check_launch("pbrl_replay_rollout");
 }
 

@@ -24,7 +24,7 @@ constexpr int NLIM = 28;  // limited hinges
 constexpr int NC = 29;    // plane contact slots: 5 spheres + 8 capsules x 2 + 2 boxes x 4
 constexpr int NCP = 32;   // padded
 constexpr int NSG = 15;   // geoms that can touch each other (everything but the floor)
-constexpr int NSP = 80;   // candidate pairs between bodies that are evaluated (SC 32 + CC 24 + SS 8 + SB 10 = 74)
+constexpr int NSP = 96;   // candidate pairs between bodies (SC 32 + CC 24 + SS 8 + SB 10 + CB 14 + BB 1 = 89)
 constexpr int KS = 8;     // body-vs-body contacts kept per env and substep (inside the margin at the same time)
 constexpr int NFAC = 1432;  // rank-1 update operations of one tree-sparse L^T D L factorisation
 constexpr int MAXANC = 12;  // deepest dof chain (ancestors of one dof); checked against the compiled tree below
@@ -127,7 +127,9 @@ struct DevModel {
     // body-vs-body candidates: geom table + pair list ordered [sphere-capsule][capsule-capsule][sphere-sphere][sphere-box]
     // so that the 32 lanes of a pass run (mostly) the same distance function
     int nsp, nsp_sc, nsp_cc, nsp_ss;   // pairs in total / sphere-capsule / capsule-capsule / sphere-sphere (0 pairs: self-collision off)
-    int nbox_pairs;                    // capsule-box and box-box candidates: not evaluated
+    int nsp_sb, nsp_cb, nsp_bb;        // sphere-box / capsule-box (2 contact slots each) / box-box (4 contact slots) pairs
+    int nbox_pairs;                    // capsule-box + box-box candidates
+    float box_bound[NSG];              // boxes: radius of the bounding sphere (prefilter of the capsule-box / box-box pairs)
     float self_margin, self_mu, self_invw_scale;  // includemargin, sliding friction, (1 + mu^2) 2 mu^2 / impratio
     float body_invw[NB];               // body_invweight0[:, 0]
     float sg_pos[NSG][3], sg_axis[NSG][3], sg_r[NSG], sg_hl[NSG];  // (boxes: sg_axis holds the half sizes, the box frame is the body frame)
@@ -376,6 +378,8 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             if (d.geom_type[g] == 6) {
                 if (q[0] != 1.0) return "box geoms must be aligned with their body frame";
                 for (int k = 0; k < 3; k++) m.sg_axis[nsg][k] = (float)d.geom_size[3 * g + k];
+                m.box_bound[nsg] = (float)std::sqrt(d.geom_size[3 * g] * d.geom_size[3 * g] + d.geom_size[3 * g + 1] * d.geom_size[3 * g + 1] +
+                                                    d.geom_size[3 * g + 2] * d.geom_size[3 * g + 2]);
             }
             nsg++;
         }
@@ -383,14 +387,15 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
         int np = d.npair[0];
         if (np < 0 || np > PBRL_MAXPAIR) return "bad npair";
         bool first = true;
-        for (int pass = 0; pass < 4; pass++) {  // 0: sphere-capsule, 1: capsule-capsule, 2: sphere-sphere, 3: sphere-box
+        for (int pass = 0; pass < 6; pass++) {  // 0: sphere-capsule, 1: capsule-capsule, 2: sphere-sphere, 3: sphere-box, 4: capsule-box, 5: box-box
             for (int q = 0; q < np; q++) {
                 const int g1 = d.pair_geom1[q], g2 = d.pair_geom2[q];
                 if (g1 < 0 || g2 < 0 || g1 >= NG || g2 >= NG) return "pair geom out of range";
                 const int t1 = d.geom_type[g1], t2 = d.geom_type[g2];
                 if (g1 == plane || g2 == plane) continue;  // floor pairs are the contact slots above
-                if (t1 == 6 || (t2 == 6 && t1 != 2)) { if (pass == 0) m.nbox_pairs++; continue; }
-                const int kind = (t1 == 2 && t2 == 3) ? 0 : (t1 == 3 && t2 == 3) ? 1 : (t1 == 2 && t2 == 2) ? 2 : (t1 == 2 && t2 == 6) ? 3 : -1;
+                if ((t1 == 6 || (t2 == 6 && t1 != 2)) && pass == 0) m.nbox_pairs++;
+                const int kind = (t1 == 2 && t2 == 3) ? 0 : (t1 == 3 && t2 == 3) ? 1 : (t1 == 2 && t2 == 2) ? 2 : (t1 == 2 && t2 == 6) ? 3 :
+                                 (t1 == 3 && t2 == 6) ? 4 : (t1 == 6 && t2 == 6) ? 5 : -1;
                 if (kind < 0) return "pair geoms must be ordered by type (sphere before capsule)";
                 if (kind != pass) continue;
                 if (m.nsp >= NSP) return "too many body-vs-body pairs";
@@ -404,7 +409,11 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             if (pass == 0) m.nsp_sc = m.nsp;
             if (pass == 1) m.nsp_cc = m.nsp - m.nsp_sc;
             if (pass == 2) m.nsp_ss = m.nsp - m.nsp_sc - m.nsp_cc;
+            if (pass == 3) m.nsp_sb = m.nsp - m.nsp_sc - m.nsp_cc - m.nsp_ss;
+            if (pass == 4) m.nsp_cb = m.nsp - m.nsp_sc - m.nsp_cc - m.nsp_ss - m.nsp_sb;
+            if (pass == 5) m.nsp_bb = m.nsp - m.nsp_sc - m.nsp_cc - m.nsp_ss - m.nsp_sb - m.nsp_cb;
         }
+        if (m.nsp_cb + 3 * m.nsp_bb > 24) return "too many capsule-box / box-box pairs for the narrow-phase scratch";
         m.self_invw_scale = (1.f + m.self_mu * m.self_mu) * 2.f * m.self_mu * m.self_mu / (float)d.impratio[0];
     }
     if (d.jnt_dofadr[0] != 0) return "the free joint must own dofs 0..5";

@@ -83,7 +83,16 @@ int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* r
 int emu_replay_item_fk(const float* qpos, float* xpos, float* xquat) {
     ReplayTables T;
     replay_tables_from(g_model, T);
-    replay_item_fk(T, qpos, xpos, xquat);
+    replay_item_fk<true>(T, qpos, xpos, xquat);
+    return 0;
+}
+// the convex narrow-phase functions on their own (tests/test_self_collision.py): rows of [pos(3), dist, normal(3), -]
+int emu_capsule_box(const float* c, const float* axis_hl, float r, const float* bc, const float* R, const float* half, float* out16) {
+    capsule_box_dev(c, axis_hl, r, bc, R, half, out16);
+    return 0;
+}
+int emu_box_box(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out32) {
+    box_box_dev(c1, R1, h1, c2, R2, h2, out32);
     return 0;
 }
 int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, const float* qpos, const float* qvel,

@@ -245,3 +245,9 @@ def test_solver_rule_mjx_and_options(model_grav):
     the same options; and the distance between the two rules' answers on contact-rich states."""
     out = pc.check_solver_rule(lambda m: GpuBackend(m), model_grav, N=128, seed=72)
     print("solver_rule", out)
+
+
+def test_capsule_box_and_box_box_contacts(gpu_grav, model_grav):
+    """The 15 candidates against the foot boxes (capsule-box x 14, box-box x 1) on the CUDA path: census 89 / 89."""
+    out = pc.check_box_pair_contacts(gpu_grav, model_grav, want=300, seeds=range(400, 480))
+    print("box pairs", out)

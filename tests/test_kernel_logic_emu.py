@@ -155,3 +155,8 @@ def test_alt_rate_1200hz_40_frames(model_nograv, model_grav):
 def test_solver_rule_mjx_and_options(model_grav):
     """PbrlModelDesc.iterations / tolerance / ls_iterations / ls_tolerance are honoured under solver_rule = 1 (MJX's stop rule)."""
     pc.check_solver_rule(lambda m: EmuBackend(m), model_grav, N=32)
+
+
+def test_capsule_box_and_box_box_contacts(emu_grav, model_grav):
+    """The 15 candidates against the foot boxes: same contacts and forces as the oracle."""
+    pc.check_box_pair_contacts(emu_grav, model_grav, want=60)

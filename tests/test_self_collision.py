@@ -228,3 +228,198 @@ def test_segment_distances_against_brute_force():
         pb = b0[None, :] + np.linspace(0, 1, 20001)[:, None] * (b1 - b0)
         dmin = np.sqrt(((pb - c) ** 2).sum(-1)).min() - 0.095
         assert abs(dist.value - dmin) < 2e-5, (case, dist.value, dmin)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# capsule-box and box-box candidates (the 15 pairs against the foot boxes, models/final_humanoid.xml:87,106)
+def _rot(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+
+def _capsule_box(cpos, cmat, r, hl, bpos, bmat, half):
+    lib, ctypes = _hook("orc_test_capsule_box")
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    a = [np.ascontiguousarray(x, float).ravel().copy() for x in (cpos, cmat, bpos, bmat, half)]
+    dist, pos, nrm = np.zeros(2), np.zeros(6), np.zeros(6)
+    lib.orc_test_capsule_box(P(a[0]), P(a[1]), ctypes.c_double(r), ctypes.c_double(hl), P(a[2]), P(a[3]), P(a[4]), P(dist), P(pos), P(nrm))
+    return dist, pos.reshape(2, 3), nrm.reshape(2, 3)
+
+
+def _box_box(c1, m1, h1, c2, m2, h2):
+    lib, ctypes = _hook("orc_test_box_box")
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    a = [np.ascontiguousarray(x, float).ravel().copy() for x in (c1, m1, h1, c2, m2, h2)]
+    dist, pos, nrm = np.zeros(4), np.zeros(12), np.zeros(12)
+    lib.orc_test_box_box(*[P(x) for x in a], P(dist), P(pos), P(nrm))
+    return dist, pos.reshape(4, 3), nrm.reshape(4, 3)
+
+
+FOOT = np.array([0.0885, 0.045, 0.0275])
+
+
+def test_capsule_box_closed_forms():
+    """The oracle's capsule-box function (mjx capsule_convex) on hand-computable placements of a shin-sized capsule
+    (radius .05, half length .155) against a foot-sized box."""
+    r, hl = 0.05, 0.155
+    I = np.eye(3)
+    big = np.array([0.5, 0.5, 0.0275])                 # a wide box: the face case without an edge nearby
+    # lying flat (axis along x) on the top face, 2 mm deep: two contacts under the segment's end points, normal capsule -> box
+    lay = _rot([0, 1, 0], np.pi / 2)                    # capsule z axis -> world x
+    d, pos, n = _capsule_box([0.0, 0.0, 0.0275 + r - 0.002], lay, r, hl, np.zeros(3), I, big)
+    assert np.allclose(d, [-0.002, -0.002], atol=1e-12) and np.allclose(n, [[0, 0, -1]] * 2)
+    assert np.allclose(sorted(pos[:, 0]), [-hl, hl], atol=1e-12) and np.allclose(pos[:, 2], 0.0275 - 0.001, atol=1e-12)
+    # the same capsule overhanging the +x side: its axis passes 48 mm (< radius) above the face's +x edge, and MJX then reports
+    # ONE contact against that edge (and switches the second slot off) instead of the two face contacts
+    d, pos, n = _capsule_box([0.45, 0.0, 0.0275 + r - 0.002], lay, r, hl, np.zeros(3), I, big)
+    assert abs(d[0] + 0.002) < 1e-9 and d[1] == 1.0 and np.allclose(n[0], [0, 0, -1], atol=1e-4) and np.allclose(pos[0], [0.5, 0, 0.0275 - 0.001], atol=1e-5)  # (the 1e-6 regulariser of closest_segment_point shifts the edge point by microns)
+    # tilted by 20 degrees so that the overhanging end rises clear of the edge: the low end is a face contact, the segment is
+    # clipped at the face's side plane (x = 0.5) where the capsule hovers far above the face (slot on, distance positive)
+    th = np.deg2rad(20.0)
+    tilt = _rot([0, 1, 0], np.pi / 2 - th)              # capsule axis = (cos th, 0, sin th)
+    c = np.array([0.40, 0.0, 0.0275 + r - 0.002 + hl * np.sin(th)])
+    d, pos, n = _capsule_box(c, tilt, r, hl, np.zeros(3), I, big)
+    lo_x = 0.40 - hl * np.cos(th)
+    h_clip = (r - 0.002) + (0.5 - lo_x) * np.tan(th)    # height of the axis above the face where it leaves the footprint
+    assert np.allclose(sorted(d), [-0.002, h_clip - r], atol=1e-9) and np.allclose(n, [[0, 0, -1]] * 2)
+    assert np.allclose(sorted(pos[:, 0]), [lo_x, 0.5], atol=1e-9)
+    # hovering 3 mm above: separated along the face normal -> nothing inside the 1 mm margin
+    d, pos, n = _capsule_box([0.0, 0.0, 0.0275 + r + 0.003], lay, r, hl, np.zeros(3), I, big)
+    assert (d > 0.001).all()
+    # standing upright on the middle of the small (foot) box, lower cap 1 mm into the top face: the closest edge is 66 mm from
+    # the segment (> radius), so these are face contacts -- the lower end 1 mm deep, the upper end far above the face
+    d, pos, n = _capsule_box([0.0, 0.0, 0.0275 + hl + r - 0.001], I, r, hl, np.zeros(3), I, FOOT)
+    assert np.allclose(sorted(d), [-0.001, 2 * hl - 0.001], atol=1e-12) and np.allclose(n, [[0, 0, -1]] * 2) and np.allclose(pos[:, :2], 0, atol=1e-12)
+    # the same capsule moved to y = 40 mm: now 5 mm from the face's +y edge (49.3 mm from the segment end) -> ONE contact against that edge, second slot off
+    d, pos, n = _capsule_box([0.0, 0.04, 0.0275 + hl + r - 0.001], I, r, hl, np.zeros(3), I, FOOT)
+    lower, edge_pt = np.array([0.0, 0.04, 0.0275 + r - 0.001]), np.array([0.0, 0.045, 0.0275])
+    gap = np.linalg.norm(lower - edge_pt)
+    assert abs(-d[0] - (r - gap)) < 1e-9 and d[1] == 1.0
+    assert np.allclose(n[0], (edge_pt - lower) / gap, atol=1e-6)                       # from the capsule towards the edge
+    assert np.allclose(pos[0], 0.5 * (edge_pt + lower + (edge_pt - lower) / gap * r), atol=1e-6)
+    # far away: both slots off
+    d, pos, n = _capsule_box([0.5, 0.5, 0.5], I, r, hl, np.zeros(3), I, FOOT)
+    assert (d > 0.001).all()
+    # frame invariance: rotating and translating both geoms together moves the contacts with them
+    R, t = _rot([1, 2, 3], 0.7), np.array([0.3, -0.2, 0.5])
+    d0, p0, n0 = _capsule_box([0.02, 0.01, 0.0275 + r - 0.002], lay, r, hl, np.zeros(3), I, big)
+    d1, p1, n1 = _capsule_box(R @ np.array([0.02, 0.01, 0.0275 + r - 0.002]) + t, R @ lay, r, hl, t, R, big)
+    assert np.allclose(d0, d1, atol=1e-12) and np.allclose(p1, p0 @ R.T + t, atol=1e-12) and np.allclose(n1, n0 @ R.T, atol=1e-12)
+
+
+def test_box_box_closed_forms():
+    """The oracle's box-box function (mjx convex_convex: separating axes + face manifold / edge contact) on hand-computable
+    placements of two foot-sized boxes."""
+    I = np.eye(3)
+    # one foot on top of the other, 2 mm deep, shifted by (2 cm, 1 cm): contacts at corners of the overlap rectangle.  With
+    # exactly parallel edges the last pick of mjx _manifold_points is a tie between a new corner and one already taken (both
+    # are equally far from the triangle's edge), so three or four distinct corners come back; the yawed case below gives four.
+    c2 = np.array([0.02, 0.01, 2 * 0.0275 - 0.002])
+    d, pos, n = _box_box(np.zeros(3), I, FOOT, c2, I, FOOT)
+    on = d < 0
+    assert on.sum() >= 3 and np.allclose(d[on], -0.002, atol=1e-12) and (d[~on] == 1.0).all() and np.allclose(n, [[0, 0, 1]] * 4)  # normal: box 1 -> box 2
+    corners = {(round(x, 9), round(y, 9)) for x in (0.02 - 0.0885, 0.0885) for y in (0.01 - 0.045, 0.045)}
+    got = {(round(x, 9), round(y, 9)) for x, y in pos[on, :2]}
+    assert got <= corners and len(got) == on.sum()
+    assert np.allclose(pos[on, 2], 0.0275 - 0.001, atol=1e-12)                              # midway between the two faces
+    # side by side along y with a 5 mm gap: separated, nothing inside the margin
+    d, pos, n = _box_box(np.zeros(3), I, FOOT, [0, 2 * 0.045 + 0.005, 0], I, FOOT)
+    assert (d > 0.001).all()
+    # side by side, overlapping 1 mm along y: the y faces are the reference / incident pair
+    d, pos, n = _box_box(np.zeros(3), I, FOOT, [0, 2 * 0.045 - 0.001, 0], I, FOOT)
+    on = d < 0
+    assert on.sum() >= 3 and np.allclose(d[on], -0.001, atol=1e-12) and np.allclose(n, [[0, 1, 0]] * 4)
+    assert set(np.round(np.abs(pos[on, 0]), 9)) == {0.0885} and set(np.round(np.abs(pos[on, 2]), 9)) == {0.0275}
+    # edge against edge: box 2 rolled 45 degrees about x and yawed 90 degrees, lowered until its bottom edge dips 1 mm into the
+    # top +x... the two closest edges cross at right angles -> one contact, the other three slots off
+    R2 = _rot([0, 0, 1], np.pi / 2) @ _rot([1, 0, 0], np.pi / 4)
+    R1 = _rot([1, 0, 0], np.pi / 4)
+    reach1 = (0.045 + 0.0275) / np.sqrt(2)              # height of box 1's top edge (along x) above its centre
+    reach2 = (0.045 + 0.0275) / np.sqrt(2)
+    c2 = np.array([0.0, 0.0, reach1 + reach2 - 0.001])
+    d, pos, n = _box_box(np.zeros(3), R1, FOOT, c2, R2, FOOT)
+    assert abs(d[0] + 0.001) < 1e-9 and (d[1:] == 1.0).all()
+    off = (0.045 - 0.0275) / np.sqrt(2)                 # the rolled boxes' extreme edges sit this far off their centre planes
+    assert np.allclose(n[0], [0, 0, 1], atol=1e-9) and np.allclose(np.abs(pos[0]), [off, off, reach1 - 0.0005], atol=1e-5)
+    # frame invariance
+    R, t = _rot([3, 1, 2], 1.1), np.array([-0.4, 0.2, 0.9])
+    c2 = np.array([0.02, 0.01, 2 * 0.0275 - 0.002])
+    Rz = _rot([0, 0, 1], 0.3)
+    d0, p0, n0 = _box_box(np.zeros(3), I, FOOT, c2, Rz, FOOT)
+    d1, p1, n1 = _box_box(t, R, FOOT, R @ c2 + t, R @ Rz, FOOT)
+    assert (d0 < 0).sum() == 4 and np.allclose(d0, d1, atol=1e-10) and np.allclose(p1, p0 @ R.T + t, atol=1e-10) and np.allclose(n1, n0 @ R.T, atol=1e-10)
+    # the rotated overlap polygon: all four contact points lie inside both footprints and 2 mm deep
+    q = p0 - c2
+    assert (np.abs(p0[:, :2]) <= FOOT[:2] + 1e-9).all() and (np.abs(q @ Rz)[:, :2] <= FOOT[:2] + 1e-9).all() and np.allclose(d0, -0.002, atol=1e-12)
+
+
+def test_kernel_convex_functions_against_the_oracle():
+    """The kernel's capsule-box / box-box functions (compiled for the host) against the oracle's on random placements of a
+    shin-sized capsule / a second foot around a foot box.  Capsule-box agrees contact by contact.  Box-box: the last of the four
+    manifold picks can be a near tie between two valid candidates that fp32 / fp64 rounding decides differently -- in a few
+    percent of centimetre-deep random overlaps (the oracle's own fp32 build shows the same rate), well under one percent of
+    the overlaps up to 5 mm that a rollout reaches; everything else agrees contact by contact (distance, position, normal)."""
+    import ctypes
+    from helpers import build_emu
+    from oracle.oracle import HERE
+    emu = ctypes.CDLL(str(build_emu()))
+    o64, o32 = ctypes.CDLL(str(HERE / "liboracle_f64.so")), ctypes.CDLL(str(HERE / "liboracle_f32.so"))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(3)
+
+    def rot():
+        q = rng.normal(size=4)
+        w, x, y, z = q / np.linalg.norm(q)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    margin = 1e-3
+    stats = dict(bb=[0, 0], bb_shallow=[0, 0], bb_o32=[0, 0], cb=[0, 0])
+    for case in range(6000):
+        R1, R2, c2 = rot(), rot(), rng.normal(size=3) * 0.09
+        # box against box
+        a = [np.ascontiguousarray(x, float).ravel().copy() for x in (np.zeros(3), R1, FOOT, c2, R2, FOOT)]
+        b = [x.astype(np.float32) for x in a]
+        d64, p64, n64 = np.zeros(4), np.zeros(12), np.zeros(12)
+        o64.orc_test_box_box(*[P(x) for x in a], P(d64), P(p64), P(n64))
+        on64 = np.sort(d64[d64 < margin])
+        if len(on64):
+            out = np.zeros(32, np.float32)
+            emu.emu_box_box(*[P(x) for x in b], P(out))
+            dk = out.reshape(4, 8)[:, 3]
+            d32, p32, n32 = np.zeros(4, np.float32), np.zeros(12, np.float32), np.zeros(12, np.float32)
+            o32.orc_test_box_box(P(b[0]), P(b[1]), P(a[2]), P(b[3]), P(b[4]), P(a[5]), P(d32), P(p32), P(n32))
+            for name, dd, keys in (("k", dk, ("bb", "bb_shallow")), ("o32", d32, ("bb_o32",))):
+                on = np.sort(dd[dd < margin])
+                bad = len(on) != len(on64) or np.abs(on - on64).max() > 5e-6
+                stats[keys[0]][0] += bad
+                stats[keys[0]][1] += 1
+                if len(keys) > 1 and -on64.min() < 5e-3:
+                    stats[keys[1]][0] += bad
+                    stats[keys[1]][1] += 1
+                    if not bad:   # positions and normals of the shallow contacts too (order-free: match by distance)
+                        rk = out.reshape(4, 8)[np.argsort(np.where(dk < margin, dk, 9))[:len(on)]]
+                        r64 = np.argsort(np.where(d64 < margin, d64, 9))[:len(on)]
+                        if len(on) == 1 or np.diff(on64).min() > 1e-5:
+                            assert np.abs(rk[:, :3] - p64.reshape(4, 3)[r64]).max() < 5e-6 and np.abs(rk[:, 4:7] - n64.reshape(4, 3)[r64]).max() < 5e-5
+        # capsule against box
+        r, hl = 0.05, 0.155
+        cm, cc = rot(), rng.normal(size=3) * 0.12
+        dd64, pp64, nn64 = np.zeros(2), np.zeros(6), np.zeros(6)
+        ac = [np.ascontiguousarray(x, float).ravel().copy() for x in (cc, cm, np.zeros(3), R1, FOOT)]
+        o64.orc_test_capsule_box(P(ac[0]), P(ac[1]), ctypes.c_double(r), ctypes.c_double(hl), P(ac[2]), P(ac[3]), P(ac[4]), P(dd64), P(pp64), P(nn64))
+        onc = np.sort(dd64[dd64 < margin])
+        if len(onc):
+            out = np.zeros(16, np.float32)
+            axis_hl = (cm[:, 2] * hl).astype(np.float32)
+            emu.emu_capsule_box(P(ac[0].astype(np.float32)), P(axis_hl), ctypes.c_float(r), P(ac[2].astype(np.float32)), P(ac[3].astype(np.float32)),
+                                P(ac[4].astype(np.float32)), P(out))
+            dk = out.reshape(2, 8)[:, 3]
+            on = np.sort(dk[dk < margin])
+            bad = len(on) != len(onc) or np.abs(on - onc).max() > 5e-6
+            stats["cb"][0] += bad
+            stats["cb"][1] += 1
+    assert stats["bb"][1] > 1500 and stats["bb_shallow"][1] > 100 and stats["cb"][1] > 1000, stats
+    assert stats["bb_shallow"][0] <= max(1, 0.01 * stats["bb_shallow"][1]), stats   # shallow overlaps: a tie-decided fourth pick at most once in a few hundred
+    assert stats["cb"][0] <= 0.01 * stats["cb"][1], stats             # capsule-box: no tie-sensitive selection
+    assert stats["bb"][0] <= 0.06 * stats["bb"][1] and abs(stats["bb"][0] - stats["bb_o32"][0]) <= 0.02 * stats["bb"][1], stats
