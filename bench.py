@@ -54,6 +54,11 @@ def load_assets(workload):
     model = mjcf.load_model(ROOT / PKG / "assets" / f"{asset}.model.json")
     if os.environ.get("PBRL_BENCH_NO_SELF_COLLISION"):  # ablation: floor contacts only (both arms)
         model.self_collision = 0
+    if os.environ.get("PBRL_BENCH_NO_BOX_PAIRS"):  # ablation: drop the 15 capsule-box / box-box candidates (round-1 coverage: 74 of 89)
+        keep = [i for i in range(len(model.pair_geom1))
+                if not (model.geom_type[model.pair_geom2[i]] == 6 and model.geom_type[model.pair_geom1[i]] in (3, 6))]
+        model.pair_geom1, model.pair_geom2 = model.pair_geom1[keep], model.pair_geom2[keep]
+        model.n_self_pairs_evaluated = 74
     table = mocap.MotionTable.load(ROOT / PKG / "assets" / "motions.npz")
     mdesc, keep = mimic.make_mimic_desc(model, table, clips)
     return model, clips, (table, mdesc, keep), n_env, pd_mode, descr
@@ -509,7 +514,8 @@ def main():
         print(f"stage profile: {tot / nsub:.0f} cycles per env-substep (per warp, incl. stalls)", file=sys.stderr)
         print("  newton iterations per substep: " + " ".join(f"{i - 40}:{hit[i] / nsub:.3f}" for i in range(40, 56) if hit[i]), file=sys.stderr)
         if hit[60]:  # lock-step cost: Newton votes a warp attends vs iterations it runs itself
-            print(f"  newton votes attended per substep {hit[60] / nsub:.3f}, iterations run {hit[61] / nsub:.3f}", file=sys.stderr)
+            print(f"  newton votes attended per substep {hit[60] / nsub:.3f}, iterations run {hit[61] / nsub:.3f}, of which with the dense Hessian {hit[58] / nsub:.4f}", file=sys.stderr)
+            print(f"  substeps in which a warp runs the convex narrow phase (capsule-box / box-box): {hit[63] / max(hit[62], 1):.4f}", file=sys.stderr)
         for i in range(40):
             if hit[i]:
                 print(f"  {i:2d} {names.get(i, '?'):22s} {100.0 * cyc[i] / tot:6.2f}%  hits/substep {hit[i] / nsub:7.3f}  "

@@ -1106,60 +1106,109 @@ PB_DEV bool clip_edge_4(const float* e0, const float* e1, const float (*ppt)[3],
     return mask;
 }
 // capsule (world centre c, axis x half length a, radius r) against a box (world centre bc, frame R, half sizes): two contact
-// slots, written as [pos(3), dist, normal(3)] rows; the normal points from the capsule to the box
+// slots, written as [pos(3), dist, normal(3)] rows; the normal points from the capsule to the box.
+// Register-only: after the face of least penetration is known the problem is rotated into a canonical frame in which that face
+// is the +z face with corners (-,-) (+,-) (+,+) (-,+) (a proper rotation of the box frame: x' y' = the two other axes, swapped
+// for a negative face), so that every array index below is a compile-time constant -- no local memory on this path.
+struct V3 { float x, y, z; };
+PB_DEV float pick3(const float* v, int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
+PB_DEV float dotv(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// closest point of the segment (a, b) to the plane through p0 with normal n (mjx _closest_segment_point_plane)
+PB_DEV V3 seg_plane_v(V3 a, V3 b, V3 p0, V3 n) {
+    const V3 ab = {b.x - a.x, b.y - a.y, b.z - a.z};
+    const float dd = dotv(p0, n), denom = dotv(n, ab);
+    float t = (dd - dotv(n, a)) / (denom + (denom == 0.f ? 1e-6f : 0.f));
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    return V3{a.x + t * ab.x, a.y + t * ab.y, a.z + t * ab.z};
+}
 PB_DEVN void capsule_box_dev(const float* c, const float* a, float r, const float* bc, const float* R, const float* half, float* out) {
     const float dl[3] = {c[0] - bc[0], c[1] - bc[1], c[2] - bc[2]};
-    float cp[3], ax[3], p0[3], p1[3];
+    float cp[3], ax[3], q0[3], q1[3];
     matT_vec(R, dl, cp);
     matT_vec(R, a, ax);
-    for (int k = 0; k < 3; k++) { p0[k] = cp[k] - ax[k]; p1[k] = cp[k] + ax[k]; }
-    float best = 0.f, fv[4][3], fn[3];
-    int bf = 0;
+    for (int k = 0; k < 3; k++) { q0[k] = cp[k] - ax[k]; q1[k] = cp[k] + ax[k]; }
+    float best = 0.f, bsg = 1.f;
+    int bk = 0;
     bool separated = false;
+#pragma unroll
     for (int f = 0; f < 6; f++) {  // support of face f: the lower end of the inflated segment against the face plane
         const int k = f >> 1;
         const float sg = (f & 1) ? -1.f : 1.f;
-        float sup = fminf(sg * p0[k], sg * p1[k]) - r - half[k];
+        float sup = fminf(sg * q0[k], sg * q1[k]) - r - half[k];
         if (sup >= 0.f) { sup = -1e12f; separated = true; }
-        if (f == 0 || sup > best) { best = sup; bf = f; }
+        if (f == 0 || sup > best) { best = sup; bk = k; bsg = sg; }
     }
-    box_face_dev(half, bf, fv, fn);
-    float ep0[4][3], en[4][3], cl[2][3], lp[2][3], ln[2][3], pen[2];
-    for (int i = 0; i < 4; i++) {
-        float e[3];
-        for (int k = 0; k < 3; k++) { ep0[i][k] = fv[(i + 3) & 3][k]; e[k] = fv[i][k] - ep0[i][k]; }
-        cross3(e, fn, en[i]);
+    // canonical frame: z' = sg * axis k, (x', y') = the other two axes in cyclic order, swapped for a negative face
+    const int ia = bk == 2 ? 0 : bk + 1, ib = ia == 2 ? 0 : ia + 1, ix = bsg > 0.f ? ia : ib, iy = bsg > 0.f ? ib : ia;
+    const V3 p0 = {pick3(q0, ix), pick3(q0, iy), bsg * pick3(q0, bk)}, p1 = {pick3(q1, ix), pick3(q1, iy), bsg * pick3(q1, bk)};
+    const float hx = pick3(half, ix), hy = pick3(half, iy), hz = pick3(half, bk);
+    // side planes of the face in edge order (edge i runs from corner i-1 to corner i): x' = -hx, y' = -hy, x' = +hx, y' = +hy
+    const V3 pp[4] = {{-hx, hy, hz}, {-hx, -hy, hz}, {hx, -hy, hz}, {hx, hy, hz}};       // edge start points (corner i-1)
+    const V3 pe[4] = {{-hx, -hy, hz}, {hx, -hy, hz}, {hx, hy, hz}, {-hx, hy, hz}};       // edge end points (corner i)
+    // (edge x face normal, unnormalised like mjx: length of the edge)
+    const V3 pn[4] = {{-2.f * hy, 0.f, 0.f}, {0.f, -2.f * hx, 0.f}, {2.f * hy, 0.f, 0.f}, {0.f, 2.f * hx, 0.f}};
+    // mjx _clip_edge_to_planes on the segment
+    const V3 e01 = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, e10 = {-e01.x, -e01.y, -e01.z};
+    V3 n0 = p0, n1 = p1;
+    float best0 = 0.f, best1 = 0.f;
+    bool both = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const V3 t0 = {p0.x - pp[k].x, p0.y - pp[k].y, p0.z - pp[k].z}, t1 = {p1.x - pp[k].x, p1.y - pp[k].y, p1.z - pp[k].z};
+        const bool in0 = dotv(t0, pn[k]) > 1e-6f, in1 = dotv(t1, pn[k]) > 1e-6f;
+        both |= in0 && in1;
+        const V3 cand = seg_plane_v(p0, p1, pp[k], pn[k]);
+        const V3 c0 = in0 ? cand : p0, c1 = in1 ? cand : p1;
+        const V3 u0 = {c0.x - p0.x, c0.y - p0.y, c0.z - p0.z}, u1 = {c1.x - p1.x, c1.y - p1.y, c1.z - p1.z};
+        const float d0 = dotv(u0, e01), d1 = dotv(u1, e10);
+        if (k == 0 || d0 > best0) { best0 = d0; n0 = c0; }
+        if (k == 0 || d1 > best1) { best1 = d1; n1 = c1; }
     }
-    const bool mask = clip_edge_4(p0, p1, ep0, en, cl) && !separated;
-    for (int i = 0; i < 2; i++) {
-        float fp[3], t[3];
-        for (int k = 0; k < 3; k++) cl[i][k] -= fn[k] * r;
-        project_on_plane(cl[i], fv[0], fn, fp);
-        for (int k = 0; k < 3; k++) { lp[i][k] = 0.5f * (cl[i][k] + fp[k]); ln[i][k] = -fn[k]; t[k] = fp[k] - cl[i][k]; }
-        pen[i] = mask ? dot3(t, fn) : -1.f;
-    }
-    float bd = 0.f, ec[3] = {0.f, 0.f, 0.f}, cc[3] = {0.f, 0.f, 0.f};
-    for (int i = 0; i < 4; i++) {  // the edge of that face closest to the capsule's segment
+    bool mask = !both;
+    V3 cl0 = mask ? n0 : p0, cl1 = mask ? n1 : p1;
+    { const V3 dn = {cl0.x - cl1.x, cl0.y - cl1.y, cl0.z - cl1.z}; if (dotv(e10, dn) < 0.f) mask = false; }
+    mask = mask && !separated;
+    // face contacts: the clipped end points lowered by the radius, against the face plane z' = hz
+    cl0.z -= r; cl1.z -= r;
+    V3 lp0 = {cl0.x, cl0.y, 0.5f * (cl0.z + hz)}, lp1 = {cl1.x, cl1.y, 0.5f * (cl1.z + hz)};
+    V3 ln0 = {0.f, 0.f, -1.f}, ln1 = {0.f, 0.f, -1.f};
+    float pen0 = mask ? hz - cl0.z : -1.f, pen1 = mask ? hz - cl1.z : -1.f;
+    // a potential edge contact: the edge of that face closest to the capsule's segment
+    float bd = 0.f;
+    V3 ec = {0.f, 0.f, 0.f}, cc = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
         float e_[3], c_[3];
-        seg_seg(ep0[i], fv[i], p0, p1, e_, c_);
+        const float s0[3] = {pp[k].x, pp[k].y, pp[k].z}, s1[3] = {pe[k].x, pe[k].y, pe[k].z}, t0[3] = {p0.x, p0.y, p0.z}, t1[3] = {p1.x, p1.y, p1.z};
+        seg_seg(s0, s1, t0, t1, e_, c_);
         const float t[3] = {e_[0] - c_[0], e_[1] - c_[1], e_[2] - c_[2]}, dd = dot3(t, t);
-        if (i == 0 || dd < bd) { bd = dd; for (int k = 0; k < 3; k++) { ec[k] = e_[k]; cc[k] = c_[k]; } }
+        if (k == 0 || dd < bd) { bd = dd; ec = V3{e_[0], e_[1], e_[2]}; cc = V3{c_[0], c_[1], c_[2]}; }
     }
-    const float ea[3] = {cc[0] - ec[0], cc[1] - ec[1], cc[2] - ec[2]};
-    float eax[3];
-    const float ed = normalize_with_norm(ea, eax);
-    if (r - ed > 0.f && ed > 0.f) {
-        for (int k = 0; k < 3; k++) { lp[0][k] = 0.5f * (ec[k] + (cc[k] - eax[k] * r)); ln[0][k] = -eax[k]; }
-        pen[0] = r - ed;
-        pen[1] = -1.f;
+    {
+        const float ea[3] = {cc.x - ec.x, cc.y - ec.y, cc.z - ec.z};
+        float eax[3];
+        const float ed = normalize_with_norm(ea, eax);
+        if (r - ed > 0.f && ed > 0.f) {
+            lp0 = V3{0.5f * (ec.x + (cc.x - eax[0] * r)), 0.5f * (ec.y + (cc.y - eax[1] * r)), 0.5f * (ec.z + (cc.z - eax[2] * r))};
+            ln0 = V3{-eax[0], -eax[1], -eax[2]};
+            pen0 = r - ed;
+            pen1 = -1.f;
+        }
     }
-    for (int i = 0; i < 2; i++) {
-        float pw[3], nw[3];
-        mat_vec(R, lp[i], pw);
-        mat_vec(R, ln[i], nw);
-        for (int k = 0; k < 3; k++) { out[8 * i + k] = pw[k] + bc[k]; out[8 * i + 4 + k] = nw[k]; }
-        out[8 * i + 3] = -pen[i];
-    }
+    // back to the box frame (component ix <- x', iy <- y', bk <- sg z'), then to the world
+    auto emit = [&](V3 lp, V3 ln, float pen, float* o) {
+        float pl[3], nl[3], pw[3], nw[3];
+        for (int k = 0; k < 3; k++) {
+            pl[k] = k == ix ? lp.x : (k == iy ? lp.y : bsg * lp.z);
+            nl[k] = k == ix ? ln.x : (k == iy ? ln.y : bsg * ln.z);
+        }
+        mat_vec(R, pl, pw);
+        mat_vec(R, nl, nw);
+        for (int k = 0; k < 3; k++) { o[k] = pw[k] + bc[k]; o[4 + k] = nw[k]; }
+        o[3] = -pen;
+    };
+    emit(lp0, ln0, pen0, out);
+    emit(lp1, ln1, pen1, out + 8);
 }
 // mjx _manifold_points over 16 candidates
 PB_DEV void manifold_points_16(const float (*pt)[3], const bool* mask, const float* nrm, int* idx) {
@@ -1187,8 +1236,23 @@ PB_DEV void manifold_points_16(const float (*pt)[3], const bool* mask, const flo
     idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = s2 > s1 ? d2 : d1;
 }
 // box against box: four contact slots [pos(3), dist, normal(3)], normal from box 1 to box 2
-PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out) {
-    float ax[15][3], bestd = 0.f, bestax[3] = {1.f, 0.f, 0.f};
+// `scratch`: 300 floats of the caller's shared-memory workspace (the arrays below are indexed dynamically; in local memory they
+// cost an L2 round trip per access)
+PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out,
+                         float* scratch) {
+    float (*ax)[3] = reinterpret_cast<float (*)[3]>(scratch);               // [15][3]
+    float (*rv)[3] = reinterpret_cast<float (*)[3]>(scratch + 45);          // [4][3] reference face corners
+    float (*iv)[3] = reinterpret_cast<float (*)[3]>(scratch + 57);          // [4][3] incident face corners
+    float (*lv)[3] = reinterpret_cast<float (*)[3]>(scratch + 69);          // [4][3]
+    float (*rp0)[3] = reinterpret_cast<float (*)[3]>(scratch + 81);         // side planes of the reference / incident face
+    float (*rpn)[3] = reinterpret_cast<float (*)[3]>(scratch + 93);
+    float (*ip0)[3] = reinterpret_cast<float (*)[3]>(scratch + 105);
+    float (*ipn)[3] = reinterpret_cast<float (*)[3]>(scratch + 117);
+    float (*cand)[3] = reinterpret_cast<float (*)[3]>(scratch + 129);       // [16][3]
+    float (*onref)[3] = reinterpret_cast<float (*)[3]>(scratch + 177);      // [16][3]
+    float (*rproj)[3] = reinterpret_cast<float (*)[3]>(scratch + 225);      // [4][3]
+    bool* cmask = reinterpret_cast<bool*>(scratch + 237);                   // [16]
+    float bestd = 0.f, bestax[3] = {1.f, 0.f, 0.f};
     const float dc[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
     int besti = -1;
     for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { ax[i][k] = R1[3 * k + i]; ax[3 + i][k] = R2[3 * k + i]; }
@@ -1237,15 +1301,14 @@ PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, cons
     }
     const bool ref1 = amax >= -bmin;  // the reference face belongs to box 1
     const float *rc = ref1 ? c1 : c2, *rm = ref1 ? R1 : R2, *ic = ref1 ? c2 : c1, *im = ref1 ? R2 : R1, *rh = ref1 ? h1 : h2, *ih = ref1 ? h2 : h1;
-    float rv[4][3], rn[3], iv[4][3], inn[3], lv[4][3], ln[3];
+    float rn[3], inn[3], ln[3];
     box_face_dev(rh, ref1 ? af : bfc, lv, ln);
     for (int q = 0; q < 4; q++) { mat_vec(rm, lv[q], rv[q]); for (int k = 0; k < 3; k++) rv[q][k] += rc[k]; }
     mat_vec(rm, ln, rn);
     box_face_dev(ih, ref1 ? bfc : af, lv, ln);
     for (int q = 0; q < 4; q++) { mat_vec(im, lv[q], iv[q]); for (int k = 0; k < 3; k++) iv[q][k] += ic[k]; }
     mat_vec(im, ln, inn);
-    float rp0[4][3], rpn[4][3], ip0[4][3], ipn[4][3], cand[16][3], out2[2][3], e[3];
-    bool cmask[16];
+    float out2[2][3], e[3];
     for (int q = 0; q < 4; q++) {
         for (int k = 0; k < 3; k++) { rp0[q][k] = rv[(q + 3) & 3][k]; e[k] = rv[q][k] - rp0[q][k]; }
         cross3(e, rn, rpn[q]);
@@ -1257,7 +1320,6 @@ PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, cons
         for (int k = 0; k < 3; k++) { cand[2 * q][k] = out2[0][k]; cand[2 * q + 1][k] = out2[1][k]; }
         cmask[2 * q] = cmask[2 * q + 1] = mk;
     }
-    float rproj[4][3];
     const float dpl = dot3(iv[0], inn), den = dot3(rn, inn);
     for (int q = 0; q < 4; q++) {  // reference corners moved onto the incident plane along the reference normal
         const float t = (dpl - dot3(rv[q], inn)) / (den + (den == 0.f ? 1e-6f : 0.f));
@@ -1268,7 +1330,6 @@ PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, cons
         for (int k = 0; k < 3; k++) { cand[8 + 2 * q][k] = out2[0][k]; cand[8 + 2 * q + 1][k] = out2[1][k]; }
         cmask[8 + 2 * q] = cmask[8 + 2 * q + 1] = mk;
     }
-    float onref[16][3];
     for (int q = 0; q < 16; q++) {
         const float t[3] = {cand[q][0] - rv[0][0], cand[q][1] - rv[0][1], cand[q][2] - rv[0][2]};
         project_on_plane(cand[q], rv[0], rn, onref[q]);
@@ -1300,7 +1361,7 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
     float* pr = w.buf6;         // [32] x 8: pos(3), dist, normal(3) of the pair a lane evaluated  (buf6 is idle here)
     float* px = w.K + 8 * NSG;  // [NXROW] x 8: the further contact slots of the capsule-box (1 each) / box-box (3 each) pairs
     constexpr int NXROW = 24;
-    static_assert(8 * NSG + 8 * NXROW <= NB * S21, "narrow-phase scratch");
+    static_assert(8 * NSG + 8 * NXROW <= NB * S21 && NM >= 300, "narrow-phase scratch (box_box_dev works in the idle factor workspace LD)");
     // row of slot q >= 1 of convex pair e (counted from the first capsule-box pair)
     auto xrow = [&](int e, int q) { return e < m.nsp_cb ? e : m.nsp_cb + 3 * (e - m.nsp_cb) + (q - 1); };
     LANE_IF(g, NSG) {
@@ -1348,46 +1409,14 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
         total += pop_count(act);
         WSYNC();
     };
-    for (int pass = 0; pass * 32 < m.nsp; pass++) {
-        // bounding-volume test of the capsule-box / box-box pairs of this pass: does any lane have to run the convex functions?
-        const unsigned need_convex = wballot(lane, 32, [&](int l) {
-            const int p = l + 32 * pass;
-            if (p < n_one || p >= m.nsp) return false;
-            const int g1 = m.sp_g1[p], g2 = m.sp_g2[p];
-            const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2;
-            if (p < n_one + m.nsp_cb) {  // box centre against the capsule's segment
-                const float *h1 = ga + 4 * g1;
-                const float a0[3] = {c1[0] - h1[0], c1[1] - h1[1], c1[2] - h1[2]}, a1[3] = {c1[0] + h1[0], c1[1] + h1[1], c1[2] + h1[2]};
-                float q[3];
-                seg_point(a0, a1, c2, q);
-                const float d[3] = {q[0] - c2[0], q[1] - c2[1], q[2] - c2[2]}, reach = m.sg_r[g1] + m.box_bound[g2] + m.self_margin;
-                return dot3(d, d) <= reach * reach;
-            }
-            const float d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]}, reach = m.box_bound[g1] + m.box_bound[g2] + m.self_margin;
-            return dot3(d, d) <= reach * reach;
-        });
+    // ---- pairs with one contact slot: 32 per pass, ordered so that a pass runs (mostly) one distance function
+    for (int pass = 0; pass * 32 < n_one; pass++) {
         const unsigned act = wballot(lane, 32, [&](int l) {
             const int p = l + 32 * pass;
-            if (p >= m.nsp) return false;
+            if (p >= n_one) return false;
             const int g1 = m.sp_g1[p], g2 = m.sp_g2[p];
             const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1, *h2 = ga + 4 * g2;
             float* o = pr + 8 * l;
-            const float bodies = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
-            if (p >= n_one) {  // capsule-box (2 slots) / box-box (4 slots)
-                if (!((need_convex >> l) & 1u)) return false;
-                float res[32];
-                const int nslot = p < n_one + m.nsp_cb ? 2 : 4;
-                if (nslot == 2) capsule_box_dev(c1, h1, m.sg_r[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
-                else box_box_dev(c1, w.xmat + S9 * m.sg_body[g1], m.sg_axis[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
-                for (int k = 0; k < 7; k++) o[k] = res[k];
-                o[7] = bodies;
-                for (int q = 1; q < nslot; q++) {
-                    float* x = px + 8 * xrow(p - n_one, q);
-                    for (int k = 0; k < 7; k++) x[k] = res[8 * q + k];
-                    x[7] = bodies;
-                }
-                return res[3] < m.self_margin;
-            }
             float p1[3], p2[3];
             if (p < m.nsp_sc) {  // sphere - capsule
                 const float b0[3] = {c2[0] - h2[0], c2[1] - h2[1], c2[2] - h2[2]}, b1[3] = {c2[0] + h2[0], c2[1] + h2[1], c2[2] + h2[2]};
@@ -1424,19 +1453,76 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
             const float dist = nrm - (r1 + r2);
             for (int k = 0; k < 3; k++) { o[k] = p1[k] + n[k] * (r1 + 0.5f * dist); o[4 + k] = n[k]; }
             o[3] = dist;
-            o[7] = bodies;
+            o[7] = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
             return dist < m.self_margin;
         });
         WSYNC();
         commit(act);
-        if (need_convex != 0u) {  // (warp-uniform, rare) the further slots of the capsule-box / box-box pairs, one round per slot
-            for (int q = 1; q < 4; q++) {
-                const unsigned more = wballot(lane, 32, [&](int l) {
-                    const int p = l + 32 * pass;
-                    if (!((need_convex >> l) & 1u) || q >= (p < n_one + m.nsp_cb ? 2 : 4)) return false;
-                    const float* x = px + 8 * xrow(p - n_one, q);
+    }
+    // ---- capsule-box (two slots) and box-box (four slots) pairs: lane e = pair n_one + e.  Off the hot path: a lane runs the
+    // out-of-line convex functions only if its pair passes a bounding test, and the warp skips the section if no lane does.
+    const int n_cvx = m.nsp_cb + m.nsp_bb;
+    if (n_cvx > 0) {
+        // box-box (foot against foot): separating-axis test along the six face normals, one lane per axis, with the contact margin.
+        // A pair separated along a face normal has no contact inside the margin (the feet of a standing or walking humanoid are).
+        const unsigned bb_axes = wballot(lane, 32, [&](int l) {
+            const int q = l / 6, a = l - 6 * q;
+            if (q >= m.nsp_bb) return false;
+            const int p = n_one + m.nsp_cb + q, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+            const float *R1 = w.xmat + S9 * m.sg_body[g1], *R2 = w.xmat + S9 * m.sg_body[g2], *h1 = m.sg_axis[g1], *h2 = m.sg_axis[g2];
+            const float *Ra = a < 3 ? R1 : R2, *Rb = a < 3 ? R2 : R1, *ha = a < 3 ? h1 : h2, *hb = a < 3 ? h2 : h1;
+            const int i = a < 3 ? a : a - 3;
+            const float L[3] = {Ra[i], Ra[3 + i], Ra[6 + i]};   // column i: face normal
+            const float d[3] = {gc[4 * g2] - gc[4 * g1], gc[4 * g2 + 1] - gc[4 * g1 + 1], gc[4 * g2 + 2] - gc[4 * g1 + 2]};
+            float reach = ha[i] + m.self_margin;
+            for (int j = 0; j < 3; j++) reach += hb[j] * fabsf(L[0] * Rb[j] + L[1] * Rb[3 + j] + L[2] * Rb[6 + j]);
+            return fabsf(dot3(d, L)) > reach;   // separated along this axis
+        });
+        const unsigned need = wballot(lane, 32, [&](int e) {
+            if (e >= n_cvx) return false;
+            const int p = n_one + e, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+            if (e < m.nsp_cb) {  // the capsule's segment in the box frame: interval test per box axis, inflated by radius + margin
+                const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1, *R = w.xmat + S9 * m.sg_body[g2], *half = m.sg_axis[g2];
+                const float dl[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]}, pad = m.sg_r[g1] + m.self_margin;
+                float cp[3], ax[3];
+                matT_vec(R, dl, cp);
+                matT_vec(R, h1, ax);
+                bool overlap = true;
+                for (int k = 0; k < 3; k++) overlap = overlap && fabsf(cp[k]) - fabsf(ax[k]) <= half[k] + pad;
+                return overlap;
+            }
+            return ((bb_axes >> (6 * (e - m.nsp_cb))) & 63u) == 0u;   // not separated along any face normal
+        });
+        PROF_COUNT(62);
+        if (need != 0u) {  // (warp-uniform, rare)
+            PROF_COUNT(63);
+            const unsigned act = wballot(lane, 32, [&](int e) {
+                if (!((need >> e) & 1u)) return false;
+                const int p = n_one + e, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+                const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1;
+                const float bodies = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
+                float res[32];
+                const int nslot = e < m.nsp_cb ? 2 : 4;
+                if (nslot == 2) capsule_box_dev(c1, h1, m.sg_r[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
+                else box_box_dev(c1, w.xmat + S9 * m.sg_body[g1], m.sg_axis[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res, w.LD);
+                float* o = pr + 8 * e;
+                for (int k = 0; k < 7; k++) o[k] = res[k];
+                o[7] = bodies;
+                for (int q = 1; q < nslot; q++) {
+                    float* x = px + 8 * xrow(e, q);
+                    for (int k = 0; k < 7; k++) x[k] = res[8 * q + k];
+                    x[7] = bodies;
+                }
+                return res[3] < m.self_margin;
+            });
+            WSYNC();
+            commit(act);
+            for (int q = 1; q < 4; q++) {  // the further slots, one round per slot
+                const unsigned more = wballot(lane, 32, [&](int e) {
+                    if (!((need >> e) & 1u) || q >= (e < m.nsp_cb ? 2 : 4)) return false;
+                    const float* x = px + 8 * xrow(e, q);
                     if (!(x[3] < m.self_margin)) return false;
-                    float* o = pr + 8 * l;
+                    float* o = pr + 8 * e;
                     for (int k = 0; k < 8; k++) o[k] = x[k];
                     return true;
                 });
@@ -1580,6 +1666,7 @@ PB_DEVN void rows_JTf(const DevModel& m, Ws& w, const float* base, float* out, i
             for (int k = 0; k < 6; k++) f[k] += t[k];
         }
         const unsigned sub = m.body_submask[m.dof_bodyid[i]];
+#pragma unroll 1   // warp-uniform trip count, zero for most envs: a real loop (unrolled and predicated it costs 470 instructions per call)
         for (int c = 0; c < nsc; c++) {  // +force where body2 hangs below this dof, -force where body1 does (both: they cancel)
             const int bb = w.sc_bb[c];
             const float sg = (float)((int)((sub >> (bb >> 8)) & 1u) - (int)((sub >> (bb & 0xff)) & 1u));
@@ -1942,6 +2029,8 @@ PB_DEVN void dense_factor_solve(const DevModel& m, Ws& w, unsigned sact, float* 
 
 // ---------------------------------------------------------------------------------- Newton solver on qacc
 // minimise 1/2 (a-a_s)^T M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2   
+// MJX_RULE: the stop rule is a template parameter, so that the default (exact active set) carries none of the tolerance rule's work
+template <bool MJX_RULE>
 PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     const unsigned lim_rows = wballot(lane, NLIM, [&](int l) { return w.lim_sign[l] != 0.f; });
     w.niter = 0;
@@ -1981,7 +2070,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
     int it = 0, ndense = 0;
     bool running = constrained;
     // stop rule (include/pbrl.h: solver_rule): exact active set (default) or MuJoCo / MJX's tolerance-scaled improvement / gradient
-    const bool mjx_rule = m.solver_rule == PBRL_SOLVER_MJX;
+    constexpr bool mjx_rule = MJX_RULE;
     const int maxit = mjx_rule ? m.solver_iterations : (m.solver_iterations < NEWTON_MAXIT ? m.solver_iterations : NEWTON_MAXIT);
     const int ls_maxit = mjx_rule ? m.ls_iterations : LS_MAXIT;
     for (;;) {
@@ -2006,7 +2095,7 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
         WSYNC();
         // active body-vs-body rows couple two branches of the tree: their Hessian is not tree-sparse -> dense factorisation
         const unsigned sact = wballot(lane, 32, [&](int l) { return l < nsr && w.sc_jar[l] < 0.f; });
-        if (sact != 0u) { dense_factor_solve(m, w, sact, w.p, lane); ndense++; }
+        if (sact != 0u) { dense_factor_solve(m, w, sact, w.p, lane); ndense++; PROF_COUNT(58); }
         else ldl_factor_solve(m, w, w.p, lane);
         PROF(15);
         tree_Mx(m, w, w.p, w.Mp, lane);
@@ -2059,20 +2148,20 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
             if (l < nsr) {
                 const float x0 = w.sc_jar[l], x1 = x0 + alpha * w.sc_jp[l];
                 w.sc_jar[l] = x1;
-                drow += row_cost(w.sc_r[(l & ~3) + 3], x0, x1);
+                if (mjx_rule) drow += row_cost(w.sc_r[(l & ~3) + 3], x0, x1);
                 bits |= (x1 < 0.f) ? 64 : 0;
             }
             if (l < NLIM && w.lim_sign[l] != 0.f) {
                 const float x0 = w.lim_jar[l], x1 = x0 + alpha * w.lim_jp[l];
                 w.lim_jar[l] = x1;
-                drow += row_cost(w.lim_D[l], x0, x1);
+                if (mjx_rule) drow += row_cost(w.lim_D[l], x0, x1);
                 bits |= (x1 < 0.f) ? 1 : 0;
             }
             if (l < NC && w.con_on[l])
                 for (int e = 0; e < 4; e++) {
                     const float x0 = w.con_jar[4 * l + e], x1 = x0 + alpha * w.con_jp[4 * l + e];
                     w.con_jar[4 * l + e] = x1;
-                    drow += row_cost(w.con_D[l], x0, x1);
+                    if (mjx_rule) drow += row_cost(w.con_D[l], x0, x1);
                     bits |= (x1 < 0.f) ? (2 << e) : 0;
                 }
             // act_bits[l] still holds the active set this iteration's Hessian was built from
@@ -2132,7 +2221,8 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
         w.asmooth[i] = f;
     }
     PROF(9);
-    solve_constraints(m, w, lane);
+    if (m.solver_rule == PBRL_SOLVER_MJX) solve_constraints<true>(m, w, lane);
+    else solve_constraints<false>(m, w, lane);
 }
 
 // mjx.step: forward, warmstart <- qacc, Euler with implicit joint damping, integrate

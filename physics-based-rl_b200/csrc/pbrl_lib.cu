@@ -149,7 +149,7 @@ k_replay(const DevModel* __restrict__ gm, int N, const float* qpos, const float*
 // copied straight from the clip (a few KB, L1-resident).  The model tables are read through L1 with warp-uniform loads:
 // no per-CTA model copy, so four CTAs (16 warps) fit an SM and hide the latency of the per-thread kinematic chain.
 #ifndef PBRL_RR_ITEMS
-#define PBRL_RR_ITEMS 128
+#define PBRL_RR_ITEMS 32
 #endif
 constexpr int RR_ITEMS = PBRL_RR_ITEMS;    // items (= threads) per CTA
 constexpr int RR_ROW = NB * 3 + NB * 4 + 1;  // 99 floats, odd

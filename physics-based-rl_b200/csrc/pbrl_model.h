@@ -414,6 +414,7 @@ inline std::string build_dev_model(const PbrlModelDesc& d, DevModel& m) {
             if (pass == 5) m.nsp_bb = m.nsp - m.nsp_sc - m.nsp_cc - m.nsp_ss - m.nsp_sb - m.nsp_cb;
         }
         if (m.nsp_cb + 3 * m.nsp_bb > 24) return "too many capsule-box / box-box pairs for the narrow-phase scratch";
+        if (m.nsp_bb > 1) return "at most one box-box pair (its manifold construction owns the warp's scratch rows)";
         m.self_invw_scale = (1.f + m.self_mu * m.self_mu) * 2.f * m.self_mu * m.self_mu / (float)d.impratio[0];
     }
     if (d.jnt_dofadr[0] != 0) return "the free joint must own dofs 0..5";

@@ -251,3 +251,8 @@ def test_capsule_box_and_box_box_contacts(gpu_grav, model_grav):
     """The 15 candidates against the foot boxes (capsule-box x 14, box-box x 1) on the CUDA path: census 89 / 89."""
     out = pc.check_box_pair_contacts(gpu_grav, model_grav, want=300, seeds=range(400, 480))
     print("box pairs", out)
+
+
+def test_quiet_stance_carries_the_body_weight(gpu_grav, model_grav):
+    out = pc.check_quiet_stance(gpu_grav, model_grav)
+    print("quiet stance", out)

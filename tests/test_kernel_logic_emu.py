@@ -160,3 +160,9 @@ def test_solver_rule_mjx_and_options(model_grav):
 def test_capsule_box_and_box_box_contacts(emu_grav, model_grav):
     """The 15 candidates against the foot boxes: same contacts and forces as the oracle."""
     pc.check_box_pair_contacts(emu_grav, model_grav, want=60)
+
+
+def test_quiet_stance_carries_the_body_weight(emu_grav, model_grav):
+    """Contact self-consistency (stand-in for the missing MJX contact goldens): weight support within 5 %, pyramid edge forces
+    >= 0 (friction cone), ~zero normal velocity, sub-millimetre penetration -- oracle and kernel logic."""
+    pc.check_quiet_stance(emu_grav, model_grav)
