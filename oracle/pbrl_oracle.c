@@ -362,6 +362,11 @@ static void sphere_box(const REAL* sp, REAL r, const REAL* bp, const REAL* bm, c
     make_frame(frame, nw);
 }
 static int argmax_(const REAL* v, int n) { int b = 0; for (int i = 1; i < n; i++) if (v[i] > v[b]) b = i; return b; }
+/* mjx _manifold_points adds -1e6 to the score of a masked-out candidate, in jax's default float32 (the reference never enables
+ * x64): the sum lands on float32's grid at 1e6 (spacing 0.0625).  That rounding decides the picks when EVERY candidate is masked
+ * out (a foot box hovering inside the margin without penetrating): scores below 0.03125 collapse onto -1e6 and the first index
+ * wins.  The checker reproduces that one rounding whatever REAL is. */
+static REAL mask_add(REAL s, int ok) { return ok ? s : (REAL)((float)s + -1e6f); }
 /* ---- capsule / box against a box (mjx collision_convex.py: capsule_convex, convex_convex through _create_contact_manifold,
  *      _clip, _clip_edge_to_planes, _closest_segment_point_plane, _project_pt_onto_plane, _manifold_points) [M: restated from the
  *      published algorithm, mujoco-mjx 3.1.x; no golden exists for these rows -- parity unpinned].  Conventions of this
@@ -421,11 +426,11 @@ static void manifold_points(REAL (*pt)[3], const int* mask, int n, const REAL* n
     REAL sc[32], ab[3], ac[3], bc[3], e[3], t[3];
     for (int i = 0; i < n; i++) sc[i] = mask[i] ? 0 : R(-1e6);
     int a = argmax_(sc, n);
-    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = dot3(t, t) + (mask[i] ? 0 : R(-1e6)); }
+    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = mask_add(dot3(t, t), mask[i]); }
     int b = argmax_(sc, n);
     for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[b][k];
     cross3(ab, nrm, e);
-    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = R(fabs((double)dot3(t, ab))) + (mask[i] ? 0 : R(-1e6)); }
+    for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; sc[i] = mask_add(R(fabs((double)dot3(t, ab))), mask[i]); }
     int c = argmax_(sc, n);
     for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[c][k];
     cross3(ac, nrm, e);
@@ -433,13 +438,13 @@ static void manifold_points(REAL (*pt)[3], const int* mask, int n, const REAL* n
     cross3(bc, nrm, e);
     for (int i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) t[k] = pt[b][k] - pt[i][k];
-        sc[i] = R(fabs((double)dot3(t, bc))) + (mask[i] ? 0 : R(-1e6));
+        sc[i] = mask_add(R(fabs((double)dot3(t, bc))), mask[i]);
     }
     int d1 = argmax_(sc, n);
     REAL s1 = sc[d1];
     for (int i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k];
-        sc[i] = R(fabs((double)dot3(t, ac))) + (mask[i] ? 0 : R(-1e6));
+        sc[i] = mask_add(R(fabs((double)dot3(t, ac))), mask[i]);
     }
     int d2 = argmax_(sc, n);
     idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = sc[d2] > s1 ? d2 : d1;
@@ -674,7 +679,7 @@ static void collision(const OrcModel* m, OrcData* d) {
                     for (int v = 0; v < 8; v++) {
                         REAL s = 0;
                         for (int k = 0; k < 3; k++) s += (vert[ia][k] - vert[v][k]) * (vert[ia][k] - vert[v][k]);
-                        score[v] = s + dmask[v];
+                        score[v] = mask_add(s, dmask[v] == 0);
                     }
                     int ib = argmax_(score, 8);
                     REAL ab[3], ac[3], bc[3], e[3];
@@ -682,7 +687,7 @@ static void collision(const OrcModel* m, OrcData* d) {
                     cross3(ab, nl, e);
                     for (int v = 0; v < 8; v++) {
                         for (int k = 0; k < 3; k++) tmp[k] = vert[ia][k] - vert[v][k];
-                        score[v] = R(fabs((double)dot3(tmp, ab))) + dmask[v];
+                        score[v] = mask_add(R(fabs((double)dot3(tmp, ab))), dmask[v] == 0);
                     }
                     int ic = argmax_(score, 8);
                     for (int k = 0; k < 3; k++) e[k] = vert[ia][k] - vert[ic][k];
@@ -691,9 +696,9 @@ static void collision(const OrcModel* m, OrcData* d) {
                     cross3(bc, nl, e);
                     for (int v = 0; v < 8; v++) {
                         for (int k = 0; k < 3; k++) tmp[k] = vert[ib][k] - vert[v][k];
-                        score[v] = R(fabs((double)dot3(tmp, bc))) + dmask[v];
+                        score[v] = mask_add(R(fabs((double)dot3(tmp, bc))), dmask[v] == 0);
                         for (int k = 0; k < 3; k++) tmp[k] = vert[ia][k] - vert[v][k];
-                        score[8 + v] = R(fabs((double)dot3(tmp, ac))) + dmask[v];
+                        score[8 + v] = mask_add(R(fabs((double)dot3(tmp, ac))), dmask[v] == 0);
                     }
                     int id = argmax_(score, 16) % 8;
                     idx[0] = ia; idx[1] = ib; idx[2] = ic; idx[3] = id;

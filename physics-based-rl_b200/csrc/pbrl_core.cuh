@@ -885,13 +885,17 @@ PB_DEV float impedance(const DevModel& m, float pos) {
     if (x > 1.f) imp = m.sol_dmax;
     return imp;
 }
-PB_DEV int argmax_masked(const float* score, const bool* ok, int n) {  // first maximum among ok[]; 0 if none
-    int best = -1;
+// first maximum of score[i] + (ok[i] ? 0 : -1e6), added in fp32 as mjx _manifold_points does (jax's default dtype): with every
+// candidate masked out the sums collapse onto fp32's grid at 1e6 (spacing 0.0625) and that rounding decides the pick
+PB_DEV int argmax_masked(const float* score, const bool* ok, int n) {
+    int best = 0;
     float bs = 0.f;  // running best score (no indexed read of score[])
 #pragma unroll
-    for (int i = 0; i < n; i++)
-        if (ok[i] && (best < 0 || score[i] > bs)) { best = i; bs = score[i]; }
-    return best < 0 ? 0 : best;
+    for (int i = 0; i < n; i++) {
+        const float s = ok[i] ? score[i] : score[i] + -1e6f;
+        if (i == 0 || s > bs) { best = i; bs = s; }
+    }
+    return best;
 }
 // pyramid edge e of a contact: w = n + sg*mu*t, j6 = [r x w ; w]
 PB_DEV void contact_j6(const float* r, const float* t1, float mu, int e, float* j6) {

@@ -462,6 +462,73 @@ def check_contact_rich_statistics(backend, model_grav, table, mdesc, N=1024, ste
     return float(np.abs(rew - rew_ref).max()), float((first == first_ref).mean())
 
 
+def check_hovering_foot_boxes(backend, model_grav):
+    """Foot boxes that hover inside the 1 mm margin without penetrating the floor: mjx plane_convex masks every corner out
+    (`support > max(0, max(support) - 1e-3)` is false everywhere) and `_manifold_points` then adds -1e6 to every score in
+    float32.  The squared distances of the corners across the foot's long side (4 x 0.0885^2 = 0.0313 > half a float32 step at
+    1e6) survive that rounding, the others collapse: the picks are corner 0, corner 4, 0, 0, i.e. TWO contacts per foot (exact
+    arithmetic would give four, a masked arg-max one).  Oracle and back end must both list exactly those, at several tilts."""
+    orc = _oracle(model_grav)
+    rng = np.random.default_rng(77)
+    q, tot = [], 0
+    for k in range(16):
+        qpos = np.array(model_grav.qpos0, np.float64)
+        ang = rng.uniform(-0.004, 0.004, 3) if k else np.zeros(3)   # small tilts keep all eight corners inside the margin band
+        qq = np.array([1.0, *(0.5 * ang)])
+        qpos[3:7] = qq / np.linalg.norm(qq)
+        d = orc.new_data()
+        d.qpos[:35] = qpos.astype(np.float32)
+        orc.forward(d)
+        nf = int(d.ncon[0]) - int(d.nself[0])
+        box = [c for c in range(nf) if int(model_grav.geom_type[int(d.con_geom[c])]) == 6]
+        # lowest corner 0.4 mm above the floor: use the exact corner heights (xpos of the feet), not the manifold's picks
+        lo = min(_box_corner_heights(model_grav, d))
+        qpos[2] += 0.0004 - lo
+        q.append(qpos)
+    q32 = np.array(q, np.float32)
+    N = len(q32)
+    z = np.zeros
+    out = backend.debug_forward(q32, z((N, 34), np.float32), z((N, 28), np.float32), z((N, 34), np.float32))
+    for e in range(N):
+        d = orc.new_data()
+        d.qpos[:35] = q32[e]
+        orc.forward(d)
+        nf = int(d.ncon[0]) - int(d.nself[0])
+        act = d.con_dist[:nf] - d.con_includemargin[:nf] < 0
+        box_act = [c for c in range(nf) if act[c] and int(model_grav.geom_type[int(d.con_geom[c])]) == 6]
+        get = lambda k: out[e, DBG[k][0]:DBG[k][0] + DBG[k][1]]
+        assert int(get("ncon_active")[0]) == int(act.sum()), (e, get("ncon_active"), int(act.sum()))
+        # the rows sit 0.4 - 1 mm from the floor: a float32 ulp of the corner height (1e-7 m) is 2e-4 of their violation
+        assert relerr(get("qacc"), d.qacc[:34]) <= 2e-4 and relerr(get("qfrc_constraint"), d.qfrc_constraint[:34]) <= 2e-4
+        if e == 0:  # level feet: corners 0 and 4 of each foot
+            assert len(box_act) == 4, box_act
+        tot += len(box_act)
+    assert tot >= 2 * N
+    return tot
+
+
+def _box_corner_heights(model, d):
+    hs = []
+    for g in range(len(model.geom_type)):
+        if int(model.geom_type[g]) != 6:
+            continue
+        b = int(model.geom_bodyid[g])
+        R = _quat_mat(np.array(d.xquat[4 * b:4 * b + 4]))
+        gp = np.array(d.xpos[3 * b:3 * b + 3]) + R @ model.geom_pos[g]
+        Rg = R @ _quat_mat(model.geom_quat[g])
+        for v in range(8):
+            c = np.array([(1 if (v >> (2 - k)) & 1 else -1) * model.geom_size[g][k] for k in range(3)])
+            hs.append(float((gp + Rg @ c)[2]))
+    return hs
+
+
+def _quat_mat(q):
+    w, x, y, z = q
+    return np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+
+
 def check_sphere_box_contacts(backend, model_grav, want=12):
     """Sphere-box candidates (torso / wrist spheres against the foot boxes, mjx _sphere_convex): random poses that contain
     such a contact, found with the oracle; the back end must list the same contacts (distances) and resolve them alike."""

@@ -139,6 +139,10 @@ def test_contact_rich_statistics(model_grav):
     pc.check_contact_rich_statistics(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc)
 
 
+def test_hovering_foot_boxes(gpu_grav, model_grav):
+    pc.check_hovering_foot_boxes(gpu_grav, model_grav)
+
+
 def test_sphere_box_contacts(gpu_grav, model_grav):
     pc.check_sphere_box_contacts(gpu_grav, model_grav, want=30)
 

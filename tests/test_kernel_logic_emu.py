@@ -100,6 +100,10 @@ def test_forward_stages_general_solimp_power(model_grav):
     pc.check_forward_stages(EmuBackend(m), m, gravity=True, N=12, seed=9)
 
 
+def test_hovering_foot_boxes(emu_grav, model_grav):
+    pc.check_hovering_foot_boxes(emu_grav, model_grav)
+
+
 def test_sphere_box_contacts(emu_grav, model_grav):
     pc.check_sphere_box_contacts(emu_grav, model_grav)
 
