@@ -508,7 +508,7 @@ def main():
         names = {0: "load", 1: "pd_torque", 2: "fk", 3: "com", 4: "crb", 5: "collide", 6: "comvel", 7: "bias", 8: "rows",
                  9: "fsmooth", 10: "free:factor", 11: "free:solve", 12: "newton:init", 13: "newton:grad(JTf)", 14: "newton:hessian",
                  15: "newton:factor", 16: "newton:solve", 17: "newton:Mp,Jp", 18: "newton:linesearch", 19: "newton:update",
-                 20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 27: "barrier: substep start", 28: "barrier: after position", 29: "barrier: after rows", 30: "barrier: after solver"}
+                 20: "fcon(JTf)", 21: "euler:factor", 22: "euler:solve", 23: "integrate", 24: "store", 25: "epilogue", 27: "barrier: substep start", 28: "barrier: after position", 29: "barrier: after rows", 30: "barrier: after solver", 31: "barrier: after collide"}
         nsub = n_env * (steps + warmup) * N_FRAMES
         tot = sum(cyc[:40])
         print(f"stage profile: {tot / nsub:.0f} cycles per env-substep (per warp, incl. stalls)", file=sys.stderr)

@@ -88,6 +88,9 @@ __device__ unsigned long long g_stage_hits[64];
 #endif
 
 namespace pbrl {
+#if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)
+static long g_emu_cnt[16] = {0};
+#endif
 
 // row strides of the per-body / per-dof arrays.  6-vectors are packed (24-byte rows moved as three 8-byte accesses: with
 // consecutive rows in consecutive lanes a 64-bit access touches every bank pair once per half warp, where 8-float rows
@@ -355,6 +358,22 @@ PB_DEV void cross_force(const float* v, const float* f, float* r) {
 // symmetric 6x6 stored as 21 floats, row-major upper triangle
 PB_DEV int sym21(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
 
+// sine / cosine of a hinge half angle: odd / even polynomials after a reduction to |r| <= pi / 2 (error < 1e-7), branch-free
+PB_DEV void sincos_half_angle(float x, float* sn, float* cs) {
+    // x = k pi + r, |r| <= pi / 2 (two-term Cody-Waite: exact enough for the |x| < ~100 a joint angle can reach), then
+    // sin x = (-1)^k sin r, cos x = (-1)^k cos r: branch-free, no library fallback to inline at each of the 28 hinges
+    const float k = rintf(x * 0.31830988618f);
+    float r = fmaf(k, -3.14159274101f, x);
+    r = fmaf(k, 8.74227766e-8f, r);   // pi = 3.14159274101 (fp32) - 8.74227766e-8
+    const float sgn = ((int)k & 1) ? -1.f : 1.f;
+    const float z = r * r;
+    float s = fmaf(z, -2.5052108e-8f, 2.7557319e-6f);   // Taylor to r^13 / r^12: truncation below 1e-8 on the interval
+    s = fmaf(s, z, -1.9841270e-4f); s = fmaf(s, z, 8.3333333e-3f); s = fmaf(s, z, -1.6666667e-1f);
+    *sn = sgn * fmaf(r * z, s, r);
+    float c = fmaf(z, 2.0876757e-9f, -2.7557319e-7f);
+    c = fmaf(c, z, 2.4801587e-5f); c = fmaf(c, z, -1.3888889e-3f); c = fmaf(c, z, 4.1666667e-2f); c = fmaf(c, z, -0.5f);
+    *cs = sgn * fmaf(c, z, 1.0f);
+}
 // ---------------------------------------------------------------------------------- kinematics
 // Flat form: everything that does not depend on the parent pose runs lane-parallel over joints / bodies first (joint
 // rotations, their product per body, the joint axes in the parent-side frame); the level recursion then only composes
@@ -368,7 +387,7 @@ PB_DEVN void stage_fk(const DevModel& m, Ws& w, const float* qpos, int lane) {
         if (m.jnt_type[j] != 0) {
             const int qa = m.jnt_qposadr[j];
             float sn, cs;
-            sincosf(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
+            sincos_half_angle(0.5f * (qpos[qa] - m.qpos0[qa]), &sn, &cs);
             jq[4 * j] = cs; jq[4 * j + 1] = m.jnt_axis[j][0] * sn; jq[4 * j + 2] = m.jnt_axis[j][1] * sn; jq[4 * j + 3] = m.jnt_axis[j][2] * sn;
         }
     }
@@ -1482,7 +1501,7 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
             for (int j = 0; j < 3; j++) reach += hb[j] * fabsf(L[0] * Rb[j] + L[1] * Rb[3 + j] + L[2] * Rb[6 + j]);
             return fabsf(dot3(d, L)) > reach;   // separated along this axis
         });
-        const unsigned need = wballot(lane, 32, [&](int e) {
+        unsigned need_ = wballot(lane, 32, [&](int e) {
             if (e >= n_cvx) return false;
             const int p = n_one + e, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
             if (e < m.nsp_cb) {  // the capsule's segment in the box frame: interval test per box axis, inflated by radius + margin
@@ -1493,11 +1512,27 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
                 matT_vec(R, h1, ax);
                 bool overlap = true;
                 for (int k = 0; k < 3; k++) overlap = overlap && fabsf(cp[k]) - fabsf(ax[k]) <= half[k] + pad;
+                // ... and the three axes ax x e_k (the segment projects onto a point): a gap wider than pad along any unit
+                // direction bounds the distance from below.  A diagonal shin or thigh over a foot passes the interval test
+                // six times more often than it touches; these axes reject most of those.
+                for (int k = 0; k < 3; k++) {
+                    const int i = (k + 1) % 3, j = (k + 2) % 3;   // L = ax x e_k: L_i = ax_j, L_j = -ax_i, L_k = 0
+                    const float gap = fabsf(cp[i] * ax[j] - cp[j] * ax[i]) - (half[i] * fabsf(ax[j]) + half[j] * fabsf(ax[i]));
+                    if (gap > 0.f && gap * gap > pad * pad * (ax[i] * ax[i] + ax[j] * ax[j])) overlap = false;   // gap / |L| > pad
+                }
                 return overlap;
             }
             return ((bb_axes >> (6 * (e - m.nsp_cb))) & 63u) == 0u;   // not separated along any face normal
         });
         PROF_COUNT(62);
+#if defined(PBRL_DEV_CONVEX_MASK)   // dev ablation: drop convex pairs after the prefilter
+        need_ &= PBRL_DEV_CONVEX_MASK;
+#endif
+        const unsigned need = need_;
+#if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)
+        g_emu_cnt[0]++; if (need) g_emu_cnt[1]++; if (need & ((1u << m.nsp_cb) - 1u)) g_emu_cnt[2]++; if (need >> m.nsp_cb) g_emu_cnt[3]++;
+        g_emu_cnt[4] += pop_count(need);
+#endif
         if (need != 0u) {  // (warp-uniform, rare)
             PROF_COUNT(63);
             const unsigned act = wballot(lane, 32, [&](int e) {
@@ -1520,6 +1555,9 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
                 return res[3] < m.self_margin;
             });
             WSYNC();
+#if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)
+            if (act) g_emu_cnt[5]++; g_emu_cnt[6] += pop_count(act); if (act >> m.nsp_cb) g_emu_cnt[7]++;
+#endif
             commit(act);
             for (int q = 1; q < 4; q++) {  // the further slots, one round per slot
                 const unsigned more = wballot(lane, 32, [&](int e) {
@@ -2192,7 +2230,8 @@ PB_DEVN void solve_constraints(const DevModel& m, Ws& w, int lane) {
 // ---------------------------------------------------------------------------------- one mjx.forward + Euler
 // forward: everything up to qacc / qfrc_constraint at (w.qpos, w.qvel, w.ctrl, w.warm)
 // Phase lock: bit k of w.phase_lock places a CTA barrier at stage-group boundary k of every substep
-// (0 substep start, 1 after the position stage, 2 after the constraint rows, 3 after the solver).  The barriers keep
+// (0 substep start, 1 after the position stage, 2 after the constraint rows, 3 after the solver, 5 after the collision stage;
+// bit 4 is the cooperative Newton vote of solve_constraints).  The barriers keep
 // the CTA's warps inside one instruction-cache window; every warp of a CTA executes the same number of them.
 PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     const int lock = w.phase_lock;
@@ -2209,6 +2248,8 @@ PB_DEVN void forward(const DevModel& m, Ws& w, int lane) {
     stage_collide(m, w, lane);
     stage_collide_self(m, w, lane);
     PROF(5);
+    if (lock & 32) CTA_SYNC();  // a warp that ran the convex narrow phase rejoins the others before the velocity stages
+    PROF(31);
     stage_comvel(m, w, w.qvel, lane);
     PROF(6);
     stage_bias(m, w, lane);
@@ -2327,6 +2368,9 @@ PB_DEVN void pd_torque(const DevModel& m, Ws& w, int pd_mode, int action_cols, c
 // =====================================================================================================
 namespace pbrl {
 
+#if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)
+static int* g_emu_trace = nullptr;  // dev study only: (niter, dense iterations) per (env, substep)
+#endif
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
@@ -2388,6 +2432,9 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
         }
         substep(m, w, time, lane);
+#if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)
+        if (g_emu_trace) { g_emu_trace[2 * ((size_t)env * a.n_frames + f)] = w.niter; g_emu_trace[2 * ((size_t)env * a.n_frames + f) + 1] = (w.work - w.niter) / PBRL_DENSE_WEIGHT; }
+#endif
         cost = cost > w.work ? cost : w.work;  // the most expensive substep decides how long the CTA's barriers wait for this env
         cost_sum += w.work;
     }
@@ -2453,21 +2500,6 @@ PB_DEVN void env_replay(const DevModel& m, Ws& w, const float* qpos, const float
 // Thread-serial, so the scalar cost matters: half-angle sine / cosine by odd / even polynomials after a reduction to
 // |r| <= pi / 2 (error < 1e-7), reciprocal square roots for the normalisations, vectors rotated by
 // the quaternion directly (v + w t + u x t, t = 2 u x v) instead of through a rotation matrix.
-PB_DEV void sincos_half_angle(float x, float* sn, float* cs) {
-    // x = k pi + r, |r| <= pi / 2 (two-term Cody-Waite: exact enough for the |x| < ~100 a joint angle can reach), then
-    // sin x = (-1)^k sin r, cos x = (-1)^k cos r: branch-free, no library fallback to inline at each of the 28 hinges
-    const float k = rintf(x * 0.31830988618f);
-    float r = fmaf(k, -3.14159274101f, x);
-    r = fmaf(k, 8.74227766e-8f, r);   // pi = 3.14159274101 (fp32) - 8.74227766e-8
-    const float sgn = ((int)k & 1) ? -1.f : 1.f;
-    const float z = r * r;
-    float s = fmaf(z, -2.5052108e-8f, 2.7557319e-6f);   // Taylor to r^13 / r^12: truncation below 1e-8 on the interval
-    s = fmaf(s, z, -1.9841270e-4f); s = fmaf(s, z, 8.3333333e-3f); s = fmaf(s, z, -1.6666667e-1f);
-    *sn = sgn * fmaf(r * z, s, r);
-    float c = fmaf(z, 2.0876757e-9f, -2.7557319e-7f);
-    c = fmaf(c, z, 2.4801587e-5f); c = fmaf(c, z, -1.3888889e-3f); c = fmaf(c, z, 4.1666667e-2f); c = fmaf(c, z, -0.5f);
-    *cs = sgn * fmaf(c, z, 1.0f);
-}
 PB_DEV void quat_normalize_fast(float* q) {
     const float ss = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     if (ss < 1e-30f) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }

@@ -5,6 +5,8 @@
 // every warp walks a grid-stride loop over environments, so any N runs with full SMs and no tail CTA.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -69,24 +71,40 @@ __device__ __forceinline__ const DevModel& stage_model(const DevModel* __restric
 __device__ __forceinline__ int first_env() { return blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5); }
 __device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; }
 
-__global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a) {
+// Groups of WARPS_PER_CTA envs are handed out dynamically (one atomic per group): with the balanced processing order the
+// groups arrive most expensive first, so the CTAs finish within one cheap group of each other (longest-processing-time-first);
+// a static round-robin gives CTA 0 the most expensive group of every pass.  `sched` = {next group, CTAs finished}: the last
+// CTA to leave re-arms the pair for the next launch.
+__global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a, int* __restrict__ sched) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
     const DevModel& sm = stage_model(gm);
     init_ws_tables(sm, w, lane);
     frames_init(w, lane);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // every warp of the CTA makes the same number of passes so that the per-substep CTA barrier (phase lock) is legal
-    for (int base = blockIdx.x * WARPS_PER_CTA; base < a.N; base += env_stride()) {
-        const int slot = base + (threadIdx.x >> 5);
+    __shared__ int s_group;
+    const int ngroups = (a.N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    // every warp of the CTA makes the same passes so that the per-substep CTA barrier (phase lock) is legal
+    for (;;) {
+        __syncthreads();  // (the previous pass has read s_group)
+        if (threadIdx.x == 0) s_group = atomicAdd(&sched[0], 1);
+        __syncthreads();
+        const int group = s_group;
+        if (group >= ngroups) break;
+        const int slot = group * WARPS_PER_CTA + (threadIdx.x >> 5);
         if (slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
         else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
-                for (int k = 0; k < __popc(a.phase_lock & 7); k++) CTA_SYNC();
+                for (int k = 0; k < __popc(a.phase_lock & 39); k++) CTA_SYNC();
                 if (a.phase_lock & 16) while (CTA_OR(0)) {}
                 if (a.phase_lock & 8) CTA_SYNC();
             }
         }
+    }
+    if (threadIdx.x == 0 && atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {  // every CTA has drawn its terminal index
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
     }
     if (a.buf.stats && a.reward_mode == PBRL_REWARD_MIMIC && lane < 6 && acc[5] > 0.f) {
         float v = acc[0];  // one atomic per (warp, statistic): lane k publishes statistic k
@@ -294,14 +312,19 @@ struct PbrlModel {
     int ctas_per_sm = 1;
     int rr_ctas_per_sm = 1;
     bool axes_match = false;  // the model's hinge axes equal the compiled table topo::JNT_AXIS_KIND (replay kinematics specialisation)
-    int phase_lock = 16;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per
-                          // iteration is the only CTA-wide sync; PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
+                          // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
+                          // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
     DevModel* dev = nullptr;
     DevMimic mimic{};
     bool has_mimic = false;
     float* frames = nullptr;
+    // k_step's group counters: a ring of {next group, CTAs finished} pairs, one pair per launch in flight
+    static constexpr int SCHED_RING = 32;
+    int* sched = nullptr;
+    mutable std::atomic<unsigned> sched_next{0};
 };
 
 namespace {
@@ -360,7 +383,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     m->device = device;
     m->sm_count = prop.multiProcessorCount;
     m->ctas_per_sm = 0;
-    { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 31; }
+    { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 63; }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) return bail(err);
@@ -386,6 +409,8 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     }
     CREATE_OK(cudaMalloc(&m->dev, sizeof(DevModel)));
     CREATE_OK(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
+    CREATE_OK(cudaMalloc(&m->sched, 2 * PbrlModel::SCHED_RING * sizeof(int)));
+    CREATE_OK(cudaMemset(m->sched, 0, 2 * PbrlModel::SCHED_RING * sizeof(int)));
     if (mimic) {
         std::string merr = build_dev_mimic(*mimic, m->host, m->mimic);
         if (!merr.empty()) return bail(merr);
@@ -404,6 +429,7 @@ void pbrl_model_destroy(PbrlModel* m) {
     DeviceGuard guard(m->device);
     if (m->dev) cudaFree(m->dev);
     if (m->frames) cudaFree(m->frames);
+    if (m->sched) cudaFree(m->sched);
     delete m;
 }
 
@@ -478,7 +504,8 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
     a.phase_lock = m->phase_lock;
     a.cost_mode = m->cost_mode;
-    k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a);
+    int* sched = m->sched + 2 * (m->sched_next.fetch_add(1) % PbrlModel::SCHED_RING);
+    k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, sched);
     return check_launch("pbrl_step");
 }
 

@@ -148,7 +148,7 @@ PB_DEVN void mimic_reference(const DevModel& m, const DevMimic& mm, const float*
                 } else {
                     float sn, cs;
                     const int j = m.body_jntadr[b];
-                    sincosf(0.5f * w.rhinge[b], &sn, &cs);
+                    sincos_half_angle(0.5f * w.rhinge[b], &sn, &cs);
                     ql[0] = cs; ql[1] = m.jnt_axis[j][0] * sn; ql[2] = m.jnt_axis[j][1] * sn; ql[3] = m.jnt_axis[j][2] * sn;
                 }
                 quat_mul(w.rxquat + S4 * p, ql, q);

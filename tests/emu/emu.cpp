@@ -74,6 +74,10 @@ int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* act
     if (buf->stats && reward_mode == PBRL_REWARD_MIMIC) for (int k = 0; k < 6; k++) buf->stats[k] += acc[k];
     return 0;
 }
+#ifdef PBRL_EMU_TRACE
+void emu_set_trace(int* p) { g_emu_trace = p; }
+long* emu_counters() { return g_emu_cnt; }
+#endif
 int emu_replay(int N, const float* qpos, const float* qvel, float* obs, float* reward, float* done, float* xpos, float* xquat) {
     std::vector<Ws> ws(1);
     init_ws_tables(g_model, ws[0], 0);
