@@ -1085,16 +1085,6 @@ PB_DEV float self_row_dot(const Ws& w, const float* j6, const float* vec6, int s
 // surfaces, manifold picks that coincide with an earlier one switched off like plane_convex does for repeated indices).  These candidates (14 capsule-box,
 // 1 box-box) are far apart in almost every pose: a lane runs the out-of-line functions below only when its pair passes a
 // bounding-volume test, and the warp skips them when no lane does.
-PB_DEV void box_face_dev(const float* half, int f, float (*v)[3], float* n) {
-    const int k = f >> 1, a = k == 2 ? 0 : k + 1, b = a == 2 ? 0 : a + 1;
-    const float sg = (f & 1) ? -1.f : 1.f;
-    for (int i = 0; i < 4; i++) {
-        const int j = (f & 1) ? ((4 - i) & 3) : i;  // reversed order for the negative face: counter-clockwise seen from outside
-        const float su = (j == 1 || j == 2) ? 1.f : -1.f, sv = (j >= 2) ? 1.f : -1.f;
-        v[i][k] = sg * half[k]; v[i][a] = su * half[a]; v[i][b] = sv * half[b];
-    }
-    n[0] = n[1] = n[2] = 0.f; n[k] = sg;
-}
 PB_DEV void project_on_plane(const float* pt, const float* plane_pt, const float* n, float* out) {
     const float t[3] = {pt[0] - plane_pt[0], pt[1] - plane_pt[1], pt[2] - plane_pt[2]}, dd = dot3(t, n);
     for (int k = 0; k < 3; k++) out[k] = pt[k] - dd * n[k];
@@ -1233,88 +1223,113 @@ PB_DEVN void capsule_box_dev(const float* c, const float* a, float r, const floa
     emit(lp0, ln0, pen0, out);
     emit(lp1, ln1, pen1, out + 8);
 }
-// mjx _manifold_points over 16 candidates
-PB_DEV void manifold_points_16(const float (*pt)[3], const bool* mask, const float* nrm, int* idx) {
-    float t[3], e[3], ab[3], ac[3], bc[3];
-    int a = 0;
-    for (int i = 15; i >= 0; i--) if (mask[i]) a = i;  // first masked candidate (0 if none)
-    auto pick = [&](auto score) {  // first maximum of score(i) + (mask ? 0 : -1e6)
-        int b = 0;
-        float bs = 0.f;
-        for (int i = 0; i < 16; i++) { const float sc = score(i) + (mask[i] ? 0.f : -1e6f); if (i == 0 || sc > bs) { bs = sc; b = i; } }
-        return b;
-    };
-    const int b = pick([&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return dot3(t, t); });
-    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[b][k];
-    cross3(nrm, e, ab);
-    const int c = pick([&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return fabsf(dot3(t, ab)); });
-    for (int k = 0; k < 3; k++) e[k] = pt[a][k] - pt[c][k];
-    cross3(nrm, e, ac);
-    for (int k = 0; k < 3; k++) e[k] = pt[b][k] - pt[c][k];
-    cross3(nrm, e, bc);
-    auto sbp = [&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[b][k] - pt[i][k]; return fabsf(dot3(t, bc)); };
-    auto sap = [&](int i) { for (int k = 0; k < 3; k++) t[k] = pt[a][k] - pt[i][k]; return fabsf(dot3(t, ac)); };
-    const int d1 = pick(sbp), d2 = pick(sap);
-    const float s1 = sbp(d1) + (mask[d1] ? 0.f : -1e6f), s2 = sap(d2) + (mask[d2] ? 0.f : -1e6f);
-    idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = s2 > s1 ? d2 : d1;
+// index of the first maximum of score(i), i < n <= 32 (a serial scan with a strict comparison): one candidate per lane, butterfly
+// on (score, index) pairs where the lower index wins a tie
+template <class Fn>
+PB_DEV int warg_max_first(int lane, int n, Fn score) {
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+    float s = lane < n ? score(lane) : -3.0e38f;
+    int i = lane < n ? lane : 255;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float so = __shfl_xor_sync(0xffffffffu, s, o);
+        const int io = __shfl_xor_sync(0xffffffffu, i, o);
+        if (so > s || (so == s && io < i)) { s = so; i = io; }
+    }
+    return i;
+#else
+    int b = 0;
+    float bs = 0.f;
+    for (int i = 0; i < n; i++) { const float sc = score(i); if (i == 0 || sc > bs) { bs = sc; b = i; } }
+    (void)lane;
+    return b;
+#endif
 }
-// box against box: four contact slots [pos(3), dist, normal(3)], normal from box 1 to box 2
-// `scratch`: 300 floats of the caller's shared-memory workspace (the arrays below are indexed dynamically; in local memory they
-// cost an L2 round trip per access)
-PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out,
-                         float* scratch) {
+// corner i (counter-clockwise seen from outside) of face f of a box, faces listed +x, -x, +y, -y, +z, -z
+PB_DEV void box_face_corner(const float* half, int f, int i, float* v) {
+    const int k = f >> 1, a = k == 2 ? 0 : k + 1, b = a == 2 ? 0 : a + 1;
+    const int j = (f & 1) ? ((4 - i) & 3) : i;  // reversed order for the negative face
+    const float su = (j == 1 || j == 2) ? 1.f : -1.f, sv = (j >= 2) ? 1.f : -1.f;
+    v[k] = ((f & 1) ? -1.f : 1.f) * half[k]; v[a] = su * half[a]; v[b] = sv * half[b];
+}
+// box against box: four contact slots [pos(3), dist, normal(3)], normal from box 1 to box 2; slot 0 goes to o0, slots 1..3 to
+// ox, ox + 8, ox + 16.  Warp-cooperative (one call per pair, every lane of the env's warp takes part): the 15 separating axes,
+// the 8 edge clips and the 16 manifold candidates each get a lane, the picks are warp arg-max reductions -- the serial form of the
+// same arithmetic kept one lane busy for ~35 k cycles while the CTA waited at its next barrier.
+// `scratch`: 256 floats of the caller's shared-memory workspace.
+PB_DEV void box_box_warp(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* o0,
+                         float* ox, float* scratch, int lane) {
     float (*ax)[3] = reinterpret_cast<float (*)[3]>(scratch);               // [15][3]
     float (*rv)[3] = reinterpret_cast<float (*)[3]>(scratch + 45);          // [4][3] reference face corners
     float (*iv)[3] = reinterpret_cast<float (*)[3]>(scratch + 57);          // [4][3] incident face corners
-    float (*lv)[3] = reinterpret_cast<float (*)[3]>(scratch + 69);          // [4][3]
-    float (*rp0)[3] = reinterpret_cast<float (*)[3]>(scratch + 81);         // side planes of the reference / incident face
-    float (*rpn)[3] = reinterpret_cast<float (*)[3]>(scratch + 93);
-    float (*ip0)[3] = reinterpret_cast<float (*)[3]>(scratch + 105);
-    float (*ipn)[3] = reinterpret_cast<float (*)[3]>(scratch + 117);
-    float (*cand)[3] = reinterpret_cast<float (*)[3]>(scratch + 129);       // [16][3]
-    float (*onref)[3] = reinterpret_cast<float (*)[3]>(scratch + 177);      // [16][3]
-    float (*rproj)[3] = reinterpret_cast<float (*)[3]>(scratch + 225);      // [4][3]
-    bool* cmask = reinterpret_cast<bool*>(scratch + 237);                   // [16]
-    float bestd = 0.f, bestax[3] = {1.f, 0.f, 0.f};
+    float (*rp0)[3] = reinterpret_cast<float (*)[3]>(scratch + 69);         // side planes of the reference / incident face
+    float (*rpn)[3] = reinterpret_cast<float (*)[3]>(scratch + 81);
+    float (*ip0)[3] = reinterpret_cast<float (*)[3]>(scratch + 93);
+    float (*ipn)[3] = reinterpret_cast<float (*)[3]>(scratch + 105);
+    float (*cand)[3] = reinterpret_cast<float (*)[3]>(scratch + 117);       // [16][3]
+    float (*onref)[3] = reinterpret_cast<float (*)[3]>(scratch + 165);      // [16][3]
+    float (*rproj)[3] = reinterpret_cast<float (*)[3]>(scratch + 213);      // [4][3]
+    int* cmask = reinterpret_cast<int*>(scratch + 225);                     // [16]
+    float* bax = scratch + 241;                                             // [3] best axis, [3] its overlap
+    static_assert(245 <= 256, "box-box scratch");
+    auto slot = [&](int q) { return q == 0 ? o0 : ox + 8 * (q - 1); };
     const float dc[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
-    int besti = -1;
-    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { ax[i][k] = R1[3 * k + i]; ax[3 + i][k] = R2[3 * k + i]; }
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) cross3(ax[i], ax[3 + j], ax[6 + 3 * i + j]);
-    for (int a = 0; a < 15; a++) {
+    LANE_IF(a, 15) {
+        float v[3];
+        if (a < 3) { for (int k = 0; k < 3; k++) v[k] = R1[3 * k + a]; }
+        else if (a < 6) { for (int k = 0; k < 3; k++) v[k] = R2[3 * k + a - 3]; }
+        else {
+            const int i = (a - 6) / 3, j = (a - 6) % 3;
+            const float u1[3] = {R1[i], R1[3 + i], R1[6 + i]}, u2[3] = {R2[j], R2[3 + j], R2[6 + j]};
+            cross3(u1, u2, v);
+        }
+        for (int k = 0; k < 3; k++) ax[a][k] = v[k];
+    }
+    WSYNC();
+    // overlap along axis a (negative: separated) and the signed unit axis from box 1 towards box 2
+    auto sat_axis = [&](int a, float* L) {
         const float nn = sqrtf(dot3(ax[a], ax[a]));
         const bool degenerate = nn < 1e-6f;
-        float L[3];
         for (int k = 0; k < 3; k++) L[k] = degenerate ? ax[a][k] : ax[a][k] / nn;
         float r1 = 0.f, r2 = 0.f;
         for (int i = 0; i < 3; i++) { r1 += h1[i] * fabsf(dot3(ax[i], L)); r2 += h2[i] * fabsf(dot3(ax[3 + i], L)); }
         const float pc = dot3(dc, L), d1 = r1 + r2 - pc, d2 = r1 + r2 + pc;
-        float dd = fminf(d1, d2);
         const float sg = d1 > d2 ? -1.f : 1.f;
-        if (degenerate) dd = 1e6f;
-        if (besti < 0 || dd < bestd) { bestd = dd; besti = a; for (int k = 0; k < 3; k++) bestax[k] = sg * L[k]; }
+        for (int k = 0; k < 3; k++) L[k] *= sg;
+        return degenerate ? 1e6f : fminf(d1, d2);
+    };
+    const int besti = warg_max_first(lane, 15, [&](int a) { float L[3]; return -sat_axis(a, L); });   // first minimum of the overlap
+    LANE_IF(a, 15) if (a == besti) { float L[3]; sat_axis(a, L); for (int k = 0; k < 3; k++) bax[k] = L[k]; }
+    WSYNC();
+    const float bestax[3] = {bax[0], bax[1], bax[2]};
+    LANE_IF(q, 4) {
+        float* o = slot(q);
+        for (int k = 0; k < 3; k++) { o[k] = 0.5f * (c1[k] + c2[k]); o[4 + k] = bestax[k]; }
+        o[3] = 1.f;
     }
-    for (int q = 0; q < 4; q++) {
-        for (int k = 0; k < 3; k++) { out[8 * q + k] = 0.5f * (c1[k] + c2[k]); out[8 * q + 4 + k] = bestax[k]; }
-        out[8 * q + 3] = 1.f;
-    }
-    if (besti >= 6) {  // edge against edge
-        const int i = (besti - 6) / 3, j = (besti - 6) % 3;
-        float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
-        for (int k = 0; k < 3; k++) { a0[k] = c1[k]; b0[k] = c2[k]; }
-        for (int q = 0; q < 3; q++) {
-            if (q != i) { const float sq = dot3(ax[q], bestax) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) a0[k] += sq * h1[q] * ax[q][k]; }
-            if (q != j) { const float sq = dot3(ax[3 + q], bestax) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) b0[k] += sq * h2[q] * ax[3 + q][k]; }
+    WSYNC();
+    if (besti >= 6) {  // edge against edge (warp-uniform)
+        LANE_IF(z, 1) {
+            const int i = (besti - 6) / 3, j = (besti - 6) % 3;
+            float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
+            for (int k = 0; k < 3; k++) { a0[k] = c1[k]; b0[k] = c2[k]; }
+            for (int q = 0; q < 3; q++) {
+                if (q != i) { const float sq = dot3(ax[q], bestax) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) a0[k] += sq * h1[q] * ax[q][k]; }
+                if (q != j) { const float sq = dot3(ax[3 + q], bestax) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) b0[k] += sq * h2[q] * ax[3 + q][k]; }
+            }
+            for (int k = 0; k < 3; k++) {
+                a1[k] = a0[k] + h1[i] * ax[i][k]; a0[k] -= h1[i] * ax[i][k];
+                b1[k] = b0[k] + h2[j] * ax[3 + j][k]; b0[k] -= h2[j] * ax[3 + j][k];
+            }
+            seg_seg(a0, a1, b0, b1, pa, pb);
+            const float t[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+            for (int k = 0; k < 3; k++) o0[k] = 0.5f * (pa[k] + pb[k]);
+            o0[3] = dot3(t, bestax);
         }
-        for (int k = 0; k < 3; k++) {
-            a1[k] = a0[k] + h1[i] * ax[i][k]; a0[k] -= h1[i] * ax[i][k];
-            b1[k] = b0[k] + h2[j] * ax[3 + j][k]; b0[k] -= h2[j] * ax[3 + j][k];
-        }
-        seg_seg(a0, a1, b0, b1, pa, pb);
-        const float t[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
-        for (int k = 0; k < 3; k++) out[k] = 0.5f * (pa[k] + pb[k]);
-        out[3] = dot3(t, bestax);
+        WSYNC();
         return;
     }
+    // face against face: reference face = the face most aligned with the axis (every lane derives the same choice)
     float amax = 0.f, bmin = 0.f;
     int af = 0, bfc = 0;
     for (int f = 0; f < 6; f++) {
@@ -1324,53 +1339,84 @@ PB_DEVN void box_box_dev(const float* c1, const float* R1, const float* h1, cons
     }
     const bool ref1 = amax >= -bmin;  // the reference face belongs to box 1
     const float *rc = ref1 ? c1 : c2, *rm = ref1 ? R1 : R2, *ic = ref1 ? c2 : c1, *im = ref1 ? R2 : R1, *rh = ref1 ? h1 : h2, *ih = ref1 ? h2 : h1;
-    float rn[3], inn[3], ln[3];
-    box_face_dev(rh, ref1 ? af : bfc, lv, ln);
-    for (int q = 0; q < 4; q++) { mat_vec(rm, lv[q], rv[q]); for (int k = 0; k < 3; k++) rv[q][k] += rc[k]; }
-    mat_vec(rm, ln, rn);
-    box_face_dev(ih, ref1 ? bfc : af, lv, ln);
-    for (int q = 0; q < 4; q++) { mat_vec(im, lv[q], iv[q]); for (int k = 0; k < 3; k++) iv[q][k] += ic[k]; }
-    mat_vec(im, ln, inn);
-    float out2[2][3], e[3];
-    for (int q = 0; q < 4; q++) {
+    const int rf = ref1 ? af : bfc, inf = ref1 ? bfc : af;
+    float rn[3], inn[3];
+    for (int k = 0; k < 3; k++) {   // face normals: +- the face's axis in the world
+        rn[k] = ((rf & 1) ? -1.f : 1.f) * rm[3 * k + (rf >> 1)];
+        inn[k] = ((inf & 1) ? -1.f : 1.f) * im[3 * k + (inf >> 1)];
+    }
+    LANE_IF(q, 4) {
+        float lv[3];
+        box_face_corner(rh, rf, q, lv);
+        mat_vec(rm, lv, rv[q]);
+        for (int k = 0; k < 3; k++) rv[q][k] += rc[k];
+        box_face_corner(ih, inf, q, lv);
+        mat_vec(im, lv, iv[q]);
+        for (int k = 0; k < 3; k++) iv[q][k] += ic[k];
+    }
+    WSYNC();
+    const float dpl = dot3(iv[0], inn), den = dot3(rn, inn);
+    LANE_IF(q, 4) {
+        float e[3];
         for (int k = 0; k < 3; k++) { rp0[q][k] = rv[(q + 3) & 3][k]; e[k] = rv[q][k] - rp0[q][k]; }
         cross3(e, rn, rpn[q]);
         for (int k = 0; k < 3; k++) { ip0[q][k] = iv[(q + 3) & 3][k]; e[k] = iv[q][k] - ip0[q][k]; }
         cross3(e, inn, ipn[q]);
-    }
-    for (int q = 0; q < 4; q++) {  // incident edges against the reference side planes
-        const bool mk = clip_edge_4(ip0[q], iv[q], rp0, rpn, out2);
-        for (int k = 0; k < 3; k++) { cand[2 * q][k] = out2[0][k]; cand[2 * q + 1][k] = out2[1][k]; }
-        cmask[2 * q] = cmask[2 * q + 1] = mk;
-    }
-    const float dpl = dot3(iv[0], inn), den = dot3(rn, inn);
-    for (int q = 0; q < 4; q++) {  // reference corners moved onto the incident plane along the reference normal
+        // reference corners moved onto the incident plane along the reference normal
         const float t = (dpl - dot3(rv[q], inn)) / (den + (den == 0.f ? 1e-6f : 0.f));
         for (int k = 0; k < 3; k++) rproj[q][k] = rv[q][k] + t * rn[k];
     }
-    for (int q = 0; q < 4; q++) {  // ... and their edges against the incident side planes
-        const bool mk = clip_edge_4(rproj[(q + 3) & 3], rproj[q], ip0, ipn, out2);
-        for (int k = 0; k < 3; k++) { cand[8 + 2 * q][k] = out2[0][k]; cand[8 + 2 * q + 1][k] = out2[1][k]; }
-        cmask[8 + 2 * q] = cmask[8 + 2 * q + 1] = mk;
+    WSYNC();
+    LANE_IF(l, 8) {  // lanes 0..3: incident edges against the reference side planes; 4..7: projected reference edges against the incident ones
+        const int q = l & 3;
+        float out2[2][3];
+        const bool mk = l < 4 ? clip_edge_4(ip0[q], iv[q], rp0, rpn, out2) : clip_edge_4(rproj[(q + 3) & 3], rproj[q], ip0, ipn, out2);
+        for (int k = 0; k < 3; k++) { cand[2 * l][k] = out2[0][k]; cand[2 * l + 1][k] = out2[1][k]; }
+        cmask[2 * l] = cmask[2 * l + 1] = mk ? 1 : 0;
     }
-    for (int q = 0; q < 16; q++) {
+    WSYNC();
+    LANE_IF(q, 16) {
         const float t[3] = {cand[q][0] - rv[0][0], cand[q][1] - rv[0][1], cand[q][2] - rv[0][2]};
         project_on_plane(cand[q], rv[0], rn, onref[q]);
-        cmask[q] = cmask[q] && (-dot3(t, rn) > 1e-6f);  // behind the reference face
+        cmask[q] = (cmask[q] && (-dot3(t, rn) > 1e-6f)) ? 1 : 0;  // behind the reference face
     }
-    int idx[4];
-    manifold_points_16(onref, cmask, rn, idx);
-    for (int q = 0; q < 4; q++) {
-        const int p = idx[q];
+    WSYNC();
+    // mjx _manifold_points over the 16 candidates (scores: first maximum of score + (mask ? 0 : -1e6), added in fp32)
+    const unsigned mk16 = wballot(lane, 16, [&](int i) { return cmask[i] != 0; });
+    const int ia = mk16 ? first_bit(mk16) : 0;
+    auto masked = [&](int i, float sc) { return sc + (cmask[i] ? 0.f : -1e6f); };
+    auto dist2 = [&](int from, int i) { const float t[3] = {onref[from][0] - onref[i][0], onref[from][1] - onref[i][1], onref[from][2] - onref[i][2]}; return dot3(t, t); };
+    const int ib = warg_max_first(lane, 16, [&](int i) { return masked(i, dist2(ia, i)); });
+    float e3[3], ab[3], ac[3], bc[3];
+    for (int k = 0; k < 3; k++) e3[k] = onref[ia][k] - onref[ib][k];
+    cross3(rn, e3, ab);
+    auto along = [&](int from, const float* dir, int i) {
+        const float t[3] = {onref[from][0] - onref[i][0], onref[from][1] - onref[i][1], onref[from][2] - onref[i][2]};
+        return fabsf(dot3(t, dir));
+    };
+    const int ic3 = warg_max_first(lane, 16, [&](int i) { return masked(i, along(ia, ab, i)); });
+    for (int k = 0; k < 3; k++) e3[k] = onref[ia][k] - onref[ic3][k];
+    cross3(rn, e3, ac);
+    for (int k = 0; k < 3; k++) e3[k] = onref[ib][k] - onref[ic3][k];
+    cross3(rn, e3, bc);
+    const int d1 = warg_max_first(lane, 16, [&](int i) { return masked(i, along(ib, bc, i)); });
+    const int d2 = warg_max_first(lane, 16, [&](int i) { return masked(i, along(ia, ac, i)); });
+    const int id = masked(d2, along(ia, ac, d2)) > masked(d1, along(ib, bc, d1)) ? d2 : d1;
+    LANE_IF(q, 4) {
+        const int idx[4] = {ia, ib, ic3, id};
+        const int p = q == 0 ? ia : (q == 1 ? ib : (q == 2 ? ic3 : id));
         bool unique = true;
-        for (int r2 = 0; r2 < q; r2++) {  // a pick that coincides with an earlier one (within 10 microns) is switched off
+        for (int r2 = 0; r2 < 3; r2++) {  // a pick that coincides with an earlier one (within 10 microns) is switched off
+            if (r2 >= q) break;
             const float u[3] = {onref[p][0] - onref[idx[r2]][0], onref[p][1] - onref[idx[r2]][1], onref[p][2] - onref[idx[r2]][2]};
             unique = unique && !(dot3(u, u) < 1e-10f);
         }
         const float t[3] = {cand[p][0] - onref[p][0], cand[p][1] - onref[p][1], cand[p][2] - onref[p][2]};
-        out[8 * q + 3] = (cmask[p] && unique) ? dot3(t, rn) : 1.f;   // dist = -penetration = (incident - reference) . n_ref
-        for (int k = 0; k < 3; k++) out[8 * q + k] = 0.5f * (cand[p][k] + onref[p][k]);
+        float* o = slot(q);
+        o[3] = (cmask[p] && unique) ? dot3(t, rn) : 1.f;   // dist = -penetration = (incident - reference) . n_ref
+        for (int k = 0; k < 3; k++) o[k] = 0.5f * (cand[p][k] + onref[p][k]);
     }
+    WSYNC();
 }
 
 PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
@@ -1384,7 +1430,7 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
     float* pr = w.buf6;         // [32] x 8: pos(3), dist, normal(3) of the pair a lane evaluated  (buf6 is idle here)
     float* px = w.K + 8 * NSG;  // [NXROW] x 8: the further contact slots of the capsule-box (1 each) / box-box (3 each) pairs
     constexpr int NXROW = 24;
-    static_assert(8 * NSG + 8 * NXROW <= NB * S21 && NM >= 300, "narrow-phase scratch (box_box_dev works in the idle factor workspace LD)");
+    static_assert(8 * NSG + 8 * NXROW <= NB * S21 && NM >= 300, "narrow-phase scratch (box_box_warp works in the idle factor workspace LD)");
     // row of slot q >= 1 of convex pair e (counted from the first capsule-box pair)
     auto xrow = [&](int e, int q) { return e < m.nsp_cb ? e : m.nsp_cb + 3 * (e - m.nsp_cb) + (q - 1); };
     LANE_IF(g, NSG) {
@@ -1535,24 +1581,29 @@ PB_DEVN void stage_collide_self(const DevModel& m, Ws& w, int lane) {
 #endif
         if (need != 0u) {  // (warp-uniform, rare)
             PROF_COUNT(63);
+            for (int e = m.nsp_cb; e < n_cvx; e++) {  // box-box pairs (the two feet): the whole warp works on one pair
+                if (!((need >> e) & 1u)) continue;
+                const int p = n_one + e, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
+                box_box_warp(gc + 4 * g1, w.xmat + S9 * m.sg_body[g1], m.sg_axis[g1], gc + 4 * g2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2],
+                             pr + 8 * e, px + 8 * xrow(e, 1), w.LD, lane);
+            }
             const unsigned act = wballot(lane, 32, [&](int e) {
                 if (!((need >> e) & 1u)) return false;
                 const int p = n_one + e, g1 = m.sp_g1[p], g2 = m.sp_g2[p];
-                const float *c1 = gc + 4 * g1, *c2 = gc + 4 * g2, *h1 = ga + 4 * g1;
                 const float bodies = int_bits_as_float((int)m.sg_body[g1] | ((int)m.sg_body[g2] << 8));
-                float res[32];
-                const int nslot = e < m.nsp_cb ? 2 : 4;
-                if (nslot == 2) capsule_box_dev(c1, h1, m.sg_r[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
-                else box_box_dev(c1, w.xmat + S9 * m.sg_body[g1], m.sg_axis[g1], c2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res, w.LD);
                 float* o = pr + 8 * e;
-                for (int k = 0; k < 7; k++) o[k] = res[k];
-                o[7] = bodies;
-                for (int q = 1; q < nslot; q++) {
-                    float* x = px + 8 * xrow(e, q);
-                    for (int k = 0; k < 7; k++) x[k] = res[8 * q + k];
+                if (e < m.nsp_cb) {  // capsule-box: one lane per pair
+                    float res[16];
+                    capsule_box_dev(gc + 4 * g1, ga + 4 * g1, m.sg_r[g1], gc + 4 * g2, w.xmat + S9 * m.sg_body[g2], m.sg_axis[g2], res);
+                    for (int k = 0; k < 7; k++) o[k] = res[k];
+                    float* x = px + 8 * xrow(e, 1);
+                    for (int k = 0; k < 7; k++) x[k] = res[8 + k];
                     x[7] = bodies;
+                } else {
+                    for (int q = 1; q < 4; q++) px[8 * xrow(e, q) + 7] = bodies;
                 }
-                return res[3] < m.self_margin;
+                o[7] = bodies;
+                return o[3] < m.self_margin;
             });
             WSYNC();
 #if defined(PBRL_HOST_EMU) && defined(PBRL_EMU_TRACE)

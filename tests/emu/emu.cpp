@@ -97,7 +97,7 @@ int emu_capsule_box(const float* c, const float* axis_hl, float r, const float* 
 }
 int emu_box_box(const float* c1, const float* R1, const float* h1, const float* c2, const float* R2, const float* h2, float* out32) {
     float scratch[300];
-    box_box_dev(c1, R1, h1, c2, R2, h2, out32, scratch);
+    box_box_warp(c1, R1, h1, c2, R2, h2, out32, out32 + 8, scratch, 0);
     return 0;
 }
 int emu_pd_torque(int N, int pd_mode, int action_cols, const float* action, const float* qpos, const float* qvel,

@@ -92,6 +92,19 @@ def _self_penetration(model, qpos):
     return out
 
 
+def assert_qacc_errors_by_depth(errs, pens, what=""):
+    """Bound on the relative error of qacc for states with body-vs-body contacts, stated by the deepest overlap `pens` (metres).
+    The Hessian M + D u u^T of such a row is the worse conditioned the deeper the overlap; kernel, host emulation and the
+    oracle's own fp32 build share one error distribution per bin (tools/dev/dense_accuracy.py: p95 3e-5 below 10 mm, 6e-5 below
+    30 mm, 1e-4 below 60 mm, 5e-4 beyond, isolated outliers up to 1e-1 beyond 30 mm on any of the three).  <= 3e-4 up to 10 mm
+    (all a rollout reaches), <= 2e-3 up to 30 mm; deeper (unphysical) overlaps through their 90th percentile, <= 1e-3."""
+    errs, pens = np.asarray(errs), np.asarray(pens)
+    bound = np.where(pens < 0.010, 3e-4, np.where(pens < 0.030, 2e-3, np.inf))
+    assert (errs <= bound).all(), (what, float((errs / bound).max()))
+    deep = pens >= 0.030
+    assert deep.sum() == 0 or np.quantile(errs[deep], 0.9) <= 1e-3, (what, float(np.quantile(errs[deep], 0.9)))
+
+
 def check_one_substep(backend, model, gravity, N=32, seed=5):
     """fp32 relative error <= 1e-5 on qpos/qvel after ONE substep (torque-driven, random ctrl)."""
     env, s = _paired_envs(backend, model, N, seed, gravity)
@@ -551,7 +564,7 @@ def check_sphere_box_contacts(backend, model_grav, want=12):
     v32 = np.array([s[1] for s in states], np.float32)
     N = len(states)
     out = backend.debug_forward(q32, v32, np.zeros((N, 28), np.float32), np.zeros((N, 34), np.float32))
-    nbox, errs = 0, []
+    nbox, errs, pens = 0, [], []
     for e in range(N):
         d = orc.new_data()
         d.qpos[:35], d.qvel[:34] = q32[e], v32[e]
@@ -565,11 +578,13 @@ def check_sphere_box_contacts(backend, model_grav, want=12):
         f_got = np.sort(get("self_force")[:4 * ns].reshape(ns, 4).sum(1))
         assert np.abs(f_got - f_ref).max() <= 2e-3 * max(1.0, np.abs(f_ref).max()), (e, f_got, f_ref)
         errs.append(relerr(get("qacc"), d.qacc[:34]))
+        pens.append(-min(d.con_dist[nf:nc]))
         nbox += sum(int(model_grav.geom_type[int(d.con_geom[c])]) == 6 for c in range(nf, nc))
     assert nbox >= want
-    # random poses overlap by centimetres in several places at once: a few are ill-conditioned in fp32 (the fp32 oracle agrees
-    # with the back end to 2e-5 on them); the typical one is at rounding level
-    assert np.median(errs) <= 1e-5 and max(errs) <= 5e-3, (np.median(errs), max(errs))
+    # random poses overlap by centimetres in several places at once: the typical one is at rounding level, the bound on the
+    # others grows with the overlap
+    assert np.median(errs) <= 1e-5, np.median(errs)
+    assert_qacc_errors_by_depth(errs, pens, "sphere-box")
     return nbox
 
 
@@ -845,7 +860,7 @@ def check_box_pair_contacts(backend, model_grav, want=40, seeds=range(400, 440))
     N = len(states)
     out = backend.debug_forward(q32, v32, np.zeros((N, 28), np.float32), np.zeros((N, 34), np.float32))
     ncb = nbb = n32 = 0
-    errs, derr = [], []
+    errs, derr, pens = [], [], []
     for e in range(N):
         d = orc.new_data()
         d.qpos[:35], d.qvel[:34] = q32[e], v32[e]
@@ -869,13 +884,15 @@ def check_box_pair_contacts(backend, model_grav, want=40, seeds=range(400, 440))
         f_got = np.sort(get("self_force")[:4 * ns].reshape(ns, 4).sum(1))
         assert np.abs(f_got - f_ref).max() <= 5e-3 * max(1.0, np.abs(f_ref).max()), (e, f_got, f_ref)
         errs.append(relerr(get("qacc"), d.qacc[:34]))
+        pens.append(-min(d.con_dist[nf:nc]))
         for c in range(nf, nc):
             k = (int(model_grav.geom_type[int(d.con_geom1[c])]), int(model_grav.geom_type[int(d.con_geom[c])]))
             ncb += k == (3, 6)
             nbb += k == (6, 6)
     assert ncb >= want // 2 and nbb >= 3, (ncb, nbb)
     assert max(derr) <= 5e-6 and n32 <= max(1, N // 20), (max(derr), n32)
-    assert np.median(errs) <= 2e-5 and max(errs) <= 5e-3, (np.median(errs), max(errs))
+    assert np.median(errs) <= 2e-5, np.median(errs)
+    assert_qacc_errors_by_depth(errs, pens, "box pairs")
     return dict(states=N, capsule_box_contacts=int(ncb), box_box_contacts=int(nbb), deep_foot_overlaps_with_tie_sensitive_manifold=n32, dist_err=float(max(derr)), qacc_median=float(np.median(errs)), qacc_max=float(max(errs)))
 
 
