@@ -574,7 +574,9 @@ def main():
                 "e2e": {"value": total_envs * N_FRAMES * steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": n_env * 28 * 4 + 2 * 28 * 4, "d2h_bytes_per_step": n_env * (69 + 3 + 1) * 4 + 32,
                         "steps": steps, "api": "pbrl_batch_step_host (C ABI, pinned host buffers)",
-                        "note": "wall clock around each host call (it returns after its own stream synchronize); L2 evicted between calls outside the clock"},
+                        "note": "wall clock around each host call (it returns after its own stream synchronize); L2 evicted between calls outside the clock; "
+                                "the buffers are pinned and device-mapped, so k_step reads the action rows and writes obs / reward / done in place over PCIe "
+                                "(the byte counts are the rows that cross the bus per step; PBRL_HOST_ZERO_COPY=0 stages them through cudaMemcpyAsync instead)"},
                 # kernels launched inside the timed regions and their warm-ups: k_step (+ k_balance_order, + k_autoreset in the stationary loop), k_reset
                 "gpu_launches": D.launches + 1,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -189,13 +189,17 @@ def test_balance_order_is_a_permutation(gpu_grav):
             assert (np.diff(key) <= 0).all(), (N, kind)
 
 
-def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav):
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav, pinned):
     """pbrl_batch_reset_host / pbrl_batch_step_host / pbrl_batch_get_state_host (the API bench.py's e2e number flows through)
     against pbrl_reset / pbrl_step (+ pbrl_balance_order) on device buffers: identical obs / reward / done / stats and
-    state, bit for bit, over several env steps in mimic mode and in reference mode."""
+    state, bit for bit, over several env steps in mimic mode and in reference mode.  `pinned`: the caller's buffers are
+    page-locked, device-mapped host memory -- k_step then reads the action rows and writes obs / reward / done in place (no
+    staging copies); pageable buffers take the copies."""
     import ctypes
     import numpy as np
     import torch
+    host = (lambda *s: torch.zeros(s, dtype=torch.float32).pin_memory().numpy()) if pinned else (lambda *s: np.zeros(s, np.float32))
     table, mdesc, keep = pc.mimic_setup(model_grav)
     be = GpuBackend(model_grav, mimic_desc=mdesc)
     L, lib = be.L, be.L.lib()
@@ -209,7 +213,7 @@ def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav):
     for reward_mode in (1, 0):
         batch = ctypes.c_void_p()
         L.check(lib.pbrl_batch_create(be.model.handle, N, ctypes.byref(batch)))
-        h_obs, h_rew, h_done, h_stats = np.zeros((N, 69), np.float32), np.zeros((N, 3), np.float32), np.zeros(N, np.float32), np.zeros(8, np.float32)
+        h_obs, h_rew, h_done, h_stats, h_act = host(N, 69), host(N, 3), host(N), np.zeros(8, np.float32), host(N, 28)
         L.check(lib.pbrl_batch_reset_host(batch, reward_mode, vp(mid) if reward_mode else None, vp(t0) if reward_mode else None, vp(h_obs)))
         # the same on device buffers
         z = lambda *s: torch.zeros(s, device=be.dev)
@@ -225,7 +229,9 @@ def test_host_buffer_layer_is_bit_identical_to_device_buffers(model_grav):
         kpd, kdd = be._dp(kp), be._dp(kd)
         for k in range(3):
             act = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
-            L.check(lib.pbrl_batch_step_host(batch, 8, 3, 1, vp(act), vp(kp), vp(kd), ctypes.c_float(0.002), reward_mode, vp(h_obs), vp(h_rew),
+            h_act[:] = act
+            h_obs[:], h_rew[:], h_done[:] = -7, -7, -7
+            L.check(lib.pbrl_batch_step_host(batch, 8, 3, 1, vp(h_act), vp(kp), vp(kd), ctypes.c_float(0.002), reward_mode, vp(h_obs), vp(h_rew),
                                              vp(h_done), vp(h_stats)))
             a = torch.from_numpy(act).to(be.dev)
             d["stats"].zero_()

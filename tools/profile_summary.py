@@ -32,7 +32,7 @@ get = lambda h: float(vals[hdr.index(h)].replace(",", ""))
 scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
 rd = get("dram__bytes_read.sum") * scale[units[hdr.index("dram__bytes_read.sum")]]
 wr = get("dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum")]]
-(P / "r1_traffic.json").write_text(json.dumps({
+(P / f"{name.split(chr(95))[0]}_traffic.json").write_text(json.dumps({
     "kernel": "k_step", "workload": "mimic_mixed", "envs_per_gpu": 16384, "dram_bytes_per_launch": int(rd + wr),
     "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "algorithmic_bytes_per_launch": 16384 * 1248,
     "warp_instructions_per_launch": int(get("smsp__inst_executed.sum")), "warp_instructions_per_env_substep": get("smsp__inst_executed.sum") / (16384 * 8),
