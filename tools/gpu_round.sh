@@ -5,12 +5,12 @@ T=${1:-r1}
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_$T.log 2>&1; tail -3 $O/pytest_$T.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$T.log 2>&1; tail -1 $O/smoke_$T.log
-python bench.py > $O/bench_${T}_n1.json 2> $O/bench_${T}_n1.err
-python bench.py --impl reference --steps 8 --warmup 1 > $O/bench_${T}_ref.json 2> $O/bench_${T}_ref.err
+python bench.py --steps 20 --warmup 5 > $O/bench_${T}_n1.json 2> $O/bench_${T}_n1.err
+python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_${T}_ref.json 2> $O/bench_${T}_ref.err
 for W in contact_free contact_rich cpu64; do python bench.py --workload $W --steps 16 --warmup 3 --no-cpu-baseline > $O/bench_${T}_$W.json 2>> $O/bench_${T}_n1.err; done
 python bench.py --workload replay --steps 64 --warmup 4 > $O/bench_${T}_replay.json 2>> $O/bench_${T}_n1.err
-PBRL_BENCH_NO_BALANCE=1 python bench.py --no-cpu-baseline > $O/bench_${T}_nobalance.json 2>> $O/bench_${T}_n1.err
-PBRL_BENCH_NO_SELF_COLLISION=1 python bench.py > $O/bench_${T}_noself.json 2>> $O/bench_${T}_n1.err
+PBRL_BENCH_NO_BALANCE=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_${T}_nobalance.json 2>> $O/bench_${T}_n1.err
+PBRL_BENCH_NO_SELF_COLLISION=1 python bench.py --steps 20 --warmup 5 > $O/bench_${T}_noself.json 2>> $O/bench_${T}_n1.err
 for f in n1 ref contact_free contact_rich cpu64 replay nobalance noself; do python - <<PY
 import json
 try:
