@@ -28,7 +28,7 @@ METRIC = "humanoid-mimic env-substeps/sec"
 UNIT = "env-substeps/s"
 N_FRAMES = 8
 BYTES_PER_ENV_LAUNCH = 1248  # 528 in + 416 state out + 304 epilogue, fp32, unpadded
-# k_replay_rollout writes, per (env, frame) item: obs 276 + reward 12 + done 4 + xpos 168 + xquat 224 = 684 B; it reads the clip
+# pbrl_replay_rollout (k_replay_gather / k_replay_rollout) writes, per (env, frame) item: obs 276 + reward 12 + done 4 + xpos 168 + xquat 224 = 684 B; it reads the clip
 # (10 KB, L1/L2-resident), not 276 B per item.  SURVEY 8(d)'s 580 (+364) B figure describes the per-step launch k_replay, which
 # does read qpos/qvel rows: 276 in + 304 out + 364 poses = 944 B.
 BYTES_PER_REPLAY_ROLLOUT_ITEM = 276 + 12 + 4 + 168 + 224
@@ -200,18 +200,28 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
     def one():
         L.check(lib.pbrl_replay_rollout(M.handle, n_env, K_INNER, L._ptr(dpos), L._ptr(dvel), F, L._ptr(frame0), L._ptr(obs), L._ptr(rew),
                                         L._ptr(done), L._ptr(xpos), L._ptr(xquat), stream))
+    def timed_launches(n):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for k in range(n):
+            evs[k][0].record(); one(); evs[k][1].record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+    # the other form of the same entry point, for the record: kinematics per item (what the launch does when the items do not
+    # outnumber the clip's rows); the default below evaluates them once per clip row per launch and gathers
+    os.environ["PBRL_REPLAY_PER_ITEM"] = "1"
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    t_item_ms = timed_launches(min(steps, 16)) / min(steps, 16)
+    os.environ.pop("PBRL_REPLAY_PER_ITEM")
     for _ in range(warmup):
         one()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if not quiet:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for k in range(steps):
-        ev[k][0].record(); one(); ev[k][1].record()
-    torch.cuda.synchronize()
+    t_ms = timed_launches(steps)
     clocks = sampler.stop() if not quiet else None
-    t_ms = sum(a.elapsed_time(b) for a, b in ev)
     # the per-step launch the env facade makes (4096 envs x 944 B = 3.9 MB: launch-latency bound), L2 flushed in between
     qpos1, qvel1 = dpos[frame0.long()].contiguous(), dvel[frame0.long()].contiguous()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -240,20 +250,25 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
     peak, src = measured_peak()
     items = n_env * K_INNER
     ach = items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_ms * 1e-3 / steps) / 1e9
-    tr = measured_traffic("k_replay_rollout")
+    tr = measured_traffic("k_replay_gather")
     traffic = tr["dram_bytes_per_launch"] if tr and tr.get("envs_per_gpu") == n_env and tr.get("replay_steps_per_launch") == K_INNER else None
     return {"metric": "humanoid replay env-steps/sec", "value": items * steps / (t_ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": t_ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "replay", "description": "BASELINE configs[1]: kinematic replay of walk, FK + obs/reward + body poses",
-                       "envs_per_gpu": n_env, "replay_steps_per_launch": K_INNER,
+                       "envs_per_gpu": n_env, "replay_steps_per_launch": K_INNER, "clip_rows": int(F),
+                       "kinematics": "once per clip row per launch (frame table), rows gathered per item; per-item form reported beside it",
                        "l2": "each launch writes 0.72 GB (> 126 MB L2); inputs are the 10 KB clip"},
             "e2e": {"value": items / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n_env * 4, "d2h_bytes_per_step": n_env * 69 * 4, "steps": e2e_steps,
                     "api": "pbrl_replay_rollout, frame indices from pinned host memory, last observations back"},
-            "gpu_launches": steps + warmup + 35 + e2e_steps,
+            "gpu_launches": 2 * (steps + warmup + e2e_steps) + (warmup + min(steps, 16)) + 35,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "peak_source": src, "kernel": "k_replay_rollout", "algorithmic_bytes_per_env_launch": BYTES_PER_REPLAY_ROLLOUT_ITEM,
-                         "note": "per (env, frame) item: obs 276 + reward 12 + done 4 + xpos 168 + xquat 224 B written; the 10 KB clip it reads stays on chip"},
+                         "peak_source": src, "kernel": "k_replay_gather (+ k_replay_frames, both inside the timed launch)",
+                         "algorithmic_bytes_per_env_launch": BYTES_PER_REPLAY_ROLLOUT_ITEM,
+                         "note": "per (env, frame) item: obs 276 + reward 12 + done 4 + xpos 168 + xquat 224 B written; the 10 KB clip and the frame table it reads stay on chip"},
+            "per_item_kinematics": {"kernel": "k_replay_rollout (PBRL_REPLAY_PER_ITEM=1: kinematics per (env, frame) item, no frame table)", "ms_per_step": t_item_ms,
+                                    "env_steps_per_s": items / (t_item_ms * 1e-3),
+                                    "roofline_frac": items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_item_ms * 1e-3) / 1e9 / peak},
             "per_step_launch": {"kernel": "k_replay", "ms": t1_ms, "env_steps_per_s": n_env / (t1_ms * 1e-3),
                                 "algorithmic_bytes_per_env_launch": BYTES_PER_REPLAY_STEP_ENV,
                                 "achieved_GBps": n_env * BYTES_PER_REPLAY_STEP_ENV / (t1_ms * 1e-3) / 1e9},
@@ -547,7 +562,7 @@ def main():
                 extra[wl] = {"error": str(ex)[:200]}
         try:
             r = replay_bench(args, local_rank, quiet=True)
-            extra["replay"] = {k2: r[k2] for k2 in ("metric", "value", "unit", "ms_per_step", "steps", "roofline", "per_step_launch", "e2e")}
+            extra["replay"] = {k2: r[k2] for k2 in ("metric", "value", "unit", "ms_per_step", "steps", "roofline", "per_item_kinematics", "per_step_launch", "e2e")}
             extra["replay"]["envs_per_gpu"] = r["config"]["envs_per_gpu"]
             extra["replay"]["replay_steps_per_launch"] = r["config"]["replay_steps_per_launch"]
         except Exception as ex:

@@ -239,6 +239,99 @@ k_replay_rollout(const __grid_constant__ ReplayTables T, int N, int K, const flo
         __syncthreads();
     }
 }
+// Replay rollout through a frame table.  An item's poses depend on its clip frame only, and a rollout of N x K items walks a
+// clip of F rows (39 for the walk clip, 697 for all seven): when F is much smaller than N x K the kinematics are evaluated once
+// per FRAME per launch (k_replay_frames: one thread per frame, the same replay_item_fk arithmetic, so the rows are bit-identical
+// to the per-item kernel's) and the rollout itself becomes what its byte count says it is, a row gather: k_replay_gather copies,
+// per item, the clip row into obs and the table row into xpos / xquat, one warp per item, four items in flight per warp.
+// The table (F x 100 floats, L1 / L2-resident) lives in a scratch buffer of the model.
+constexpr int RT_ROW = 100;           // xpos 42 | 2 pad | xquat 56: 16-byte aligned halves
+constexpr int RT_QUAT = 44;
+template <bool AXSPEC>
+__global__ void __launch_bounds__(64) k_replay_frames(const __grid_constant__ ReplayTables T, int F, const float* __restrict__ data_pos, float* __restrict__ tab) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < F) replay_item_fk<AXSPEC>(T, data_pos + (size_t)f * NQ, tab + (size_t)f * RT_ROW, tab + (size_t)f * RT_ROW + RT_QUAT);
+}
+constexpr int RG_THREADS = 256, RG_UNROLL = 4;
+// ALL: every output array is present (the fast path: no per-array tests, output pointers advance by a constant per pass and
+// every store of the four items has an immediate offset)
+template <bool ALL>
+__global__ void __launch_bounds__(RG_THREADS)
+k_replay_gather(int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel, int F, const int* __restrict__ frame0,
+                const float* __restrict__ tab, float* obs, float* reward, float* done, float* xpos, float* xquat) {
+    static_assert(NQ == 35 && NV == 34 && PBRL_OBS == 69 && NB * 3 == 42 && NB * 4 == 56, "lane / column split of the rows");
+    const long long total = (long long)N * K;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (RG_THREADS / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (RG_THREADS / 32);
+    const bool b_in_qpos = lane < NQ - 32;
+    const bool has_obs = ALL || obs, has_pos = ALL || xpos, has_quat = ALL || xquat;
+    // (step, env) of the warp's first item and its increments per pass: no division inside the loop (a 64-bit division per item,
+    // executed by every warp, cost more issue slots than the copy itself)
+    const long long step = nwarps * RG_UNROLL;
+    long long g0 = warp * RG_UNROLL;
+    int e0 = (int)(g0 % N), kf0 = (int)((g0 / N) % F);
+    const int de = (int)(step % N), dkf = (int)((step / N) % F);
+    // per-lane source columns (element offsets inside a clip row / table row) and output cursors
+    const int col_b = b_in_qpos ? 32 + lane : lane - (NQ - 32);
+    const float* src_b = b_in_qpos ? data_pos : data_vel;
+    const int stride_b = b_in_qpos ? NQ : NV;
+    float* o_obs = obs ? obs + g0 * PBRL_OBS + lane : nullptr;
+    float* o_pos = xpos ? xpos + g0 * 42 + lane : nullptr;
+    float* o_quat = xquat ? xquat + g0 * 56 + lane : nullptr;
+    float* o_rew = reward ? reward + g0 * 3 + lane : nullptr;
+    float* o_done = done ? done + g0 + lane : nullptr;
+    for (; g0 < total; g0 += step) {
+        int f[RG_UNROLL];
+        float oa[RG_UNROLL], ob[RG_UNROLL], oc[RG_UNROLL], pa[RG_UNROLL], pb[RG_UNROLL], qa[RG_UNROLL], qb[RG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RG_UNROLL; u++) {
+            int e = e0 + u, kf = kf0;
+            while (e >= N) { e -= N; kf = kf + 1 == F ? 0 : kf + 1; }   // (at most one pass unless N < RG_UNROLL)
+            // past the end (the last pass of the last warps) the loads repeat a valid row; nothing is stored for them
+            f[u] = (int)(((unsigned)(frame0 ? __ldg(frame0 + e) : e) + (unsigned)kf) % (unsigned)F);
+        }
+        e0 += de; kf0 += dkf;
+        if (e0 >= N) { e0 -= N; kf0++; }
+        if (kf0 >= F) kf0 -= F;
+#pragma unroll
+        for (int u = 0; u < RG_UNROLL; u++) {  // every load of the four items is in flight before the first store
+            const float* tr = tab + f[u] * RT_ROW + lane;
+            if (has_obs) {
+                oa[u] = __ldg(data_pos + f[u] * NQ + lane);                                   // obs columns 0..31
+                ob[u] = __ldg(src_b + f[u] * stride_b + col_b);                               // 32..63: qpos 32..34, qvel 0..28
+                oc[u] = lane < PBRL_OBS - 64 ? __ldg(data_vel + f[u] * NV + 64 - NQ + lane) : 0.f;   // 64..68: qvel 29..33
+            }
+            if (has_pos) { pa[u] = __ldg(tr); pb[u] = lane < 42 - 32 ? __ldg(tr + 32) : 0.f; }
+            if (has_quat) { qa[u] = __ldg(tr + RT_QUAT); qb[u] = lane < 56 - 32 ? __ldg(tr + RT_QUAT + 32) : 0.f; }
+        }
+        const bool full = g0 + RG_UNROLL <= total;
+#pragma unroll
+        for (int u = 0; u < RG_UNROLL; u++) {
+            if (!full && g0 + u >= total) break;
+            if (has_obs) {
+                __stcs(o_obs + u * PBRL_OBS, oa[u]);
+                __stcs(o_obs + u * PBRL_OBS + 32, ob[u]);
+                if (lane < PBRL_OBS - 64) __stcs(o_obs + u * PBRL_OBS + 64, oc[u]);
+            }
+            if (has_pos) {
+                __stcs(o_pos + u * 42, pa[u]);
+                if (lane < 42 - 32) __stcs(o_pos + u * 42 + 32, pb[u]);
+            }
+            if (has_quat) {
+                __stcs(o_quat + u * 56, qa[u]);
+                if (lane < 56 - 32) __stcs(o_quat + u * 56 + 32, qb[u]);
+            }
+        }
+        // reward (agent_replay_motion.py: zeros(3)) and done (ones) of the four items: 12 + 4 contiguous floats
+        if (ALL || reward) { if (lane < (full ? 3 * RG_UNROLL : 3 * (int)(total - g0))) __stcs(o_rew, 0.f); }
+        if (ALL || done) { if (lane < (full ? RG_UNROLL : (int)(total - g0))) __stcs(o_done, 1.0f); }
+        if (ALL || obs) o_obs += step * PBRL_OBS;
+        if (ALL || xpos) o_pos += step * 42;
+        if (ALL || xquat) o_quat += step * 56;
+        if (ALL || reward) o_rew += step * 3;
+        if (ALL || done) o_done += step;
+    }
+}
 __global__ void __launch_bounds__(CTA_THREADS)
 k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
      const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
@@ -325,6 +418,18 @@ struct PbrlModel {
     static constexpr int SCHED_RING = 32;
     int* sched = nullptr;
     mutable std::atomic<unsigned> sched_next{0};
+    // pbrl_replay_rollout's frame table (grow-only scratch; a rollout is stream-ordered behind the previous one on its stream,
+    // two streams replaying different clips through one model at the same time must not share it -> one table per frame count)
+    mutable std::mutex scratch_mu;
+    mutable std::vector<std::pair<int, float*>> frame_tabs;
+    float* frame_table(int F) const {
+        std::lock_guard<std::mutex> lk(scratch_mu);
+        for (auto& t : frame_tabs) if (t.first == F) return t.second;
+        float* p = nullptr;
+        if (cudaMalloc(&p, (size_t)F * 100 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        frame_tabs.emplace_back(F, p);
+        return p;
+    }
 };
 
 namespace {
@@ -430,6 +535,7 @@ void pbrl_model_destroy(PbrlModel* m) {
     if (m->dev) cudaFree(m->dev);
     if (m->frames) cudaFree(m->frames);
     if (m->sched) cudaFree(m->sched);
+    for (auto& t : m->frame_tabs) cudaFree(t.second);
     delete m;
 }
 
@@ -525,13 +631,34 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
     ON_DEVICE(m);
     if (N <= 0 || K <= 0) return 0;
     if (!data_pos || !data_vel || F <= 0) return fail("null frame data");
-    const long long ctas = ((long long)N * K + RR_ITEMS - 1) / RR_ITEMS;
-    const long long cap = (long long)m->sm_count * m->rr_ctas_per_sm;
     ReplayTables T;
     replay_tables_from(m->host, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    // frame table when the items outnumber the clip's rows (and poses are asked for): see k_replay_gather
+    const char* per_item_env = getenv("PBRL_REPLAY_PER_ITEM");   // (read per call: bench.py times both forms in one process)
+    const bool per_item_only = per_item_env && atoi(per_item_env) != 0;
+    if (!per_item_only && (long long)N * K >= 4ll * F && F < (1 << 24)) {   // (row offsets of the table are 32-bit)
+        float* tab = nullptr;
+        if (xpos || xquat) {
+            tab = m->frame_table(F);
+            if (!tab) return fail("pbrl_replay_rollout: cannot allocate the frame table");
+            if (m->axes_match) k_replay_frames<true><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
+            else k_replay_frames<false><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
+        }
+        const long long need = ((long long)N * K + RG_UNROLL * (RG_THREADS / 32) - 1) / (RG_UNROLL * (RG_THREADS / 32));
+        const long long cap2 = (long long)m->sm_count * 8;
+        const unsigned grid2 = (unsigned)(need < cap2 ? need : cap2);
+        if (obs && reward && done && xpos && xquat)
+            k_replay_gather<true><<<grid2, RG_THREADS, 0, st>>>(N, K, data_pos, data_vel, F, frame0, tab, obs, reward, done, xpos, xquat);
+        else
+            k_replay_gather<false><<<grid2, RG_THREADS, 0, st>>>(N, K, data_pos, data_vel, F, frame0, tab, obs, reward, done, xpos, xquat);
+        return check_launch("pbrl_replay_rollout");
+    }
+    const long long ctas = ((long long)N * K + RR_ITEMS - 1) / RR_ITEMS;
+    const long long cap = (long long)m->sm_count * m->rr_ctas_per_sm;
     const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    if (m->axes_match) k_replay_rollout<true><<<grid, RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
-    else k_replay_rollout<false><<<grid, RR_ITEMS, RR_SMEM, (cudaStream_t)stream>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+    if (m->axes_match) k_replay_rollout<true><<<grid, RR_ITEMS, RR_SMEM, st>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
+    else k_replay_rollout<false><<<grid, RR_ITEMS, RR_SMEM, st>>>(T, N, K, data_pos, data_vel, F, frame0, obs, reward, done, xpos, xquat);
     return check_launch("pbrl_replay_rollout");
 }
 

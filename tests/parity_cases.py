@@ -438,6 +438,22 @@ def check_replay_rollout(backend, model, F=39, N=50, K=7, seed=37):
     assert np.array_equal(out2["obs"][k2][:, :35], q32[(np.arange(N) + k2) % F])
 
 
+def check_replay_rollout_paths_agree(backend, model, F=39, N=256, K=8, seed=40):
+    """pbrl_replay_rollout has two forms: kinematics per item (few items per clip row), or once per clip row into a frame table
+    that the rollout then gathers from (many items per row).  Same replay_item_fk arithmetic: the poses must be bit-identical."""
+    rng = np.random.default_rng(seed)
+    qpos, qvel = random_states(model, F, seed, vel_scale=1.0, joint_frac=0.9)
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    per_item = backend.replay_rollout(q32, v32, np.arange(F, dtype=np.int32), F, 1)       # F items < 4 F: one item per row
+    frame0 = rng.integers(0, F, N).astype(np.int32)
+    assert N * K >= 4 * F
+    table = backend.replay_rollout(q32, v32, frame0, N, K)                                 # the frame-table form
+    for k in range(K):
+        f = (frame0 + k) % F
+        for name in ("obs", "xpos", "xquat", "reward", "done"):
+            assert np.array_equal(table[name][k], per_item[name][0][f]), (name, k)
+
+
 def check_contact_rich_statistics(backend, model_grav, table, mdesc, N=1024, steps=24, seed=43):
     """North star: 'contact-rich rollouts are additionally checked by matching termination steps and reward statistics'.
     The bench workload (reference-state init over all clips, random target angles, stable PD, mimic reward) on the back end
