@@ -2425,6 +2425,7 @@ static int* g_emu_trace = nullptr;  // dev study only: (niter, dense iterations)
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
+    int tail_split;  // k_step: split the groups of a batch smaller than the GPU over the idle SMs
     int cost_mode;   // work estimate written to buf.cost: 0 most expensive substep, 1 sum over the substeps, 2 last substep
     const float *action, *kp, *kd, *pd_time;
     float pd_dt;

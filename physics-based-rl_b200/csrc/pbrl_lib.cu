@@ -82,18 +82,34 @@ __global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict
     init_ws_tables(sm, w, lane);
     frames_init(w, lane);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    __shared__ int s_group;
+    __shared__ int s_unit;
     const int ngroups = (a.N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    // A batch with fewer groups than CTAs (64 envs = 4 groups on 148 SMs) is handed out in `split` parts of WARPS_PER_CTA / split
+    // envs per group, so that the idle SMs share the work: a CTA with 8 (4, 1) active warps steps its envs in 0.79 (0.6, 0.45) of
+    // the time 16 take.  split = the largest power of two with split x groups <= gridDim; the other warps of such a CTA mirror
+    // the barrier sequence like the warps past the last env.  (Splitting the unfilled LAST wave of a large batch the same way
+    // measured 4 % slower at 8 192 envs: the CTAs finish staggered and the dynamic hand-out already fills the gaps.)
+    const int rem = ngroups < (int)gridDim.x ? ngroups : 0;
+    int split = 1;
+    while (a.tail_split && rem > 0 && split < WARPS_PER_CTA && WARPS_PER_CTA % (2 * split) == 0 && 2 * split * rem <= (int)gridDim.x) split *= 2;
+    const int nwhole = ngroups - rem, nunits = nwhole + rem * split, per_part = WARPS_PER_CTA / split;
     // every warp of the CTA makes the same passes so that the per-substep CTA barrier (phase lock) is legal
     for (;;) {
-        __syncthreads();  // (the previous pass has read s_group)
-        if (threadIdx.x == 0) s_group = atomicAdd(&sched[0], 1);
+        __syncthreads();  // (the previous pass has read s_unit)
+        if (threadIdx.x == 0) s_unit = atomicAdd(&sched[0], 1);
         __syncthreads();
-        const int group = s_group;
-        if (group >= ngroups) break;
-        const int slot = group * WARPS_PER_CTA + (threadIdx.x >> 5);
-        if (slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
-        else {  // no env left for this warp: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
+        const int unit = s_unit;
+        if (unit >= nunits) break;
+        const int wid = threadIdx.x >> 5;
+        int group = unit;
+        bool mine = true;
+        if (unit >= nwhole) {
+            group = nwhole + (unit - nwhole) / split;
+            mine = wid / per_part == (unit - nwhole) % split;
+        }
+        const int slot = group * WARPS_PER_CTA + wid;
+        if (mine && slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
+        else {  // no env for this warp in this pass: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = 0; f < a.n_frames; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 39); k++) CTA_SYNC();
                 if (a.phase_lock & 16) while (CTA_OR(0)) {}
@@ -408,6 +424,7 @@ struct PbrlModel {
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
                           // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int tail_split = 1;   // k_step splits the groups of a batch smaller than the GPU over the idle SMs; PBRL_TAIL_SPLIT=0 turns it off (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
     DevModel* dev = nullptr;
@@ -489,6 +506,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     m->sm_count = prop.multiProcessorCount;
     m->ctas_per_sm = 0;
     { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 63; }
+    { const char* e = getenv("PBRL_TAIL_SPLIT"); if (e) m->tail_split = atoi(e) != 0; }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) return bail(err);
@@ -610,8 +628,11 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     a.action = action; a.kp = kp; a.kd = kd; a.pd_time = pd_time; a.pd_dt = pd_dt; a.ctrl_mask = ctrl_mask; a.buf = *buf;
     a.phase_lock = m->phase_lock;
     a.cost_mode = m->cost_mode;
+    a.tail_split = m->tail_split;
     int* sched = m->sched + 2 * (m->sched_next.fetch_add(1) % PbrlModel::SCHED_RING);
-    k_step<<<grid_for(m, N), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, sched);
+    // small batches: more CTAs than groups, so that the groups can be split over them (down to one env per CTA)
+    const int cap = m->sm_count * m->ctas_per_sm, grid = m->tail_split ? (N < cap ? N : cap) : grid_for(m, N);
+    k_step<<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, sched);
     return check_launch("pbrl_step");
 }
 
