@@ -194,7 +194,10 @@ int pbrl_replay(const PbrlModel* model, int N, const float* qpos, const float* q
  * (testing_forward_env.ipynb cell 10: for every frame write data_pos[i] / data_vel[i] into the state, then step).
  * Env e replays frame (frame0[e] + k) mod F at step k = 0 .. K-1 (frame0 NULL: frame0[e] = e).  data_pos [F][35] and
  * data_vel [F][34] are device arrays.  Outputs are step-major: obs [K][N][69], reward [K][N][3] (zeros), done [K][N] (ones),
- * xpos [K][N][14][3], xquat [K][N][14][4]; any of them may be NULL. */
+ * xpos [K][N][14][3], xquat [K][N][14][4]; any of them may be NULL.
+ * When the N x K items outnumber the F clip rows (>= 4 items per row) the kinematics are evaluated once per clip row per call
+ * into a frame table owned by the model and the items gather their rows from it; otherwise per item.  Same arithmetic, same
+ * bits (PBRL_REPLAY_PER_ITEM=1 forces the per-item form). */
 int pbrl_replay_rollout(const PbrlModel* model, int N, int K, const float* data_pos, const float* data_vel, int F,
                         const int* frame0, float* obs, float* reward, float* done, float* xpos, float* xquat, void* stream);
 
@@ -232,8 +235,11 @@ int pbrl_debug_forward(const PbrlModel* model, int N, const float* qpos, const f
 int pbrl_debug_stage_profile(unsigned long long* cycles, unsigned long long* hits, int reset);
 
 /* ---- host-buffer convenience layer: what a Python/JAX host that keeps its data on the CPU calls.
- * Owns device state for N envs and pinned staging; every call copies host->device, launches, copies
- * device->host on the handle's stream and returns after the results are in the host buffers. */
+ * Owns device state for N envs; every call moves the inputs host->device, launches, moves the outputs device->host on the
+ * handle's stream and returns after the results are in the host buffers.  action / obs_out / reward_out / done_out that are
+ * page-locked, device-mapped host memory (cudaHostAlloc, cudaHostRegister, torch pin_memory) are read and written IN PLACE by
+ * the kernel -- the rows cross PCIe while the other envs are being stepped; pageable buffers are staged through
+ * cudaMemcpyAsync (PBRL_HOST_ZERO_COPY=0 forces the staging). */
 typedef struct PbrlBatch PbrlBatch;
 int pbrl_batch_create(const PbrlModel* model, int N, PbrlBatch** out);
 void pbrl_batch_destroy(PbrlBatch* batch);
