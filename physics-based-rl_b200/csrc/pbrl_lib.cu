@@ -75,7 +75,12 @@ __device__ __forceinline__ int env_stride() { return gridDim.x * WARPS_PER_CTA; 
 // groups arrive most expensive first, so the CTAs finish within one cheap group of each other (longest-processing-time-first);
 // a static round-robin gives CTA 0 the most expensive group of every pass.  `sched` = {next group, CTAs finished}: the last
 // CTA to leave re-arms the pair for the next launch.
-__global__ void __launch_bounds__(CTA_THREADS) k_step(const DevModel* __restrict__ gm, StepArgs a, int* __restrict__ sched) {
+#ifdef PBRL_STEP_MAXNREG   // dev sweeps: cap k_step's registers below what the launch bound allows
+#define PBRL_STEP_BOUNDS __maxnreg__(PBRL_STEP_MAXNREG)
+#else
+#define PBRL_STEP_BOUNDS __launch_bounds__(CTA_THREADS)
+#endif
+__global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArgs a, int* __restrict__ sched) {
     Ws& w = my_ws();
     const int lane = threadIdx.x & 31;
     const DevModel& sm = stage_model(gm);

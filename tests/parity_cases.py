@@ -117,13 +117,15 @@ def check_one_substep(backend, model, gravity, N=32, seed=5):
     eq, ev = row_relerr(s.qpos, env.qpos), row_relerr(s.qvel, env.qvel)
     # Random poses interpenetrate by centimetres (limbs inside the torso): forces of 1e3 N on an ill-conditioned
     # closest-point problem.  The north-star tolerance is asserted on the envs whose bodies overlap by at most 2 mm
-    # (every state a rollout can reach); the deeply overlapping ones get the fp32 conditioning bound.
-    deep = _self_penetration(model, q0) < -2e-3
+    # (every state a rollout can reach); the bound on the others grows with the overlap (512 random states per model, host
+    # emulation and the oracle's own fp32 build alike: max 8e-6 up to 10 mm, 3e-5 up to 30 mm, 5e-5 up to 60 mm, 2e-4 beyond).
+    pen = -_self_penetration(model, q0)
+    deep = pen > 2e-3
     assert (~deep).sum() >= N // 3
     assert eq[~deep].max() <= TOL_1 and ev[~deep].max() <= TOL_1, (eq[~deep].max(), ev[~deep].max())
-    assert eq.max() <= TOL_1 and ev.max() <= 3e-4, (eq.max(), ev.max())
-    # (the oracle's own fp32 build differs from its float64 build by up to 3.5e-5 on those states: the envelope is the
-    # conditioning of the problem in fp32, not the kernel's arithmetic)
+    bound = np.where(pen <= 2e-3, TOL_1, np.where(pen <= 0.010, 2e-5, np.where(pen <= 0.030, 5e-5, np.where(pen <= 0.060, 1e-4, 3e-4))))
+    assert eq.max() <= TOL_1 and (ev <= bound).all(), (eq.max(), (ev / bound).max())
+    # (the envelope is the conditioning of the problem in fp32, not the kernel's arithmetic)
     env32 = OracleEnv(Oracle(model, "f32"), N)
     env32.set_state(q0.astype(np.float32), np.asarray(s0v, np.float32))
     env32.step(tau, kp, kd, pd_mode=0, n_frames=1)
