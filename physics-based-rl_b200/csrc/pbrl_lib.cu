@@ -9,6 +9,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -758,6 +759,9 @@ struct PbrlBatch {
     float* ref_t0;
     int* order;        // device, processing order of the next step (pbrl_balance_order)
     std::vector<void*> allocs;
+    cudaEvent_t results_ready = nullptr;  // recorded after the last device->host copy of a step
+    float gains_host[2 * NU] = {0};       // what b->gains holds (the gains are re-uploaded only when they change)
+    bool gains_valid = false;
 };
 
 int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
@@ -766,6 +770,7 @@ int pbrl_batch_create(const PbrlModel* m, int N, PbrlBatch** out) {
     PbrlBatch* b = new PbrlBatch();
     b->model = m; b->N = N;
     if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return fail("cudaStreamCreate failed"); }
+    if (cudaEventCreateWithFlags(&b->results_ready, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(b->stream); delete b; return fail("cudaEventCreate failed"); }
     bool failed = false;
     auto alloc = [&](size_t n) -> float* {
         void* p = nullptr;
@@ -799,6 +804,7 @@ void pbrl_batch_destroy(PbrlBatch* b) {
     DeviceGuard guard(b->model->device);
     cudaStreamSynchronize(b->stream);
     for (void* p : b->allocs) if (p) cudaFree(p);
+    if (b->results_ready) cudaEventDestroy(b->results_ready);
     cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -835,9 +841,11 @@ int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_col
         CUDA_OK(cudaMemcpyAsync(b->action, action, (size_t)N * NU * action_cols * sizeof(float), cudaMemcpyHostToDevice, b->stream));
         action_dev = b->action;
     }
-    if (kp && kd) {
-        CUDA_OK(cudaMemcpyAsync(b->gains, kp, NU * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-        CUDA_OK(cudaMemcpyAsync(b->gains + NU, kd, NU * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    if (kp && kd && !(b->gains_valid && !memcmp(b->gains_host, kp, NU * sizeof(float)) && !memcmp(b->gains_host + NU, kd, NU * sizeof(float)))) {
+        memcpy(b->gains_host, kp, NU * sizeof(float));
+        memcpy(b->gains_host + NU, kd, NU * sizeof(float));
+        CUDA_OK(cudaMemcpyAsync(b->gains, b->gains_host, 2 * NU * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+        b->gains_valid = true;
     }
     if (stats_out) CUDA_OK(cudaMemsetAsync(b->buf.stats, 0, 8 * sizeof(float), b->stream));
     PbrlBuffers buf = b->buf;
@@ -849,12 +857,15 @@ int pbrl_batch_step_host(PbrlBatch* b, int n_frames, int pd_mode, int action_col
     if (done_dev) buf.done = done_dev;
     if (pbrl_step(b->model, N, n_frames, pd_mode, action_cols, action_dev, b->gains, b->gains + NU, pd_dt, nullptr, 0x0FFFFFFFu,
                   reward_mode, &buf, b->stream)) return -1;
-    if (pbrl_balance_order(b->model, N, b->buf.cost, b->order, b->stream)) return -1;  // next step's processing order
     if (obs_out && !obs_dev) CUDA_OK(cudaMemcpyAsync(obs_out, b->buf.obs, (size_t)N * PBRL_OBS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (reward_out && !reward_dev) CUDA_OK(cudaMemcpyAsync(reward_out, b->buf.reward, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (done_out && !done_dev) CUDA_OK(cudaMemcpyAsync(done_out, b->buf.done, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, b->buf.stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    CUDA_OK(cudaStreamSynchronize(b->stream));
+    CUDA_OK(cudaEventRecord(b->results_ready, b->stream));
+    // the next step's processing order is computed behind the results: the caller does not wait for it (the next call's
+    // launch is ordered after it on the stream)
+    if (pbrl_balance_order(b->model, N, b->buf.cost, b->order, b->stream)) return -1;
+    CUDA_OK(cudaEventSynchronize(b->results_ready));
     return 0;
 }
 int pbrl_batch_get_state_host(PbrlBatch* b, float* qpos, float* qvel, float* time) {
