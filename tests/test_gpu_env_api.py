@@ -250,5 +250,5 @@ def test_ppo_loop_consumes_the_env(mods):
     hist, net = ppo.train(num_envs=256, iters=3, horizon=8, log=lambda r: None)
     assert len(hist) == 3 and all(np.isfinite([h["mean_reward"], h["loss"], h["done_frac"]]).all() for h in hist)
     assert all(0.0 <= h["mean_reward"] <= 1.0 + 1e-6 for h in hist)          # the mimic reward is a convex mix of exp(-k e) terms
-    assert float(net.pi[-1].bias.abs().max()) > 0.0                              # the optimiser moved the policy off its initial zero offset
+    assert float(net.pi[-1].bias.detach().abs().max()) > 0.0                              # the optimiser moved the policy off its initial zero offset
     assert all(torch.isfinite(p).all() for p in net.parameters())

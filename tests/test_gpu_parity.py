@@ -269,3 +269,34 @@ def test_capsule_box_and_box_box_contacts(gpu_grav, model_grav):
 def test_quiet_stance_carries_the_body_weight(gpu_grav, model_grav):
     out = pc.check_quiet_stance(gpu_grav, model_grav)
     print("quiet stance", out)
+
+
+def test_small_batches_split_over_the_sms_bit_identically(model_grav):
+    """k_step hands a batch with fewer groups of 16 envs than SMs out in parts of 8 / 4 / 2 / 1 envs per CTA (the other warps of
+    the CTA mirror the barrier sequence).  Which warp of which CTA steps an env must not change a bit of its result: the same
+    rollout with the split on (default) and off (PBRL_TAIL_SPLIT=0 at model creation), for batch sizes on either side of every
+    split factor and a ragged last group."""
+    import os
+    import numpy as np
+    kp, kd = pc.util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    os.environ["PBRL_TAIL_SPLIT"] = "0"
+    try:
+        be_off = GpuBackend(model_grav)
+    finally:
+        os.environ.pop("PBRL_TAIL_SPLIT")
+    be_on = GpuBackend(model_grav)
+    for N in (1, 9, 17, 100, 300, 600, 1190, 2368 + 5):
+        rng = np.random.default_rng(N)
+        qpos, qvel = pc.random_states(model_grav, N, N, gravity_heights=True)
+        acts = rng.uniform(lo, hi, (2, N, 28)).astype(np.float32)
+        res = []
+        for be in (be_on, be_off):
+            s = be.new_state(N)
+            s.set_state(qpos.astype(np.float32), qvel.astype(np.float32))
+            for k in range(2):
+                be.step(s, acts[k], kp, kd)
+            res.append(s)
+        for name in ("qpos", "qvel", "warm", "ctrl", "obs", "time", "qpos_lag", "qvel_lag"):
+            assert np.array_equal(getattr(res[0], name), getattr(res[1], name)), (N, name)
+        assert np.isfinite(res[0].qpos).all() and (res[0].status & 7 == 0).all()
