@@ -329,6 +329,7 @@ class Dynamics:
         self.pending = [None, None]
         self.balance = not os.environ.get("PBRL_BENCH_NO_BALANCE")
         self.launches = 0
+        self.step_launches = int(self.lib.pbrl_step_launches(self.M.handle, n_env, N_FRAMES, ctypes.byref(self.bufs[0])))
 
     def restart(self):
         for k2, v in self.init.items():
@@ -343,7 +344,7 @@ class Dynamics:
         self.stats2[i].zero_()
         L.check(lib.pbrl_step(self.M.handle, self.n_env, N_FRAMES, self.pd_mode, 1, L._ptr(a), L._ptr(self.kp), L._ptr(self.kd), ctypes.c_float(0.002),
                               None, ctypes.c_uint(0x0FFFFFFF), 1, ctypes.byref(self.bufs[i]), self.stream))
-        self.launches += 1
+        self.launches += self.step_launches   # 1, or 3 when the library regroups the envs inside the step (two k_step parts + the sort)
         if self.world > 1:
             # per-step reward / termination statistics all-reduce (32 B, NCCL over NVLink): asynchronous on NCCL's own stream,
             # which waits for k_step; the compute stream goes straight on to the next step and joins before the buffer is reused
@@ -433,7 +434,7 @@ class Dynamics:
             e2e_step(k)
             total += time.perf_counter() - t0
         lib.pbrl_batch_destroy(batch)
-        self.launches += 2 * (steps + 3) + 2
+        self.launches += (self.step_launches + 1) * (steps + 3) + 2   # per host-buffer step: pbrl_step's kernels + the balance sort
         return self.max_over_ranks(total)
 
 

@@ -12,6 +12,7 @@
  *   pbrl_replay_rollout  the frame loop around it /root/reference/testing_forward_env.ipynb cell 10 (write frame i, step, next)
  *   pbrl_autoreset  brax AutoResetWrapper.step    brax 0.10.3 envs/wrappers/training.py (imported by agent_mimic.py:14-15 via ppo)
  *   pbrl_balance_order   no counterpart: a scheduling hint for pbrl_step (which envs share a CTA)
+ *   pbrl_step_launches   no counterpart: how many kernels a pbrl_step call launches (bench.py's gpu_launches)
  *   pbrl_pd_torque  standard/feedback/stable PD   /root/reference/agents_env/pds_controllers_agents.py:17-172
  *                   and the *_mjx signature twins /root/reference/agents_env/pds_controllers_mjx.py:17-191
  *   pbrl_debug_forward  fields of brax `pipeline_state` the reference reads back
@@ -180,6 +181,12 @@ int pbrl_autoreset(const PbrlModel* model, int N, int reward_mode, const float* 
                    const float* next_ref_t0 /* [N] or NULL */, int* steps /* [N] or NULL */, const PbrlBuffers* buf,
                    void* stream);
 
+/* pbrl_step is one kernel launch, except for large batches (>= 2 groups of 16 envs per SM-resident CTA) that pass env_order,
+ * cost and status: those steps run in two parts (PD law + the first 4 substeps in the caller's order; the other substeps and
+ * the epilogue with the envs re-sorted by the work of the first part, in a scratch order of the model), because an env's
+ * solver work is predicted far better by its previous substep than by its previous env step.  Results do not depend on it
+ * (PBRL_REGROUP_AFTER=0 at model creation: always one launch).  pbrl_step_launches tells how many kernels a call launches. */
+int pbrl_step_launches(const PbrlModel* model, int N, int n_frames, const PbrlBuffers* buf);
 int pbrl_step(const PbrlModel* model, int N, int n_frames, int pd_mode, int action_cols /* 1 or 4 */,
               const float* action /* [N][28][action_cols] */, const float* kp /* [28] */,
               const float* kd /* [28] */, float pd_dt, const float* pd_time /* [N] or NULL = state time */,

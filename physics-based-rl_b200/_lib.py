@@ -64,7 +64,7 @@ def check(rc):
 
 
 EXPORTS = ["pbrl_model_desc_size", "pbrl_model_desc_field", "pbrl_last_error", "pbrl_device_count",
-           "pbrl_model_create", "pbrl_model_destroy", "pbrl_reset", "pbrl_balance_order", "pbrl_autoreset", "pbrl_step", "pbrl_replay", "pbrl_replay_rollout", "pbrl_pd_torque",
+           "pbrl_model_create", "pbrl_model_destroy", "pbrl_reset", "pbrl_balance_order", "pbrl_autoreset", "pbrl_step", "pbrl_step_launches", "pbrl_replay", "pbrl_replay_rollout", "pbrl_pd_torque",
            "pbrl_debug_forward", "pbrl_debug_stage_profile", "pbrl_batch_create", "pbrl_batch_destroy", "pbrl_batch_reset_host",
            "pbrl_batch_step_host", "pbrl_batch_get_state_host"]
 

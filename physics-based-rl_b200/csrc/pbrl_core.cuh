@@ -2424,6 +2424,7 @@ static int* g_emu_trace = nullptr;  // dev study only: (niter, dense iterations)
 #endif
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
+    int f_begin, f_end;  // the substeps of the env step this launch runs: [0, n_frames) is the whole step (see env_step)
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
     int tail_split;  // k_step: split the groups of a batch smaller than the GPU over the idle SMs
     int cost_mode;   // work estimate written to buf.cost: 0 most expensive substep, 1 sum over the substeps, 2 last substep
@@ -2449,12 +2450,15 @@ PB_DEV void frames_prefetch(const float* frames, const DevMimic& mm, Ws& w, int 
 PB_DEVN void mimic_epilogue(const DevModel& m, const DevMimic& mm, const float* frames, Ws& w, const PbrlBuffers& B,
                             int env, int clip, float t, float* acc, int lane);
 
-// HumanoidTrain.step (agent_mimic.py:58-91): PD law once, n_frames substeps with the torque held
+// HumanoidTrain.step (agent_mimic.py:58-91): PD law once, n_frames substeps with the torque held.
+// A launch runs the substeps [f_begin, f_end) of the env step: the PD law belongs to the part that starts at substep 0, the
+// observation / reward epilogue to the part that ends at n_frames; in between the state lives in the caller's buffers
+// (qpos, qvel, warm, ctrl, time, status, cost).  One launch with [0, n_frames) is the whole step.
 PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, float* acc, int lane) {
     const PbrlBuffers& B = a.buf;
     const bool mimic = a.reward_mode == PBRL_REWARD_MIMIC;
+    const bool first = a.f_begin == 0, last = a.f_end == a.n_frames;
     const int clip = mimic ? B.motion_id[env] : 0;
-    const float t_end = mimic ? B.ref_t0[env] + B.time[env] + (float)a.n_frames * m.timestep : 0.f;
     PROF_START();
     load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
     load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
@@ -2462,23 +2466,25 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
     float* lag_q = w.fsmooth;  // dead until the first substep
     float* lag_v = w.qacc;
-    if (a.pd_mode >= PBRL_PD_FEEDBACK) {
+    if (first && a.pd_mode >= PBRL_PD_FEEDBACK) {
         load_row(lag_q, B.qpos_lag + (size_t)env * NQ, NQ, lane);
         load_row(lag_v, B.qvel_lag + (size_t)env * NV, NV, lane);
     }
-    LANE_IF(z, 1) w.status = 0;
+    LANE_IF(z, 1) w.status = first ? 0 : B.status[env];   // (a step in two parts needs the status buffer: checked by the caller)
     WSYNC();
     float time = B.time[env];
     PROF(0);
-    pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
-              a.pd_time ? a.pd_time[env] : time, a.pd_dt, lag_q, lag_v, lane);
-    LANE_IF(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
-    WSYNC();
+    if (first) {
+        pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
+                  a.pd_time ? a.pd_time[env] : time, a.pd_dt, lag_q, lag_v, lane);
+        LANE_IF(k, NU) if ((a.ctrl_mask >> k) & 1u) w.ctrl[k] = w.tau[k];
+        WSYNC();
+    }
     LANE_IF(z, 1) w.phase_lock = a.phase_lock;
     WSYNC();
     PROF(1);
-    int cost = 0, cost_sum = 0;
-    for (int f = 0; f < a.n_frames; f++) {
+    int cost = first ? 0 : B.cost[env], cost_sum = cost;
+    for (int f = a.f_begin; f < a.f_end; f++) {
         if (f == a.n_frames - 1) {  // the state entering the last forward is what the next PD law evaluates M / bias at
             store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);
@@ -2492,18 +2498,20 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     }
     if (a.cost_mode == 1) cost = cost_sum;
     else if (a.cost_mode == 2) cost = w.work;
-    if (mimic) frames_prefetch(a.frames, a.mm, w, clip, t_end, lane);  // into the (now dead) factor workspace; lands during the stores
+    // the two reference frames at the clip time the step ends on, into the (now dead) factor workspace; they land during the stores
+    if (mimic && last) frames_prefetch(a.frames, a.mm, w, clip, B.ref_t0[env] + time, lane);
     float bad = wsum(lane, NQ + NV, [&](int i) { float v = i < NQ ? w.qpos[i] : w.qvel[i - NQ]; return (v == v && fabsf(v) < 1e30f) ? 0.f : 1.f; });
     store_row(B.qpos + (size_t)env * NQ, w.qpos, NQ, lane);
     store_row(B.qvel + (size_t)env * NV, w.qvel, NV, lane);
     store_row(B.warm + (size_t)env * NV, w.warm, NV, lane);
-    store_row(B.ctrl + (size_t)env * NU, w.ctrl, NU, lane);
+    if (first) store_row(B.ctrl + (size_t)env * NU, w.ctrl, NU, lane);
     LANE_IF(z, 1) {
         B.time[env] = time;
         if (B.status) B.status[env] = w.status | (bad > 0.f ? PBRL_STATUS_NAN : 0);
         if (B.cost) B.cost[env] = cost;
     }
     PROF(24);
+    if (!last) { WSYNC(); return; }
     if (mimic) {
         if (B.obs) { store_row(B.obs + (size_t)env * PBRL_OBS, w.qpos, NQ, lane); store_row(B.obs + (size_t)env * PBRL_OBS + NQ, w.qvel, NV, lane); }
         mimic_epilogue(m, a.mm, a.frames, w, B, env, clip, B.ref_t0[env] + time, acc, lane);

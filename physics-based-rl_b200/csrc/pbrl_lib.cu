@@ -116,7 +116,7 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
         const int slot = group * WARPS_PER_CTA + wid;
         if (mine && slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
         else {  // no env for this warp in this pass: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
-            for (int f = 0; f < a.n_frames; f++) {
+            for (int f = a.f_begin; f < a.f_end; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 39); k++) CTA_SYNC();
                 if (a.phase_lock & 16) while (CTA_OR(0)) {}
                 if (a.phase_lock & 8) CTA_SYNC();
@@ -430,6 +430,8 @@ struct PbrlModel {
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
                           // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int regroup_every = 0;   // ... and again every that many substeps (0: once); PBRL_REGROUP_EVERY
+    int regroup_after = 4;   // pbrl_step: > 0 = re-sort the envs after that many substeps of the step (two launches); PBRL_REGROUP_AFTER
     int tail_split = 1;   // k_step splits the groups of a batch smaller than the GPU over the idle SMs; PBRL_TAIL_SPLIT=0 turns it off (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
@@ -445,6 +447,22 @@ struct PbrlModel {
     // two streams replaying different clips through one model at the same time must not share it -> one table per frame count)
     mutable std::mutex scratch_mu;
     mutable std::vector<std::pair<int, float*>> frame_tabs;
+    // pbrl_step's order for the second part of a regrouped step: a ring of grow-only buffers, one per call in flight
+    static constexpr int ORDER_RING = 4;
+    mutable int* order_bufs[ORDER_RING] = {nullptr, nullptr, nullptr, nullptr};
+    mutable int order_cap[ORDER_RING] = {0, 0, 0, 0};
+    mutable unsigned order_next = 0;
+    int* regroup_order(int N) const {
+        std::lock_guard<std::mutex> lk(scratch_mu);
+        const int i = order_next++ % ORDER_RING;
+        if (order_cap[i] < N) {
+            if (order_bufs[i]) cudaFree(order_bufs[i]);   // (cudaFree waits for the work that still reads it)
+            order_bufs[i] = nullptr; order_cap[i] = 0;
+            if (cudaMalloc(&order_bufs[i], (size_t)N * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            order_cap[i] = N;
+        }
+        return order_bufs[i];
+    }
     float* frame_table(int F) const {
         std::lock_guard<std::mutex> lk(scratch_mu);
         for (auto& t : frame_tabs) if (t.first == F) return t.second;
@@ -513,6 +531,8 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     m->ctas_per_sm = 0;
     { const char* e = getenv("PBRL_PHASE_LOCK"); if (e) m->phase_lock = atoi(e) & 63; }
     { const char* e = getenv("PBRL_TAIL_SPLIT"); if (e) m->tail_split = atoi(e) != 0; }
+    { const char* e = getenv("PBRL_REGROUP_AFTER"); if (e) m->regroup_after = atoi(e); }
+    { const char* e = getenv("PBRL_REGROUP_EVERY"); if (e) m->regroup_every = atoi(e); }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) return bail(err);
@@ -560,6 +580,7 @@ void pbrl_model_destroy(PbrlModel* m) {
     if (m->frames) cudaFree(m->frames);
     if (m->sched) cudaFree(m->sched);
     for (auto& t : m->frame_tabs) cudaFree(t.second);
+    for (int* p : m->order_bufs) if (p) cudaFree(p);
     delete m;
 }
 
@@ -612,6 +633,17 @@ int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done
     return check_launch("pbrl_autoreset");
 }
 
+// how many kernels pbrl_step launches for this batch (1, or the parts of a regrouped step plus the sorts between them)
+int pbrl_step_launches(const PbrlModel* m, int N, int n_frames, const PbrlBuffers* buf) {
+    if (!m || !buf || N <= 0) return 0;
+    const int cap = m->sm_count * m->ctas_per_sm, r = m->regroup_after;
+    if (!(r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap)) return 1;
+    const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
+    int parts = 1;
+    for (int f = r; f < n_frames; f += every) parts++;
+    return 2 * parts - 1;
+}
+
 int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_cols, const float* action, const float* kp,
               const float* kd, float pd_dt, const float* pd_time, unsigned ctrl_mask, int reward_mode, const PbrlBuffers* buf,
               void* stream) {
@@ -635,10 +667,34 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     a.phase_lock = m->phase_lock;
     a.cost_mode = m->cost_mode;
     a.tail_split = m->tail_split;
-    int* sched = m->sched + 2 * (m->sched_next.fetch_add(1) % PbrlModel::SCHED_RING);
     // small batches: more CTAs than groups, so that the groups can be split over them (down to one env per CTA)
     const int cap = m->sm_count * m->ctas_per_sm, grid = m->tail_split ? (N < cap ? N : cap) : grid_for(m, N);
-    k_step<<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, sched);
+    auto launch = [&](int f_begin, int f_end) {
+        a.f_begin = f_begin; a.f_end = f_end;
+        int* sched = m->sched + 2 * (m->sched_next.fetch_add(1) % PbrlModel::SCHED_RING);
+        k_step<<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, sched);
+    };
+    // Regrouping inside the step: how much solver work an env needs is far better predicted by its previous SUBSTEP (94 % of
+    // the dense-Hessian envs stay dense from one substep to the next) than by its previous env step (a quarter of them were not
+    // dense then).  With `regroup_after` = r > 0 the step is two launches: PD law + r substeps in the caller's processing order,
+    // then -- the envs re-sorted by the work of those substeps (into a scratch order of the model) -- the other substeps and
+    // the epilogue.  The state crosses the boundary in the caller's buffers.  Needs env_order, cost and status.
+    const int r = m->regroup_after;
+    int* order2 = nullptr;
+    if (r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap) order2 = m->regroup_order(N);
+    if (order2) {
+        const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
+        int f0 = 0;
+        for (int f1 = r; f0 < n_frames; f0 = f1, f1 = (f1 + every < n_frames ? f1 + every : n_frames)) {
+            if (f0 > 0) {
+                k_balance_order<<<1, BO_THREADS, 0, (cudaStream_t)stream>>>(N, buf->cost, order2);
+                a.buf.env_order = order2;
+            }
+            launch(f0, f1);
+        }
+    } else {
+        launch(0, n_frames);
+    }
     return check_launch("pbrl_step");
 }
 

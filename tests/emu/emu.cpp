@@ -5,6 +5,7 @@
 // (`pytest -m "not gpu"`).  It cannot see races or shuffle bugs; those are covered by the `-m gpu`
 // parity tests and compute-sanitizer.  Nothing in the product loads this library.
 #define PBRL_HOST_EMU 1
+#include <cstdlib>
 #include "../../physics-based-rl_b200/csrc/pbrl_core.cuh"
 #include "../../physics-based-rl_b200/csrc/pbrl_mimic.cuh"
 #include "../../physics-based-rl_b200/csrc/pbrl_desc_reflect.h"
@@ -70,7 +71,19 @@ int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* act
     if (reward_mode == PBRL_REWARD_MIMIC) { a.frames = g_frames.data(); a.mm = g_mimic; }
     frames_init(ws[0], 0);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+    // PBRL_EMU_SPLIT=r: the step in two parts (PD law + r substeps for every env, then the rest), as pbrl_step does when it
+    // regroups the envs inside the step
+    const char* sp = getenv("PBRL_EMU_SPLIT");
+    const int r = sp ? atoi(sp) : 0;
+    if (r > 0 && r < n_frames && buf->cost && buf->status) {
+        a.f_begin = 0; a.f_end = r;
+        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+        a.f_begin = r; a.f_end = n_frames;
+        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+    } else {
+        a.f_begin = 0; a.f_end = n_frames;
+        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+    }
     if (buf->stats && reward_mode == PBRL_REWARD_MIMIC) for (int k = 0; k < 6; k++) buf->stats[k] += acc[k];
     return 0;
 }

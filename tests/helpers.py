@@ -74,6 +74,7 @@ class _HostState:
         for n, w in STATE_SHAPES:
             setattr(self, n, np.zeros((N, w) if w else (N,), np.float32))
         self.status = np.zeros(N, np.int32)
+        self.cost = np.zeros(N, np.int32)
         self.motion_id = np.zeros(N, np.int32)
         self.ref_t0 = np.zeros(N, np.float32)
         self.stats = np.zeros(8, np.float32)
@@ -217,7 +218,7 @@ class GpuBackend:
     def _up(self, s):
         t = self.torch
         d = {n: t.from_numpy(getattr(s, n)).to(self.dev) for n, _ in STATE_SHAPES}
-        for n in ("status", "motion_id", "ref_t0", "stats"):
+        for n in ("status", "cost", "motion_id", "ref_t0", "stats"):
             d[n] = t.from_numpy(getattr(s, n)).to(self.dev)
         return d
 

@@ -300,3 +300,53 @@ def test_small_batches_split_over_the_sms_bit_identically(model_grav):
         for name in ("qpos", "qvel", "warm", "ctrl", "obs", "time", "qpos_lag", "qvel_lag"):
             assert np.array_equal(getattr(res[0], name), getattr(res[1], name)), (N, name)
         assert np.isfinite(res[0].qpos).all() and (res[0].status & 7 == 0).all()
+
+
+def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
+    """Large batches that pass env_order / cost / status are stepped in two launches with the envs re-sorted in between
+    (include/pbrl.h: pbrl_step_launches).  State, observations, rewards, status and the work estimate must be bit-identical to
+    the single launch (PBRL_REGROUP_AFTER=0 at model creation), in mimic mode and in reference mode, over several steps."""
+    import ctypes
+    import os
+    import numpy as np
+    import torch
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    os.environ["PBRL_REGROUP_AFTER"] = "0"
+    try:
+        be1 = GpuBackend(model_grav, mimic_desc=mdesc)
+    finally:
+        os.environ.pop("PBRL_REGROUP_AFTER")
+    be2 = GpuBackend(model_grav, mimic_desc=mdesc)
+    N = 5000
+    rng = np.random.default_rng(91)
+    kp, kd = pc.util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    acts = rng.uniform(lo, hi, (3, N, 28)).astype(np.float32)
+    for reward_mode in (1, 0):
+        outs = []
+        for be in (be1, be2):
+            L, lib = be.L, be.L.lib()
+            z = lambda *s: torch.zeros(s, device=be.dev)
+            d = dict(qpos=z(N, 35), qvel=z(N, 34), time=z(N), warm=z(N, 34), ctrl=z(N, 28), qpos_lag=z(N, 35), qvel_lag=z(N, 34), obs=z(N, 69),
+                     reward=z(N, 3), done=z(N), metrics=z(N, 3), status=torch.zeros(N, dtype=torch.int32, device=be.dev), stats=z(8),
+                     cost=torch.zeros(N, dtype=torch.int32, device=be.dev), env_order=torch.arange(N, dtype=torch.int32, device=be.dev),
+                     motion_id=torch.from_numpy(mid).to(be.dev), ref_t0=torch.from_numpy(t0).to(be.dev))
+            b = L.make_buffers(**d)
+            assert lib.pbrl_step_launches(be.model.handle, N, 8, ctypes.byref(b)) == (1 if be is be1 else 3)
+            assert lib.pbrl_step_launches(be.model.handle, 64, 8, ctypes.byref(b)) == 1
+            L.check(lib.pbrl_reset(be.model.handle, N, reward_mode, ctypes.byref(b), be._stream()))
+            kpd, kdd = be._dp(kp), be._dp(kd)
+            for k in range(3):
+                a = torch.from_numpy(acts[k]).to(be.dev)
+                L.check(lib.pbrl_step(be.model.handle, N, 8, 3, 1, L._ptr(a), L._ptr(kpd), L._ptr(kdd), ctypes.c_float(0.002), None,
+                                      ctypes.c_uint(0x0FFFFFFF), reward_mode, ctypes.byref(b), be._stream()))
+                L.check(lib.pbrl_balance_order(be.model.handle, N, L._ptr(d["cost"]), L._ptr(d["env_order"]), be._stream()))
+            torch.cuda.synchronize()
+            outs.append({k: v.cpu().numpy() for k, v in d.items()})
+        for name in ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics", "status", "cost"):
+            assert np.array_equal(outs[0][name], outs[1][name]), (reward_mode, name)
+        assert np.allclose(outs[0]["stats"], outs[1]["stats"], rtol=1e-5, atol=1e-3)
+        for o in outs:   # (the counting sort places equal costs in arrival order: the orders are permutations sorted alike, not equal)
+            assert np.array_equal(np.sort(o["env_order"]), np.arange(N)) and (np.diff(np.clip(o["cost"], 0, 255)[o["env_order"]]) <= 0).all()

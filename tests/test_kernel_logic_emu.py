@@ -170,3 +170,37 @@ def test_quiet_stance_carries_the_body_weight(emu_grav, model_grav):
     """Contact self-consistency (stand-in for the missing MJX contact goldens): weight support within 5 %, pyramid edge forces
     >= 0 (friction cone), ~zero normal velocity, sub-millimetre penetration -- oracle and kernel logic."""
     pc.check_quiet_stance(emu_grav, model_grav)
+
+
+def test_step_in_two_parts_is_bit_identical(model_grav):
+    """env_step over a substep range: PD law + r substeps, then the other substeps + epilogue (what pbrl_step launches when it
+    regroups the envs inside the step) gives the bits of the whole step, in reference and in mimic mode."""
+    import os
+    import numpy as np
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    N = 24
+    rng = np.random.default_rng(12)
+    kp, kd = pc.util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    acts = rng.uniform(lo, hi, (2, N, 28)).astype(np.float32)
+    for reward_mode in (1, 0):
+        res = []
+        for split in (None, "1", "4", "7"):
+            if split:
+                os.environ["PBRL_EMU_SPLIT"] = split
+            try:
+                b = EmuBackend(model_grav)
+                b.set_mimic(mdesc)
+                s = b.new_state(N)
+                s.motion_id[:], s.ref_t0[:] = mid, t0
+                b.reset(s, reward_mode=reward_mode)
+                for k in range(2):
+                    b.step(s, acts[k], kp, kd, reward_mode=reward_mode)
+            finally:
+                os.environ.pop("PBRL_EMU_SPLIT", None)
+            res.append(s)
+        for other in res[1:]:
+            for name in ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics", "status", "cost"):
+                assert np.array_equal(getattr(res[0], name), getattr(other, name)), (reward_mode, name)
