@@ -22,7 +22,7 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 stalls = sorted(h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"))
 with open(P / f"{name}_k_step_ncu_full_summary.csv", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 1: python bench.py --steps 2 --warmup 3 --no-cpu-baseline ({rep.name})\n")
+    f.write(f"# PBRL_REGROUP_AFTER=0 (the whole env step in one launch; by default a large batch is two launches of 4 substeps each) ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 1: python bench.py --steps 2 --warmup 3 --no-cpu-baseline ({rep.name})\n")
     f.write("metric,unit,value\n")
     for h in WANT + stalls:
         if h in hdr:
