@@ -443,10 +443,20 @@ struct PbrlModel {
     static constexpr int SCHED_RING = 32;
     int* sched = nullptr;
     mutable std::atomic<unsigned> sched_next{0};
-    // pbrl_replay_rollout's frame table (grow-only scratch; a rollout is stream-ordered behind the previous one on its stream,
-    // two streams replaying different clips through one model at the same time must not share it -> one table per frame count)
+    // pbrl_replay_rollout's frame tables: grow-only scratch, one per (clip pointer, row count) seen, so that rollouts of
+    // different clips through one model -- also concurrent ones on different streams -- never share a table.  A rollout is
+    // stream-ordered behind the previous one of the same clip on its stream.
     mutable std::mutex scratch_mu;
-    mutable std::vector<std::pair<int, float*>> frame_tabs;
+    struct FrameTab { const float* clip; int F; float* tab; };
+    mutable std::vector<FrameTab> frame_tabs;
+    float* frame_table(const float* clip, int F) const {
+        std::lock_guard<std::mutex> lk(scratch_mu);
+        for (auto& t : frame_tabs) if (t.clip == clip && t.F == F) return t.tab;
+        float* p = nullptr;
+        if (cudaMalloc(&p, (size_t)F * 100 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        frame_tabs.push_back({clip, F, p});
+        return p;
+    }
     // pbrl_step's order for the second part of a regrouped step: a ring of grow-only buffers, one per call in flight
     static constexpr int ORDER_RING = 4;
     mutable int* order_bufs[ORDER_RING] = {nullptr, nullptr, nullptr, nullptr};
@@ -462,14 +472,6 @@ struct PbrlModel {
             order_cap[i] = N;
         }
         return order_bufs[i];
-    }
-    float* frame_table(int F) const {
-        std::lock_guard<std::mutex> lk(scratch_mu);
-        for (auto& t : frame_tabs) if (t.first == F) return t.second;
-        float* p = nullptr;
-        if (cudaMalloc(&p, (size_t)F * 100 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        frame_tabs.emplace_back(F, p);
-        return p;
     }
 };
 
@@ -579,7 +581,7 @@ void pbrl_model_destroy(PbrlModel* m) {
     if (m->dev) cudaFree(m->dev);
     if (m->frames) cudaFree(m->frames);
     if (m->sched) cudaFree(m->sched);
-    for (auto& t : m->frame_tabs) cudaFree(t.second);
+    for (auto& t : m->frame_tabs) cudaFree(t.tab);
     for (int* p : m->order_bufs) if (p) cudaFree(p);
     delete m;
 }
@@ -723,7 +725,7 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
     if (!per_item_only && (long long)N * K >= 4ll * F && F < (1 << 24)) {   // (row offsets of the table are 32-bit)
         float* tab = nullptr;
         if (xpos || xquat) {
-            tab = m->frame_table(F);
+            tab = m->frame_table(data_pos, F);
             if (!tab) return fail("pbrl_replay_rollout: cannot allocate the frame table");
             if (m->axes_match) k_replay_frames<true><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
             else k_replay_frames<false><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
