@@ -94,9 +94,14 @@ PB_DEV void quat_slerp(const float* a, const float* b, float u, float* r) {
     for (int k = 0; k < 4; k++) r[k] = wa * a[k] + sg * wb * b[k];
     quat_normalize(r);
 }
+// geodesic angle between unit quaternions, 2 acos |a . b|, evaluated as 2 atan2(|vec(conj(a) b)|, |a . b|): the arc cosine loses
+// half the digits near 1 (a tracked pose: angles of 1e-3 rad came out 3e-4 off in fp32 and dominated the reward's error)
 PB_DEV float quat_angle(const float* a, const float* b) {
-    float d = fabsf(a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
-    return 2.f * acosf(fminf(d, 1.f));
+    const float d = fabsf(a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
+    const float vx = a[0] * b[1] - b[0] * a[1] - (a[2] * b[3] - a[3] * b[2]);
+    const float vy = a[0] * b[2] - b[0] * a[2] - (a[3] * b[1] - a[1] * b[3]);
+    const float vz = a[0] * b[3] - b[0] * a[3] - (a[1] * b[2] - a[2] * b[1]);
+    return 2.f * atan2f(sqrtf(vx * vx + vy * vy + vz * vz), d);
 }
 PB_DEV void quat_to_euler_xyz(const float* q, float* e) {
     const float w = q[0], x = q[1], y = q[2], z = q[3];

@@ -440,6 +440,32 @@ def check_replay_rollout(backend, model, F=39, N=50, K=7, seed=37):
     assert np.array_equal(out2["obs"][k2][:, :35], q32[(np.arange(N) + k2) % F])
 
 
+def check_reward_after_one_substep(backend, model_grav, table, mdesc, N=256, seed=3):
+    """North star: 'fp32 relative error <= 1e-5 on qpos/qvel and reward after one substep'.  The reward half of it, in mimic
+    mode: reference-state initialisation over the seven clips (feet on the floor), one substep of stable PD towards random
+    targets, reward (total, pose term, end-effector term) against the float64 oracle <= 1e-5, same termination flags.  (The
+    pose term needs the geodesic angle in its well-conditioned form: through the arc cosine it was 2.6e-5 off.)"""
+    rng = np.random.default_rng(seed)
+    mid = (np.arange(N) % 7).astype(np.int32)
+    t0 = (rng.uniform(0, 1, N) * table.header[mid, 2]).astype(np.float32)
+    kp, kd = util_data.generate_kp_kd_gains()
+    lo, hi = model_grav.jnt_range[1:, 0], model_grav.jnt_range[1:, 1]
+    s = backend.new_state(N)
+    s.motion_id[:], s.ref_t0[:] = mid, t0
+    backend.reset(s, reward_mode=1)
+    env = OracleEnv(_oracle(model_grav), N)
+    env.reset_mimic(mdesc, mid, t0)
+    for n in ("qpos", "qvel", "qpos_lag", "qvel_lag"):   # identical initial states: the oracle starts from the back end's fp32 rows
+        getattr(env, n)[:] = getattr(s, n)
+    tgt = rng.uniform(lo, hi, (N, 28)).astype(np.float32)
+    env.step_mimic(tgt, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=1)
+    backend.step(s, tgt, kp, kd, pd_mode=3, pd_dt=0.002, n_frames=1, reward_mode=1)
+    err = np.abs(np.asarray(s.reward, np.float64) - env.reward)
+    assert err.max() <= TOL_1 and (s.done == env.done).all(), (err.max(0), int((s.done != env.done).sum()))
+    assert np.abs(s.metrics - env.metrics).max() <= 1e-5
+    return float(err.max())
+
+
 def check_replay_rollout_paths_agree(backend, model, F=39, N=256, K=8, seed=40):
     """pbrl_replay_rollout has two forms: kinematics per item (few items per clip row), or once per clip row into a frame table
     that the rollout then gathers from (many items per row).  Same replay_item_fk arithmetic: the poses must be bit-identical."""

@@ -70,6 +70,11 @@ def test_mimic_mode(model_grav):
     pc.check_mimic(b, model_grav, table, mdesc, N=112)
 
 
+def test_reward_after_one_substep(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    print("reward after one substep", pc.check_reward_after_one_substep(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc))
+
+
 def test_autoreset(model_grav):
     table, mdesc, keep = pc.mimic_setup(model_grav)
     pc.check_autoreset(GpuBackend(model_grav, mimic_desc=mdesc), model_grav, table, mdesc, N=133)

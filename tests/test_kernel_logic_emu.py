@@ -204,3 +204,10 @@ def test_step_in_two_parts_is_bit_identical(model_grav):
         for other in res[1:]:
             for name in ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics", "status", "cost"):
                 assert np.array_equal(getattr(res[0], name), getattr(other, name)), (reward_mode, name)
+
+
+def test_reward_after_one_substep(model_grav):
+    table, mdesc, keep = pc.mimic_setup(model_grav)
+    b = EmuBackend(model_grav)
+    b.set_mimic(mdesc)
+    pc.check_reward_after_one_substep(b, model_grav, table, mdesc, N=128)
