@@ -181,11 +181,13 @@ int pbrl_autoreset(const PbrlModel* model, int N, int reward_mode, const float* 
                    const float* next_ref_t0 /* [N] or NULL */, int* steps /* [N] or NULL */, const PbrlBuffers* buf,
                    void* stream);
 
-/* pbrl_step is one kernel launch, except for large batches (>= 2 groups of 16 envs per SM-resident CTA) that pass env_order,
- * cost and status: those steps run in two parts (PD law + the first 4 substeps in the caller's order; the other substeps and
- * the epilogue with the envs re-sorted by the work of the first part, in a scratch order of the model), because an env's
- * solver work is predicted far better by its previous substep than by its previous env step.  Results do not depend on it
- * (PBRL_REGROUP_AFTER=0 at model creation: always one launch).  pbrl_step_launches tells how many kernels a call launches. */
+/* Large batches (>= 2 groups of 16 envs per SM-resident CTA) that pass env_order, cost and status are stepped in two parts:
+ * PD law + the first 4 substeps in the caller's order, then the other substeps and the epilogue with the envs regrouped by
+ * the work of the first part -- an env's solver work is predicted far better by its previous substep than by its previous
+ * env step.  Below 16 groups per SM both parts run in one launch (an env that is through part A queues for part B by work
+ * class; CTAs draw the 16 heaviest on offer); at and above, in two launches with a sort in between.  Results do not depend on
+ * it (PBRL_REGROUP_AFTER=0 at model creation: always the whole step in one pass).  pbrl_step_launches tells how many kernels a
+ * call launches. */
 int pbrl_step_launches(const PbrlModel* model, int N, int n_frames, const PbrlBuffers* buf);
 int pbrl_step(const PbrlModel* model, int N, int n_frames, int pd_mode, int action_cols /* 1 or 4 */,
               const float* action /* [N][28][action_cols] */, const float* kp /* [28] */,

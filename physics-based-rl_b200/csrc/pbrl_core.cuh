@@ -2425,6 +2425,8 @@ static int* g_emu_trace = nullptr;  // dev study only: (niter, dense iterations)
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
     int f_begin, f_end;  // the substeps of the env step this launch runs: [0, n_frames) is the whole step (see env_step)
+    int fused_r;         // > 0: one launch runs the step in two parts, [0, fused_r) and [fused_r, n_frames), regrouping in between
+    int* fused_queue;    // [FUSED_CLASSES][N] env ids + 1 by work class (zeroed by the host before the launch)
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
     int tail_split;  // k_step: split the groups of a batch smaller than the GPU over the idle SMs
     int cost_mode;   // work estimate written to buf.cost: 0 most expensive substep, 1 sum over the substeps, 2 last substep
@@ -2437,6 +2439,16 @@ struct StepArgs {
 };
 
 PB_DEV void load_row(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = src[i]; }
+// loads that bypass L1: rows another CTA wrote earlier in this launch (the fused two-part step).  A 140-byte row shares its
+// 128-byte lines with its neighbours, and this SM may hold such a line from before the row was written.
+#if defined(__CUDACC__) && !defined(PBRL_HOST_EMU)
+PB_DEV float ld_fresh(const float* p) { return __ldcg(p); }
+PB_DEV int ld_fresh(const int* p) { return __ldcg(p); }
+#else
+PB_DEV float ld_fresh(const float* p) { return *p; }
+PB_DEV int ld_fresh(const int* p) { return *p; }
+#endif
+PB_DEV void load_row_fresh(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = ld_fresh(src + i); }
 PB_DEV void store_row(float* dst, const float* src, int n, int lane) { LANE_LOOP(i, n) dst[i] = src[i]; }
 
 PB_DEV void write_obs_reference(const StepArgs& a, Ws& w, int env, float done_value, int lane) {
@@ -2454,25 +2466,33 @@ PB_DEVN void mimic_epilogue(const DevModel& m, const DevMimic& mm, const float* 
 // A launch runs the substeps [f_begin, f_end) of the env step: the PD law belongs to the part that starts at substep 0, the
 // observation / reward epilogue to the part that ends at n_frames; in between the state lives in the caller's buffers
 // (qpos, qvel, warm, ctrl, time, status, cost).  One launch with [0, n_frames) is the whole step.
-PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, float* acc, int lane) {
+// `fresh`: the state rows were written earlier in this launch by another CTA (fused two-part step): load them past L1.
+PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, float* acc, int lane, int f_begin, int f_end, bool fresh) {
     const PbrlBuffers& B = a.buf;
     const bool mimic = a.reward_mode == PBRL_REWARD_MIMIC;
-    const bool first = a.f_begin == 0, last = a.f_end == a.n_frames;
+    const bool first = f_begin == 0, last = f_end == a.n_frames;
     const int clip = mimic ? B.motion_id[env] : 0;
     PROF_START();
-    load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
-    load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
-    load_row(w.warm, B.warm + (size_t)env * NV, NV, lane);
-    load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
+    if (fresh) {
+        load_row_fresh(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
+        load_row_fresh(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
+        load_row_fresh(w.warm, B.warm + (size_t)env * NV, NV, lane);
+        load_row_fresh(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
+    } else {
+        load_row(w.qpos, B.qpos + (size_t)env * NQ, NQ, lane);
+        load_row(w.qvel, B.qvel + (size_t)env * NV, NV, lane);
+        load_row(w.warm, B.warm + (size_t)env * NV, NV, lane);
+        load_row(w.ctrl, B.ctrl + (size_t)env * NU, NU, lane);
+    }
     float* lag_q = w.fsmooth;  // dead until the first substep
     float* lag_v = w.qacc;
     if (first && a.pd_mode >= PBRL_PD_FEEDBACK) {
         load_row(lag_q, B.qpos_lag + (size_t)env * NQ, NQ, lane);
         load_row(lag_v, B.qvel_lag + (size_t)env * NV, NV, lane);
     }
-    LANE_IF(z, 1) w.status = first ? 0 : B.status[env];   // (a step in two parts needs the status buffer: checked by the caller)
+    LANE_IF(z, 1) w.status = first ? 0 : (fresh ? ld_fresh(B.status + env) : B.status[env]);   // (a step in parts needs the status buffer: checked by the caller)
     WSYNC();
-    float time = B.time[env];
+    float time = fresh ? ld_fresh(B.time + env) : B.time[env];
     PROF(0);
     if (first) {
         pd_torque(m, w, a.pd_mode, a.action_cols, a.action + (size_t)env * NU * a.action_cols, a.kp, a.kd,
@@ -2483,8 +2503,8 @@ PB_DEVN void env_step(const DevModel& m, Ws& w, const StepArgs& a, int env, floa
     LANE_IF(z, 1) w.phase_lock = a.phase_lock;
     WSYNC();
     PROF(1);
-    int cost = first ? 0 : B.cost[env], cost_sum = cost;
-    for (int f = a.f_begin; f < a.f_end; f++) {
+    int cost = first ? 0 : (fresh ? ld_fresh(B.cost + env) : B.cost[env]), cost_sum = cost;
+    for (int f = f_begin; f < f_end; f++) {
         if (f == a.n_frames - 1) {  // the state entering the last forward is what the next PD law evaluates M / bias at
             store_row(B.qpos_lag + (size_t)env * NQ, w.qpos, NQ, lane);
             store_row(B.qvel_lag + (size_t)env * NV, w.qvel, NV, lane);

@@ -28,6 +28,7 @@ namespace {
 #define PBRL_WARPS_PER_CTA 16
 #endif
 constexpr int WARPS_PER_CTA = PBRL_WARPS_PER_CTA;
+constexpr int FUSED_CLASSES = 16;   // work classes of the fused two-part step (k_step)
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 static_assert(WARPS_PER_CTA % PBRL_LOCK_GROUP == 0, "lock groups tile the CTA");
 
@@ -90,6 +91,95 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     __shared__ int s_unit;
     const int ngroups = (a.N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (a.fused_r > 0) {
+        // ---- the env step in two parts inside ONE launch (regrouping without the drain of a launch boundary) -----------------
+        // Part A (PD law + the first fused_r substeps) is handed out in groups of the caller's order, heaviest first, as below.
+        // An env that finished part A is appended to the queue of its work class (its solver work so far); a CTA that finds no
+        // part-A group left draws the 16 heaviest envs on offer for part B (the other substeps + epilogue) as soon as 16 are on
+        // offer, and whatever is left once every env is through part A.  sched: [0] next A group, [2] envs through
+        // part A, [4 + c] entries appended to class c, [4 + NCLS + c] entries of class c taken; queue entries are env + 1
+        // (0 = reserved, not yet written).  The host zeroes sched and the queue before the launch.
+        constexpr int NCLS = FUSED_CLASSES;
+        __shared__ int s_kind, s_envs[WARPS_PER_CTA];
+        volatile int* vs = sched;
+        int* queue = a.fused_queue;
+        const int wid = threadIdx.x >> 5;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int kind = 0;
+                const int u = vs[0] < ngroups ? atomicAdd(&sched[0], 1) : ngroups;
+                if (u < ngroups) { kind = 1; s_unit = u; }
+                else {
+                    for (int spin = 0;; spin++) {
+                        const bool all = vs[2] >= a.N;   // (read first: what is in the queues now is at least what was there then)
+                        int total = 0;
+                        for (int c = 0; c < NCLS; c++) total += vs[4 + c] - vs[4 + NCLS + c];
+                        int got = 0;
+                        if (total >= WARPS_PER_CTA || (all && total > 0)) {   // the 16 heaviest envs on offer (the last ones: what is left)
+                            for (int c = NCLS - 1; c >= 0 && got < WARPS_PER_CTA; c--) {
+                                for (;;) {
+                                    const int h = vs[4 + NCLS + c], avail = vs[4 + c] - h, want = WARPS_PER_CTA - got;
+                                    if (avail <= 0) break;
+                                    const int take = avail < want ? avail : want;
+                                    if (atomicCAS(&sched[4 + NCLS + c], h, h + take) != h) continue;   // another CTA drew from this class: look again
+                                    for (int k = 0; k < take; k++) {
+                                        volatile int* slot = queue + (size_t)c * a.N + h + k;
+                                        int e;
+                                        while ((e = *slot) == 0) {}   // reserved by its writer, lands within a few hundred cycles
+                                        s_envs[got + k] = e - 1;
+                                    }
+                                    got += take;
+                                    break;
+                                }
+                            }
+                        }
+                        if (got > 0) { for (int k = got; k < WARPS_PER_CTA; k++) s_envs[k] = -1; kind = 2; break; }
+                        if (all && total <= 0) break;   // every env is through part A and every queue is empty: done
+                        __nanosleep(spin < 8 ? 200 : 1000);
+                    }
+                    __threadfence();   // the envs' part-A state is visible before this CTA loads it
+                }
+                s_kind = kind;
+            }
+            __syncthreads();
+            const int kind = s_kind;
+            if (kind == 0) break;
+            int env = -1;
+            if (kind == 1) {
+                const int slot = s_unit * WARPS_PER_CTA + wid;
+                if (slot < a.N) env = a.buf.env_order ? a.buf.env_order[slot] : slot;
+            } else env = s_envs[wid];
+            const int fb = kind == 1 ? 0 : a.fused_r, fe = kind == 1 ? a.fused_r : a.n_frames;
+            if (env >= 0) {
+                env_step(sm, w, a, env, acc, lane, fb, fe, kind == 2);
+                if (kind == 1) {
+                    __threadfence();   // this env's state before its queue entry
+                    if (lane == 0) {
+                        int c = a.buf.cost[env];
+                        c = c < 0 ? 0 : (c >= NCLS ? NCLS - 1 : c);
+                        const int at = atomicAdd(&sched[4 + c], 1);
+                        queue[(size_t)c * a.N + at] = env + 1;
+                        __threadfence();
+                        atomicAdd(&sched[2], 1);
+                    }
+                }
+            } else {
+                for (int f = fb; f < fe; f++) {
+                    for (int k = 0; k < __popc(a.phase_lock & 39); k++) CTA_SYNC();
+                    if (a.phase_lock & 16) while (CTA_OR(0)) {}
+                    if (a.phase_lock & 8) CTA_SYNC();
+                }
+            }
+        }
+        if (a.buf.stats && a.reward_mode == PBRL_REWARD_MIMIC && lane < 6 && acc[5] > 0.f) {
+            float v = acc[0];
+#pragma unroll
+            for (int k = 1; k < 6; k++) v = lane == k ? acc[k] : v;
+            atomicAdd(a.buf.stats + lane, v);
+        }
+        return;
+    }
     // A batch with fewer groups than CTAs (64 envs = 4 groups on 148 SMs) is handed out in `split` parts of WARPS_PER_CTA / split
     // envs per group, so that the idle SMs share the work: a CTA with 8 (4, 1) active warps steps its envs in 0.79 (0.6, 0.45) of
     // the time 16 take.  split = the largest power of two with split x groups <= gridDim; the other warps of such a CTA mirror
@@ -114,7 +204,7 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
             mine = wid / per_part == (unit - nwhole) % split;
         }
         const int slot = group * WARPS_PER_CTA + wid;
-        if (mine && slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane);
+        if (mine && slot < a.N) env_step(sm, w, a, a.buf.env_order ? a.buf.env_order[slot] : slot, acc, lane, a.f_begin, a.f_end, false);
         else {  // no env for this warp in this pass: mirror the barrier sequence of a substep (forward / solve_constraints / substep)
             for (int f = a.f_begin; f < a.f_end; f++) {
                 for (int k = 0; k < __popc(a.phase_lock & 39); k++) CTA_SYNC();
@@ -430,6 +520,9 @@ struct PbrlModel {
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
                           // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int regroup_fused = -1;  // 1: the two parts of a regrouped step in ONE launch (work-class queues); 0: two launches with a sort in
+                             // between; -1: one launch below 16 groups per SM (where a launch boundary's drain costs more than the
+                             // coarser grouping: +2.4 % at 16 384 envs), two at and above (-2 % at 65 536); PBRL_REGROUP_FUSED
     int regroup_every = 0;   // ... and again every that many substeps (0: once); PBRL_REGROUP_EVERY
     int regroup_after = 4;   // pbrl_step: > 0 = re-sort the envs after that many substeps of the step (two launches); PBRL_REGROUP_AFTER
     int tail_split = 1;   // k_step splits the groups of a batch smaller than the GPU over the idle SMs; PBRL_TAIL_SPLIT=0 turns it off (dev sweeps)
@@ -535,6 +628,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     { const char* e = getenv("PBRL_TAIL_SPLIT"); if (e) m->tail_split = atoi(e) != 0; }
     { const char* e = getenv("PBRL_REGROUP_AFTER"); if (e) m->regroup_after = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_EVERY"); if (e) m->regroup_every = atoi(e); }
+    { const char* e = getenv("PBRL_REGROUP_FUSED"); if (e) m->regroup_fused = atoi(e); }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) return bail(err);
@@ -640,6 +734,7 @@ int pbrl_step_launches(const PbrlModel* m, int N, int n_frames, const PbrlBuffer
     if (!m || !buf || N <= 0) return 0;
     const int cap = m->sm_count * m->ctas_per_sm, r = m->regroup_after;
     if (!(r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap)) return 1;
+    if (m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0) return 1;
     const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
     int parts = 1;
     for (int f = r; f < n_frames; f += every) parts++;
@@ -682,8 +777,19 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     // then -- the envs re-sorted by the work of those substeps (into a scratch order of the model) -- the other substeps and
     // the epilogue.  The state crosses the boundary in the caller's buffers.  Needs env_order, cost and status.
     const int r = m->regroup_after;
+    const bool regroup = r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap;
+    const bool fused = m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0;
+    if (regroup && fused) {
+        // the two parts in one launch: scheduler block (64 ints) + one queue of N entries per work class, zeroed per launch
+        int* blk = m->regroup_order(64 + FUSED_CLASSES * N);
+        if (!blk) return fail("pbrl_step: cannot allocate the regrouping queues");
+        CUDA_OK(cudaMemsetAsync(blk, 0, (size_t)(64 + FUSED_CLASSES * N) * sizeof(int), (cudaStream_t)stream));
+        a.f_begin = 0; a.f_end = n_frames; a.fused_r = r; a.fused_queue = blk + 64;
+        k_step<<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, blk);
+        return check_launch("pbrl_step");
+    }
     int* order2 = nullptr;
-    if (r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap) order2 = m->regroup_order(N);
+    if (regroup) order2 = m->regroup_order(N);
     if (order2) {
         const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
         int f0 = 0;

@@ -76,13 +76,10 @@ int emu_step(int N, int n_frames, int pd_mode, int action_cols, const float* act
     const char* sp = getenv("PBRL_EMU_SPLIT");
     const int r = sp ? atoi(sp) : 0;
     if (r > 0 && r < n_frames && buf->cost && buf->status) {
-        a.f_begin = 0; a.f_end = r;
-        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
-        a.f_begin = r; a.f_end = n_frames;
-        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0, 0, r, false);
+        for (int e = N - 1; e >= 0; e--) env_step(g_model, ws[0], a, e, acc, 0, r, n_frames, true);   // (another order: the parts are independent per env)
     } else {
-        a.f_begin = 0; a.f_end = n_frames;
-        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0);
+        for (int e = 0; e < N; e++) env_step(g_model, ws[0], a, e, acc, 0, 0, n_frames, false);
     }
     if (buf->stats && reward_mode == PBRL_REWARD_MIMIC) for (int k = 0; k < 6; k++) buf->stats[k] += acc[k];
     return 0;

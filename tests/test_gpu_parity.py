@@ -321,7 +321,16 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
         be1 = GpuBackend(model_grav, mimic_desc=mdesc)
     finally:
         os.environ.pop("PBRL_REGROUP_AFTER")
-    be2 = GpuBackend(model_grav, mimic_desc=mdesc)
+    os.environ["PBRL_REGROUP_FUSED"] = "0"   # two launches with the sort in between (the default for batches of >= 16 groups per SM)
+    try:
+        be2 = GpuBackend(model_grav, mimic_desc=mdesc)
+    finally:
+        os.environ.pop("PBRL_REGROUP_FUSED")
+    os.environ["PBRL_REGROUP_FUSED"] = "1"   # the two parts inside one launch (work-class queues between them; the default below that)
+    try:
+        be3 = GpuBackend(model_grav, mimic_desc=mdesc)
+    finally:
+        os.environ.pop("PBRL_REGROUP_FUSED")
     N = 5000
     rng = np.random.default_rng(91)
     kp, kd = pc.util_data.generate_kp_kd_gains()
@@ -331,7 +340,7 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
     acts = rng.uniform(lo, hi, (3, N, 28)).astype(np.float32)
     for reward_mode in (1, 0):
         outs = []
-        for be in (be1, be2):
+        for be in (be1, be2, be3):
             L, lib = be.L, be.L.lib()
             z = lambda *s: torch.zeros(s, device=be.dev)
             d = dict(qpos=z(N, 35), qvel=z(N, 34), time=z(N), warm=z(N, 34), ctrl=z(N, 28), qpos_lag=z(N, 35), qvel_lag=z(N, 34), obs=z(N, 69),
@@ -339,7 +348,7 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
                      cost=torch.zeros(N, dtype=torch.int32, device=be.dev), env_order=torch.arange(N, dtype=torch.int32, device=be.dev),
                      motion_id=torch.from_numpy(mid).to(be.dev), ref_t0=torch.from_numpy(t0).to(be.dev))
             b = L.make_buffers(**d)
-            assert lib.pbrl_step_launches(be.model.handle, N, 8, ctypes.byref(b)) == (1 if be is be1 else 3)
+            assert lib.pbrl_step_launches(be.model.handle, N, 8, ctypes.byref(b)) == (3 if be is be2 else 1)
             assert lib.pbrl_step_launches(be.model.handle, 64, 8, ctypes.byref(b)) == 1
             L.check(lib.pbrl_reset(be.model.handle, N, reward_mode, ctypes.byref(b), be._stream()))
             kpd, kdd = be._dp(kp), be._dp(kd)
@@ -350,8 +359,9 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
                 L.check(lib.pbrl_balance_order(be.model.handle, N, L._ptr(d["cost"]), L._ptr(d["env_order"]), be._stream()))
             torch.cuda.synchronize()
             outs.append({k: v.cpu().numpy() for k, v in d.items()})
-        for name in ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics", "status", "cost"):
-            assert np.array_equal(outs[0][name], outs[1][name]), (reward_mode, name)
-        assert np.allclose(outs[0]["stats"], outs[1]["stats"], rtol=1e-5, atol=1e-3)
+        for other in outs[1:]:
+            for name in ("qpos", "qvel", "time", "warm", "ctrl", "qpos_lag", "qvel_lag", "obs", "reward", "done", "metrics", "status", "cost"):
+                assert np.array_equal(outs[0][name], other[name]), (reward_mode, name)
+            assert np.allclose(outs[0]["stats"], other["stats"], rtol=1e-5, atol=1e-3)
         for o in outs:   # (the counting sort places equal costs in arrival order: the orders are permutations sorted alike, not equal)
             assert np.array_equal(np.sort(o["env_order"]), np.arange(N)) and (np.diff(np.clip(o["cost"], 0, 255)[o["env_order"]]) <= 0).all()
