@@ -32,8 +32,18 @@ constexpr int FUSED_CLASSES = 16;   // work classes of the fused two-part step (
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 static_assert(WARPS_PER_CTA % PBRL_LOCK_GROUP == 0, "lock groups tile the CTA");
 
+// last error: per thread (the message of the calling thread's own failed call), with the process-wide last message behind it for
+// a caller that asks from another thread than the one that made the call
 thread_local std::string g_error;
-int fail(const std::string& msg) { g_error = msg; return -1; }
+std::mutex g_error_mu;
+std::string g_error_any;
+thread_local std::string g_error_ret;
+int fail(const std::string& msg) {
+    g_error = msg;
+    std::lock_guard<std::mutex> lk(g_error_mu);
+    g_error_any = msg;
+    return -1;
+}
 #define CUDA_OK(call)                                                                              \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -593,7 +603,12 @@ int check_launch(const char* what) {
 
 extern "C" {
 
-const char* pbrl_last_error(void) { return g_error.c_str(); }
+const char* pbrl_last_error(void) {
+    if (!g_error.empty()) return g_error.c_str();
+    std::lock_guard<std::mutex> lk(g_error_mu);
+    g_error_ret = g_error_any;
+    return g_error_ret.c_str();
+}
 int pbrl_model_desc_size(void) { return (int)sizeof(PbrlModelDesc); }
 int pbrl_model_desc_field(const char* name, int* offset, int* count, int* is_int) { return model_desc_field(name, offset, count, is_int); }
 int pbrl_device_count(void) {
