@@ -104,7 +104,7 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
     if (a.fused_r > 0) {
         // ---- the env step in two parts inside ONE launch (regrouping without the drain of a launch boundary) -----------------
         // Part A (PD law + the first fused_r substeps) is handed out in groups of the caller's order, heaviest first, as below.
-        // An env that finished part A is appended to the queue of its work class (its solver work so far); a CTA that finds no
+        // An env that finished part A is appended to the queue of its work class (the solver work of its last substep); a CTA that finds no
         // part-A group left draws the 16 heaviest envs on offer for part B (the other substeps + epilogue) as soon as 16 are on
         // offer, and whatever is left once every env is through part A.  sched: [0] next A group, [2] envs through
         // part A, [4 + c] entries appended to class c, [4 + NCLS + c] entries of class c taken; queue entries are env + 1
@@ -166,7 +166,7 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
                 if (kind == 1) {
                     __threadfence();   // this env's state before its queue entry
                     if (lane == 0) {
-                        int c = a.buf.cost[env];
+                        int c = w.work;   // the work of the LAST substep of part A: the best predictor of the next one (+0.5 % over the maximum)
                         c = c < 0 ? 0 : (c >= NCLS ? NCLS - 1 : c);
                         const int at = atomicAdd(&sched[4 + c], 1);
                         queue[(size_t)c * a.N + at] = env + 1;
