@@ -569,10 +569,15 @@ struct PbrlModel {
         std::lock_guard<std::mutex> lk(scratch_mu);
         const int i = order_next++ % ORDER_RING;
         if (order_cap[i] < N) {
-            if (order_bufs[i]) cudaFree(order_bufs[i]);   // (cudaFree waits for the work that still reads it)
-            order_bufs[i] = nullptr; order_cap[i] = 0;
-            if (cudaMalloc(&order_bufs[i], (size_t)N * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-            order_cap[i] = N;
+            // grow EVERY slot of the ring now: an allocation synchronises the device and costs milliseconds, so it must happen
+            // on the first call (a caller's warm-up), never one slot at a time over the first four steps
+            for (int k = 0; k < ORDER_RING; k++) {
+                if (order_cap[k] >= N) continue;
+                if (order_bufs[k]) cudaFree(order_bufs[k]);   // (cudaFree waits for the work that still reads it)
+                order_bufs[k] = nullptr; order_cap[k] = 0;
+                if (cudaMalloc(&order_bufs[k], (size_t)N * sizeof(int)) != cudaSuccess) { cudaGetLastError(); if (k == i) return nullptr; continue; }
+                order_cap[k] = N;
+            }
         }
         return order_bufs[i];
     }
