@@ -534,7 +534,8 @@ struct PbrlModel {
                              // between; -1: one launch below 16 groups per SM (where a launch boundary's drain costs more than the
                              // coarser grouping: +2.4 % at 16 384 envs), two at and above (-2 % at 65 536); PBRL_REGROUP_FUSED
     int regroup_every = 0;   // ... and again every that many substeps (0: once); PBRL_REGROUP_EVERY
-    int regroup_after = 4;   // pbrl_step: > 0 = re-sort the envs after that many substeps of the step (two launches); PBRL_REGROUP_AFTER
+    int regroup_after = -1;  // pbrl_step: regroup the envs after that many substeps of the step; -1 = after half of them (4 of 8), 0 = never;
+                             // PBRL_REGROUP_AFTER
     int tail_split = 1;   // k_step splits the groups of a batch smaller than the GPU over the idle SMs; PBRL_TAIL_SPLIT=0 turns it off (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
@@ -752,7 +753,7 @@ int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done
 // how many kernels pbrl_step launches for this batch (1, or the parts of a regrouped step plus the sorts between them)
 int pbrl_step_launches(const PbrlModel* m, int N, int n_frames, const PbrlBuffers* buf) {
     if (!m || !buf || N <= 0) return 0;
-    const int cap = m->sm_count * m->ctas_per_sm, r = m->regroup_after;
+    const int cap = m->sm_count * m->ctas_per_sm, r = m->regroup_after < 0 ? n_frames / 2 : m->regroup_after;
     if (!(r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap)) return 1;
     if (m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0) return 1;
     const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
@@ -796,7 +797,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     // dense then).  With `regroup_after` = r > 0 the step is two launches: PD law + r substeps in the caller's processing order,
     // then -- the envs re-sorted by the work of those substeps (into a scratch order of the model) -- the other substeps and
     // the epilogue.  The state crosses the boundary in the caller's buffers.  Needs env_order, cost and status.
-    const int r = m->regroup_after;
+    const int r = m->regroup_after < 0 ? n_frames / 2 : m->regroup_after;
     const bool regroup = r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap;
     const bool fused = m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0;
     if (regroup && fused) {
