@@ -138,6 +138,9 @@ def test_replay_rollout(gpu_nograv, model_nograv):
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=227, N=4096, K=3, seed=38)   # several CTAs per step, ragged tail
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=1, K=1, seed=39)
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=600, N=300, K=5, seed=41)    # fewer than 4 items per clip row: kinematics per item
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=2, K=41, seed=43)      # frame table with fewer envs than items per warp pass
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=4, N=3, K=7, seed=44)
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=7, N=1, K=64, seed=45)
     pc.check_replay_rollout_paths_agree(gpu_nograv, model_nograv)
     pc.check_replay_rollout_paths_agree(gpu_nograv, model_nograv, F=227, N=1000, K=3, seed=42)
 
