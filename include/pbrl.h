@@ -181,7 +181,7 @@ int pbrl_autoreset(const PbrlModel* model, int N, int reward_mode, const float* 
                    const float* next_ref_t0 /* [N] or NULL */, int* steps /* [N] or NULL */, const PbrlBuffers* buf,
                    void* stream);
 
-/* Large batches (>= 2 groups of 16 envs per SM-resident CTA) that pass env_order, cost and status are stepped in two parts:
+/* Batches of at least one group of 16 envs per SM that pass env_order, cost and status are stepped in two parts:
  * PD law + the first half of the substeps (4 of 8) in the caller's order, then the other substeps and the epilogue with the envs regrouped by
  * the work of the first part -- an env's solver work is predicted far better by its previous substep than by its previous
  * env step.  Below 16 groups per SM both parts run in one launch (an env that is through part A queues for part B by work

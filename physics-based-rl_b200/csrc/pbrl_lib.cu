@@ -530,6 +530,8 @@ struct PbrlModel {
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
                           // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int regroup_min_groups = 1;   // regroup only batches of at least that many groups of 16 envs per SM (4 096 envs, 1.7 per SM: +8 %;
+                                  // 2 368, one per SM: +1 %); PBRL_REGROUP_MIN_GROUPS
     int regroup_fused = -1;  // 1: the two parts of a regrouped step in ONE launch (work-class queues); 0: two launches with a sort in
                              // between; -1: one launch below 16 groups per SM (where a launch boundary's drain costs more than the
                              // coarser grouping: +2.4 % at 16 384 envs), two at and above (-2 % at 65 536); PBRL_REGROUP_FUSED
@@ -650,6 +652,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     { const char* e = getenv("PBRL_REGROUP_AFTER"); if (e) m->regroup_after = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_EVERY"); if (e) m->regroup_every = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_FUSED"); if (e) m->regroup_fused = atoi(e); }
+    { const char* e = getenv("PBRL_REGROUP_MIN_GROUPS"); if (e) m->regroup_min_groups = atoi(e) > 0 ? atoi(e) : 1; }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
     if (!err.empty()) return bail(err);
@@ -754,7 +757,7 @@ int pbrl_autoreset(const PbrlModel* m, int N, int reward_mode, const float* done
 int pbrl_step_launches(const PbrlModel* m, int N, int n_frames, const PbrlBuffers* buf) {
     if (!m || !buf || N <= 0) return 0;
     const int cap = m->sm_count * m->ctas_per_sm, r = m->regroup_after < 0 ? n_frames / 2 : m->regroup_after;
-    if (!(r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap)) return 1;
+    if (!(r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= m->regroup_min_groups * WARPS_PER_CTA * cap)) return 1;
     if (m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0) return 1;
     const int every = m->regroup_every > 0 ? m->regroup_every : n_frames;
     int parts = 1;
@@ -798,7 +801,7 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     // then -- the envs re-sorted by the work of those substeps (into a scratch order of the model) -- the other substeps and
     // the epilogue.  The state crosses the boundary in the caller's buffers.  Needs env_order, cost and status.
     const int r = m->regroup_after < 0 ? n_frames / 2 : m->regroup_after;
-    const bool regroup = r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= 2 * WARPS_PER_CTA * cap;
+    const bool regroup = r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= m->regroup_min_groups * WARPS_PER_CTA * cap;
     const bool fused = m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0;
     if (regroup && fused) {
         // the two parts in one launch: scheduler block (64 ints) + one queue of N entries per work class, zeroed per launch
