@@ -2425,8 +2425,8 @@ static int* g_emu_trace = nullptr;  // dev study only: (niter, dense iterations)
 struct StepArgs {
     int N, n_frames, pd_mode, action_cols, reward_mode;
     int f_begin, f_end;  // the substeps of the env step this launch runs: [0, n_frames) is the whole step (see env_step)
-    int fused_r;         // > 0: one launch runs the step in two parts, [0, fused_r) and [fused_r, n_frames), regrouping in between
-    int* fused_queue;    // [FUSED_CLASSES][N] env ids + 1 by work class (zeroed by the host before the launch)
+    int fused_parts;     // > 1: one launch runs the step in that many parts (equal shares of the substeps), regrouping in between
+    int* fused_queue;    // [fused_parts - 1][FUSED_CLASSES][N] env ids + 1 by work class (zeroed by the host before the launch)
     int phase_lock;  // bit mask of CTA barriers per substep (see forward); every warp of a CTA makes the same number of passes
     int tail_split;  // k_step: split the groups of a batch smaller than the GPU over the idle SMs
     int cost_mode;   // work estimate written to buf.cost: 0 most expensive substep, 1 sum over the substeps, 2 last substep

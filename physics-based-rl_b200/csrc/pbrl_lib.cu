@@ -101,40 +101,49 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     __shared__ int s_unit;
     const int ngroups = (a.N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    if (a.fused_r > 0) {
-        // ---- the env step in two parts inside ONE launch (regrouping without the drain of a launch boundary) -----------------
-        // Part A (PD law + the first fused_r substeps) is handed out in groups of the caller's order, heaviest first, as below.
-        // An env that finished part A is appended to the queue of its work class (the solver work of its last substep); a CTA that finds no
-        // part-A group left draws the 16 heaviest envs on offer for part B (the other substeps + epilogue) as soon as 16 are on
-        // offer, and whatever is left once every env is through part A.  sched: [0] next A group, [2] envs through
-        // part A, [4 + c] entries appended to class c, [4 + NCLS + c] entries of class c taken; queue entries are env + 1
-        // (0 = reserved, not yet written).  The host zeroes sched and the queue before the launch.
+    if (a.fused_parts > 1) {
+        // ---- the env step in P parts inside ONE launch (regrouping without the drain of a launch boundary) -------------------
+        // Part 0 (PD law + the first substeps) is handed out in groups of the caller's order, heaviest first, as below.  An env
+        // that finished part p - 1 is appended to queue p under its work class (the solver work of its last substep); a CTA that
+        // finds no part-0 group left draws the 16 heaviest envs on offer in the earliest queue that offers 16 (the longest
+        // remaining work first), and whatever is left in a queue once every env has been through the part before it.
+        // Part p runs the substeps [p n / P, (p + 1) n / P); the last one ends with the epilogue.
+        // sched: [0] next part-0 group; per queue p = 1 .. P - 1 at base(p) = 4 + (p - 1)(1 + 2 NCLS): [base] envs appended,
+        // [base + 1 + c] entries appended to class c, [base + 1 + NCLS + c] entries of class c taken.  Queue entries are env + 1
+        // (0 = reserved, not yet written).  The host zeroes sched and the queues before the launch.
         constexpr int NCLS = FUSED_CLASSES;
+        const int P = a.fused_parts;
         __shared__ int s_kind, s_envs[WARPS_PER_CTA];
         volatile int* vs = sched;
-        int* queue = a.fused_queue;
         const int wid = threadIdx.x >> 5;
+        auto base = [&](int q) { return 4 + (q - 1) * (1 + 2 * NCLS); };
+        auto queue = [&](int q) { return a.fused_queue + (size_t)(q - 1) * NCLS * a.N; };
+        auto bound = [&](int q) { return (int)((long long)q * a.n_frames / P); };
         for (;;) {
             __syncthreads();
             if (threadIdx.x == 0) {
-                int kind = 0;
+                int kind = 0;   // 0: done, 1 + p: a unit of part p
                 const int u = vs[0] < ngroups ? atomicAdd(&sched[0], 1) : ngroups;
                 if (u < ngroups) { kind = 1; s_unit = u; }
                 else {
-                    for (int spin = 0;; spin++) {
-                        const bool all = vs[2] >= a.N;   // (read first: what is in the queues now is at least what was there then)
-                        int total = 0;
-                        for (int c = 0; c < NCLS; c++) total += vs[4 + c] - vs[4 + NCLS + c];
-                        int got = 0;
-                        if (total >= WARPS_PER_CTA || (all && total > 0)) {   // the 16 heaviest envs on offer (the last ones: what is left)
+                    for (int spin = 0; kind == 0; spin++) {
+                        bool finished = true;
+                        for (int q = 1; q < P && kind == 0; q++) {
+                            const int b = base(q);
+                            const bool all = vs[b] >= a.N;   // (read first: what is in the queue now is at least what was there then)
+                            int total = 0;
+                            for (int c = 0; c < NCLS; c++) total += vs[b + 1 + c] - vs[b + 1 + NCLS + c];
+                            if (!all || total > 0) finished = false;
+                            if (!(total >= WARPS_PER_CTA || (all && total > 0))) continue;
+                            int got = 0;
                             for (int c = NCLS - 1; c >= 0 && got < WARPS_PER_CTA; c--) {
                                 for (;;) {
-                                    const int h = vs[4 + NCLS + c], avail = vs[4 + c] - h, want = WARPS_PER_CTA - got;
+                                    const int h = vs[b + 1 + NCLS + c], avail = vs[b + 1 + c] - h, want = WARPS_PER_CTA - got;
                                     if (avail <= 0) break;
                                     const int take = avail < want ? avail : want;
-                                    if (atomicCAS(&sched[4 + NCLS + c], h, h + take) != h) continue;   // another CTA drew from this class: look again
+                                    if (atomicCAS(&sched[b + 1 + NCLS + c], h, h + take) != h) continue;   // another CTA drew from this class: look again
                                     for (int k = 0; k < take; k++) {
-                                        volatile int* slot = queue + (size_t)c * a.N + h + k;
+                                        volatile int* slot = queue(q) + (size_t)c * a.N + h + k;
                                         int e;
                                         while ((e = *slot) == 0) {}   // reserved by its writer, lands within a few hundred cycles
                                         s_envs[got + k] = e - 1;
@@ -143,35 +152,37 @@ __global__ void PBRL_STEP_BOUNDS k_step(const DevModel* __restrict__ gm, StepArg
                                     break;
                                 }
                             }
+                            if (got > 0) { for (int k = got; k < WARPS_PER_CTA; k++) s_envs[k] = -1; kind = 1 + q; }
                         }
-                        if (got > 0) { for (int k = got; k < WARPS_PER_CTA; k++) s_envs[k] = -1; kind = 2; break; }
-                        if (all && total <= 0) break;   // every env is through part A and every queue is empty: done
+                        if (kind != 0 || finished) break;   // finished: every env is through every part but the last and every queue is empty
                         __nanosleep(spin < 8 ? 200 : 1000);
                     }
-                    __threadfence();   // the envs' part-A state is visible before this CTA loads it
+                    __threadfence();   // the envs' state of the part before is visible before this CTA loads it
                 }
                 s_kind = kind;
             }
             __syncthreads();
             const int kind = s_kind;
             if (kind == 0) break;
+            const int part = kind - 1;
             int env = -1;
-            if (kind == 1) {
+            if (part == 0) {
                 const int slot = s_unit * WARPS_PER_CTA + wid;
                 if (slot < a.N) env = a.buf.env_order ? a.buf.env_order[slot] : slot;
             } else env = s_envs[wid];
-            const int fb = kind == 1 ? 0 : a.fused_r, fe = kind == 1 ? a.fused_r : a.n_frames;
+            const int fb = bound(part), fe = bound(part + 1);
             if (env >= 0) {
-                env_step(sm, w, a, env, acc, lane, fb, fe, kind == 2);
-                if (kind == 1) {
+                env_step(sm, w, a, env, acc, lane, fb, fe, part > 0);
+                if (part + 1 < P) {
                     __threadfence();   // this env's state before its queue entry
                     if (lane == 0) {
-                        int c = w.work;   // the work of the LAST substep of part A: the best predictor of the next one (+0.5 % over the maximum)
+                        int c = w.work;   // the work of the LAST substep of the part: the best predictor of the next one (+0.5 % over the maximum)
                         c = c < 0 ? 0 : (c >= NCLS ? NCLS - 1 : c);
-                        const int at = atomicAdd(&sched[4 + c], 1);
-                        queue[(size_t)c * a.N + at] = env + 1;
+                        const int b = base(part + 1);
+                        const int at = atomicAdd(&sched[b + 1 + c], 1);
+                        queue(part + 1)[(size_t)c * a.N + at] = env + 1;
                         __threadfence();
-                        atomicAdd(&sched[2], 1);
+                        atomicAdd(&sched[b], 1);
                     }
                 }
             } else {
@@ -530,14 +541,16 @@ struct PbrlModel {
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
                           // the others before the velocity stages); PBRL_PHASE_LOCK overrides it at model creation (dev sweeps)
+    int regroup_parts = 2;        // parts of a step regrouped inside one launch (equal shares of the substeps).  More parts: 16 384 envs
+                                  // 3: +0.2 %, 4: -1.4 %; 4 096 envs 3: +1.8 %, 4: +2.3 %; 2 368 envs 4: -3 %; PBRL_REGROUP_PARTS
     int regroup_min_groups = 1;   // regroup only batches of at least that many groups of 16 envs per SM (4 096 envs, 1.7 per SM: +8 %;
                                   // 2 368, one per SM: +1 %); PBRL_REGROUP_MIN_GROUPS
     int regroup_fused = -1;  // 1: the two parts of a regrouped step in ONE launch (work-class queues); 0: two launches with a sort in
                              // between; -1: one launch below 16 groups per SM (where a launch boundary's drain costs more than the
                              // coarser grouping: +2.4 % at 16 384 envs), two at and above (-2 % at 65 536); PBRL_REGROUP_FUSED
     int regroup_every = 0;   // ... and again every that many substeps (0: once); PBRL_REGROUP_EVERY
-    int regroup_after = -1;  // pbrl_step: regroup the envs after that many substeps of the step; -1 = after half of them (4 of 8), 0 = never;
-                             // PBRL_REGROUP_AFTER
+    int regroup_after = -1;  // pbrl_step: 0 = never regroup the envs inside a step; otherwise the split point of the two-launch form (-1 = after
+                             // half of the substeps, 4 of 8); the one-launch form splits the step into regroup_parts equal shares; PBRL_REGROUP_AFTER
     int tail_split = 1;   // k_step splits the groups of a batch smaller than the GPU over the idle SMs; PBRL_TAIL_SPLIT=0 turns it off (dev sweeps)
     int cost_mode = 0;    // which work estimate k_step reports (StepArgs::cost_mode); PBRL_COST_MODE overrides it (dev sweeps)
     DevModel host{};
@@ -652,6 +665,7 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
     { const char* e = getenv("PBRL_REGROUP_AFTER"); if (e) m->regroup_after = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_EVERY"); if (e) m->regroup_every = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_FUSED"); if (e) m->regroup_fused = atoi(e); }
+    { const char* e = getenv("PBRL_REGROUP_PARTS"); if (e) m->regroup_parts = atoi(e); }
     { const char* e = getenv("PBRL_REGROUP_MIN_GROUPS"); if (e) m->regroup_min_groups = atoi(e) > 0 ? atoi(e) : 1; }
     { const char* e = getenv("PBRL_COST_MODE"); if (e) m->cost_mode = atoi(e); }
     std::string err = build_dev_model(*desc, m->host);
@@ -804,11 +818,16 @@ int pbrl_step(const PbrlModel* m, int N, int n_frames, int pd_mode, int action_c
     const bool regroup = r > 0 && r < n_frames && buf->env_order && buf->cost && buf->status && N >= m->regroup_min_groups * WARPS_PER_CTA * cap;
     const bool fused = m->regroup_fused < 0 ? N < 16 * WARPS_PER_CTA * cap : m->regroup_fused != 0;
     if (regroup && fused) {
-        // the two parts in one launch: scheduler block (64 ints) + one queue of N entries per work class, zeroed per launch
-        int* blk = m->regroup_order(64 + FUSED_CLASSES * N);
+        // the parts in one launch: scheduler block (256 ints) + per later part one queue of N entries per work class, zeroed per launch
+        int P = m->regroup_parts > 1 ? m->regroup_parts : 2;
+        if (P > n_frames) P = n_frames;
+        if (P > 7) P = 7;
+        const size_t ints = 256 + (size_t)(P - 1) * FUSED_CLASSES * N;
+        if (ints > 0x7fffffffull) return fail("pbrl_step: batch too large for the regrouping queues");
+        int* blk = m->regroup_order((int)ints);
         if (!blk) return fail("pbrl_step: cannot allocate the regrouping queues");
-        CUDA_OK(cudaMemsetAsync(blk, 0, (size_t)(64 + FUSED_CLASSES * N) * sizeof(int), (cudaStream_t)stream));
-        a.f_begin = 0; a.f_end = n_frames; a.fused_r = r; a.fused_queue = blk + 64;
+        CUDA_OK(cudaMemsetAsync(blk, 0, ints * sizeof(int), (cudaStream_t)stream));
+        a.f_begin = 0; a.f_end = n_frames; a.fused_parts = P; a.fused_queue = blk + 256;
         k_step<<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(m->dev, a, blk);
         return check_launch("pbrl_step");
     }

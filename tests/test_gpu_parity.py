@@ -334,6 +334,13 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
         be3 = GpuBackend(model_grav, mimic_desc=mdesc)
     finally:
         os.environ.pop("PBRL_REGROUP_FUSED")
+    os.environ["PBRL_REGROUP_FUSED"] = "1"
+    os.environ["PBRL_REGROUP_PARTS"] = "4"   # ... in four parts (three regroupings)
+    try:
+        be4 = GpuBackend(model_grav, mimic_desc=mdesc)
+    finally:
+        os.environ.pop("PBRL_REGROUP_FUSED")
+        os.environ.pop("PBRL_REGROUP_PARTS")
     N = 5000
     rng = np.random.default_rng(91)
     kp, kd = pc.util_data.generate_kp_kd_gains()
@@ -343,7 +350,7 @@ def test_step_in_two_parts_with_regrouping_is_bit_identical(model_grav):
     acts = rng.uniform(lo, hi, (3, N, 28)).astype(np.float32)
     for reward_mode in (1, 0):
         outs = []
-        for be in (be1, be2, be3):
+        for be in (be1, be2, be3, be4):
             L, lib = be.L, be.L.lib()
             z = lambda *s: torch.zeros(s, device=be.dev)
             d = dict(qpos=z(N, 35), qvel=z(N, 34), time=z(N), warm=z(N, 34), ctrl=z(N, 28), qpos_lag=z(N, 35), qvel_lag=z(N, 34), obs=z(N, 69),
