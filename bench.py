@@ -208,12 +208,18 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
         return sum(a.elapsed_time(b) for a, b in evs)
     # the other form of the same entry point, for the record: kinematics per item (what the launch does when the items do not
     # outnumber the clip's rows); the default below evaluates them once per clip row per launch and gathers
-    os.environ["PBRL_REPLAY_PER_ITEM"] = "1"
-    for _ in range(warmup):
-        one()
-    torch.cuda.synchronize()
-    t_item_ms = timed_launches(min(steps, 16)) / min(steps, 16)
-    os.environ.pop("PBRL_REPLAY_PER_ITEM")
+    def form_ms(var, val):
+        os.environ[var] = val
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        t = timed_launches(min(steps, 16)) / min(steps, 16)
+        os.environ.pop(var)
+        return t
+    t_item_ms = form_ms("PBRL_REPLAY_PER_ITEM", "1")
+    # the two store paths of the frame-table form: ordinary 4-byte-per-lane stores, or rows staged in shared memory and handed to
+    # the bulk-copy engine in 64-byte aligned blocks of 16 items (the launch below runs whichever the library defaults to)
+    t_lsu_ms, t_bulk_ms = form_ms("PBRL_REPLAY_BULK", "0"), form_ms("PBRL_REPLAY_BULK", "1")
     for _ in range(warmup):
         one()
     torch.cuda.synchronize()
@@ -250,7 +256,9 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
     peak, src = measured_peak()
     items = n_env * K_INNER
     ach = items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_ms * 1e-3 / steps) / 1e9
-    tr = measured_traffic("k_replay_gather")
+    bulk = os.environ.get("PBRL_REPLAY_BULK", "1") != "0"   # the library's default store path (csrc/pbrl_lib.cu: PBRL_REPLAY_BULK_DEFAULT)
+    gather = "k_replay_gather_bulk" if bulk else "k_replay_gather"
+    tr = measured_traffic(gather)
     traffic = tr["dram_bytes_per_launch"] if tr and tr.get("envs_per_gpu") == n_env and tr.get("replay_steps_per_launch") == K_INNER else None
     return {"metric": "humanoid replay env-steps/sec", "value": items * steps / (t_ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": t_ms / steps, "higher_is_better": True,
@@ -258,17 +266,22 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
             "config": {"workload": "replay", "description": "BASELINE configs[1]: kinematic replay of walk, FK + obs/reward + body poses",
                        "envs_per_gpu": n_env, "replay_steps_per_launch": K_INNER, "clip_rows": int(F),
                        "kinematics": "once per clip row per launch (frame table), rows gathered per item; per-item form reported beside it",
+                       "stores": "rows of 16 consecutive items staged in shared memory, written by the bulk-copy engine (64-byte aligned blocks); ordinary stores reported beside it" if bulk else "ordinary 4-byte-per-lane streaming stores",
                        "l2": "each launch writes 0.72 GB (> 126 MB L2); inputs are the 10 KB clip"},
             "e2e": {"value": items / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n_env * 4, "d2h_bytes_per_step": n_env * 69 * 4, "steps": e2e_steps,
                     "api": "pbrl_replay_rollout, frame indices from pinned host memory, last observations back"},
-            "gpu_launches": 2 * (steps + warmup + e2e_steps) + (warmup + min(steps, 16)) + 35,
+            "gpu_launches": 2 * (steps + warmup + e2e_steps) + 5 * (warmup + min(steps, 16)) + 35,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "peak_source": src, "kernel": "k_replay_gather (+ k_replay_frames, both inside the timed launch)",
+                         "peak_source": src, "kernel": gather + " (+ k_replay_frames, both inside the timed launch)",
                          "algorithmic_bytes_per_env_launch": BYTES_PER_REPLAY_ROLLOUT_ITEM,
                          "note": "per (env, frame) item: obs 276 + reward 12 + done 4 + xpos 168 + xquat 224 B written; the 10 KB clip and the frame table it reads stay on chip"},
             "per_item_kinematics": {"kernel": "k_replay_rollout (PBRL_REPLAY_PER_ITEM=1: kinematics per (env, frame) item, no frame table)", "ms_per_step": t_item_ms,
                                     "env_steps_per_s": items / (t_item_ms * 1e-3),
                                     "roofline_frac": items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_item_ms * 1e-3) / 1e9 / peak},
+            "store_paths": {"ordinary_stores": {"kernel": "k_replay_gather (PBRL_REPLAY_BULK=0)", "ms_per_step": t_lsu_ms,
+                                                "roofline_frac": items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_lsu_ms * 1e-3) / 1e9 / peak},
+                            "bulk_stores": {"kernel": "k_replay_gather_bulk (PBRL_REPLAY_BULK=1: cp.async.bulk.global.shared::cta)", "ms_per_step": t_bulk_ms,
+                                            "roofline_frac": items * BYTES_PER_REPLAY_ROLLOUT_ITEM / (t_bulk_ms * 1e-3) / 1e9 / peak}},
             "per_step_launch": {"kernel": "k_replay", "ms": t1_ms, "env_steps_per_s": n_env / (t1_ms * 1e-3),
                                 "algorithmic_bytes_per_env_launch": BYTES_PER_REPLAY_STEP_ENV,
                                 "achieved_GBps": n_env * BYTES_PER_REPLAY_STEP_ENV / (t1_ms * 1e-3) / 1e9},
@@ -563,7 +576,7 @@ def main():
                 extra[wl] = {"error": str(ex)[:200]}
         try:
             r = replay_bench(args, local_rank, quiet=True)
-            extra["replay"] = {k2: r[k2] for k2 in ("metric", "value", "unit", "ms_per_step", "steps", "roofline", "per_item_kinematics", "per_step_launch", "e2e")}
+            extra["replay"] = {k2: r[k2] for k2 in ("metric", "value", "unit", "ms_per_step", "steps", "roofline", "store_paths", "per_item_kinematics", "per_step_launch", "e2e")}
             extra["replay"]["envs_per_gpu"] = r["config"]["envs_per_gpu"]
             extra["replay"]["replay_steps_per_launch"] = r["config"]["replay_steps_per_launch"]
         except Exception as ex:

@@ -380,9 +380,11 @@ k_replay_rollout(const __grid_constant__ ReplayTables T, int N, int K, const flo
 // The table (F x 100 floats, L1 / L2-resident) lives in a scratch buffer of the model.
 constexpr int RT_ROW = 100;           // xpos 42 | 2 pad | xquat 56: 16-byte aligned halves
 constexpr int RT_QUAT = 44;
+constexpr int RB_PARTS = 16, RB_CLAIM_STRIDE = 32;   // block counters of a k_replay_gather_bulk launch: one per range of blocks, 128 bytes apart
 template <bool AXSPEC>
-__global__ void __launch_bounds__(64) k_replay_frames(const __grid_constant__ ReplayTables T, int F, const float* __restrict__ data_pos, float* __restrict__ tab) {
+__global__ void __launch_bounds__(64) k_replay_frames(const __grid_constant__ ReplayTables T, int F, const float* __restrict__ data_pos, float* __restrict__ tab, unsigned* claim) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (claim && f < RB_PARTS) claim[f * RB_CLAIM_STRIDE] = 0u;   // the block counters of the k_replay_gather_bulk launch behind this one (blockDim 64 >= RB_PARTS)
     if (f < F) replay_item_fk<AXSPEC>(T, data_pos + (size_t)f * NQ, tab + (size_t)f * RT_ROW, tab + (size_t)f * RT_ROW + RT_QUAT);
 }
 constexpr int RG_THREADS = 256, RG_UNROLL = 4;
@@ -465,6 +467,138 @@ k_replay_gather(int N, int K, const float* __restrict__ data_pos, const float* _
         if (ALL || done) o_done += step;
     }
 }
+// The same gather with the stores handed to the bulk-copy engine.  k_replay_gather is bound by its own store instructions (nine
+// 4-byte-per-lane stores per item, rows that start on any 4-byte boundary: lg_throttle is its top stall, 3.4 sectors per request).
+// Here a warp assembles the rows of RB_ITEMS consecutive items in shared memory -- consecutive items are contiguous in every
+// output array, and with 16 items every block of every array starts and ends on a 64-byte boundary (16 x 276 / 168 / 224 / 12 /
+// 4 bytes), so no 32-byte sector is written in part -- and one lane hands the five blocks to cp.async.bulk.global.shared::cta.
+// reward (zeros) and done (ones) never change: their blocks are written to shared memory once per CTA.
+// The last block of a rollout whose item count is not a multiple of RB_ITEMS leaves through ordinary stores.
+#ifndef PBRL_REPLAY_BULK_DEFAULT
+#define PBRL_REPLAY_BULK_DEFAULT 1
+#endif
+#ifndef PBRL_RB_WARPS   // warps per CTA, items whose loads are in flight together, resident CTAs per SM the registers are capped for
+#define PBRL_RB_WARPS 8
+#define PBRL_RB_CHUNK 8
+#define PBRL_RB_CTAS 2
+#endif
+constexpr int RB_ITEMS = 16, RB_WARPS = PBRL_RB_WARPS, RB_THREADS = 32 * RB_WARPS, RB_CHUNK = PBRL_RB_CHUNK;
+constexpr int RB_OBS = RB_ITEMS * PBRL_OBS, RB_POS = RB_ITEMS * 42, RB_QUAT = RB_ITEMS * 56, RB_STAGE = RB_OBS + RB_POS + RB_QUAT;
+constexpr int RB_CONST = RB_ITEMS * 4;   // floats: reward block (3 per item) | done block (1 per item)
+constexpr size_t RB_SMEM = sizeof(float) * (RB_CONST + RB_WARPS * RB_STAGE);
+static_assert(RB_PARTS <= 64, "k_replay_frames zeroes the counters with the threads of its first CTA");
+static_assert((RB_OBS * 4) % 16 == 0 && (RB_POS * 4) % 16 == 0 && (RB_QUAT * 4) % 16 == 0 && (RB_STAGE * 4) % 16 == 0 && (RB_CONST * 4) % 16 == 0 &&
+              (RB_ITEMS * 3 * 4) % 16 == 0, "bulk copies move 16-byte multiples between 16-byte aligned addresses");
+__device__ __forceinline__ void bulk_store(float* dst, const float* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(__cvta_generic_to_global(dst)), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(RB_THREADS, PBRL_RB_CTAS)
+k_replay_gather_bulk(int N, int K, const float* __restrict__ data_pos, const float* __restrict__ data_vel, int F, const int* __restrict__ frame0,
+                     const float* __restrict__ tab, unsigned* claim, float* obs, float* reward, float* done, float* xpos, float* xquat) {
+    static_assert(NQ == 35 && NV == 34 && PBRL_OBS == 69 && NB * 3 == 42 && NB * 4 == 56, "lane / column split of the rows");
+    extern __shared__ __align__(128) unsigned char rb_smem[];
+    float* s_const = reinterpret_cast<float*>(rb_smem);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* s_obs = s_const + RB_CONST + wid * RB_STAGE;
+    float* s_pos = s_obs + RB_OBS;
+    float* s_quat = s_pos + RB_POS;
+    if (threadIdx.x < RB_CONST) s_const[threadIdx.x] = threadIdx.x < RB_ITEMS * 3 ? 0.f : 1.0f;   // agent_replay_motion.py: zeros(3), ones
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const long long total = (long long)N * K, nblocks = (total + RB_ITEMS - 1) / RB_ITEMS;
+    const long long warp = (long long)blockIdx.x * RB_WARPS + wid;
+    const bool b_in_qpos = lane < NQ - 32;
+    // Blocks are claimed, not dealt: the SMs drain their write queues at different rates (an even deal left them busy for 77 - 96 %
+    // of the launch).  One counter for the whole launch would be one address taking an atomic every 1.7 ns -- as fast as an L2 slice
+    // serves them, and slower than that when the slice sits on the other die -- so the blocks are split into RB_PARTS ranges with a
+    // counter each (128 bytes apart, zeroed by k_replay_frames); a warp claims from its own range and moves on to the next one
+    // when that is used up.  The claim for the pass after this one is in flight while this one runs.
+    const long long per_part = (nblocks + RB_PARTS - 1) / RB_PARTS;
+    int part = (int)(warp % RB_PARTS), dry = 0;
+    unsigned claimed = 0;
+    if (lane == 0) claimed = atomicAdd(claim + part * RB_CLAIM_STRIDE, 1u);
+    for (;;) {
+        const unsigned mine = __shfl_sync(0xffffffffu, claimed, 0);
+        const long long first = part * per_part, left = nblocks - first, size = left < per_part ? left : per_part;
+        if ((long long)mine >= size) {   // this range is used up (for good): try the next one, stop after a full round
+            if (++dry == RB_PARTS) break;
+            part = part + 1 == RB_PARTS ? 0 : part + 1;
+            if (lane == 0) claimed = atomicAdd(claim + part * RB_CLAIM_STRIDE, 1u);
+            continue;
+        }
+        dry = 0;
+        if (lane == 0) claimed = atomicAdd(claim + part * RB_CLAIM_STRIDE, 1u);
+        const long long g0 = (first + mine) * RB_ITEMS;
+        // (step, env) of the block's first item: one division pair per 16 items (32-bit whenever the rollout allows it)
+        int e0, kf0;
+        if (total <= 0x7fffffffll) { const unsigned g = (unsigned)g0, k = g / (unsigned)N; e0 = (int)(g - k * (unsigned)N); kf0 = (int)(k % (unsigned)F); }
+        else { const long long k = g0 / N; e0 = (int)(g0 - k * N); kf0 = (int)(k % F); }
+        // lane u < RB_ITEMS: the clip row of item g0 + u (past the end: a valid row that is never stored)
+        int fu;
+        {
+            int e = e0 + (lane & (RB_ITEMS - 1)), kf = kf0;
+            while (e >= N) { e -= N; kf = kf + 1 == F ? 0 : kf + 1; }
+            fu = (int)(((unsigned)(frame0 ? __ldg(frame0 + e) : e) + (unsigned)kf) % (unsigned)F);
+        }
+#pragma unroll 1
+        for (int c = 0; c < RB_ITEMS / RB_CHUNK; c++) {   // RB_CHUNK items' loads are in flight before their first shared-memory store
+            float oa[RB_CHUNK], ob[RB_CHUNK], oc[RB_CHUNK], pa[RB_CHUNK], pb[RB_CHUNK], qa[RB_CHUNK], qb[RB_CHUNK];
+#pragma unroll
+            for (int u = 0; u < RB_CHUNK; u++) {
+                const unsigned f = (unsigned)__shfl_sync(0xffffffffu, fu, c * RB_CHUNK + u);
+                // three row pointers per item, every load at a constant offset from one of them
+                const float* rp = data_pos + lane + (size_t)f * NQ;
+                const float* rv = data_vel + lane + (size_t)f * NV;
+                const float* tr = tab + lane + (size_t)f * RT_ROW;
+                oa[u] = __ldg(rp);                                                            // obs columns 0..31
+                ob[u] = __ldg(b_in_qpos ? rp + 32 : rv - (NQ - 32));                          // 32..63: qpos 32..34, qvel 0..28
+                oc[u] = lane < PBRL_OBS - 64 ? __ldg(rv + (64 - NQ)) : 0.f;                   // 64..68: qvel 29..33
+                pa[u] = __ldg(tr); pb[u] = lane < 42 - 32 ? __ldg(tr + 32) : 0.f;
+                qa[u] = __ldg(tr + RT_QUAT); qb[u] = lane < 56 - 32 ? __ldg(tr + RT_QUAT + 32) : 0.f;
+            }
+            if (c == 0) {   // the engine has read the previous block's rows (waited for behind this block's first loads)
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            float* so = s_obs + c * (RB_CHUNK * PBRL_OBS) + lane;
+            float* sp = s_pos + c * (RB_CHUNK * 42) + lane;
+            float* sq = s_quat + c * (RB_CHUNK * 56) + lane;
+#pragma unroll
+            for (int u = 0; u < RB_CHUNK; u++) {
+                so[u * PBRL_OBS] = oa[u];
+                so[u * PBRL_OBS + 32] = ob[u];
+                if (lane < PBRL_OBS - 64) so[u * PBRL_OBS + 64] = oc[u];
+                sp[u * 42] = pa[u];
+                if (lane < 42 - 32) sp[u * 42 + 32] = pb[u];
+                sq[u * 56] = qa[u];
+                if (lane < 56 - 32) sq[u * 56 + 32] = qb[u];
+            }
+        }
+        if (g0 + RB_ITEMS <= total) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rows above, written through the generic proxy, before the engine reads them
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(obs + g0 * PBRL_OBS, s_obs, RB_OBS * 4);
+                bulk_store(xpos + g0 * 42, s_pos, RB_POS * 4);
+                bulk_store(xquat + g0 * 56, s_quat, RB_QUAT * 4);
+                bulk_store(reward + g0 * 3, s_const, RB_ITEMS * 3 * 4);
+                bulk_store(done + g0, s_const + RB_ITEMS * 3, RB_ITEMS * 4);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {   // the rollout's last, partial block
+            __syncwarp();
+            const int n = (int)(total - g0);
+            for (int i = lane; i < n * PBRL_OBS; i += 32) __stcs(obs + g0 * PBRL_OBS + i, s_obs[i]);
+            for (int i = lane; i < n * 42; i += 32) __stcs(xpos + g0 * 42 + i, s_pos[i]);
+            for (int i = lane; i < n * 56; i += 32) __stcs(xquat + g0 * 56 + i, s_quat[i]);
+            for (int i = lane; i < n * 3; i += 32) __stcs(reward + g0 * 3 + i, 0.f);
+            for (int i = lane; i < n; i += 32) __stcs(done + g0 + i, 1.0f);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays allocated until the engine has read it
+}
 __global__ void __launch_bounds__(CTA_THREADS)
 k_pd(const DevModel* __restrict__ gm, int N, int pd_mode, int action_cols, const float* action, const float* qpos,
      const float* qvel, const float* qpos_lag, const float* qvel_lag, const float* kp, const float* kd,
@@ -537,6 +671,7 @@ struct PbrlModel {
     int sm_count = 0;
     int ctas_per_sm = 1;
     int rr_ctas_per_sm = 1;
+    int rb_ctas_per_sm = 0;   // k_replay_gather_bulk: resident CTAs per SM (0: the kernel does not fit, never used)
     bool axes_match = false;  // the model's hinge axes equal the compiled table topo::JNT_AXIS_KIND (replay kinematics specialisation)
     int phase_lock = 48;  // CTA barrier mask of k_step (pbrl_core.cuh: forward): the cooperative Newton loop's vote per iteration
                           // (16) and one barrier after the collision stage (32: a warp that ran the convex narrow phase rejoins
@@ -575,6 +710,15 @@ struct PbrlModel {
         if (cudaMalloc(&p, (size_t)F * 100 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         frame_tabs.push_back({clip, F, p});
         return p;
+    }
+    // block counters of k_replay_gather_bulk: a ring of slots, one per call in flight (zeroed in-stream by k_replay_frames)
+    static constexpr int CLAIM_SLOTS = 8, CLAIM_SLOT_WORDS = RB_PARTS * RB_CLAIM_STRIDE;
+    mutable unsigned* claim_buf = nullptr;
+    mutable unsigned claim_next = 0;
+    unsigned* claim_slot() const {
+        std::lock_guard<std::mutex> lk(scratch_mu);
+        if (!claim_buf && cudaMalloc(&claim_buf, CLAIM_SLOTS * CLAIM_SLOT_WORDS * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); claim_buf = nullptr; return nullptr; }
+        return claim_buf + (size_t)(claim_next++ % CLAIM_SLOTS) * CLAIM_SLOT_WORDS;
     }
     // pbrl_step's order for the second part of a regrouped step: a ring of grow-only buffers, one per call in flight
     static constexpr int ORDER_RING = 4;
@@ -680,6 +824,8 @@ int pbrl_model_create(const PbrlModelDesc* desc, const PbrlMimicDesc* mimic, int
         CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_replay_rollout<false>, RR_ITEMS, RR_SMEM));
         if (nb < 1 || nb2 < 1) return bail("k_replay_rollout does not fit on an SM");
         m->rr_ctas_per_sm = nb < nb2 ? nb : nb2;
+        CREATE_OK(cudaFuncSetAttribute(k_replay_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+        CREATE_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->rb_ctas_per_sm, k_replay_gather_bulk, RB_THREADS, RB_SMEM));
         m->axes_match = true;
         for (int j = 0; j < NJ; j++) {
             const int kind = topo::JNT_AXIS_KIND[j];
@@ -715,6 +861,7 @@ void pbrl_model_destroy(PbrlModel* m) {
     if (m->sched) cudaFree(m->sched);
     for (auto& t : m->frame_tabs) cudaFree(t.tab);
     for (int* p : m->order_bufs) if (p) cudaFree(p);
+    if (m->claim_buf) cudaFree(m->claim_buf);
     delete m;
 }
 
@@ -876,12 +1023,27 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
         if (xpos || xquat) {
             tab = m->frame_table(data_pos, F);
             if (!tab) return fail("pbrl_replay_rollout: cannot allocate the frame table");
-            if (m->axes_match) k_replay_frames<true><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
-            else k_replay_frames<false><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab);
         }
         const long long need = ((long long)N * K + RG_UNROLL * (RG_THREADS / 32) - 1) / (RG_UNROLL * (RG_THREADS / 32));
         const long long cap2 = (long long)m->sm_count * 8;
         const unsigned grid2 = (unsigned)(need < cap2 ? need : cap2);
+        // every output present and 16-byte aligned: the stores go through the bulk-copy engine (PBRL_REPLAY_BULK=0: ordinary stores)
+        const char* bulk_env = getenv("PBRL_REPLAY_BULK");
+        const bool bulk = (bulk_env ? atoi(bulk_env) != 0 : PBRL_REPLAY_BULK_DEFAULT) && m->rb_ctas_per_sm > 0 && obs && reward && done && xpos && xquat &&
+                          (((uintptr_t)obs | (uintptr_t)reward | (uintptr_t)done | (uintptr_t)xpos | (uintptr_t)xquat) & 15) == 0;
+        unsigned* claim = bulk ? m->claim_slot() : nullptr;
+        if (bulk && !claim) return fail("pbrl_replay_rollout: cannot allocate the block counters");
+        if (tab) {
+            if (m->axes_match) k_replay_frames<true><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab, claim);
+            else k_replay_frames<false><<<(F + 63) / 64, 64, 0, st>>>(T, F, data_pos, tab, claim);
+        }
+        if (bulk) {
+            const long long needb = ((long long)N * K + RB_ITEMS * RB_WARPS - 1) / (RB_ITEMS * RB_WARPS);
+            const long long capb = (long long)m->sm_count * m->rb_ctas_per_sm;
+            k_replay_gather_bulk<<<(unsigned)(needb < capb ? needb : capb), RB_THREADS, RB_SMEM, st>>>(N, K, data_pos, data_vel, F, frame0, tab, claim,
+                                                                                                    obs, reward, done, xpos, xquat);
+            return check_launch("pbrl_replay_rollout");
+        }
         if (obs && reward && done && xpos && xquat)
             k_replay_gather<true><<<grid2, RG_THREADS, 0, st>>>(N, K, data_pos, data_vel, F, frame0, tab, obs, reward, done, xpos, xquat);
         else

@@ -133,7 +133,10 @@ def test_edge_sizes_and_full_size_batch_invariance(gpu_grav, model_grav):
     assert np.array_equal(sp.qpos, s.qpos) and np.array_equal(sp.qvel, s.qvel) and np.array_equal(sp.warm, s.warm)
 
 
-def test_replay_rollout(gpu_nograv, model_nograv):
+@pytest.mark.parametrize("bulk", ["0", "1"])
+def test_replay_rollout(gpu_nograv, model_nograv, bulk, monkeypatch):
+    # both store paths of the frame-table form (ordinary stores / bulk-copy engine; the library reads the switch per call)
+    monkeypatch.setenv("PBRL_REPLAY_BULK", bulk)
     pc.check_replay_rollout(gpu_nograv, model_nograv)
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=227, N=4096, K=3, seed=38)   # several CTAs per step, ragged tail
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=1, K=1, seed=39)
@@ -141,6 +144,7 @@ def test_replay_rollout(gpu_nograv, model_nograv):
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=5, N=2, K=41, seed=43)      # frame table with fewer envs than items per warp pass
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=4, N=3, K=7, seed=44)
     pc.check_replay_rollout(gpu_nograv, model_nograv, F=7, N=1, K=64, seed=45)
+    pc.check_replay_rollout(gpu_nograv, model_nograv, F=227, N=4099, K=37, seed=46)  # several passes per warp, ragged last block
     pc.check_replay_rollout_paths_agree(gpu_nograv, model_nograv)
     pc.check_replay_rollout_paths_agree(gpu_nograv, model_nograv, F=227, N=1000, K=3, seed=42)
 
