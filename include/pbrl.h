@@ -206,7 +206,8 @@ int pbrl_replay(const PbrlModel* model, int N, const float* qpos, const float* q
  * xpos [K][N][14][3], xquat [K][N][14][4]; any of them may be NULL.
  * When the N x K items outnumber the F clip rows (>= 4 items per row) the kinematics are evaluated once per clip row per call
  * into a frame table owned by the model and the items gather their rows from it; otherwise per item.  Same arithmetic, same
- * bits (PBRL_REPLAY_PER_ITEM=1 forces the per-item form). */
+ * bits (PBRL_REPLAY_PER_ITEM=1 forces the per-item form).  When every output array is given and 16-byte aligned, the gathered
+ * rows leave through the bulk-copy engine in blocks of 16 items (PBRL_REPLAY_BULK=0: ordinary stores; same bits). */
 int pbrl_replay_rollout(const PbrlModel* model, int N, int K, const float* data_pos, const float* data_vel, int F,
                         const int* frame0, float* obs, float* reward, float* done, float* xpos, float* xquat, void* stream);
 
