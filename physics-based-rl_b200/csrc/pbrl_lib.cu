@@ -384,6 +384,9 @@ constexpr int RB_PARTS = 16, RB_CLAIM_STRIDE = 32;   // block counters of a k_re
 template <bool AXSPEC>
 __global__ void __launch_bounds__(64) k_replay_frames(const __grid_constant__ ReplayTables T, int F, const float* __restrict__ data_pos, float* __restrict__ tab, unsigned* claim) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    // the gather behind this kernel is launched programmatically dependent: its CTAs may become resident and run their prologue now;
+    // they wait (griddepcontrol.wait) for this grid to have completed before they touch the counters or the table
+    asm volatile("griddepcontrol.launch_dependents;");
     if (claim && f < RB_PARTS) claim[f * RB_CLAIM_STRIDE] = 0u;   // the block counters of the k_replay_gather_bulk launch behind this one (blockDim 64 >= RB_PARTS)
     if (f < F) replay_item_fk<AXSPEC>(T, data_pos + (size_t)f * NQ, tab + (size_t)f * RT_ROW, tab + (size_t)f * RT_ROW + RT_QUAT);
 }
@@ -506,6 +509,7 @@ k_replay_gather_bulk(int N, int K, const float* __restrict__ data_pos, const flo
     if (threadIdx.x < RB_CONST) s_const[threadIdx.x] = threadIdx.x < RB_ITEMS * 3 ? 0.f : 1.0f;   // agent_replay_motion.py: zeros(3), ones
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // k_replay_frames (same stream, just ahead) has written the table and zeroed the counters
     const long long total = (long long)N * K, nblocks = (total + RB_ITEMS - 1) / RB_ITEMS;
     const long long warp = (long long)blockIdx.x * RB_WARPS + wid;
     const bool b_in_qpos = lane < NQ - 32;
@@ -1040,8 +1044,20 @@ int pbrl_replay_rollout(const PbrlModel* m, int N, int K, const float* data_pos,
         if (bulk) {
             const long long needb = ((long long)N * K + RB_ITEMS * RB_WARPS - 1) / (RB_ITEMS * RB_WARPS);
             const long long capb = (long long)m->sm_count * m->rb_ctas_per_sm;
-            k_replay_gather_bulk<<<(unsigned)(needb < capb ? needb : capb), RB_THREADS, RB_SMEM, st>>>(N, K, data_pos, data_vel, F, frame0, tab, claim,
-                                                                                                    obs, reward, done, xpos, xquat);
+            // programmatic dependent launch: the CTAs take their places while k_replay_frames (a handful of CTAs) is still running
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(needb < capb ? needb : capb));
+            cfg.blockDim = dim3(RB_THREADS);
+            cfg.dynamicSmemBytes = RB_SMEM;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, k_replay_gather_bulk, N, K, data_pos, data_vel, F, frame0, (const float*)tab, claim, obs,
+                                                      reward, done, xpos, xquat);
+            if (le != cudaSuccess) { cudaGetLastError(); return fail(std::string("pbrl_replay_rollout: ") + cudaGetErrorString(le)); }
             return check_launch("pbrl_replay_rollout");
         }
         if (obs && reward && done && xpos && xquat)

@@ -35,4 +35,5 @@ except Exception as e:
     print("n1 FAILED", e)
 PY
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_replay_gather_bulk -s 4 -c 1 -f -o $O/prof_replay_$T python bench.py --workload replay --steps 4 --warmup 3 > $O/ncu_fr_$T.log 2>&1
+timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches_replay_$T.csv python bench.py --workload replay --steps 4 --warmup 3 > $O/ncu_lr_$T.log 2>&1
 ls -la $O | tail -4
