@@ -124,3 +124,50 @@ def test_static_stance_supports_weight(model_grav):
     assert 0.85 < np.mean(ratios) < 1.2, np.mean(ratios)
     nc = int(d.ncon[0])
     assert d.con_dist[:nc].min() > -1e-3
+
+
+def test_solver_optimum_against_an_independent_minimiser(model_grav):
+    """The constraint solve is `argmin 1/2 (a - a_s)^T M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2` (SURVEY.md App. A.9,
+    MuJoCo's primal problem with pyramidal cones).  Whatever iteration the oracle runs, its qacc must be THE minimiser of that
+    strictly convex cost: checked here without any of the oracle's solver code -- (i) stationarity in numpy, (ii) the same point
+    reached by scipy's trust-region Newton from a different start, (iii) the dual reading: row forces f = -D min(0, J a - aref)
+    are non-negative, complementary to the row residuals, and qfrc_constraint = J^T f.  States: random contact-rich poses (floor
+    contacts, joint limits, limbs touching), the oracle at tolerance 1e-14."""
+    from scipy.optimize import minimize
+    from helpers import random_states
+    orc = Oracle(model_grav, "f64", tolerance=1e-14)
+    qpos, qvel = random_states(model_grav, 16, 77, gravity_heights=True, vel_scale=1.0, joint_frac=0.9)
+    qpos[:, 2] = np.linspace(0.05, 0.9, 16)   # lying on / sunk into the floor ... standing height
+    rng = np.random.default_rng(78)
+    nv, rows_seen, self_rows = 34, 0, 0
+    for e in range(16):
+        d = orc.new_data()
+        d.qpos[:35], d.qvel[:34], d.ctrl[:28], d.qacc_warmstart[:34] = qpos[e], qvel[e], rng.uniform(-1, 1, 28), rng.normal(size=34)
+        orc.forward(d)
+        ne = int(d.nefc[0])
+        on = np.array(d.efc_enabled[:ne]) != 0   # rows that exist in MuJoCo's list: limits / contacts inside their margin
+        M = np.array(d.qM_dense(), np.float64)
+        J = np.array(d.efc_J, np.float64).reshape(-1, 36)[:ne, :nv][on]
+        D, aref = np.array(d.efc_D[:ne], np.float64)[on], np.array(d.efc_aref[:ne], np.float64)[on]
+        ne = int(on.sum())
+        a, a_s = np.array(d.qacc[:nv], np.float64), np.array(d.qacc_smooth[:nv], np.float64)
+        assert np.allclose(M, M.T) and (D > 0).all()
+        rows_seen += ne
+        self_rows += 4 * int(d.nself[0])
+        cost = lambda x: 0.5 * (x - a_s) @ M @ (x - a_s) + 0.5 * np.sum(D * np.minimum(J @ x - aref, 0.0) ** 2)
+        grad = lambda x: M @ (x - a_s) + J.T @ (D * np.minimum(J @ x - aref, 0.0))
+        hess = lambda x: M + (J * (D * (J @ x - aref < 0))[:, None]).T @ J
+        scale = np.abs(M @ (a - a_s)).max() + np.abs(M @ a_s).max()
+        # (i) stationary point of the documented cost
+        assert np.abs(grad(a)).max() <= 1e-9 * scale, (e, np.abs(grad(a)).max(), scale)
+        # (ii) an unrelated optimiser, started from zero, ends at the same point and no lower
+        res = minimize(cost, np.zeros(nv), jac=grad, hess=hess, method="trust-exact", options={"gtol": 1e-10 * scale, "maxiter": 500})
+        assert np.abs(res.x - a).max() <= 1e-6 * max(1.0, np.abs(a).max()), (e, np.abs(res.x - a).max())
+        assert cost(a) <= res.fun + 1e-9 * max(1.0, abs(res.fun))
+        # (iii) forces
+        jar = J @ a - aref
+        f = -D * np.minimum(jar, 0.0)
+        assert (f >= 0).all() and (ne == 0 or np.abs(f * np.maximum(jar, 0.0)).max() == 0.0)
+        assert np.allclose(np.array(d.efc_force[:len(on)], np.float64)[on], f, rtol=1e-10, atol=1e-10 * scale)
+        assert np.allclose(np.array(d.qfrc_constraint[:nv], np.float64), J.T @ f, rtol=1e-9, atol=1e-9 * scale)
+    assert rows_seen >= 200 and self_rows > 0, (rows_seen, self_rows)   # the set really contains contact rows of both kinds
