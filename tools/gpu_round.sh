@@ -24,5 +24,5 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/plain_$T.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_$T.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_l_$T.log 2>&1
 PBRL_REGROUP_AFTER=0 ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 1 -f -o $O/prof_$T python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_f_$T.log 2>&1
 python bench.py --workload replay --steps 4 --warmup 3 > $O/plain_replay_$T.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_replay_gather -s 4 -c 1 -f -o $O/prof_replay_$T python bench.py --workload replay --steps 4 --warmup 3 > $O/ncu_fr_$T.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_replay_gather_bulk -s 4 -c 1 -f -o $O/prof_replay_$T python bench.py --workload replay --steps 4 --warmup 3 > $O/ncu_fr_$T.log 2>&1
 ls -la $O | tail -5

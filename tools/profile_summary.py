@@ -45,20 +45,21 @@ if rrep.exists():
     r2 = list(csv.reader(io.StringIO(raw2)))
     h2, u2, v2 = r2[0], r2[1], r2[2]
     st2 = sorted(h for h in h2 if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"))
-    with open(P / f"{name}_k_replay_gather_ncu_full_summary.csv", "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_replay_gather -s 4 -c 1: python bench.py --workload replay --steps 4 --warmup 3 ({rrep.name})\n")
+    with open(P / f"{name}_k_replay_gather_bulk_ncu_full_summary.csv", "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_replay_gather_bulk -s 4 -c 1: python bench.py --workload replay --steps 4 --warmup 3 ({rrep.name})\n")
         f.write("metric,unit,value\n")
-        for h in WANT + ["l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"] + st2:
+        for h in WANT + ["l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+                         "sm__cycles_active.min", "sm__cycles_active.max", "sm__cycles_elapsed.avg"] + st2:
             if h in h2:
                 i = h2.index(h)
                 f.write(f"{h},{u2[i]},{v2[i]}\n")
     g2 = lambda h: float(v2[h2.index(h)].replace(",", "")) * scale[u2[h2.index(h)]]
     tp = P / f"{name.split(chr(95))[0]}_traffic.json"
     tj = json.loads(tp.read_text())
-    tj["k_replay_gather"] = {"kernel": "k_replay_gather", "workload": "replay", "envs_per_gpu": 4096, "replay_steps_per_launch": 256,
+    tj["k_replay_gather_bulk"] = {"kernel": "k_replay_gather_bulk", "workload": "replay", "envs_per_gpu": 4096, "replay_steps_per_launch": 256,
                              "dram_bytes_per_launch": int(g2("dram__bytes_read.sum") + g2("dram__bytes_write.sum")),
                              "dram_bytes_write": int(g2("dram__bytes_write.sum")), "algorithmic_bytes_per_launch": 4096 * 256 * 684,
-                             "source": f"ncu --set full --clock-control none, one k_replay_gather launch (profiles/{name}_k_replay_gather_ncu_full_summary.csv)"}
+                             "source": f"ncu --set full --clock-control none, one k_replay_gather_bulk launch (profiles/{name}_k_replay_gather_bulk_ncu_full_summary.csv)"}
     tp.write_text(json.dumps(tj, indent=1))
 
 # launch list
