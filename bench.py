@@ -209,12 +209,16 @@ def replay_bench(args, local_rank, first_env=0, quiet=False):
     # the other form of the same entry point, for the record: kinematics per item (what the launch does when the items do not
     # outnumber the clip's rows); the default below evaluates them once per clip row per launch and gathers
     def form_ms(var, val):
+        before = os.environ.get(var)
         os.environ[var] = val
         for _ in range(warmup):
             one()
         torch.cuda.synchronize()
         t = timed_launches(min(steps, 16)) / min(steps, 16)
-        os.environ.pop(var)
+        if before is None:
+            os.environ.pop(var)
+        else:
+            os.environ[var] = before
         return t
     t_item_ms = form_ms("PBRL_REPLAY_PER_ITEM", "1")
     # the two store paths of the frame-table form: ordinary 4-byte-per-lane stores, or rows staged in shared memory and handed to
