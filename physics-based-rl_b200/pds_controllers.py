@@ -68,3 +68,52 @@ stable_pd_controller_custom_trajectory = _brax(3)
 standard_pd_controller_mjx = _mjx(1)
 feedback_pd_controller_mjx = _mjx(2)
 stable_pd_controller_custom_trajectory_mjx = _mjx(3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The building blocks of the reference's stable PD, for callers that assemble the law themselves
+# (/root/reference/agents_env/pds_controllers_agents.py:83-134, pds_controllers_mjx.py:85-153).  They are
+# host-side conveniences over device tensors (batched: a leading env dimension everywhere), not the product
+# path: stable_pd_controller_custom_trajectory above evaluates the whole law inside one kernel, with the
+# tree-sparse factorisation instead of a dense one.  Same argument order and return order as the reference.
+def init_corolis_mass_external_diagonal(*args):
+    """(state, kp_array, kd_array) as pds_controllers_agents.py:83, or (mj_model, mj_data, mjx_data, kp_array, kd_array)
+    as pds_controllers_mjx.py:85 -> C [N,34] (qfrc_bias), M [N,34,34] (dense qM), KP, KD (diagonal matrices of the gains as
+    given: the reference passes them padded to 34), tau_ext [N,34] (qfrc_applied, zeros)."""
+    if len(args) == 3:
+        ps, kp_array, kd_array = args[0].pipeline_state, args[1], args[2]
+    elif len(args) == 5:
+        ps, kp_array, kd_array = args[2], args[3], args[4]
+    else:
+        raise TypeError("init_corolis_mass_external_diagonal(state, kp, kd) or (mj_model, mj_data, mjx_data, kp, kd)")
+    M, C = ps._lag_dynamics()   # one launch for both
+    dev = C.device
+    KP = torch.diag(torch.as_tensor(kp_array, dtype=torch.float32, device=dev).reshape(-1))
+    KD = torch.diag(torch.as_tensor(kd_array, dtype=torch.float32, device=dev).reshape(-1))
+    return C, M, KP, KD, ps.qfrc_applied
+
+
+def calculate_new_mass(M, KD, dt):
+    """M + KD dt (pds_controllers_agents.py:99-104; the reference also prints M)."""
+    return M + KD * dt
+
+
+def calculate_new_mass_check_if_invertible(M, KD, dt, time):
+    """pds_controllers_mjx.py:104-127: M + KD dt, plus 1e-6 I when time == 1, and a warning when the condition number
+    reaches 1 / eps of the dtype."""
+    new_mass = M + KD * dt
+    t = torch.as_tensor(time)
+    if t.numel() == 1 and float(t) == 1:
+        new_mass = new_mass + 1e-6 * torch.eye(new_mass.shape[-1], dtype=new_mass.dtype, device=new_mass.device)
+    cond = torch.linalg.cond(new_mass)
+    if bool((cond >= 1.0 / torch.finfo(new_mass.dtype).eps).any()):
+        print(f"Warning: High condition number ({float(cond.max())}) indicates potential numerical instability. current time {time}")
+    return new_mass
+
+
+def compute_acceleration(q_error, qdot, C, tau_ext, new_mass, KP, KD):
+    """new_mass^-1 (-C - KP q_error - KD qdot + tau_ext) by a Cholesky solve (pds_controllers_agents.py:106-134); vectors
+    are [N,34] or [34], matrices [N,34,34] or [34,34]."""
+    rhs = -C - q_error @ KP.transpose(-1, -2) - qdot @ KD.transpose(-1, -2) + tau_ext
+    L = torch.linalg.cholesky(new_mass)
+    return torch.cholesky_solve(rhs.unsqueeze(-1), L).squeeze(-1)
