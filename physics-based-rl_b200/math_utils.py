@@ -1,8 +1,12 @@
 """Cubic point-to-point joint trajectories used as stable-PD targets.
 
-Same functions as /root/reference/some_math/math_utils.py:75-121 (numpy instead of jax).
+Same functions as /root/reference/some_math/math_utils.py:75-121 (numpy instead of jax).  The mocap half of that module
+(`align_position`, `align_rotation`, `calc_rot_vel`, :15-65) lives in mocap.py and is re-exported here, so that
+`from math_utils import *` finds what the reference's module offers.
 """
 import numpy as np
+
+from .mocap import align_position, align_rotation, calc_rot_vel  # noqa: F401  (re-exports)
 
 
 def generate_trajectory(t0, tf, q0, qf):

@@ -123,22 +123,32 @@ class SimpleConverter(object):
 
     def read_raw_data(self):
         self.all_states = []
-        durations = []
+        self.durations = []
         self.total_time = 0.0
         for frame in self.motions:
-            self.total_time += frame[0]
-            durations.append(frame[0])
+            self.calculate_duration(frame[0])
             state = {"root_pos": align_position(frame[1:4]), "root_rot": align_rotation(frame[4:8])}
-            off = 8
-            for joint in BODY_JOINTS_IN_DP_ORDER:
-                if DOF_DEF[joint] == 1:
-                    state[joint] = frame[off:off + 1].copy()
-                    off += 1
-                else:
-                    state[joint] = align_rotation(frame[off:off + 4])
-                    off += 4
-            self.all_states.append(state)
-        self.durations = np.array(durations)
+            self.align_joints(frame, 8, 8, state)
+        self.durations = np.array(self.durations)
+
+    def align_joints(self, frame, curr_idx, offset_idx, state):
+        """The joint entries of one raw frame, from column `offset_idx` on, in the file's joint order: a hinge is one angle, a
+        ball joint a wxyz quaternion whose axes are re-aligned (positions are relative to the parent and need nothing); the
+        filled `state` joins `all_states` (SimpleConverter.py:193-216; `curr_idx` is overwritten there too)."""
+        for joint in BODY_JOINTS_IN_DP_ORDER:
+            curr_idx = offset_idx
+            if DOF_DEF[joint] == 1:
+                offset_idx += 1
+                state[joint] = frame[curr_idx:offset_idx].copy()
+            else:
+                offset_idx += 4
+                state[joint] = align_rotation(frame[curr_idx:offset_idx])
+        self.all_states.append(state)
+
+    def calculate_duration(self, frame):
+        """`frame` is a frame's duration (its first column): add it to `total_time` and to `durations` (SimpleConverter.py:219-223)."""
+        self.total_time += frame
+        self.durations.append(frame)
 
     def convert_to_mujoco_data(self):
         self.data_vel, self.data_pos = [], []
