@@ -171,3 +171,76 @@ def test_solver_optimum_against_an_independent_minimiser(model_grav):
         assert np.allclose(np.array(d.efc_force[:len(on)], np.float64)[on], f, rtol=1e-10, atol=1e-10 * scale)
         assert np.allclose(np.array(d.qfrc_constraint[:nv], np.float64), J.T @ f, rtol=1e-9, atol=1e-9 * scale)
     assert rows_seen >= 200 and self_rows > 0, (rows_seen, self_rows)   # the set really contains contact rows of both kinds
+
+
+def test_contact_rows_are_the_kinematic_jacobian_of_the_contact_points(model_grav):
+    """A pyramidal contact row is `(n +- mu t_a) . (v_p(body2) - v_p(body1))` as a linear function of qvel, where v_p(b) is the
+    velocity of the material point of body b that sits at the contact position (MuJoCo's definition of the contact Jacobian;
+    SURVEY.md App. A.8).  Checked without the oracle's Jacobian code: every dof is nudged (world translation, body-frame
+    rotation of the free joint, hinge angles), the oracle's forward KINEMATICS moves the two material points, and central
+    differences give the rows -- floor contacts and body-vs-body contacts (where the row is a difference of two bodies).
+    A limit row is +-1 on its own dof."""
+    orc = Oracle(model_grav, "f64", tolerance=1e-14)
+    from helpers import random_states
+    qpos, qvel = random_states(model_grav, 6, 91, gravity_heights=True, vel_scale=1.0, joint_frac=0.9)
+    qpos[:, 2] = [0.1, 0.25, 0.4, 0.55, 0.7, 0.85]
+    nv, eps = 34, 1e-6
+    gb = np.asarray(model_grav.geom_bodyid)
+
+    def kin(q):
+        d = orc.new_data()
+        d.qpos[:35] = q
+        orc.forward(d)
+        return np.array(d.xpos[:42], np.float64).reshape(14, 3), np.array(d.xmat[:126], np.float64).reshape(14, 3, 3)
+
+    def nudge(q, i, h):
+        q = q.copy()
+        if i < 3:
+            q[i] += h
+        elif i < 6:   # angular dofs of the free joint are in the body frame: q <- q * exp(h e / 2)
+            w, v = q[3], q[4:7]
+            e = np.zeros(3); e[i - 3] = 1.0
+            dw, dv = np.cos(h / 2), np.sin(h / 2) * e
+            q[3], q[4:7] = w * dw - v @ dv, w * dv + dw * v + np.cross(v, dv)
+        else:
+            q[i + 1] += h
+        return q
+
+    rows_floor = rows_self = rows_limit = 0
+    for e in range(6):
+        d = orc.new_data()
+        d.qpos[:35], d.qvel[:34] = qpos[e], qvel[e]
+        orc.forward(d)
+        q0 = np.array(d.qpos[:35], np.float64)
+        xpos, xmat = kin(q0)
+        ne, nc = int(d.nefc[0]), int(d.ncon[0])
+        J = np.array(d.efc_J, np.float64).reshape(-1, 36)[:ne, :nv]
+        nlim = ne - 4 * nc
+        for r in range(nlim):   # limit rows: one +-1
+            assert np.count_nonzero(J[r]) == 1 and abs(J[r]).max() == 1.0 and np.flatnonzero(J[r])[0] >= 6
+            rows_limit += 1
+        plus = [kin(nudge(q0, i, eps)) for i in range(nv)]
+        minus = [kin(nudge(q0, i, -eps)) for i in range(nv)]
+        for c in range(nc):
+            if not np.array(d.efc_enabled[nlim + 4 * c:nlim + 4 * c + 4]).any():
+                continue
+            p = np.array(d.con_pos[3 * c:3 * c + 3], np.float64)
+            fr = np.array(d.con_frame[9 * c:9 * c + 9], np.float64).reshape(3, 3)
+            mu = float(d.con_mu[c])
+            b2, b1 = int(gb[int(d.con_geom[c])]), int(gb[int(d.con_geom1[c])])
+            def point_jac(b):
+                if b == 0:
+                    return np.zeros((3, nv))
+                local = xmat[b].T @ (p - xpos[b])
+                return np.stack([((plus[i][0][b] + plus[i][1][b] @ local) - (minus[i][0][b] + minus[i][1][b] @ local)) / (2 * eps)
+                                 for i in range(nv)], 1)
+            Jp = point_jac(b2) - point_jac(b1)
+            for k in range(4):
+                want = (fr[0] + (1.0 if k % 2 == 0 else -1.0) * mu * fr[1 + k // 2]) @ Jp
+                got = J[nlim + 4 * c + k]
+                assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max()), (e, c, k, np.abs(got - want).max())
+            if b1 == 0:
+                rows_floor += 4
+            else:
+                rows_self += 4
+    assert rows_floor >= 40 and rows_self >= 8 and rows_limit >= 6 * 28, (rows_floor, rows_self, rows_limit)
