@@ -244,3 +244,55 @@ def test_contact_rows_are_the_kinematic_jacobian_of_the_contact_points(model_gra
             else:
                 rows_self += 4
     assert rows_floor >= 40 and rows_self >= 8 and rows_limit >= 6 * 28, (rows_floor, rows_self, rows_limit)
+
+
+PENDULUM = """<mujoco model="pend">
+  <compiler angle="radian" inertiafromgeom="true"/>
+  <option timestep="0.002" gravity="0 0 -9.81"/>
+  <worldbody>
+    <body name="arm" pos="0 0 1">
+      <joint name="hinge" type="hinge" axis="0 1 0" range="-0.5 0.5" limited="true"/>
+      <geom name="rod" type="capsule" fromto="0 0 0 0 0 -0.5" size="0.05" density="1000"/>
+    </body>
+  </worldbody>
+  <actuator><motor name="m" joint="hinge" gear="1" ctrlrange="-1 1" ctrllimited="true"/></actuator>
+</mujoco>
+"""
+
+
+def test_limit_row_known_answers_on_a_one_dof_model(tmp_path):
+    """MuJoCo's documented soft-constraint law on the one system where it has a closed form: a single hinge, where the
+    diagonal approximation of A = J M^-1 J^T is exact (dof_invweight0 = 1 / M), so the constrained acceleration in row space is
+    `(1 - d) a0 + d aref` with `aref = -b v - k d r`, `b = 2 / (dmax timeconst)`, `k = 1 / (dmax^2 timeconst^2 dampratio^2)` and
+    the impedance d(r) of solimp = (0.9, 0.95, 0.001, 0.5, 2), solref = (0.02, 1) (the defaults the humanoid uses).  Hand
+    numbers: |r| >= width -> d = 0.95, k d = 2631.5789, b = 105.26316; |r| = width / 2 -> d = 0.925 (the sigmoid's midpoint).
+    finish_row (oracle) is shared by limit and contact rows, so this pins the solref / solimp arithmetic of both."""
+    from helpers import mjcf
+    xml = tmp_path / "pend.xml"
+    xml.write_text(PENDULUM)
+    m = mjcf.compile_mjcf(xml)
+    assert (m.nq, m.nv, m.nu) == (1, 1, 1)
+    orc = Oracle(m, "f64", tolerance=1e-14)
+    hi = 0.5
+    for r, v, d_want in ((-0.01, 0.0, 0.95), (-0.01, 0.7, 0.95), (-0.01, -1.3, 0.95), (-0.0005, 0.2, 0.925), (-0.002, 0.0, 0.95)):
+        for side in (+1, -1):   # upper / lower limit
+            d = orc.new_data()
+            d.qpos[0], d.qvel[0], d.ctrl[0] = side * (hi - r), side * v, 0.3
+            orc.forward(d)
+            M, a0 = float(d.qM[0]), float(d.qacc_smooth[0])
+            assert abs(float(m.dof_invweight0[0]) * M - 1.0) <= 1e-9
+            J = -side                                  # the row measures the distance to the limit
+            assert int(d.nefc[0]) == 1 and float(d.efc_J[0]) == J and float(d.efc_enabled[0]) != 0
+            assert abs(float(d.efc_pos[0]) - r) <= 1e-12
+            k, b = 1.0 / (0.95 ** 2 * 0.02 ** 2), 2.0 / (0.95 * 0.02)
+            aref = -b * (J * side * v) - k * d_want * r
+            assert abs(float(d.efc_aref[0]) - aref) <= 1e-9 * abs(aref), (r, v, side, float(d.efc_aref[0]), aref)
+            assert abs(float(d.efc_D[0]) - d_want / (1.0 - d_want) * M) <= 1e-9 * M
+            want = (1.0 - d_want) * (J * a0) + d_want * aref if J * a0 - aref < 0 else J * a0
+            assert abs(J * float(d.qacc[0]) - want) <= 1e-9 * max(1.0, abs(want)), (r, v, side, J * float(d.qacc[0]), want)
+    assert abs(k * 0.95 - 2631.5789) < 1e-3 and abs(b - 105.26316) < 1e-4
+    # inside the range: the row exists but is switched off, qacc = qacc_smooth
+    d = orc.new_data()
+    d.qpos[0], d.qvel[0] = 0.2, 0.5
+    orc.forward(d)
+    assert float(d.efc_enabled[0]) == 0 and float(d.qacc[0]) == float(d.qacc_smooth[0])
