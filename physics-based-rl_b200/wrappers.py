@@ -2,7 +2,7 @@
 `brax/envs/wrappers/training.py`: `wrap`, `EpisodeWrapper`, `AutoResetWrapper`; SURVEY.md section 8f N3 -- the
 reference imports brax's PPO, `agents_env/agent_mimic.py:14-15`, whose `train` applies exactly these).
 
-`VmapWrapper` has no counterpart: the envs of this package are batched natively (one warp per env).
+`VmapWrapper` is the identity here: the envs of this package are batched natively (one warp per env); it only checks the batch size.
 
   EpisodeWrapper   info['steps'] / info['truncation'], `done` forced at `episode_length`, `action_repeat` inner steps
                    with summed reward (elementwise bookkeeping on the device);
@@ -70,6 +70,18 @@ class EpisodeWrapper(Wrapper):
         state.info["truncation"] = torch.where(over, 1.0 - state.done, torch.zeros_like(state.done))
         state.done.copy_(torch.where(over, torch.ones_like(state.done), state.done))
         return state
+
+
+class VmapWrapper(Wrapper):
+    """brax training.py: VmapWrapper(env, batch_size) vectorises a single-env step with jax.vmap.  The envs here take and
+    return batched states already, so this wrapper forwards everything; a `batch_size` that is not the env's `num_envs` is refused."""
+
+    def __init__(self, env, batch_size=None):
+        super().__init__(env)
+        n = getattr(env, "num_envs", None)
+        if batch_size is not None and n is not None and int(batch_size) != int(n):
+            raise ValueError(f"VmapWrapper: batch_size {batch_size} != num_envs {n} (the batch is fixed when the env is built)")
+        self.batch_size = batch_size
 
 
 class AutoResetWrapper(Wrapper):
